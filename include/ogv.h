@@ -1,0 +1,184 @@
+/*
+ * ogv.h -- C-ABI of libogvit.so: hand-written sm_100a kernels for the OutGridBlock hot path
+ * (Outlooker -> MBConv -> GridAttn -> MLP, forward and backward).
+ *
+ * Every entry point replaces a stretch of PyTorch-eager code in the reference
+ * (pablo-reyes8/outlook-grid-vision-transformer); the reference file:line each one stands for
+ * is cited beside it.  The reference has no FFI of its own (it is pure Python), so this header
+ * IS the boundary a maintainer would bind (ctypes stub in INTEGRATION.md).
+ *
+ * Conventions
+ *  - all pointers are DEVICE pointers owned by the caller; no hidden allocation, no host sync;
+ *  - activations are "rows x channels" tensors: row m = (b*H + h)*W + w (NHWC flattened),
+ *    channels contiguous, dtype = OGV_F32 or OGV_BF16; statistics / parameters / gradients of
+ *    parameters are always fp32;
+ *  - `stream` is a cudaStream_t passed as void*;
+ *  - return value: 0 on success, negative error code otherwise (ogv_last_error() has the text).
+ */
+#ifndef OGV_H_
+#define OGV_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OGV_OK 0
+#define OGV_ERR_ARG (-1)
+#define OGV_ERR_CUDA (-2)
+#define OGV_ERR_UNSUPPORTED (-3)
+
+#define OGV_F32 0
+#define OGV_BF16 1
+
+#define OGV_ACT_NONE 0
+#define OGV_ACT_GELU 1
+#define OGV_ACT_SILU 2
+#define OGV_ACT_SIGMOID 3
+#define OGV_ACT_RELU 4
+
+#define OGV_ENGINE_AUTO 0
+#define OGV_ENGINE_SIMT 1 /* fp32 FFMA tiles (exact-fp32 parity mode, debugging) */
+#define OGV_ENGINE_TC 2   /* tcgen05 + TMEM + TMA (bf16 operands, fp32 accumulate) */
+
+int ogv_version(void);
+const char* ogv_last_error(void);
+int ogv_sm_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Pointwise GEMM with fused epilogue.   D[m,n] = epi( sum_k A(m,k) * B(n,k) )
+ * Stands for every nn.Conv2d 1x1 / nn.Linear on the path, forward, dgrad and wgrad:
+ *   outlook_attention.py:41-47,83-88,100,110,122 ; mbc_conv.py:17-19,67-85 ;
+ *   grid_attention.py:57-59,70,86-87 ; Out_Grid_Block.py:18-22,27-31 (and their autograd).
+ * A(m,k) = A[m*a_rs + k*a_cs], B(n,k) = B[n*b_rs + k*b_cs]  (element strides).
+ *   forward : A = activations [M,K] (a_cs=1), B = weight [N,K] (b_cs=1)
+ *   dgrad   : A = dY [M,N'],  B = W^T [K',N'] (pre-transposed copy, b_cs=1)
+ *   wgrad   : A(m,k) = dY[k, m] (a_rs=1), B(n,k) = X[k, n] (b_rs=1), reduction over rows
+ * epilogue order: v = acc (+bias[n]); pre_out[m,n] = v; v = act(v); v *= act'(dact_src[m,n]);
+ *                 v *= row_scale[m / rows_per_scale]; v += residual[m,n]; D[m,n] = v (or += v).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct ogv_gemm_args {
+  const void* A;
+  long long a_rs, a_cs;
+  const void* B;
+  long long b_rs, b_cs;
+  void* D;
+  long long ldd;
+  int M, N, K;
+  int in_dtype;  /* dtype of A and B */
+  int out_dtype; /* dtype of D, pre_out, residual, dact_src */
+  const float* bias; /* [N] or NULL */
+  void* pre_out;     /* optional [M,N] (ld_pre) */
+  long long ld_pre;
+  int act; /* OGV_ACT_* applied after bias */
+  const void* dact_src; /* optional [M,N]: multiply by act'(dact_src), act code in `dact` */
+  long long ld_dact;
+  int dact;
+  const float* row_scale; /* optional per-sample scale (stochastic depth) */
+  int rows_per_scale;
+  const void* residual; /* optional [M,N] */
+  long long ld_res;
+  int accumulate; /* 1: D is fp32 and is atomically accumulated into (split-K partial sums) */
+  int split_k;    /* >=1; >1 requires accumulate */
+  float* col_sum;   /* optional [N]: += sum_m of stored value (BatchNorm batch statistics) */
+  float* col_sumsq; /* optional [N]: += sum_m of stored value^2 */
+} ogv_gemm_args;
+
+int ogv_gemm(const ogv_gemm_args* args, int engine, void* stream);
+
+/* Layout boundary: the reference hands the block NCHW tensors (Out_Grid_Block.py:88-107). */
+int ogv_nchw_to_nhwc(const void* src, void* dst, int B, int C, int HW, int dtype, void* stream);
+int ogv_nhwc_to_nchw(const void* src, void* dst, int B, int C, int HW, int dtype, void* stream);
+
+/* fp32 master weight [rows, cols] -> compute-dtype copy dst[r*ld_dst + c] and/or transposed copy
+ * dst_t[c*ld_dst_t + r] (what torch.autocast's weight cast does per step; autocast.py:60-66). */
+int ogv_cast_transpose(const float* src, void* dst, long long ld_dst, void* dst_t, long long ld_dst_t,
+                       int rows, int cols, int dtype, void* stream);
+/* y = x * scale[row / rows_per_scale]  (DropPath, Outlook_Block.py:15-22) */
+int ogv_rowscale(const void* x, const float* scale, void* y, long long rows, int cols, int rows_per_scale,
+                 int dtype, void* stream);
+/* out[n] += sum_m x[m,n]  (bias gradients) */
+int ogv_colsum(const void* x, long long ld, float* out, long long M, int N, int dtype, void* stream);
+/* out = a * act'(pre) elementwise, n elements (SE gate backward) */
+int ogv_mul_dact(const void* a, const void* pre, void* out, long long n, int act, int dtype, void* stream);
+/* y = a + b elementwise */
+int ogv_add(const void* a, const void* b, void* y, long long n, int dtype, void* stream);
+
+/* LayerNorm over channels (outlook_attention.py:24-31 eps 1e-6; Out_Grid_Block.py:69,84 eps 1e-5). */
+int ogv_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                      long long M, int C, float eps, int dtype, void* stream);
+/* dx = dres + LN'(dy); dgamma/dbeta are accumulated (+=) */
+int ogv_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
+                      const void* dres, void* dx, float* dgamma, float* dbeta, long long M, int C, int dtype,
+                      void* stream);
+
+/* Outlook core (outlook_attention.py:104-120): `va` holds v in columns [0,C) and the k*k logits of
+ * head h in columns [C + h*9, C + h*9 + 9); row stride ld_va.  y[p,c] = sum_t softmax(logits)[t] * v[p+d_t,c]. */
+int ogv_outlook_core_fwd(const void* va, long long ld_va, void* y, int B, int H, int W, int C, int heads,
+                         int dtype, void* stream);
+/* dva gets dv in [0,C), dlogits in [C, C+9*heads), zeros up to ld_va. */
+int ogv_outlook_core_bwd(const void* va, long long ld_va, const void* dy, void* dva, int B, int H, int W, int C,
+                         int heads, int dtype, void* stream);
+
+/* BatchNorm2d (mbc_conv.py:61; training = batch statistics).  stats: sum/sumsq -> scale/shift,
+ * mean/rstd, and the running-stat update (momentum, unbiased variance). */
+int ogv_colstats(const void* x, long long ld, float* sum, float* sumsq, long long M, int N, int dtype, void* stream);
+int ogv_bn_finalize(const float* sum, const float* sumsq, const float* gamma, const float* beta,
+                    float* running_mean, float* running_var, float* scale, float* shift, float* mean, float* rstd,
+                    long long n, int C, float eps, float momentum, int training, void* stream);
+/* out = res + scale*x + shift  (res optional) */
+int ogv_bn_apply(const void* x, const float* scale, const float* shift, const void* res, void* out, long long M,
+                 int C, int dtype, void* stream);
+/* dbeta += sum dy ; dgamma += sum dy * (x-mean)*rstd */
+int ogv_bn_bwd_reduce(const void* dy, const void* x, const float* mean, const float* rstd, float* dgamma,
+                      float* dbeta, long long M, int C, int dtype, void* stream);
+/* dx = gamma*rstd*(dy - dbeta/n - xhat*dgamma/n) */
+int ogv_bn_bwd_apply(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma,
+                     const float* dgamma, const float* dbeta, void* dx, long long M, int C, int dtype,
+                     void* stream);
+
+/* Depthwise 3x3 (mbc_conv.py:73-78) with BN1-affine + SiLU applied to the input on load and the
+ * batch statistics of the output accumulated on store.  w is [Cm, 9] fp32. */
+int ogv_dwconv_fwd(const void* e_pre, const float* scale1, const float* shift1, const float* w, void* d_pre,
+                   float* sum2, float* sumsq2, int B, int H, int W, int Cm, int act, int dtype, void* stream);
+/* SE squeeze (mbc_conv.py:22-23): pool[b,c] = mean_hw act(scale2*d_pre+shift2) */
+int ogv_se_pool(const void* d_pre, const float* scale2, const float* shift2, float* pool, int B, int HW, int Cm,
+                int act, int dtype, void* stream);
+/* d_act = act(scale2*d_pre+shift2) * gate[b,c]   (mbc_conv.py:27) */
+int ogv_bn_act_gate(const void* d_pre, const float* scale2, const float* shift2, const float* gate, void* d_act,
+                    int B, int HW, int Cm, int act, int dtype, void* stream);
+/* dgate[b,c] = sum_hw dd_act * act(scale2*d_pre+shift2) */
+int ogv_se_bwd_reduce(const void* dd_act, const void* d_pre, const float* scale2, const float* shift2,
+                      float* dgate, int B, int HW, int Cm, int act, int dtype, void* stream);
+/* du = (dd_act*gate + dpool/HW) * act'(u), u = scale2*d_pre+shift2.
+ * pass 0 (reduce): dbeta2 += sum du ; dgamma2 += sum du*xhat2
+ * pass 1 (apply) : dd_pre = gamma2*rstd2*(du - dbeta2/n - xhat2*dgamma2/n) */
+int ogv_dw_bn2_bwd(int pass, const void* dd_act, const void* d_pre, const float* gate, const float* dpool,
+                   const float* scale2, const float* shift2, const float* mean2, const float* rstd2,
+                   const float* gamma2, float* dgamma2, float* dbeta2, void* dd_pre, int B, int HW, int Cm,
+                   int act, int dtype, void* stream);
+/* Depthwise backward: du1 = corr(dd_pre, w) * act'(u1); dw[c,t] += sum dd_pre[p]*act(u1[p+d_t]);
+ * dbeta1 += sum du1 ; dgamma1 += sum du1*xhat1. */
+int ogv_dwconv_bwd(const void* dd_pre, const void* e_pre, const float* scale1, const float* shift1,
+                   const float* mean1, const float* rstd1, const float* w, void* du1, float* dw, float* dgamma1,
+                   float* dbeta1, int B, int H, int W, int Cm, int act, int dtype, void* stream);
+
+/* Grid attention core (grid_partition.py:13-15 + grid_attention.py:70-86) on qkv [M,3C] in
+ * NHWC row order; the grid partition/unpartition is index arithmetic inside the kernel. */
+int ogv_grid_attn_fwd(const void* qkv, void* out, int B, int H, int W, int C, int heads, int g, int dtype,
+                      void* stream);
+int ogv_grid_attn_bwd(const void* qkv, const void* dout, void* dqkv, int B, int H, int W, int C, int heads, int g,
+                      int dtype, void* stream);
+/* attention probabilities for analysis hooks (grid_attention.py:77-78): attn [B*g*g, heads, N, N] fp32 */
+int ogv_grid_attn_probs(const void* qkv, float* attn, int B, int H, int W, int C, int heads, int g, int dtype,
+                        void* stream);
+
+/* Fused multi-tensor AdamW over a flat fp32 arena (train_full_model.py:56-57). */
+int ogv_adamw(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+              float eps, float weight_decay, float bias_c1, float bias_c2, float grad_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OGV_H_ */

@@ -1,0 +1,176 @@
+// Common device/host helpers for the OutGridBlock sm_100a kernels.
+// Activations are stored "rows x channels" (NHWC flattened: row m = (b*H + h)*W + w),
+// either fp32 or bf16; all arithmetic is fp32.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+
+typedef __nv_bfloat16 bf16;
+
+#define OGV_OK 0
+#define OGV_ERR_ARG (-1)
+#define OGV_ERR_CUDA (-2)
+#define OGV_ERR_UNSUPPORTED (-3)
+
+#define OGV_F32 0
+#define OGV_BF16 1
+
+#define OGV_ACT_NONE 0
+#define OGV_ACT_GELU 1
+#define OGV_ACT_SILU 2
+#define OGV_ACT_SIGMOID 3
+#define OGV_ACT_RELU 4
+
+void ogv_set_error(const char* fmt, ...);
+int ogv_check_launch(const char* what);
+int ogv_num_sms();
+
+#define OGV_REQUIRE(cond, ...)                 \
+  do {                                         \
+    if (!(cond)) {                             \
+      ogv_set_error(__VA_ARGS__);              \
+      return OGV_ERR_ARG;                      \
+    }                                          \
+  } while (0)
+
+// Dispatch on the activation dtype code.
+#define OGV_DISPATCH_DTYPE(dtype, T, ...)                       \
+  do {                                                          \
+    if ((dtype) == OGV_F32) {                                   \
+      typedef float T;                                          \
+      __VA_ARGS__;                                              \
+    } else if ((dtype) == OGV_BF16) {                           \
+      typedef bf16 T;                                           \
+      __VA_ARGS__;                                              \
+    } else {                                                    \
+      ogv_set_error("unsupported dtype code %d", (int)(dtype)); \
+      return OGV_ERR_ARG;                                       \
+    }                                                           \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// scalar / vector load-store in fp32 registers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float ld1(const float* p) { return *p; }
+__device__ __forceinline__ float ld1(const bf16* p) { return __bfloat162float(*p); }
+__device__ __forceinline__ void st1(float* p, float v) { *p = v; }
+__device__ __forceinline__ void st1(bf16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+// value as it will read back after being stored as T
+template <typename T> __device__ __forceinline__ float round_to(float v);
+template <> __device__ __forceinline__ float round_to<float>(float v) { return v; }
+template <> __device__ __forceinline__ float round_to<bf16>(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+
+// 8 consecutive elements (16-byte aligned for bf16, 32-byte for fp32).
+__device__ __forceinline__ void ld8(const float* p, float (&v)[8]) {
+  float4 a = *reinterpret_cast<const float4*>(p);
+  float4 b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+  v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void ld8(const bf16* p, float (&v)[8]) {
+  uint4 u = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 f = __bfloat1622float2(h[i]);
+    v[2 * i] = f.x;
+    v[2 * i + 1] = f.y;
+  }
+}
+__device__ __forceinline__ void st8(float* p, const float (&v)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void st8(bf16* p, const float (&v)[8]) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+
+// VEC-wide generic versions (VEC in {1,2,4,8}); alignment = VEC*sizeof(T).
+template <int VEC, typename T>
+__device__ __forceinline__ void ldv(const T* p, float (&v)[VEC]) {
+  if constexpr (VEC == 8) {
+    ld8(p, v);
+  } else if constexpr (VEC == 4 && sizeof(T) == 4) {
+    float4 a = *reinterpret_cast<const float4*>(p);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+  } else if constexpr (VEC == 4 && sizeof(T) == 2) {
+    uint2 u = *reinterpret_cast<const uint2*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+    float2 f0 = __bfloat1622float2(h[0]), f1 = __bfloat1622float2(h[1]);
+    v[0] = f0.x; v[1] = f0.y; v[2] = f1.x; v[3] = f1.y;
+  } else {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) v[i] = ld1(p + i);
+  }
+}
+template <int VEC, typename T>
+__device__ __forceinline__ void stv(T* p, const float (&v)[VEC]) {
+  if constexpr (VEC == 8) {
+    st8(p, v);
+  } else if constexpr (VEC == 4 && sizeof(T) == 4) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  } else if constexpr (VEC == 4 && sizeof(T) == 2) {
+    uint2 u;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+    h[0] = __floats2bfloat162_rn(v[0], v[1]);
+    h[1] = __floats2bfloat162_rn(v[2], v[3]);
+    *reinterpret_cast<uint2*>(p) = u;
+  } else {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) st1(p + i, v[i]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// activations (exact erf GELU, SiLU, sigmoid) and their derivatives w.r.t. the pre-activation
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-x)); }
+__device__ __forceinline__ float silu_f(float x) { return x * sigmoid_f(x); }
+__device__ __forceinline__ float dsilu_f(float x) {
+  float s = sigmoid_f(x);
+  return s * (1.f + x * (1.f - s));
+}
+__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float dgelu_f(float x) {
+  float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752440f));
+  float pdf = 0.39894228040143267794f * expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+__device__ __forceinline__ float act_apply(int act, float x) {
+  switch (act) {
+    case OGV_ACT_GELU: return gelu_f(x);
+    case OGV_ACT_SILU: return silu_f(x);
+    case OGV_ACT_SIGMOID: return sigmoid_f(x);
+    case OGV_ACT_RELU: return x > 0.f ? x : 0.f;
+    default: return x;
+  }
+}
+__device__ __forceinline__ float act_grad(int act, float x) {
+  switch (act) {
+    case OGV_ACT_GELU: return dgelu_f(x);
+    case OGV_ACT_SILU: return dsilu_f(x);
+    case OGV_ACT_SIGMOID: { float s = sigmoid_f(x); return s * (1.f - s); }
+    case OGV_ACT_RELU: return x > 0.f ? 1.f : 0.f;
+    default: return 1.f;
+  }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+static inline int ogv_ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }

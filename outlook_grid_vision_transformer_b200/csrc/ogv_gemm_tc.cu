@@ -1,0 +1,371 @@
+// tcgen05 GEMM engine for sm_100a:  D[M,N] = epi( A[M,K] * B[N,K]^T ), bf16 operands, fp32 accumulate.
+//
+//   * persistent, warp-specialised CTA of 192 threads, one CTA per SM:
+//       warp 0      TMA producer  (cp.async.bulk.tensor 2-D boxes, 128B swizzle, mbarrier complete_tx)
+//       warp 1      TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BN x 16, cta_group::1)
+//       warps 2..5  epilogue: tcgen05.ld (lane = output row) -> fused epilogue -> global
+//   * smem ring of STAGES x (A 128x64 | B BNx64) bf16 tiles; accumulators double-buffered in TMEM
+//     (2 x BN fp32 columns) so the epilogue of tile i overlaps the MMAs of tile i+1;
+//   * operands may be K-major (forward / dgrad) or MN-major (wgrad: reduction over the row index
+//     of both global tensors) -- only the TMA box and the UMMA descriptors differ;
+//   * split-K work items (wgrad) accumulate with fp32 atomics into D.
+#include "ogv_gemm.cuh"
+#include "ogv_ptx.cuh"
+
+namespace {
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 64;  // 64 bf16 = one 128-byte swizzle row
+constexpr int TC_THREADS = 192;
+
+template <int BN>
+struct TcCfg {
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int A_BYTES = TC_BM * TC_BK * 2;
+  static constexpr int B_BYTES = BN * TC_BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;
+  static constexpr int TMEM_COLS = 2 * BN;
+};
+
+struct TcParams {
+  int M, N, K;
+  int a_mn, b_mn;
+  int m_tiles, n_tiles, splits, chunks_per_split, k_chunks;
+  int vec_ok;
+  GemmEpi epi;
+};
+
+template <typename TO>
+__device__ __forceinline__ void epi_row16(const GemmEpi& e, int m, int n0, float (&v)[16], int vec_ok) {
+  if (vec_ok && n0 + 16 <= e.N) {
+    const float rs = e.row_scale ? e.row_scale[m / e.rows_per_scale] : 1.f;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int n = n0 + 8 * h;
+      float x[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[i] = v[8 * h + i];
+      if (e.bias) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] += __ldg(e.bias + n + i);
+      }
+      if (e.pre_out) st8(reinterpret_cast<TO*>(e.pre_out) + (long long)m * e.ld_pre + n, x);
+      if (e.act != OGV_ACT_NONE) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = act_apply(e.act, x[i]);
+      }
+      if (e.dact_src) {
+        float d[8];
+        ld8(reinterpret_cast<const TO*>(e.dact_src) + (long long)m * e.ld_dact + n, d);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] *= act_grad(e.dact, d[i]);
+      }
+      if (e.row_scale) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] *= rs;
+      }
+      if (e.residual) {
+        float r[8];
+        ld8(reinterpret_cast<const TO*>(e.residual) + (long long)m * e.ld_res + n, r);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] += r[i];
+      }
+      if (e.accumulate) {
+        float* d = reinterpret_cast<float*>(e.D) + (long long)m * e.ldd + n;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) atomicAdd(d + i, x[i]);
+      } else {
+        st8(reinterpret_cast<TO*>(e.D) + (long long)m * e.ldd + n, x);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (n0 + j < e.N) epi_scalar<TO>(e, m, n0 + j, v[j]);
+  }
+}
+
+template <int BN, typename TO>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+  using Cfg = TcCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  // 128B-swizzled TMA/UMMA tiles need 1024-byte alignment.
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + Cfg::STAGES;
+  uint64_t* tfull_bar = empty_bar + Cfg::STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    ptx::tma_prefetch_desc(&tmA);
+    ptx::tma_prefetch_desc(&tmB);
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(&tfull_bar[s], 1);
+      ptx::mbar_init(&tempty_bar[s], 4);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total = p.m_tiles * p.n_tiles * p.splits;
+
+  if (warp == 0) {
+    // ------------------------------- TMA producer -------------------------------
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = blockIdx.x; w < total; w += gridDim.x) {
+        const int nt = w % p.n_tiles;
+        const int mt = (w / p.n_tiles) % p.m_tiles;
+        const int sp = w / (p.n_tiles * p.m_tiles);
+        const int m0 = mt * TC_BM, n0 = nt * BN;
+        const int kc0 = sp * p.chunks_per_split;
+        const int kc1 = min(p.k_chunks, kc0 + p.chunks_per_split);
+        for (int kc = kc0; kc < kc1; ++kc) {
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
+          ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + Cfg::A_BYTES;
+          const int k0 = kc * TC_BK;
+          if (!p.a_mn) {
+            ptx::tma_load_2d(sa, &tmA, &full_bar[stage], k0, m0);  // box {64 k, 128 rows}
+          } else {
+#pragma unroll
+            for (int j = 0; j < TC_BM / 64; ++j)  // box {64 mn, 64 k-rows}
+              ptx::tma_load_2d(sa + j * 8192, &tmA, &full_bar[stage], m0 + 64 * j, k0);
+          }
+          if (!p.b_mn) {
+            ptx::tma_load_2d(sb, &tmB, &full_bar[stage], k0, n0);  // box {64 k, BN rows}
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              ptx::tma_load_2d(sb + j * 8192, &tmB, &full_bar[stage], n0 + 64 * j, k0);
+          }
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------- MMA issuer -------------------------------
+    if (lane == 0) {
+      const uint32_t idesc = ptx::umma_idesc_bf16(TC_BM, BN, p.a_mn, p.b_mn);
+      // K-major  : rows of 128 B, 8-row groups 1024 B apart (SBO); +32 B per UMMA_K step.
+      // MN-major : 64-element MN blocks 8192 B apart (LBO), 8-k-row groups 1024 B apart (SBO);
+      //            +2048 B (16 k-rows) per UMMA_K step.
+      const uint32_t a_lbo = p.a_mn ? 8192u : 16u, b_lbo = p.b_mn ? 8192u : 16u;
+      const uint32_t a_step = p.a_mn ? 2048u : 32u, b_step = p.b_mn ? 2048u : 32u;
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
+        const int sp = w / (p.n_tiles * p.m_tiles);
+        const int kc0 = sp * p.chunks_per_split;
+        const int kc1 = min(p.k_chunks, kc0 + p.chunks_per_split);
+        const int as = it & 1;
+        ptx::mbar_wait(&tempty_bar[as], ((it >> 1) & 1) ^ 1u);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kc = kc0; kc < kc1; ++kc) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tc_fence_after();
+          const uint32_t sa = ptx::smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t sb = sa + Cfg::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k) {
+            const uint64_t adesc = ptx::umma_smem_desc(sa + k * a_step, a_lbo, 1024u);
+            const uint64_t bdesc = ptx::umma_smem_desc(sb + k * b_step, b_lbo, 1024u);
+            ptx::umma_f16(d_tmem, adesc, bdesc, idesc, (kc > kc0 || k > 0) ? 1u : 0u);
+          }
+          ptx::umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+        }
+        ptx::umma_commit(&tfull_bar[as]);  // accumulator ready for the epilogue warps
+      }
+    }
+  } else {
+    // ------------------------------- epilogue -------------------------------
+    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    int it = 0;
+    for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
+      const int nt = w % p.n_tiles;
+      const int mt = (w / p.n_tiles) % p.m_tiles;
+      const int m0 = mt * TC_BM, n0 = nt * BN;
+      const int as = it & 1;
+      ptx::mbar_wait(&tfull_bar[as], (it >> 1) & 1);
+      ptx::tc_fence_after();
+      const int m = m0 + q * 32 + lane;
+      const uint32_t t0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 16) {
+        if (n0 + c >= p.N) break;
+        float v[16];
+        ptx::tmem_ld16(t0 + c, v);
+        if (m < p.M) epi_row16<TO>(p.epi, m, n0 + c, v, p.vec_ok);
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tempty_bar[as]);
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// 2-D bf16 tensor map: inner (contiguous) extent `inner`, outer extent `outer`, outer stride in elements.
+int make_tmap(CUtensorMap* tm, const void* ptr, long long inner, long long outer, long long ld, int box_outer) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) {
+    ogv_set_error("cuTensorMapEncodeTiled entry point not available");
+    return OGV_ERR_CUDA;
+  }
+  cuuint64_t gdim[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64u, (cuuint32_t)box_outer};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    ogv_set_error("cuTensorMapEncodeTiled failed (%d) inner=%lld outer=%lld ld=%lld box_outer=%d ptr=%p", (int)r,
+                  inner, outer, ld, box_outer, ptr);
+    return OGV_ERR_CUDA;
+  }
+  return OGV_OK;
+}
+
+// 0 = K-major (contiguous along k), 1 = MN-major (contiguous along m/n), -1 = not expressible.
+int operand_major(long long rs, long long cs) {
+  if (cs == 1) return 0;
+  if (rs == 1) return 1;
+  return -1;
+}
+
+template <int BN, typename TO>
+int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, cudaStream_t stream) {
+  using Cfg = TcCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      ogv_set_error("gemm_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+      return OGV_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  int total = p.m_tiles * p.n_tiles * p.splits;
+  int grid = total < ogv_num_sms() ? total : ogv_num_sms();
+  gemm_tc_kernel<BN, TO><<<grid, TC_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  return ogv_check_launch("gemm_tc");
+}
+
+}  // namespace
+
+bool ogv_gemm_tc_supported(const ogv_gemm_args& a, const char** why) {
+  static const char* msg = "";
+  auto fail = [&](const char* m) {
+    msg = m;
+    if (why) *why = msg;
+    return false;
+  };
+  if (a.in_dtype != OGV_BF16) return fail("operands must be bf16");
+  if (a.M < 1 || a.N < 1 || a.K < 1) return fail("empty problem");
+  int am = operand_major(a.a_rs, a.a_cs), bm = operand_major(a.b_rs, a.b_cs);
+  if (am < 0 || bm < 0) return fail("operand has no unit stride");
+  long long a_ld = am ? a.a_cs : a.a_rs, b_ld = bm ? a.b_cs : a.b_rs;
+  if (a_ld % 8 || b_ld % 8) return fail("leading dimension not a multiple of 8 elements (16 B)");
+  if ((reinterpret_cast<uintptr_t>(a.A) & 15) || (reinterpret_cast<uintptr_t>(a.B) & 15))
+    return fail("operand base not 16-byte aligned");
+  if (a.col_sum || a.col_sumsq) return fail("column statistics not fused in the tcgen05 epilogue");
+  if (a.split_k > 1 && !a.accumulate) return fail("split_k>1 needs accumulate");
+  if (a.accumulate && a.out_dtype != OGV_F32) return fail("accumulate needs fp32 output");
+  return true;
+}
+
+int ogv_gemm_tc(const ogv_gemm_args& a, cudaStream_t stream) {
+  const char* why = "";
+  if (!ogv_gemm_tc_supported(a, &why)) {
+    ogv_set_error("gemm_tc: unsupported problem: %s", why);
+    return OGV_ERR_UNSUPPORTED;
+  }
+  TcParams p;
+  p.M = a.M; p.N = a.N; p.K = a.K;
+  p.a_mn = operand_major(a.a_rs, a.a_cs);
+  p.b_mn = operand_major(a.b_rs, a.b_cs);
+  const int BN = a.N <= 64 ? 64 : (a.N <= 128 ? 128 : 256);
+  p.m_tiles = ogv_ceil_div(a.M, TC_BM);
+  p.n_tiles = ogv_ceil_div(a.N, BN);
+  p.k_chunks = ogv_ceil_div(a.K, TC_BK);
+  int split = a.split_k > 0 ? a.split_k : 1;
+  if (split > p.k_chunks) split = p.k_chunks;
+  p.chunks_per_split = ogv_ceil_div(p.k_chunks, split);
+  p.splits = ogv_ceil_div(p.k_chunks, p.chunks_per_split);
+  p.epi = make_epi(a);
+  // vector epilogue needs 8-element alignment of every [M,N] tensor it touches
+  const int esz = a.out_dtype == OGV_BF16 ? 2 : 4;
+  auto ok = [&](const void* ptr, long long ld) {
+    return ptr == nullptr || ((reinterpret_cast<uintptr_t>(ptr) % 16 == 0) && ((ld * esz) % 16 == 0) && (ld % 8 == 0 || esz == 4));
+  };
+  p.vec_ok = (a.accumulate || ok(a.D, a.ldd)) && ok(a.pre_out, a.ld_pre) && ok(a.dact_src, a.ld_dact) &&
+             ok(a.residual, a.ld_res);
+
+  CUtensorMap tmA, tmB;
+  int rc;
+  if (!p.a_mn) rc = make_tmap(&tmA, a.A, a.K, a.M, a.a_rs, TC_BM);
+  else rc = make_tmap(&tmA, a.A, a.M, a.K, a.a_cs, 64);
+  if (rc) return rc;
+  if (!p.b_mn) rc = make_tmap(&tmB, a.B, a.K, a.N, a.b_rs, BN);
+  else rc = make_tmap(&tmB, a.B, a.N, a.K, a.b_cs, 64);
+  if (rc) return rc;
+
+  const bool obf = a.out_dtype == OGV_BF16;
+  if (a.out_dtype != OGV_BF16 && a.out_dtype != OGV_F32) {
+    ogv_set_error("gemm_tc: bad out dtype %d", a.out_dtype);
+    return OGV_ERR_ARG;
+  }
+  switch (BN) {
+    case 64: return obf ? launch_tc<64, bf16>(tmA, tmB, p, stream) : launch_tc<64, float>(tmA, tmB, p, stream);
+    case 128: return obf ? launch_tc<128, bf16>(tmA, tmB, p, stream) : launch_tc<128, float>(tmA, tmB, p, stream);
+    default: return obf ? launch_tc<256, bf16>(tmA, tmB, p, stream) : launch_tc<256, float>(tmA, tmB, p, stream);
+  }
+}

@@ -1,0 +1,310 @@
+// Library plumbing (error text, launch checks, GEMM engine selection) and the small layout /
+// elementwise kernels around the hot path.
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "ogv_gemm.cuh"
+#include "ogv_reduce.cuh"
+
+// ---------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+void ogv_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+static int g_sync_mode = -1;
+int ogv_check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    ogv_set_error("%s: launch failed: %s", what, cudaGetErrorString(e));
+    return OGV_ERR_CUDA;
+  }
+  if (g_sync_mode < 0) {
+    const char* s = getenv("OGV_SYNC");
+    g_sync_mode = (s && s[0] == '1') ? 1 : 0;
+  }
+  if (g_sync_mode == 1) {  // debugging aid only: surfaces asynchronous faults at the faulting launch
+    e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+      ogv_set_error("%s: execution failed: %s", what, cudaGetErrorString(e));
+      return OGV_ERR_CUDA;
+    }
+  }
+  return OGV_OK;
+}
+int ogv_num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
+extern "C" int ogv_version(void) { return 100; }
+extern "C" const char* ogv_last_error(void) { return g_err; }
+extern "C" int ogv_sm_count(void) { return ogv_num_sms(); }
+
+extern "C" int ogv_gemm(const ogv_gemm_args* args, int engine, void* stream) {
+  if (!args) { ogv_set_error("ogv_gemm: null args"); return OGV_ERR_ARG; }
+  const ogv_gemm_args& a = *args;
+  OGV_REQUIRE(a.M >= 0 && a.N >= 0 && a.K >= 0, "ogv_gemm: negative extent");
+  OGV_REQUIRE(a.A && a.B && a.D, "ogv_gemm: null operand");
+  OGV_REQUIRE(!(a.split_k > 1 && !a.accumulate), "ogv_gemm: split_k>1 requires accumulate");
+  OGV_REQUIRE(!(a.accumulate && a.out_dtype != OGV_F32), "ogv_gemm: accumulate requires fp32 output");
+  if (a.M == 0 || a.N == 0) return OGV_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (engine == OGV_ENGINE_AUTO) {
+    static int force_simt = -1;
+    if (force_simt < 0) {
+      const char* s = getenv("OGV_FORCE_SIMT");
+      force_simt = (s && s[0] == '1') ? 1 : 0;
+    }
+    engine = (!force_simt && ogv_gemm_tc_supported(a, nullptr)) ? OGV_ENGINE_TC : OGV_ENGINE_SIMT;
+  }
+  if (engine == OGV_ENGINE_TC) return ogv_gemm_tc(a, st);
+  if (engine == OGV_ENGINE_SIMT) return ogv_gemm_simt(a, st);
+  ogv_set_error("ogv_gemm: unknown engine %d", engine);
+  return OGV_ERR_ARG;
+}
+
+// ---------------------------------------------------------------------------------------------
+// NCHW <-> NHWC per image: [C, HW] <-> [HW, C]  (32x32 smem tile transpose)
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+template <typename T>
+__global__ void transpose_batched_kernel(const T* __restrict__ src, T* __restrict__ dst, int R, int Ccols) {
+  // src: [B][R][Ccols] -> dst: [B][Ccols][R]
+  __shared__ float tile[32][33];
+  const long long base = (long long)blockIdx.z * R * Ccols;
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int r = r0 + i, c = c0 + threadIdx.x;
+    if (r < R && c < Ccols) tile[i][threadIdx.x] = ld1(src + base + (long long)r * Ccols + c);
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int c = c0 + i, r = r0 + threadIdx.x;
+    if (r < R && c < Ccols) st1(dst + base + (long long)c * R + r, tile[threadIdx.x][i]);
+  }
+}
+
+template <typename T>
+int transpose_batched(const void* src, void* dst, int B, int R, int Ccols, cudaStream_t st) {
+  if (B == 0 || R == 0 || Ccols == 0) return OGV_OK;
+  dim3 grid(ogv_ceil_div(Ccols, 32), ogv_ceil_div(R, 32), B);
+  if (grid.y > 65535 || grid.z > 65535) {
+    ogv_set_error("transpose: extent too large (R=%d B=%d)", R, B);
+    return OGV_ERR_UNSUPPORTED;
+  }
+  transpose_batched_kernel<T><<<grid, dim3(32, 8), 0, st>>>(reinterpret_cast<const T*>(src),
+                                                            reinterpret_cast<T*>(dst), R, Ccols);
+  return ogv_check_launch("transpose");
+}
+
+template <typename T>
+__global__ void cast_transpose_kernel(const float* __restrict__ src, T* __restrict__ dst, long long ld_dst,
+                                      T* __restrict__ dst_t, long long ld_dst_t, int rows, int cols) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int r = r0 + i, c = c0 + threadIdx.x;
+    if (r < rows && c < cols) {
+      float v = src[(long long)r * cols + c];
+      tile[i][threadIdx.x] = v;
+      if (dst) st1(dst + (long long)r * ld_dst + c, v);
+    }
+  }
+  __syncthreads();
+  if (dst_t) {
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+      int c = c0 + i, r = r0 + threadIdx.x;
+      if (r < rows && c < cols) st1(dst_t + (long long)c * ld_dst_t + r, tile[threadIdx.x][i]);
+    }
+  }
+}
+
+template <typename T>
+__global__ void rowscale_kernel(const T* __restrict__ x, const float* __restrict__ scale, T* __restrict__ y,
+                                long long nvec, int vec_per_row, int rows_per_scale) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    long long row = i / vec_per_row;
+    float s = scale[row / rows_per_scale];
+    float v[8];
+    ld8(x + i * 8, v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] *= s;
+    st8(y + i * 8, v);
+  }
+}
+
+template <typename T>
+__global__ void mul_dact_kernel(const T* __restrict__ a, const T* __restrict__ pre, T* __restrict__ out, long long n,
+                                int act) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    st1(out + i, ld1(a + i) * act_grad(act, ld1(pre + i)));
+}
+
+template <typename T>
+__global__ void add_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ y, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    st1(y + i, ld1(a + i) + ld1(b + i));
+}
+
+__global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                             float* __restrict__ v, long long n, float lr, float b1, float b2, float eps, float wd,
+                             float bc1, float bc2, float gscale) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float gi = g[i] * gscale;
+    float pi = p[i] * (1.f - lr * wd);
+    float mi = b1 * m[i] + (1.f - b1) * gi;
+    float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    float denom = sqrtf(vi) / sqrtf(bc2) + eps;
+    p[i] = pi - (lr / bc1) * mi / denom;
+  }
+}
+
+struct ColSumF {
+  template <typename T>
+  __device__ __forceinline__ void operator()(const T* x, long long ld, long long row, int col, float (&acc)[1][8]) const {
+    float v[8];
+    ld8(x + row * ld + col, v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[0][i] += v[i];
+  }
+};
+
+template <typename T>
+__global__ void colsum_kernel(const T* __restrict__ x, long long ld, float* __restrict__ out, long long M, int nv) {
+  float acc[1][8];
+  colreduce_init(acc);
+  COLREDUCE_LOOP(M, nv, row, cv) {
+    float v[8];
+    ld8(x + row * ld + cv * 8, v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[0][i] += v[i];
+  }
+  float* outs[1] = {out};
+  colreduce_finish<1>(acc, outs, nv);
+}
+
+template <typename T>
+__global__ void colstats_kernel(const T* __restrict__ x, long long ld, float* __restrict__ sum,
+                                float* __restrict__ sumsq, long long M, int nv) {
+  float acc[2][8];
+  colreduce_init(acc);
+  COLREDUCE_LOOP(M, nv, row, cv) {
+    float v[8];
+    ld8(x + row * ld + cv * 8, v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      acc[0][i] += v[i];
+      acc[1][i] += v[i] * v[i];
+    }
+  }
+  float* outs[2] = {sum, sumsq};
+  colreduce_finish<2>(acc, outs, nv);
+}
+
+}  // namespace
+
+extern "C" int ogv_nchw_to_nhwc(const void* src, void* dst, int B, int C, int HW, int dtype, void* stream) {
+  OGV_REQUIRE(src && dst && B >= 0 && C > 0 && HW > 0, "nchw_to_nhwc: bad args");
+  OGV_DISPATCH_DTYPE(dtype, T, return transpose_batched<T>(src, dst, B, C, HW, (cudaStream_t)stream));
+}
+extern "C" int ogv_nhwc_to_nchw(const void* src, void* dst, int B, int C, int HW, int dtype, void* stream) {
+  OGV_REQUIRE(src && dst && B >= 0 && C > 0 && HW > 0, "nhwc_to_nchw: bad args");
+  OGV_DISPATCH_DTYPE(dtype, T, return transpose_batched<T>(src, dst, B, HW, C, (cudaStream_t)stream));
+}
+
+extern "C" int ogv_cast_transpose(const float* src, void* dst, long long ld_dst, void* dst_t, long long ld_dst_t,
+                                  int rows, int cols, int dtype, void* stream) {
+  OGV_REQUIRE(src && rows > 0 && cols > 0 && (dst || dst_t), "cast_transpose: bad args");
+  dim3 grid(ogv_ceil_div(cols, 32), ogv_ceil_div(rows, 32));
+  OGV_DISPATCH_DTYPE(dtype, T, {
+    cast_transpose_kernel<T><<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(
+        src, reinterpret_cast<T*>(dst), ld_dst, reinterpret_cast<T*>(dst_t), ld_dst_t, rows, cols);
+    return ogv_check_launch("cast_transpose");
+  });
+}
+
+extern "C" int ogv_rowscale(const void* x, const float* scale, void* y, long long rows, int cols,
+                            int rows_per_scale, int dtype, void* stream) {
+  OGV_REQUIRE(x && y && scale && cols % 8 == 0 && rows_per_scale > 0, "rowscale: bad args (cols %% 8 == 0)");
+  long long nvec = rows * (cols / 8);
+  if (nvec == 0) return OGV_OK;
+  int grid = (int)((nvec + 255) / 256 < 148 * 16 ? (nvec + 255) / 256 : 148 * 16);
+  OGV_DISPATCH_DTYPE(dtype, T, {
+    rowscale_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const T*>(x), scale,
+                                                               reinterpret_cast<T*>(y), nvec, cols / 8,
+                                                               rows_per_scale);
+    return ogv_check_launch("rowscale");
+  });
+}
+
+extern "C" int ogv_mul_dact(const void* a, const void* pre, void* out, long long n, int act, int dtype,
+                            void* stream) {
+  OGV_REQUIRE(a && pre && out, "mul_dact: null");
+  if (n == 0) return OGV_OK;
+  int grid = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
+  OGV_DISPATCH_DTYPE(dtype, T, {
+    mul_dact_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const T*>(a),
+                                                               reinterpret_cast<const T*>(pre),
+                                                               reinterpret_cast<T*>(out), n, act);
+    return ogv_check_launch("mul_dact");
+  });
+}
+
+extern "C" int ogv_add(const void* a, const void* b, void* y, long long n, int dtype, void* stream) {
+  OGV_REQUIRE(a && b && y, "add: null");
+  if (n == 0) return OGV_OK;
+  int grid = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
+  OGV_DISPATCH_DTYPE(dtype, T, {
+    add_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const T*>(a),
+                                                          reinterpret_cast<const T*>(b), reinterpret_cast<T*>(y), n);
+    return ogv_check_launch("add");
+  });
+}
+
+extern "C" int ogv_adamw(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1,
+                         float beta2, float eps, float weight_decay, float bias_c1, float bias_c2, float grad_scale,
+                         void* stream) {
+  OGV_REQUIRE(p && g && m && v, "adamw: null");
+  if (n == 0) return OGV_OK;
+  int grid = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
+  adamw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bias_c1,
+                                                       bias_c2, grad_scale);
+  return ogv_check_launch("adamw");
+}
+
+extern "C" int ogv_colsum(const void* x, long long ld, float* out, long long M, int N, int dtype, void* stream) {
+  OGV_REQUIRE(x && out && N % 8 == 0 && ld % 8 == 0, "colsum: N and ld must be multiples of 8");
+  if (M == 0 || N == 0) return OGV_OK;
+  ColReduceCfg cfg;
+  if (!colreduce_config(M, N / 8, &cfg)) { ogv_set_error("colsum: N=%d too wide", N); return OGV_ERR_UNSUPPORTED; }
+  OGV_DISPATCH_DTYPE(dtype, T, {
+    colsum_kernel<T><<<cfg.grid, cfg.block, 0, (cudaStream_t)stream>>>(reinterpret_cast<const T*>(x), ld, out, M,
+                                                                         N / 8);
+    return ogv_check_launch("colsum");
+  });
+}
+
+extern "C" int ogv_colstats(const void* x, long long ld, float* sum, float* sumsq, long long M, int N, int dtype,
+                            void* stream) {
+  OGV_REQUIRE(x && sum && sumsq && N % 8 == 0 && ld % 8 == 0, "colstats: N and ld must be multiples of 8");
+  if (M == 0 || N == 0) return OGV_OK;
+  ColReduceCfg cfg;
+  if (!colreduce_config(M, N / 8, &cfg)) { ogv_set_error("colstats: N=%d too wide", N); return OGV_ERR_UNSUPPORTED; }
+  OGV_DISPATCH_DTYPE(dtype, T, {
+    colstats_kernel<T><<<cfg.grid, cfg.block, 0, (cudaStream_t)stream>>>(reinterpret_cast<const T*>(x), ld, sum,
+                                                                           sumsq, M, N / 8);
+    return ogv_check_launch("colstats");
+  });
+}

@@ -1,0 +1,349 @@
+// LayerNorm (per position over channels) and BatchNorm2d (per channel over B*H*W) kernels.
+// Reference: outlook_attention.py:17-31 (LayerNorm2d), Out_Grid_Block.py:69,84 (nn.LayerNorm),
+// mbc_conv.py:61 (nn.BatchNorm2d, batch statistics in training).
+#include "ogv_common.cuh"
+#include "ogv_reduce.cuh"
+#include "../../include/ogv.h"
+
+namespace {
+
+// ------------------------------------------------------------------ LayerNorm: one warp per row
+template <typename T, int MAXV>
+__global__ void __launch_bounds__(256) ln_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
+                                                     const float* __restrict__ beta, T* __restrict__ y,
+                                                     float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                                                     long long M, int C, float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = (gridDim.x * (long long)blockDim.x) >> 5;
+  const int nv = C >> 3;
+  const float inv_c = 1.f / (float)C;
+  for (long long row = warp0; row < M; row += nwarps) {
+    float v[MAXV][8];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < MAXV; ++j) {
+      int idx = lane + 32 * j;
+      if (idx < nv) {
+        ld8(x + row * C + idx * 8, v[j]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += v[j][i];
+      }
+    }
+    const float mean = warp_sum(s) * inv_c;
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < MAXV; ++j) {
+      int idx = lane + 32 * j;
+      if (idx < nv) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float d = v[j][i] - mean;
+          q += d * d;
+        }
+      }
+    }
+    const float rstd = 1.f / sqrtf(warp_sum(q) * inv_c + eps);
+#pragma unroll
+    for (int j = 0; j < MAXV; ++j) {
+      int idx = lane + 32 * j;
+      if (idx < nv) {
+        float g[8], b[8], o[8];
+        ld8(gamma + idx * 8, g);
+        ld8(beta + idx * 8, b);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = (v[j][i] - mean) * rstd * g[i] + b[i];
+        st8(y + row * C + idx * 8, o);
+      }
+    }
+    if (lane == 0) {
+      if (mean_out) mean_out[row] = mean;
+      if (rstd_out) rstd_out[row] = rstd;
+    }
+  }
+}
+
+template <typename T, int MAXV>
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+                                                     const float* __restrict__ gamma, const float* __restrict__ mean,
+                                                     const float* __restrict__ rstd, const T* __restrict__ dres,
+                                                     T* __restrict__ dx, float* __restrict__ dgamma,
+                                                     float* __restrict__ dbeta, long long M, int C) {
+  __shared__ float sg[1024];
+  __shared__ float sb[1024];
+  for (int i = threadIdx.x; i < C; i += blockDim.x) { sg[i] = 0.f; sb[i] = 0.f; }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = (gridDim.x * (long long)blockDim.x) >> 5;
+  const int nv = C >> 3;
+  const float inv_c = 1.f / (float)C;
+  float ag[MAXV][8], ab[MAXV][8], gm[MAXV][8];
+#pragma unroll
+  for (int j = 0; j < MAXV; ++j) {
+    int idx = lane + 32 * j;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { ag[j][i] = 0.f; ab[j][i] = 0.f; gm[j][i] = 0.f; }
+    if (idx < nv) ld8(gamma + idx * 8, gm[j]);
+  }
+  for (long long row = warp0; row < M; row += nwarps) {
+    const float mu = mean[row], rs = rstd[row];
+    float g[MAXV][8], xh[MAXV][8];
+    float c1 = 0.f, c2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < MAXV; ++j) {
+      int idx = lane + 32 * j;
+      if (idx < nv) {
+        float d[8], xv[8];
+        ld8(dy + row * C + idx * 8, d);
+        ld8(x + row * C + idx * 8, xv);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          xh[j][i] = (xv[i] - mu) * rs;
+          ag[j][i] += d[i] * xh[j][i];
+          ab[j][i] += d[i];
+          g[j][i] = d[i] * gm[j][i];
+          c1 += g[j][i];
+          c2 += g[j][i] * xh[j][i];
+        }
+      }
+    }
+    c1 = warp_sum(c1) * inv_c;
+    c2 = warp_sum(c2) * inv_c;
+#pragma unroll
+    for (int j = 0; j < MAXV; ++j) {
+      int idx = lane + 32 * j;
+      if (idx < nv) {
+        float o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = rs * (g[j][i] - c1 - xh[j][i] * c2);
+        if (dres) {
+          float r[8];
+          ld8(dres + row * C + idx * 8, r);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] += r[i];
+        }
+        st8(dx + row * C + idx * 8, o);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < MAXV; ++j) {
+    int idx = lane + 32 * j;
+    if (idx < nv) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        atomicAdd(&sg[idx * 8 + i], ag[j][i]);
+        atomicAdd(&sb[idx * 8 + i], ab[j][i]);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    if (dgamma) atomicAdd(dgamma + i, sg[i]);
+    if (dbeta) atomicAdd(dbeta + i, sb[i]);
+  }
+}
+
+// ------------------------------------------------------------------ BatchNorm
+__global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* __restrict__ sumsq,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float* __restrict__ running_mean, float* __restrict__ running_var,
+                                   float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out,
+                                   float* __restrict__ rstd_out, float n, int C, float eps, float momentum,
+                                   int training) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float mean, var;
+  if (training) {
+    mean = sum[c] / n;
+    var = fmaxf(sumsq[c] / n - mean * mean, 0.f);
+    if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+    if (running_var) {
+      float unbiased = n > 1.f ? var * n / (n - 1.f) : var;
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
+    }
+  } else {
+    mean = running_mean[c];
+    var = running_var[c];
+  }
+  float rstd = 1.f / sqrtf(var + eps);
+  float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+  scale[c] = g * rstd;
+  shift[c] = b - mean * g * rstd;
+  if (mean_out) mean_out[c] = mean;
+  if (rstd_out) rstd_out[c] = rstd;
+}
+
+template <typename T>
+__global__ void bn_apply_kernel(const T* __restrict__ x, const float* __restrict__ scale,
+                                const float* __restrict__ shift, const T* __restrict__ res, T* __restrict__ out,
+                                long long nvec, int nv) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    int cv = (int)(i % nv);
+    float v[8], sc[8], sh[8];
+    ld8(x + i * 8, v);
+    ld8(scale + cv * 8, sc);
+    ld8(shift + cv * 8, sh);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = v[k] * sc[k] + sh[k];
+    if (res) {
+      float r[8];
+      ld8(res + i * 8, r);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] += r[k];
+    }
+    st8(out + i * 8, v);
+  }
+}
+
+template <typename T>
+__global__ void bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+                                     const float* __restrict__ mean, const float* __restrict__ rstd,
+                                     float* __restrict__ dgamma, float* __restrict__ dbeta, long long M, int nv) {
+  float acc[2][8];
+  colreduce_init(acc);
+  float mu[8], rs[8];
+  {
+    const int cv0 = threadIdx.x % nv;
+    ld8(mean + cv0 * 8, mu);
+    ld8(rstd + cv0 * 8, rs);
+  }
+  COLREDUCE_LOOP(M, nv, row, cv) {
+    float d[8], xv[8];
+    ld8(dy + (row * nv + cv) * 8, d);
+    ld8(x + (row * nv + cv) * 8, xv);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      acc[0][i] += d[i];
+      acc[1][i] += d[i] * (xv[i] - mu[i]) * rs[i];
+    }
+  }
+  float* outs[2] = {dbeta, dgamma};
+  colreduce_finish<2>(acc, outs, nv);
+}
+
+template <typename T>
+__global__ void bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+                                    const float* __restrict__ mean, const float* __restrict__ rstd,
+                                    const float* __restrict__ gamma, const float* __restrict__ dgamma,
+                                    const float* __restrict__ dbeta, T* __restrict__ dx, long long nvec, int nv,
+                                    float inv_n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    int cv = (int)(i % nv);
+    float d[8], xv[8], mu[8], rs[8], g[8], dg[8], db[8], o[8];
+    ld8(dy + i * 8, d);
+    ld8(x + i * 8, xv);
+    ld8(mean + cv * 8, mu);
+    ld8(rstd + cv * 8, rs);
+    ld8(gamma + cv * 8, g);
+    ld8(dgamma + cv * 8, dg);
+    ld8(dbeta + cv * 8, db);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float xh = (xv[k] - mu[k]) * rs[k];
+      o[k] = g[k] * rs[k] * (d[k] - db[k] * inv_n - xh * dg[k] * inv_n);
+    }
+    st8(dx + i * 8, o);
+  }
+}
+
+inline int flat_grid(long long n, int threads) {
+  long long b = (n + threads - 1) / threads;
+  long long cap = (long long)ogv_num_sms() * 16;
+  return (int)(b < cap ? (b < 1 ? 1 : b) : cap);
+}
+
+}  // namespace
+
+extern "C" int ogv_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean,
+                                 float* rstd, long long M, int C, float eps, int dtype, void* stream) {
+  OGV_REQUIRE(x && gamma && beta && y, "layernorm_fwd: null pointer");
+  OGV_REQUIRE(C > 0 && C % 8 == 0 && C <= 1024, "layernorm_fwd: C=%d must be a multiple of 8 and <= 1024", C);
+  if (M == 0) return OGV_OK;
+  int grid = flat_grid(M * 32, 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  OGV_DISPATCH_DTYPE(dtype, T, {
+    const T* xp = reinterpret_cast<const T*>(x);
+    T* yp = reinterpret_cast<T*>(y);
+    if (C <= 256) ln_fwd_kernel<T, 1><<<grid, 256, 0, st>>>(xp, gamma, beta, yp, mean, rstd, M, C, eps);
+    else if (C <= 512) ln_fwd_kernel<T, 2><<<grid, 256, 0, st>>>(xp, gamma, beta, yp, mean, rstd, M, C, eps);
+    else ln_fwd_kernel<T, 4><<<grid, 256, 0, st>>>(xp, gamma, beta, yp, mean, rstd, M, C, eps);
+    return ogv_check_launch("layernorm_fwd");
+  });
+}
+
+extern "C" int ogv_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean,
+                                 const float* rstd, const void* dres, void* dx, float* dgamma, float* dbeta,
+                                 long long M, int C, int dtype, void* stream) {
+  OGV_REQUIRE(dy && x && gamma && mean && rstd && dx, "layernorm_bwd: null pointer");
+  OGV_REQUIRE(C > 0 && C % 8 == 0 && C <= 1024, "layernorm_bwd: C=%d must be a multiple of 8 and <= 1024", C);
+  if (M == 0) return OGV_OK;
+  long long want = (M * 32 + 255) / 256;
+  long long cap = (long long)ogv_num_sms() * 4;  // few CTAs: one dgamma/dbeta flush per CTA
+  int grid = (int)(want < cap ? want : cap);
+  cudaStream_t st = (cudaStream_t)stream;
+  OGV_DISPATCH_DTYPE(dtype, T, {
+    const T* dyp = reinterpret_cast<const T*>(dy);
+    const T* xp = reinterpret_cast<const T*>(x);
+    const T* rp = reinterpret_cast<const T*>(dres);
+    T* dxp = reinterpret_cast<T*>(dx);
+    if (C <= 256) ln_bwd_kernel<T, 1><<<grid, 256, 0, st>>>(dyp, xp, gamma, mean, rstd, rp, dxp, dgamma, dbeta, M, C);
+    else if (C <= 512) ln_bwd_kernel<T, 2><<<grid, 256, 0, st>>>(dyp, xp, gamma, mean, rstd, rp, dxp, dgamma, dbeta, M, C);
+    else ln_bwd_kernel<T, 4><<<grid, 256, 0, st>>>(dyp, xp, gamma, mean, rstd, rp, dxp, dgamma, dbeta, M, C);
+    return ogv_check_launch("layernorm_bwd");
+  });
+}
+
+extern "C" int ogv_bn_finalize(const float* sum, const float* sumsq, const float* gamma, const float* beta,
+                               float* running_mean, float* running_var, float* scale, float* shift, float* mean,
+                               float* rstd, long long n, int C, float eps, float momentum, int training,
+                               void* stream) {
+  OGV_REQUIRE(scale && shift && C > 0, "bn_finalize: bad args");
+  OGV_REQUIRE(training ? (sum && sumsq && n > 0) : (running_mean && running_var),
+              "bn_finalize: missing statistics for mode training=%d", training);
+  bn_finalize_kernel<<<ogv_ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(
+      sum, sumsq, gamma, beta, running_mean, running_var, scale, shift, mean, rstd, (float)n, C, eps, momentum,
+      training);
+  return ogv_check_launch("bn_finalize");
+}
+
+extern "C" int ogv_bn_apply(const void* x, const float* scale, const float* shift, const void* res, void* out,
+                            long long M, int C, int dtype, void* stream) {
+  OGV_REQUIRE(x && scale && shift && out && C % 8 == 0, "bn_apply: bad args (C %% 8 == 0)");
+  long long nvec = M * (C / 8);
+  if (nvec == 0) return OGV_OK;
+  OGV_DISPATCH_DTYPE(dtype, T, {
+    bn_apply_kernel<T><<<flat_grid(nvec, 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const T*>(x), scale, shift, reinterpret_cast<const T*>(res), reinterpret_cast<T*>(out), nvec,
+        C / 8);
+    return ogv_check_launch("bn_apply");
+  });
+}
+
+extern "C" int ogv_bn_bwd_reduce(const void* dy, const void* x, const float* mean, const float* rstd, float* dgamma,
+                                 float* dbeta, long long M, int C, int dtype, void* stream) {
+  OGV_REQUIRE(dy && x && mean && rstd && dgamma && dbeta && C % 8 == 0, "bn_bwd_reduce: bad args");
+  if (M == 0) return OGV_OK;
+  ColReduceCfg cfg;
+  if (!colreduce_config(M, C / 8, &cfg)) { ogv_set_error("bn_bwd_reduce: C=%d too wide", C); return OGV_ERR_UNSUPPORTED; }
+  OGV_DISPATCH_DTYPE(dtype, T, {
+    bn_bwd_reduce_kernel<T><<<cfg.grid, cfg.block, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const T*>(dy), reinterpret_cast<const T*>(x), mean, rstd, dgamma, dbeta, M, C / 8);
+    return ogv_check_launch("bn_bwd_reduce");
+  });
+}
+
+extern "C" int ogv_bn_bwd_apply(const void* dy, const void* x, const float* mean, const float* rstd,
+                                const float* gamma, const float* dgamma, const float* dbeta, void* dx, long long M,
+                                int C, int dtype, void* stream) {
+  OGV_REQUIRE(dy && x && mean && rstd && gamma && dgamma && dbeta && dx && C % 8 == 0, "bn_bwd_apply: bad args");
+  long long nvec = M * (C / 8);
+  if (nvec == 0) return OGV_OK;
+  OGV_DISPATCH_DTYPE(dtype, T, {
+    bn_bwd_apply_kernel<T><<<flat_grid(nvec, 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const T*>(dy), reinterpret_cast<const T*>(x), mean, rstd, gamma, dgamma, dbeta,
+        reinterpret_cast<T*>(dx), nvec, C / 8, 1.f / (float)M);
+    return ogv_check_launch("bn_bwd_apply");
+  });
+}

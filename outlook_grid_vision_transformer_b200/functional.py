@@ -1,0 +1,500 @@
+"""Autograd functions for the four fused branches of an OutGridBlock, on "rows" tensors
+([B*H*W, C], NHWC order).  Forward and backward are sequences of libogvit kernel launches; the
+backward formulas are the ones autograd derives for the reference modules.
+
+    outlook_branch : x + s * proj(outlook_core(softmax(attn(LN x)), v(LN x)))   outlook_attention.py:91-124, Outlook_Block.py:61-63
+    mlp_branch     : x + s * fc2(act(fc1(LN x)))                                 outlook_attention.py:43-49, Out_Grid_Block.py:24-32
+    mbconv         : x + BN3(Wp (SE(act(BN2(DW(act(BN1(We x))))))))              mbc_conv.py:90-98
+    grid_branch    : x + s * proj(grid_mhsa(qkv(LN x)))                          grid_attention.py:62-89,112-131
+
+`s` is the per-sample stochastic-depth scale (mask / keep_prob) or None.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import torch
+
+from . import ops
+from ._lib import ENGINE_AUTO, ENGINE_SIMT
+
+Tensor = torch.Tensor
+
+
+@dataclass
+class Geom:
+    B: int
+    H: int
+    W: int
+
+    @property
+    def P(self) -> int:
+        return self.H * self.W
+
+    @property
+    def M(self) -> int:
+        return self.B * self.H * self.W
+
+
+class PreparedLinear:
+    """Compute-dtype copies of one [out, in] weight: `w` ([out,in]) and `wt` ([in,out])."""
+
+    __slots__ = ("w", "wt")
+
+    def __init__(self, w: Tensor, wt: Tensor):
+        self.w = w
+        self.wt = wt
+
+
+def prepare_linear(weight: Tensor, dtype: torch.dtype, out_rows: Optional[int] = None) -> PreparedLinear:
+    """weight: fp32 parameter [out, in(,1,1)].  For fp32 compute the parameter itself is used."""
+    w2 = weight.detach().reshape(weight.shape[0], -1)
+    n, k = w2.shape
+    rows = out_rows or n
+    if dtype == torch.float32 and rows == n:
+        return PreparedLinear(w2, w2.t())
+    w = torch.zeros((rows, k), device=w2.device, dtype=dtype)
+    wt = torch.zeros((k, rows), device=w2.device, dtype=dtype)
+    ops.cast_transpose(w2.contiguous(), w[:n], wt[:, :n])
+    return PreparedLinear(w, wt)
+
+
+def _zeros(shape, like: Tensor) -> Tensor:
+    return torch.zeros(shape, device=like.device, dtype=torch.float32)
+
+
+def _empty(shape, like: Tensor, dtype=None) -> Tensor:
+    return torch.empty(shape, device=like.device, dtype=dtype or like.dtype)
+
+
+# =================================================================================================
+# MLP branch (MLP2d of the Outlooker and the BHWC MLP share the same math on rows)
+# =================================================================================================
+class MlpBranchFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, ln_w, ln_b, w1, b1, w2, b2, scale, meta):
+        p1: PreparedLinear = meta["p1"]
+        p2: PreparedLinear = meta["p2"]
+        act, P = meta["act"], meta["rows_per_sample"]
+        with_ln, with_res = ln_w is not None, meta["with_res"]
+        x = x.contiguous()
+        M, C = x.shape
+        Hd = p1.w.shape[0]
+        if with_ln:
+            xn, mean, rstd = ops.layernorm_fwd(x, ln_w, ln_b, meta["eps"])
+        else:
+            xn, mean, rstd = x, None, None
+        z = _empty((M, Hd), x)
+        h = _empty((M, Hd), x)
+        ops.gemm(xn, p1.w, h, bias=b1, pre_out=z, act=act)
+        y = _empty((M, C), x)
+        ops.gemm(h, p2.w, y, bias=b2, row_scale=scale, rows_per_scale=P, residual=x if with_res else None)
+        ctx.meta = meta
+        ctx.save_for_backward(x, xn, mean, rstd, z, h, ln_w, scale)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        meta = ctx.meta
+        x, xn, mean, rstd, z, h, ln_w, scale = ctx.saved_tensors
+        p1: PreparedLinear = meta["p1"]
+        p2: PreparedLinear = meta["p2"]
+        act, P = meta["act"], meta["rows_per_sample"]
+        with_ln, with_res = ln_w is not None, meta["with_res"]
+        dy = dy.contiguous()
+        M, C = x.shape
+        Hd = p1.w.shape[0]
+        gy = ops.rowscale(dy, scale, P) if scale is not None else dy
+        # one zeroed fp32 arena for all parameter gradients of the branch
+        arena = _zeros(Hd * C * 2 + Hd + C + 2 * C, x)
+        o = 0
+        dW1 = arena[o:o + Hd * C].view(Hd, C); o += Hd * C
+        dW2 = arena[o:o + C * Hd].view(C, Hd); o += C * Hd
+        db1 = arena[o:o + Hd]; o += Hd
+        db2 = arena[o:o + C]; o += C
+        dg = arena[o:o + C]; o += C
+        dbt = arena[o:o + C]; o += C
+        # fc2 backward (+ activation derivative fused into the dgrad epilogue)
+        dz = _empty((M, Hd), x)
+        ops.gemm(gy, p2.wt, dz, dact_src=z, dact=act)
+        ops.wgrad(gy, h, dW2)
+        ops.colsum(gy, db2)
+        # fc1 backward
+        dxn = _empty((M, C), x)
+        if with_ln:
+            ops.gemm(dz, p1.wt, dxn)
+        else:
+            ops.gemm(dz, p1.wt, dxn, residual=dy if with_res else None)
+        ops.wgrad(dz, xn, dW1)
+        ops.colsum(dz, db1)
+        if with_ln:
+            dx = ops.layernorm_bwd(dxn, x, ln_w, mean, rstd, dy if with_res else None, dg, dbt)
+            return dx, dg, dbt, dW1.view(meta["w1_shape"]), db1, dW2.view(meta["w2_shape"]), db2, None, None
+        return dxn, None, None, dW1.view(meta["w1_shape"]), db1, dW2.view(meta["w2_shape"]), db2, None, None
+
+
+def mlp_branch(x: Tensor, ln_w, ln_b, w1, b1, w2, b2, scale, *, p1, p2, eps: float, act: str, rows_per_sample: int,
+               with_res: bool) -> Tensor:
+    meta = dict(p1=p1, p2=p2, eps=eps, act=act, rows_per_sample=rows_per_sample, with_res=with_res,
+                w1_shape=tuple(w1.shape), w2_shape=tuple(w2.shape))
+    return MlpBranchFn.apply(x, ln_w, ln_b, w1, b1, w2, b2, scale, meta)
+
+
+# =================================================================================================
+# Outlook attention branch
+# =================================================================================================
+def outlook_npad(C: int, heads: int) -> int:
+    return (C + 9 * heads + 7) // 8 * 8
+
+
+class OutlookBranchFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, ln_w, ln_b, wv, bv, wa, ba, wp, bp, scale, meta):
+        pva: PreparedLinear = meta["pva"]   # rows: [v (C) | attn (9*heads) | zero pad]
+        pp: PreparedLinear = meta["pp"]
+        g: Geom = meta["geom"]
+        heads, with_res = meta["heads"], meta["with_res"]
+        with_ln = ln_w is not None
+        x = x.contiguous()
+        M, C = x.shape
+        npad = pva.w.shape[0]
+        if with_ln:
+            xn, mean, rstd = ops.layernorm_fwd(x, ln_w, ln_b, meta["eps"])
+        else:
+            xn, mean, rstd = x, None, None
+        va = _empty((M, npad), x)
+        ops.gemm(xn, pva.w, va, bias=meta["bva"])
+        yc = ops.outlook_core_fwd(va, g.B, g.H, g.W, C, heads)
+        y = _empty((M, C), x)
+        ops.gemm(yc, pp.w, y, bias=bp, row_scale=scale, rows_per_scale=g.P, residual=x if with_res else None)
+        ctx.meta = meta
+        ctx.save_for_backward(x, xn, mean, rstd, va, yc, ln_w, scale)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        meta = ctx.meta
+        x, xn, mean, rstd, va, yc, ln_w, scale = ctx.saved_tensors
+        pva: PreparedLinear = meta["pva"]
+        pp: PreparedLinear = meta["pp"]
+        g: Geom = meta["geom"]
+        heads, with_res = meta["heads"], meta["with_res"]
+        with_ln = ln_w is not None
+        dy = dy.contiguous()
+        M, C = x.shape
+        npad = pva.w.shape[0]
+        nl = 9 * heads
+        gy = ops.rowscale(dy, scale, g.P) if scale is not None else dy
+        arena = _zeros(npad * C + C * C + npad + C + 2 * C, x)
+        o = 0
+        dWva = arena[o:o + npad * C].view(npad, C); o += npad * C
+        dWp = arena[o:o + C * C].view(C, C); o += C * C
+        dbva = arena[o:o + npad]; o += npad
+        dbp = arena[o:o + C]; o += C
+        dg = arena[o:o + C]; o += C
+        dbt = arena[o:o + C]; o += C
+        dyc = _empty((M, C), x)
+        ops.gemm(gy, pp.wt, dyc)
+        ops.wgrad(gy, yc, dWp)
+        ops.colsum(gy, dbp)
+        dva = ops.outlook_core_bwd(va, dyc, g.B, g.H, g.W, C, heads)
+        dxn = _empty((M, C), x)
+        if with_ln:
+            ops.gemm(dva, pva.wt, dxn)
+        else:
+            ops.gemm(dva, pva.wt, dxn, residual=dy if with_res else None)
+        ops.wgrad(dva, xn, dWva)
+        ops.colsum(dva, dbva)
+        dwv = dWva[:C].reshape(meta["wv_shape"])
+        dwa = dWva[C:C + nl].reshape(meta["wa_shape"])
+        dbv = dbva[:C] if meta["has_qkv_bias"] else None
+        dba = dbva[C:C + nl] if meta["has_qkv_bias"] else None
+        if with_ln:
+            dx = ops.layernorm_bwd(dxn, x, ln_w, mean, rstd, dy if with_res else None, dg, dbt)
+            return dx, dg, dbt, dwv, dbv, dwa, dba, dWp.view(meta["wp_shape"]), dbp, None, None
+        return dxn, None, None, dwv, dbv, dwa, dba, dWp.view(meta["wp_shape"]), dbp, None, None
+
+
+def prepare_outlook_va(wv: Tensor, bv: Optional[Tensor], wa: Tensor, ba: Optional[Tensor], dtype) -> Tuple[PreparedLinear, Tensor]:
+    """Concatenate the `v` and `attn` 1x1-conv weights into one zero-padded GEMM operand."""
+    C = wv.shape[0]
+    nl = wa.shape[0]
+    npad = (C + nl + 7) // 8 * 8
+    w = torch.zeros((npad, C), device=wv.device, dtype=dtype)
+    wt = torch.zeros((C, npad), device=wv.device, dtype=dtype)
+    ops.cast_transpose(wv.detach().reshape(C, C).contiguous(), w[:C], wt[:, :C])
+    ops.cast_transpose(wa.detach().reshape(nl, C).contiguous(), w[C:C + nl], wt[:, C:C + nl])
+    bva = torch.zeros(npad, device=wv.device, dtype=torch.float32)
+    if bv is not None:
+        bva[:C].copy_(bv.detach())
+    if ba is not None:
+        bva[C:C + nl].copy_(ba.detach())
+    return PreparedLinear(w, wt), bva
+
+
+def outlook_branch(x, ln_w, ln_b, wv, bv, wa, ba, wp, bp, scale, *, pva, bva, pp, geom: Geom, heads: int, eps: float,
+                   with_res: bool) -> Tensor:
+    meta = dict(pva=pva, bva=bva, pp=pp, geom=geom, heads=heads, eps=eps, with_res=with_res,
+                wv_shape=tuple(wv.shape), wa_shape=tuple(wa.shape), wp_shape=tuple(wp.shape),
+                has_qkv_bias=bv is not None)
+    return OutlookBranchFn.apply(x, ln_w, ln_b, wv, bv, wa, ba, wp, bp, scale, meta)
+
+
+# =================================================================================================
+# Grid attention branch
+# =================================================================================================
+class GridBranchFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, ln_w, ln_b, wqkv, bqkv, wp, bp, scale, meta):
+        pq: PreparedLinear = meta["pq"]
+        pp: PreparedLinear = meta["pp"]
+        g: Geom = meta["geom"]
+        heads, gs, with_res = meta["heads"], meta["grid"], meta["with_res"]
+        with_ln = ln_w is not None
+        x = x.contiguous()
+        M, C = x.shape
+        if with_ln:
+            xn, mean, rstd = ops.layernorm_fwd(x, ln_w, ln_b, meta["eps"])
+        else:
+            xn, mean, rstd = x, None, None
+        qkv = _empty((M, 3 * C), x)
+        ops.gemm(xn, pq.w, qkv, bias=bqkv)
+        o = ops.grid_attn_fwd(qkv, g.B, g.H, g.W, C, heads, gs)
+        capture = meta.get("capture")
+        if capture is not None:
+            capture(ops.grid_attn_probs(qkv, g.B, g.H, g.W, C, heads, gs))
+        y = _empty((M, C), x)
+        ops.gemm(o, pp.w, y, bias=bp, row_scale=scale, rows_per_scale=g.P, residual=x if with_res else None)
+        ctx.meta = meta
+        ctx.save_for_backward(x, xn, mean, rstd, qkv, o, ln_w, scale)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        meta = ctx.meta
+        x, xn, mean, rstd, qkv, o, ln_w, scale = ctx.saved_tensors
+        pq: PreparedLinear = meta["pq"]
+        pp: PreparedLinear = meta["pp"]
+        g: Geom = meta["geom"]
+        heads, gs, with_res = meta["heads"], meta["grid"], meta["with_res"]
+        with_ln = ln_w is not None
+        dy = dy.contiguous()
+        M, C = x.shape
+        gy = ops.rowscale(dy, scale, g.P) if scale is not None else dy
+        arena = _zeros(3 * C * C + C * C + 3 * C + C + 2 * C, x)
+        off = 0
+        dWq = arena[off:off + 3 * C * C].view(3 * C, C); off += 3 * C * C
+        dWp = arena[off:off + C * C].view(C, C); off += C * C
+        dbq = arena[off:off + 3 * C]; off += 3 * C
+        dbp = arena[off:off + C]; off += C
+        dg = arena[off:off + C]; off += C
+        dbt = arena[off:off + C]; off += C
+        do = _empty((M, C), x)
+        ops.gemm(gy, pp.wt, do)
+        ops.wgrad(gy, o, dWp)
+        ops.colsum(gy, dbp)
+        dqkv = ops.grid_attn_bwd(qkv, do, g.B, g.H, g.W, C, heads, gs)
+        dxn = _empty((M, C), x)
+        if with_ln:
+            ops.gemm(dqkv, pq.wt, dxn)
+        else:
+            ops.gemm(dqkv, pq.wt, dxn, residual=dy if with_res else None)
+        ops.wgrad(dqkv, xn, dWq)
+        ops.colsum(dqkv, dbq)
+        dbq_out = dbq if meta["has_qkv_bias"] else None
+        if with_ln:
+            dx = ops.layernorm_bwd(dxn, x, ln_w, mean, rstd, dy if with_res else None, dg, dbt)
+            return dx, dg, dbt, dWq, dbq_out, dWp, dbp, None, None
+        return dxn, None, None, dWq, dbq_out, dWp, dbp, None, None
+
+
+def grid_branch(x, ln_w, ln_b, wqkv, bqkv, wp, bp, scale, *, pq, pp, geom: Geom, heads: int, grid: int, eps: float,
+                with_res: bool, capture=None) -> Tensor:
+    meta = dict(pq=pq, pp=pp, geom=geom, heads=heads, grid=grid, eps=eps, with_res=with_res, capture=capture,
+                has_qkv_bias=bqkv is not None)
+    return GridBranchFn.apply(x, ln_w, ln_b, wqkv, bqkv, wp, bp, scale, meta)
+
+
+# =================================================================================================
+# MBConv (expand 1x1 + BN + act -> depthwise 3x3 + BN + act -> SE -> project 1x1 + BN, + residual)
+# =================================================================================================
+class MBConvFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, we, g1, b1, wdw, g2, b2, sw1, sb1, sw2, sb2, wp, g3, b3, meta):
+        pe: PreparedLinear = meta["pe"]
+        ppj: PreparedLinear = meta["pp"]
+        g: Geom = meta["geom"]
+        act, training, eps, mom = meta["act"], meta["training"], meta["bn_eps"], meta["bn_momentum"]
+        rm1, rv1, rm2, rv2, rm3, rv3 = meta["running"]
+        x = x.contiguous()
+        M, C = x.shape
+        Cm = pe.w.shape[0]
+        Cs = sw1.shape[0]
+        # fp32 scratch for the three BatchNorms: [sum, sumsq, scale, shift, mean, rstd] x channels
+        st = _zeros(6 * (2 * Cm + C), x)
+        def carve(base, n):
+            return [st[base + i * n: base + (i + 1) * n] for i in range(6)]
+        s1 = carve(0, Cm)
+        s2 = carve(6 * Cm, Cm)
+        s3 = carve(12 * Cm, C)
+        # expand
+        e_pre = _empty((M, Cm), x)
+        ops.gemm(x, pe.w, e_pre)
+        if training:
+            ops.colstats(e_pre, s1[0], s1[1])
+        ops.bn_finalize(s1[0], s1[1], g1, b1, rm1, rv1, s1[2], s1[3], s1[4], s1[5], M, eps, mom, training)
+        # depthwise (BN1 + act on load, BN2 statistics on store)
+        wdw2 = wdw.detach().reshape(Cm, 9).contiguous()
+        d_pre = ops.dwconv_fwd(e_pre, s1[2], s1[3], wdw2, s2[0] if training else None, s2[1] if training else None,
+                               g.B, g.H, g.W, act)
+        ops.bn_finalize(s2[0], s2[1], g2, b2, rm2, rv2, s2[2], s2[3], s2[4], s2[5], M, eps, mom, training)
+        # squeeze-excite (tiny fp32 products, B rows)
+        pool = ops.se_pool(d_pre, s2[2], s2[3], g.B, g.P, act)
+        s1_pre = _empty((g.B, Cs), x, torch.float32)
+        s1a = _empty((g.B, Cs), x, torch.float32)
+        sw1m = sw1.detach().reshape(Cs, Cm)
+        sw2m = sw2.detach().reshape(Cm, Cs)
+        ops.gemm(pool, sw1m, s1a, bias=sb1, pre_out=s1_pre, act=act, engine=ENGINE_SIMT)
+        gate_pre = _empty((g.B, Cm), x, torch.float32)
+        gate = _empty((g.B, Cm), x, torch.float32)
+        ops.gemm(s1a, sw2m, gate, bias=sb2, pre_out=gate_pre, act="sigmoid", engine=ENGINE_SIMT)
+        d_act = ops.bn_act_gate(d_pre, s2[2], s2[3], gate, g.B, g.P, act)
+        # project
+        o_pre = _empty((M, C), x)
+        ops.gemm(d_act, ppj.w, o_pre)
+        if training:
+            ops.colstats(o_pre, s3[0], s3[1])
+        ops.bn_finalize(s3[0], s3[1], g3, b3, rm3, rv3, s3[2], s3[3], s3[4], s3[5], M, eps, mom, training)
+        y = ops.bn_apply(o_pre, s3[2], s3[3], x if meta["use_res"] else None)
+        ctx.meta = meta
+        ctx.wdw2 = wdw2
+        ctx.save_for_backward(x, e_pre, d_pre, d_act, o_pre, st, pool, s1_pre, s1a, gate_pre, gate, g1, g2, g3, sw1, sw2)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        meta = ctx.meta
+        if not meta["training"]:
+            raise NotImplementedError("MBConv backward in eval mode (running-statistics BatchNorm) is not implemented")
+        (x, e_pre, d_pre, d_act, o_pre, st, pool, s1_pre, s1a, gate_pre, gate, g1, g2, g3, sw1, sw2) = ctx.saved_tensors
+        pe: PreparedLinear = meta["pe"]
+        ppj: PreparedLinear = meta["pp"]
+        g: Geom = meta["geom"]
+        act = meta["act"]
+        dy = dy.contiguous()
+        M, C = x.shape
+        Cm = pe.w.shape[0]
+        Cs = sw1.shape[0]
+        def carve(base, n):
+            return [st[base + i * n: base + (i + 1) * n] for i in range(6)]
+        s1 = carve(0, Cm)
+        s2 = carve(6 * Cm, Cm)
+        s3 = carve(12 * Cm, C)
+        sizes = [Cm * C, Cm, Cm, Cm * 9, Cm, Cm, Cs * Cm, Cs, Cm * Cs, Cm, C * Cm, C, C]
+        # pad every slice to a multiple of 8 floats so vector loads of the BN partial sums stay aligned
+        offs, tot = [], 0
+        for s in sizes:
+            offs.append(tot)
+            tot += (s + 7) // 8 * 8
+        arena = _zeros(tot, x)
+        sl = [arena[o:o + s] for o, s in zip(offs, sizes)]
+        dWe, dg1, db1, dwdw, dg2, db2, dsw1, dsb1, dsw2, dsb2, dWp, dg3, db3 = sl
+        dWe = dWe.view(Cm, C); dsw1 = dsw1.view(Cs, Cm); dsw2 = dsw2.view(Cm, Cs); dWp = dWp.view(C, Cm)
+        # BN3 backward
+        ops.bn_bwd_reduce(dy, o_pre, s3[4], s3[5], dg3, db3)
+        do_pre = ops.bn_bwd_apply(dy, o_pre, s3[4], s3[5], g3, dg3, db3)
+        # project backward
+        dd_act = _empty((M, Cm), x)
+        ops.gemm(do_pre, ppj.wt, dd_act)
+        ops.wgrad(do_pre, d_act, dWp)
+        # squeeze-excite backward
+        dgate = ops.se_bwd_reduce(dd_act, d_pre, s2[2], s2[3], g.B, g.P, act)
+        dgate_pre = ops.mul_dact(dgate, gate_pre, "sigmoid")
+        sw1m = sw1.detach().reshape(Cs, Cm)
+        sw2m = sw2.detach().reshape(Cm, Cs)
+        ds1_pre = _empty((g.B, Cs), x, torch.float32)
+        ops.gemm(dgate_pre, sw2m.t(), ds1_pre, dact_src=s1_pre, dact=act, engine=ENGINE_SIMT)
+        ops.wgrad(dgate_pre, s1a, dsw2, engine=ENGINE_SIMT)
+        ops.colsum(dgate_pre, dsb2)
+        dpool = _empty((g.B, Cm), x, torch.float32)
+        ops.gemm(ds1_pre, sw1m.t(), dpool, engine=ENGINE_SIMT)
+        ops.wgrad(ds1_pre, pool, dsw1, engine=ENGINE_SIMT)
+        ops.colsum(ds1_pre, dsb1)
+        # BN2 + activation backward (two passes over the wide tensor)
+        dd_pre = _empty((M, Cm), x)
+        ops.dw_bn2_bwd(0, dd_act, d_pre, gate, dpool, s2[2], s2[3], s2[4], s2[5], g2, dg2, db2, None, g.B, g.P, act)
+        ops.dw_bn2_bwd(1, dd_act, d_pre, gate, dpool, s2[2], s2[3], s2[4], s2[5], g2, dg2, db2, dd_pre, g.B, g.P, act)
+        # depthwise backward (+ activation derivative, + BN1 reductions)
+        du1 = ops.dwconv_bwd(dd_pre, e_pre, s1[2], s1[3], s1[4], s1[5], ctx.wdw2, dwdw, dg1, db1, g.B, g.H, g.W, act)
+        de_pre = ops.bn_bwd_apply(du1, e_pre, s1[4], s1[5], g1, dg1, db1)
+        # expand backward (+ skip-connection gradient)
+        dx = _empty((M, C), x)
+        ops.gemm(de_pre, pe.wt, dx, residual=dy if meta["use_res"] else None)
+        ops.wgrad(de_pre, x, dWe)
+        return (dx, dWe.view(meta["we_shape"]), dg1, db1, dwdw.view(meta["wdw_shape"]), dg2, db2,
+                dsw1.view(meta["sw1_shape"]), dsb1, dsw2.view(meta["sw2_shape"]), dsb2, dWp.view(meta["wp_shape"]),
+                dg3, db3, None)
+
+
+def mbconv(x, we, g1, b1, wdw, g2, b2, sw1, sb1, sw2, sb2, wp, g3, b3, *, pe, pp, geom: Geom, act: str, training: bool,
+           running, bn_eps: float, bn_momentum: float, use_res: bool) -> Tensor:
+    meta = dict(pe=pe, pp=pp, geom=geom, act=act, training=training, running=running, bn_eps=bn_eps,
+                bn_momentum=bn_momentum, use_res=use_res, we_shape=tuple(we.shape), wdw_shape=tuple(wdw.shape),
+                sw1_shape=tuple(sw1.shape), sw2_shape=tuple(sw2.shape), wp_shape=tuple(wp.shape))
+    return MBConvFn.apply(x, we, g1, b1, wdw, g2, b2, sw1, sb1, sw2, sb2, wp, g3, b3, meta)
+
+
+# =================================================================================================
+# stand-alone LayerNorm on rows (LayerNorm2d) and layout conversion
+# =================================================================================================
+class LayerNormRowsFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b, eps):
+        x = x.contiguous()
+        y, mean, rstd = ops.layernorm_fwd(x, w, b, eps)
+        ctx.save_for_backward(x, w, mean, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, mean, rstd = ctx.saved_tensors
+        C = x.shape[1]
+        acc = _zeros(2 * C, x)
+        dx = ops.layernorm_bwd(dy.contiguous(), x, w, mean, rstd, None, acc[:C], acc[C:])
+        return dx, acc[:C], acc[C:], None
+
+
+def layernorm_rows(x, w, b, eps: float) -> Tensor:
+    return LayerNormRowsFn.apply(x, w, b, eps)
+
+
+class NchwToRowsFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        ctx.shape = tuple(x.shape)
+        return ops.nchw_to_rows(x.contiguous())
+
+    @staticmethod
+    def backward(ctx, dy):
+        B, C, H, W = ctx.shape
+        return ops.rows_to_nchw(dy.contiguous(), B, C, H, W)
+
+
+def to_rows(x: Tensor) -> Tuple[Tensor, Geom]:
+    """Logical NCHW tensor -> ([B*H*W, C] rows, geometry).  channels_last inputs are a free view."""
+    if x.dim() != 4:
+        raise ValueError(f"Expected a [B,C,H,W] tensor, got shape {tuple(x.shape)}")
+    if not x.is_cuda:
+        raise RuntimeError("outlook_grid_vision_transformer_b200 modules run on CUDA (sm_100a) only; "
+                           f"got a tensor on '{x.device}'. There is no CPU fallback.")
+    B, C, H, W = x.shape
+    xp = x.permute(0, 2, 3, 1)
+    if xp.is_contiguous():
+        return xp.reshape(B * H * W, C), Geom(B, H, W)
+    return NchwToRowsFn.apply(x), Geom(B, H, W)
+
+
+def from_rows(y: Tensor, geom: Geom) -> Tensor:
+    """rows -> logical NCHW view (channels_last strides; no copy)."""
+    return y.view(geom.B, geom.H, geom.W, y.shape[1]).permute(0, 3, 1, 2)

@@ -1,0 +1,180 @@
+"""The callers the hot path drops into: Model A (MaxOutNet, src/Model_A_OutGridNet.py:9-67) and
+Model B (OutlookerFrontGridNet, src/Model_B_OutGridNet.py:11-100), re-stated so the framework is
+self-contained on a box without the reference checkout.  Constructor signatures, attribute names
+and state_dict keys match the reference, so its checkpoints load with strict=True.
+
+Out of the hot-path scope: the 3x3 stem, the 3x3 stride-2 Downsample
+convs, the head BatchNorm + global average pool + classifier stay on cuDNN/cuBLAS through PyTorch.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Literal
+
+import torch
+import torch.nn as nn
+
+from .config import StageCfg, build_stages
+from .modules import GridOnlyBlock, OutGridBlock, OutlookerBlock2d, make_activation
+
+DownsampleType = Literal["conv", "pool"]
+
+
+def make_dpr(total_blocks: int, dpr_max: float) -> List[float]:
+    """Linear stochastic-depth schedule over all blocks.  (stem_head.py:17-20)"""
+    if total_blocks <= 1:
+        return [dpr_max]
+    return [dpr_max * i / (total_blocks - 1) for i in range(total_blocks)]
+
+
+class ConvStem(nn.Module):
+    """3x3 stride-1 conv + BN + act.  (stem_head.py:23-32)"""
+
+    def __init__(self, in_ch: int, out_ch: int, act: str = "silu", use_bn: bool = True):
+        super().__init__()
+        norm = nn.BatchNorm2d(out_ch) if use_bn else nn.Identity()
+        self.stem = nn.Sequential(nn.Conv2d(in_ch, out_ch, kernel_size=3, stride=1, padding=1, bias=not use_bn), norm,
+                                  make_activation(act))
+
+    def forward(self, x):
+        return self.stem(x)
+
+
+@dataclass(frozen=True)
+class DownsampleConfig:
+    kind: DownsampleType = "conv"
+    act: str = "silu"
+    use_bn: bool = True
+
+
+class Downsample(nn.Module):
+    """conv: 3x3 s2 + BN + act; pool: avgpool 2x2 + 1x1 + BN + act.  (downsampling.py:28-65)"""
+
+    def __init__(self, in_ch: int, out_ch: int, cfg: DownsampleConfig = DownsampleConfig()):
+        super().__init__()
+        if in_ch <= 0 or out_ch <= 0:
+            raise ValueError("in_ch and out_ch must be > 0")
+        self.in_ch, self.out_ch, self.kind = in_ch, out_ch, cfg.kind
+        norm = nn.BatchNorm2d(out_ch) if cfg.use_bn else nn.Identity()
+        act = make_activation(cfg.act)
+        if cfg.kind == "conv":
+            self.op = nn.Sequential(
+                nn.Conv2d(in_ch, out_ch, kernel_size=3, stride=2, padding=1, bias=not cfg.use_bn), norm, act)
+        elif cfg.kind == "pool":
+            self.op = nn.Sequential(
+                nn.AvgPool2d(kernel_size=2, stride=2),
+                nn.Conv2d(in_ch, out_ch, kernel_size=1, stride=1, padding=0, bias=not cfg.use_bn), norm, act)
+        else:
+            raise ValueError("cfg.kind must be 'conv' or 'pool'")
+
+    def forward(self, x):
+        return self.op(x)
+
+
+def _with_drop_path(scfg: StageCfg, p: float) -> StageCfg:
+    return StageCfg(**{**scfg.__dict__, "drop_path": p})
+
+
+class _Backbone(nn.Module):
+    def _build_common(self, num_classes, stages, in_ch, stem_dim):
+        assert len(stages) >= 1
+        self.stem = ConvStem(in_ch, stem_dim, act="silu", use_bn=True)
+        self.proj_in = nn.Identity()
+        if stem_dim != stages[0].dim:
+            self.proj_in = nn.Conv2d(stem_dim, stages[0].dim, kernel_size=1, bias=True)
+
+    def _build_head(self, stages, num_classes):
+        self.head_norm = nn.BatchNorm2d(stages[-1].dim)
+        self.classifier = nn.Linear(stages[-1].dim, num_classes)
+
+    def _run_stages(self, x):
+        for si, blocks in enumerate(self.stages):
+            for blk in blocks:
+                x = blk(x)
+            if si < len(self.downs):
+                x = self.downs[si](x)
+        return x
+
+    def _head(self, x):
+        x = self.head_norm(x)
+        return self.classifier(x.mean(dim=(2, 3)))
+
+
+class MaxOutNet(_Backbone):
+    """Model A: stem -> [OutGridBlock x depth -> Downsample] x S -> BN -> GAP -> Linear."""
+
+    def __init__(self, num_classes: int, stages: List[StageCfg], in_ch: int = 3, stem_dim: int = 64,
+                 dpr_max: float = 0.1, down_cfg: DownsampleConfig = DownsampleConfig(kind="conv", act="silu", use_bn=True)):
+        super().__init__()
+        self._build_common(num_classes, stages, in_ch, stem_dim)
+        dprs = make_dpr(sum(s.depth for s in stages), dpr_max)
+        idx = 0
+        self.stages = nn.ModuleList()
+        self.downs = nn.ModuleList()
+        for si, scfg in enumerate(stages):
+            blocks = nn.ModuleList()
+            for _ in range(scfg.depth):
+                blocks.append(OutGridBlock(_with_drop_path(scfg, dprs[idx])))
+                idx += 1
+            self.stages.append(blocks)
+            if si < len(stages) - 1:
+                self.downs.append(Downsample(scfg.dim, stages[si + 1].dim, cfg=down_cfg))
+        self._build_head(stages, num_classes)
+
+    def forward(self, x):
+        x = self.proj_in(self.stem(x))
+        return self._head(self._run_stages(x))
+
+
+class OutlookerFrontGridNet(_Backbone):
+    """Model B: stem -> OutlookerBlock2d x L -> [GridOnlyBlock x depth -> Downsample] x S -> head."""
+
+    def __init__(self, num_classes: int, stages: List[StageCfg], in_ch: int = 3, stem_dim: int = 64,
+                 outlooker_front_depth: int = 2, dpr_max: float = 0.1,
+                 down_cfg: DownsampleConfig = DownsampleConfig(kind="conv", act="silu", use_bn=True)):
+        super().__init__()
+        self._build_common(num_classes, stages, in_ch, stem_dim)
+        dprs = make_dpr(outlooker_front_depth + sum(s.depth for s in stages), dpr_max)
+        idx = 0
+        c = stages[0]
+        self.front = nn.ModuleList()
+        for _ in range(outlooker_front_depth):
+            self.front.append(OutlookerBlock2d(dim=c.dim, num_heads=c.outlook_heads, kernel_size=c.outlook_kernel,
+                                               stride=1, mlp_ratio=c.outlook_mlp_ratio, attn_drop=c.attn_drop,
+                                               proj_drop=c.proj_drop, mlp_drop=c.ffn_drop, drop_path=dprs[idx],
+                                               act=c.mlp_act))
+            idx += 1
+        self.stages = nn.ModuleList()
+        self.downs = nn.ModuleList()
+        for si, scfg in enumerate(stages):
+            blocks = nn.ModuleList()
+            for _ in range(scfg.depth):
+                blocks.append(GridOnlyBlock(_with_drop_path(scfg, dprs[idx])))
+                idx += 1
+            self.stages.append(blocks)
+            if si < len(stages) - 1:
+                self.downs.append(Downsample(scfg.dim, stages[si + 1].dim, cfg=down_cfg))
+        self._build_head(stages, num_classes)
+
+    def forward(self, x):
+        x = self.proj_in(self.stem(x))
+        for blk in self.front:
+            x = blk(x)
+        return self._head(self._run_stages(x))
+
+
+def build_model(model_cfg: dict) -> nn.Module:
+    """YAML `model:` section -> model (scripts/train.py:33-60)."""
+    model_type = str(model_cfg.get("type", "model_a")).lower()
+    stages = build_stages(model_cfg.get("stages", []))
+    if not stages:
+        raise ValueError("model.stages must have at least one stage config")
+    down_cfg = DownsampleConfig(**model_cfg.get("downsample", {}))
+    common = dict(num_classes=int(model_cfg.get("num_classes", 100)), stages=stages,
+                  in_ch=int(model_cfg.get("in_ch", 3)), stem_dim=int(model_cfg.get("stem_dim", 64)),
+                  dpr_max=float(model_cfg.get("dpr_max", 0.1)), down_cfg=down_cfg)
+    if model_type in ("a", "model_a", "maxout", "outgrid"):
+        return MaxOutNet(**common)
+    if model_type in ("b", "model_b", "outlooker_front", "front"):
+        return OutlookerFrontGridNet(outlooker_front_depth=int(model_cfg.get("outlooker_front_depth", 2)), **common)
+    raise ValueError(f"Unknown model.type '{model_type}'. Use 'model_a' (MaxOutNet) or 'model_b' (OutlookerFrontGridNet)")

@@ -1,0 +1,320 @@
+"""Tensor-level wrappers over the C-ABI (one python function per `ogv_*` entry point).
+
+PyTorch is used here only for device memory, the current stream and dtype bookkeeping; every
+computation is a libogvit kernel launched on `torch.cuda.current_stream()`.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import ACT, BF16, ENGINE_AUTO, ENGINE_SIMT, ENGINE_TC, F32, GemmArgs, check
+
+Tensor = torch.Tensor
+
+
+def _require_cuda(*ts: Optional[Tensor]) -> None:
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError(
+                "outlook_grid_vision_transformer_b200 runs on CUDA (sm_100a) only; got a tensor on "
+                f"'{t.device}'. There is no CPU fallback.")
+
+
+def dtype_code(t: Tensor) -> int:
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise TypeError(f"unsupported activation dtype {t.dtype}; use float32 or bfloat16")
+
+
+def _p(t: Optional[Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _f32(t: Optional[Tensor], name: str) -> None:
+    if t is not None and (t.dtype != torch.float32 or not t.is_contiguous()):
+        raise TypeError(f"{name} must be a contiguous float32 tensor")
+
+
+def _rows(t: Tensor, name: str) -> None:
+    if t.dim() != 2 or t.stride(1) != 1:
+        raise ValueError(f"{name} must be a 2-D tensor with unit column stride, got {tuple(t.shape)} / {t.stride()}")
+
+
+# ------------------------------------------------------------------------------------------- GEMM
+def gemm(A: Tensor, B: Tensor, D: Tensor, *, bias: Optional[Tensor] = None, pre_out: Optional[Tensor] = None,
+         act: Optional[str] = None, dact_src: Optional[Tensor] = None, dact: Optional[str] = None,
+         row_scale: Optional[Tensor] = None, rows_per_scale: int = 1, residual: Optional[Tensor] = None,
+         accumulate: bool = False, split_k: int = 1, engine: int = ENGINE_AUTO) -> Tensor:
+    """D[m,n] = epi(sum_k A[m,k] * B[n,k]); A:[M,K], B:[N,K] (any strides), D:[M,N] row-major."""
+    _require_cuda(A, B, D, bias, pre_out, dact_src, row_scale, residual)
+    if A.dim() != 2 or B.dim() != 2 or D.dim() != 2:
+        raise ValueError("gemm operands must be 2-D")
+    M, K = A.shape
+    N, K2 = B.shape
+    if K != K2 or tuple(D.shape) != (M, N):
+        raise ValueError(f"gemm shape mismatch A{tuple(A.shape)} B{tuple(B.shape)} D{tuple(D.shape)}")
+    if A.dtype != B.dtype:
+        raise TypeError("gemm: A and B must share a dtype")
+    _rows(D, "D")
+    for name, t in (("pre_out", pre_out), ("dact_src", dact_src), ("residual", residual)):
+        if t is not None:
+            _rows(t, name)
+            if t.dtype != D.dtype or tuple(t.shape) != (M, N):
+                raise ValueError(f"gemm: {name} must match D in dtype and shape")
+    _f32(bias, "bias")
+    _f32(row_scale, "row_scale")
+    a = GemmArgs()
+    a.A, a.a_rs, a.a_cs = A.data_ptr(), A.stride(0), A.stride(1)
+    a.B, a.b_rs, a.b_cs = B.data_ptr(), B.stride(0), B.stride(1)
+    a.D, a.ldd = D.data_ptr(), D.stride(0)
+    a.M, a.N, a.K = M, N, K
+    a.in_dtype, a.out_dtype = dtype_code(A), dtype_code(D)
+    a.bias = bias.data_ptr() if bias is not None else None
+    a.pre_out, a.ld_pre = (pre_out.data_ptr(), pre_out.stride(0)) if pre_out is not None else (None, 0)
+    a.act = ACT[act]
+    a.dact_src, a.ld_dact = (dact_src.data_ptr(), dact_src.stride(0)) if dact_src is not None else (None, 0)
+    a.dact = ACT[dact]
+    a.row_scale = row_scale.data_ptr() if row_scale is not None else None
+    a.rows_per_scale = int(rows_per_scale)
+    a.residual, a.ld_res = (residual.data_ptr(), residual.stride(0)) if residual is not None else (None, 0)
+    a.accumulate, a.split_k = int(accumulate), int(split_k)
+    a.col_sum, a.col_sumsq = None, None
+    check(_lib.lib().ogv_gemm(ctypes.byref(a), engine, _stream()), "ogv_gemm")
+    return D
+
+
+def wgrad(dY: Tensor, X: Tensor, out: Tensor, engine: int = ENGINE_AUTO) -> Tensor:
+    """out[n,k] += sum_m dY[m,n] * X[m,k]   (out fp32, pre-zeroed by the caller)."""
+    M, N = dY.shape
+    K = X.shape[1]
+    tiles = max(1, math.ceil(N / 128) * math.ceil(K / 128))
+    split = max(1, min(math.ceil(M / 256), (2 * sm_count()) // tiles))
+    return gemm(dY.t(), X.t(), out, accumulate=True, split_k=split, engine=engine)
+
+
+_SM = None
+
+
+def sm_count() -> int:
+    global _SM
+    if _SM is None:
+        _SM = int(_lib.lib().ogv_sm_count())
+    return _SM
+
+
+# --------------------------------------------------------------------------------- layout / misc
+def nchw_to_rows(x: Tensor) -> Tensor:
+    """[B,C,H,W] (NCHW-contiguous) -> [B*H*W, C] rows."""
+    _require_cuda(x)
+    B, C, H, W = x.shape
+    y = torch.empty((B * H * W, C), device=x.device, dtype=x.dtype)
+    check(_lib.lib().ogv_nchw_to_nhwc(_p(x), _p(y), B, C, H * W, dtype_code(x), _stream()), "nchw_to_nhwc")
+    return y
+
+
+def rows_to_nchw(y: Tensor, B: int, C: int, H: int, W: int) -> Tensor:
+    _require_cuda(y)
+    x = torch.empty((B, C, H, W), device=y.device, dtype=y.dtype)
+    check(_lib.lib().ogv_nhwc_to_nchw(_p(y), _p(x), B, C, H * W, dtype_code(y), _stream()), "nhwc_to_nchw")
+    return x
+
+
+def cast_transpose(src: Tensor, dst: Optional[Tensor], dst_t: Optional[Tensor]) -> None:
+    """src fp32 [rows, cols] -> dst[rows, cols] and/or dst_t[cols, rows] (compute dtype; strided views ok)."""
+    _require_cuda(src, dst, dst_t)
+    _f32(src, "src")
+    rows, cols = src.shape
+    ref = dst if dst is not None else dst_t
+    check(_lib.lib().ogv_cast_transpose(_p(src), _p(dst), dst.stride(0) if dst is not None else 0, _p(dst_t),
+                                        dst_t.stride(0) if dst_t is not None else 0, rows, cols, dtype_code(ref),
+                                        _stream()), "cast_transpose")
+
+
+def rowscale(x: Tensor, scale: Tensor, rows_per_scale: int) -> Tensor:
+    _require_cuda(x, scale)
+    _f32(scale, "scale")
+    y = torch.empty_like(x)
+    check(_lib.lib().ogv_rowscale(_p(x), _p(scale), _p(y), x.shape[0], x.shape[1], rows_per_scale, dtype_code(x),
+                                  _stream()), "rowscale")
+    return y
+
+
+def colsum(x: Tensor, out: Tensor) -> Tensor:
+    """out[n] += sum_m x[m,n]"""
+    _require_cuda(x, out)
+    _rows(x, "x")
+    _f32(out, "out")
+    check(_lib.lib().ogv_colsum(_p(x), x.stride(0), _p(out), x.shape[0], x.shape[1], dtype_code(x), _stream()),
+          "colsum")
+    return out
+
+
+def mul_dact(a: Tensor, pre: Tensor, act: str) -> Tensor:
+    out = torch.empty_like(a)
+    check(_lib.lib().ogv_mul_dact(_p(a), _p(pre), _p(out), a.numel(), ACT[act], dtype_code(a), _stream()),
+          "mul_dact")
+    return out
+
+
+def add(a: Tensor, b: Tensor) -> Tensor:
+    y = torch.empty_like(a)
+    check(_lib.lib().ogv_add(_p(a), _p(b), _p(y), a.numel(), dtype_code(a), _stream()), "add")
+    return y
+
+
+# ------------------------------------------------------------------------------------- LayerNorm
+def layernorm_fwd(x: Tensor, gamma: Tensor, beta: Tensor, eps: float):
+    _require_cuda(x, gamma, beta)
+    M, C = x.shape
+    y = torch.empty_like(x)
+    mean = torch.empty(M, device=x.device, dtype=torch.float32)
+    rstd = torch.empty(M, device=x.device, dtype=torch.float32)
+    check(_lib.lib().ogv_layernorm_fwd(_p(x), _p(gamma), _p(beta), _p(y), _p(mean), _p(rstd), M, C, float(eps),
+                                       dtype_code(x), _stream()), "layernorm_fwd")
+    return y, mean, rstd
+
+
+def layernorm_bwd(dy: Tensor, x: Tensor, gamma: Tensor, mean: Tensor, rstd: Tensor, dres: Optional[Tensor],
+                  dgamma: Tensor, dbeta: Tensor) -> Tensor:
+    M, C = x.shape
+    dx = torch.empty_like(x)
+    check(_lib.lib().ogv_layernorm_bwd(_p(dy), _p(x), _p(gamma), _p(mean), _p(rstd), _p(dres), _p(dx), _p(dgamma),
+                                       _p(dbeta), M, C, dtype_code(x), _stream()), "layernorm_bwd")
+    return dx
+
+
+# --------------------------------------------------------------------------------------- outlook
+def outlook_core_fwd(va: Tensor, B: int, H: int, W: int, C: int, heads: int) -> Tensor:
+    _require_cuda(va)
+    y = torch.empty((va.shape[0], C), device=va.device, dtype=va.dtype)
+    check(_lib.lib().ogv_outlook_core_fwd(_p(va), va.stride(0), _p(y), B, H, W, C, heads, dtype_code(va), _stream()),
+          "outlook_core_fwd")
+    return y
+
+
+def outlook_core_bwd(va: Tensor, dy: Tensor, B: int, H: int, W: int, C: int, heads: int) -> Tensor:
+    dva = torch.empty_like(va)
+    check(_lib.lib().ogv_outlook_core_bwd(_p(va), va.stride(0), _p(dy), _p(dva), B, H, W, C, heads, dtype_code(va),
+                                          _stream()), "outlook_core_bwd")
+    return dva
+
+
+# ------------------------------------------------------------------------------------- BatchNorm
+def colstats(x: Tensor, ssum: Tensor, ssq: Tensor) -> None:
+    _rows(x, "x")
+    check(_lib.lib().ogv_colstats(_p(x), x.stride(0), _p(ssum), _p(ssq), x.shape[0], x.shape[1], dtype_code(x),
+                                  _stream()), "colstats")
+
+
+def bn_finalize(ssum, ssq, gamma, beta, running_mean, running_var, scale, shift, mean, rstd, n: int, eps: float,
+                momentum: float, training: bool) -> None:
+    C = scale.numel()
+    check(_lib.lib().ogv_bn_finalize(_p(ssum), _p(ssq), _p(gamma), _p(beta), _p(running_mean), _p(running_var),
+                                     _p(scale), _p(shift), _p(mean), _p(rstd), n, C, float(eps), float(momentum),
+                                     int(training), _stream()), "bn_finalize")
+
+
+def bn_apply(x: Tensor, scale: Tensor, shift: Tensor, res: Optional[Tensor]) -> Tensor:
+    out = torch.empty_like(x)
+    check(_lib.lib().ogv_bn_apply(_p(x), _p(scale), _p(shift), _p(res), _p(out), x.shape[0], x.shape[1],
+                                  dtype_code(x), _stream()), "bn_apply")
+    return out
+
+
+def bn_bwd_reduce(dy, x, mean, rstd, dgamma, dbeta) -> None:
+    check(_lib.lib().ogv_bn_bwd_reduce(_p(dy), _p(x), _p(mean), _p(rstd), _p(dgamma), _p(dbeta), x.shape[0],
+                                       x.shape[1], dtype_code(x), _stream()), "bn_bwd_reduce")
+
+
+def bn_bwd_apply(dy, x, mean, rstd, gamma, dgamma, dbeta) -> Tensor:
+    dx = torch.empty_like(x)
+    check(_lib.lib().ogv_bn_bwd_apply(_p(dy), _p(x), _p(mean), _p(rstd), _p(gamma), _p(dgamma), _p(dbeta), _p(dx),
+                                      x.shape[0], x.shape[1], dtype_code(x), _stream()), "bn_bwd_apply")
+    return dx
+
+
+# ---------------------------------------------------------------------------------------- MBConv
+def dwconv_fwd(e_pre, scale1, shift1, w, ssum2, ssq2, B, H, W, act: str) -> Tensor:
+    d_pre = torch.empty_like(e_pre)
+    check(_lib.lib().ogv_dwconv_fwd(_p(e_pre), _p(scale1), _p(shift1), _p(w), _p(d_pre), _p(ssum2), _p(ssq2), B, H, W,
+                                    e_pre.shape[1], ACT[act], dtype_code(e_pre), _stream()), "dwconv_fwd")
+    return d_pre
+
+
+def dwconv_bwd(dd_pre, e_pre, scale1, shift1, mean1, rstd1, w, dw, dgamma1, dbeta1, B, H, W, act: str) -> Tensor:
+    du1 = torch.empty_like(e_pre)
+    check(_lib.lib().ogv_dwconv_bwd(_p(dd_pre), _p(e_pre), _p(scale1), _p(shift1), _p(mean1), _p(rstd1), _p(w),
+                                    _p(du1), _p(dw), _p(dgamma1), _p(dbeta1), B, H, W, e_pre.shape[1], ACT[act],
+                                    dtype_code(e_pre), _stream()), "dwconv_bwd")
+    return du1
+
+
+def se_pool(d_pre, scale2, shift2, B, HW, act: str) -> Tensor:
+    pool = torch.empty((B, d_pre.shape[1]), device=d_pre.device, dtype=torch.float32)
+    check(_lib.lib().ogv_se_pool(_p(d_pre), _p(scale2), _p(shift2), _p(pool), B, HW, d_pre.shape[1], ACT[act],
+                                 dtype_code(d_pre), _stream()), "se_pool")
+    return pool
+
+
+def bn_act_gate(d_pre, scale2, shift2, gate, B, HW, act: str) -> Tensor:
+    d_act = torch.empty_like(d_pre)
+    check(_lib.lib().ogv_bn_act_gate(_p(d_pre), _p(scale2), _p(shift2), _p(gate), _p(d_act), B, HW, d_pre.shape[1],
+                                     ACT[act], dtype_code(d_pre), _stream()), "bn_act_gate")
+    return d_act
+
+
+def se_bwd_reduce(dd_act, d_pre, scale2, shift2, B, HW, act: str) -> Tensor:
+    dgate = torch.empty((B, d_pre.shape[1]), device=d_pre.device, dtype=torch.float32)
+    check(_lib.lib().ogv_se_bwd_reduce(_p(dd_act), _p(d_pre), _p(scale2), _p(shift2), _p(dgate), B, HW,
+                                       d_pre.shape[1], ACT[act], dtype_code(d_pre), _stream()), "se_bwd_reduce")
+    return dgate
+
+
+def dw_bn2_bwd(pass_: int, dd_act, d_pre, gate, dpool, scale2, shift2, mean2, rstd2, gamma2, dgamma2, dbeta2, dd_pre,
+               B, HW, act: str) -> None:
+    check(_lib.lib().ogv_dw_bn2_bwd(pass_, _p(dd_act), _p(d_pre), _p(gate), _p(dpool), _p(scale2), _p(shift2),
+                                    _p(mean2), _p(rstd2), _p(gamma2), _p(dgamma2), _p(dbeta2), _p(dd_pre), B, HW,
+                                    d_pre.shape[1], ACT[act], dtype_code(d_pre), _stream()), "dw_bn2_bwd")
+
+
+# --------------------------------------------------------------------------------- grid attention
+def grid_attn_fwd(qkv: Tensor, B, H, W, C, heads, g) -> Tensor:
+    _require_cuda(qkv)
+    out = torch.empty((qkv.shape[0], C), device=qkv.device, dtype=qkv.dtype)
+    check(_lib.lib().ogv_grid_attn_fwd(_p(qkv), _p(out), B, H, W, C, heads, g, dtype_code(qkv), _stream()),
+          "grid_attn_fwd")
+    return out
+
+
+def grid_attn_bwd(qkv: Tensor, dout: Tensor, B, H, W, C, heads, g) -> Tensor:
+    dqkv = torch.empty_like(qkv)
+    check(_lib.lib().ogv_grid_attn_bwd(_p(qkv), _p(dout), _p(dqkv), B, H, W, C, heads, g, dtype_code(qkv), _stream()),
+          "grid_attn_bwd")
+    return dqkv
+
+
+def grid_attn_probs(qkv: Tensor, B, H, W, C, heads, g) -> Tensor:
+    N = (H // g) * (W // g)
+    attn = torch.empty((B * g * g, heads, N, N), device=qkv.device, dtype=torch.float32)
+    check(_lib.lib().ogv_grid_attn_probs(_p(qkv), _p(attn), B, H, W, C, heads, g, dtype_code(qkv), _stream()),
+          "grid_attn_probs")
+    return attn
+
+
+# ----------------------------------------------------------------------------------------- AdamW
+def adamw(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step: int, grad_scale: float = 1.0) -> None:
+    bc1 = 1.0 - beta1 ** step
+    bc2 = 1.0 - beta2 ** step
+    check(_lib.lib().ogv_adamw(_p(p), _p(g), _p(m), _p(v), p.numel(), lr, beta1, beta2, eps, weight_decay, bc1, bc2,
+                               grad_scale, _stream()), "adamw")
