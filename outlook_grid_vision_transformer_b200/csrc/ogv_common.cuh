@@ -131,17 +131,37 @@ __device__ __forceinline__ void stv(T* p, const float (&v)[VEC]) {
 // ---------------------------------------------------------------------------------------------
 // activations (exact erf GELU, SiLU, sigmoid) and their derivatives w.r.t. the pre-activation
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-x)); }
+// Transcendentals are MUFU-throughput bound on the wide (4C) tensors, so the fast hardware paths are
+// used: ex2.approx / rcp.approx (rel. error ~1e-6, far below both parity tolerances) and the
+// Abramowitz-Stegun 7.1.26 rational erf (abs. error 1.5e-7) sharing ONE exponential between
+// erf(x/sqrt2) and the Gaussian pdf of GELU'.
+__device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 __device__ __forceinline__ float silu_f(float x) { return x * sigmoid_f(x); }
 __device__ __forceinline__ float dsilu_f(float x) {
   float s = sigmoid_f(x);
   return s * (1.f + x * (1.f - s));
 }
-__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
+// returns erf(x / sqrt(2)); *gauss = exp(-x^2 / 2)
+__device__ __forceinline__ float erf_gauss(float x, float* gauss) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float e = __expf(-z * z);
+  const float t = __fdividef(1.f, fmaf(0.3275911f, z, 1.f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float r = 1.f - p * t * e;
+  *gauss = e;
+  return copysignf(r, x);
+}
+__device__ __forceinline__ float gelu_f(float x) {
+  float e;
+  return 0.5f * x * (1.f + erf_gauss(x, &e));
+}
 __device__ __forceinline__ float dgelu_f(float x) {
-  float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752440f));
-  float pdf = 0.39894228040143267794f * expf(-0.5f * x * x);
-  return cdf + x * pdf;
+  float e;
+  const float cdf = 0.5f * (1.f + erf_gauss(x, &e));
+  return fmaf(x * 0.39894228040143267794f, e, cdf);
 }
 __device__ __forceinline__ float act_apply(int act, float x) {
   switch (act) {

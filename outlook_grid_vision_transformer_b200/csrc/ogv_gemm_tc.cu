@@ -1,14 +1,18 @@
 // tcgen05 GEMM engine for sm_100a:  D[M,N] = epi( A[M,K] * B[N,K]^T ), bf16 operands, fp32 accumulate.
 //
-//   * persistent, warp-specialised CTA of 192 threads, one CTA per SM:
-//       warp 0      TMA producer  (cp.async.bulk.tensor 2-D boxes, 128B swizzle, mbarrier complete_tx)
-//       warp 1      TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BN x 16, cta_group::1)
-//       warps 2..5  epilogue: tcgen05.ld (lane = output row) -> fused epilogue -> global
-//   * smem ring of STAGES x (A 128x64 | B BNx64) bf16 tiles; accumulators double-buffered in TMEM
+//   * persistent, warp-specialised CTA of 18 warps, one CTA per SM:
+//       warps 0..15  epilogue: tcgen05.ld (lane = output row, warp%4 = TMEM lane quarter, warp/4 =
+//                    column group) -> fused epilogue -> swizzled smem staging -> TMA store; the
+//                    residual / saved-pre-activation operand of the epilogue arrives by TMA load
+//                    into the same staging slot.  (The fused epilogues are ALU/MUFU heavy -- GELU,
+//                    GELU' -- so they get 16 warps, 4 per scheduler.)
+//       warp 16      TMA producer (cp.async.bulk.tensor 2-D boxes, 128B swizzle, mbarrier complete_tx)
+//       warp 17      TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BN x 16, cta_group::1)
+//   * smem ring of `stages` x (A 128x64 | B BNx64) bf16 tiles; accumulators double-buffered in TMEM
 //     (2 x BN fp32 columns) so the epilogue of tile i overlaps the MMAs of tile i+1;
 //   * operands may be K-major (forward / dgrad) or MN-major (wgrad: reduction over the row index
 //     of both global tensors) -- only the TMA box and the UMMA descriptors differ;
-//   * split-K work items (wgrad) accumulate with fp32 atomics into D.
+//   * split-K work items (wgrad) accumulate with fp32 atomics into D (direct, non-TMA epilogue).
 #include "ogv_gemm.cuh"
 #include "ogv_ptx.cuh"
 
@@ -16,29 +20,32 @@ namespace {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;  // 64 bf16 = one 128-byte swizzle row
-constexpr int TC_THREADS = 192;
-
-template <int BN>
-struct TcCfg {
-  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
-  static constexpr int A_BYTES = TC_BM * TC_BK * 2;
-  static constexpr int B_BYTES = BN * TC_BK * 2;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;
-  static constexpr int TMEM_COLS = 2 * BN;
-};
+constexpr int EPI_WARPS = 16;
+constexpr int TC_THREADS = (EPI_WARPS + 2) * 32;
+constexpr int PRODUCER_WARP = EPI_WARPS;
+constexpr int MMA_WARP = EPI_WARPS + 1;
+constexpr int CH = 32;                     // epilogue chunk: 32 columns = 64 B of bf16 per row
+constexpr int SLOT_BYTES = 32 * CH * 2;    // one warp's 32 x 32 bf16 staging tile (64B-swizzled)
+constexpr int MAX_STAGES = 8;
+constexpr int SMEM_LIMIT = 227 * 1024;
+constexpr int BAR_BYTES = (2 * MAX_STAGES + 4 + 2 * EPI_WARPS) * 8 + 16;
 
 struct TcParams {
   int M, N, K;
   int a_mn, b_mn;
   int m_tiles, n_tiles, splits, chunks_per_split, k_chunks;
-  int vec_ok;
+  int stages;       // smem ring depth
+  int slots;        // staging slots per epilogue warp (0: direct epilogue, 2, or 4 with pre_out)
+  int epi_load;     // 0 none, 1 residual, 2 dact_src -- operand fetched by TMA into the staging slot
+  int vec_ok;       // direct epilogue may use 8-wide vector accesses
   GemmEpi epi;
 };
 
+// ---------------------------------------------------------------------------------------------
+// direct (non-TMA) epilogue pieces: fp32 output, split-K atomics, unaligned tensors
+// ---------------------------------------------------------------------------------------------
 template <typename TO>
-__device__ __forceinline__ void epi_row16(const GemmEpi& e, int m, int n0, float (&v)[16], int vec_ok) {
+__device__ __forceinline__ void epi_row16(const GemmEpi& e, int m, int n0, const float* v, int vec_ok) {
   if (vec_ok && n0 + 16 <= e.N) {
     const float rs = e.row_scale ? e.row_scale[m / e.rows_per_scale] : 1.f;
 #pragma unroll
@@ -87,37 +94,75 @@ __device__ __forceinline__ void epi_row16(const GemmEpi& e, int m, int n0, float
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// staged epilogue helpers: a warp's 32 x 32 bf16 tile in the TMA SWIZZLE_64B layout
+// (byte address bits [4,6) ^= bits [7,9)): conflict-free 16-byte row-owner accesses.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t sw64(int row, int c16) { return row * 64 + ((c16 ^ ((row >> 1) & 3)) << 4); }
+
+__device__ __forceinline__ void stage_write_row(uint8_t* slot, int row, const float (&v)[32]) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint4 u;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[8 * c + 2 * i], v[8 * c + 2 * i + 1]);
+    *reinterpret_cast<uint4*>(slot + sw64(row, c)) = u;
+  }
+}
+__device__ __forceinline__ void stage_read_row(const uint8_t* slot, int row, float (&r)[32]) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint4 u = *reinterpret_cast<const uint4*>(slot + sw64(row, c));
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float2 f = __bfloat1622float2(h[i]);
+      r[8 * c + 2 * i] = f.x;
+      r[8 * c + 2 * i + 1] = f.y;
+    }
+  }
+}
+
 template <int BN, typename TO>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
-  using Cfg = TcCfg<BN>;
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmP,
+               const __grid_constant__ CUtensorMap tmL, const TcParams p) {
+  constexpr int A_BYTES = TC_BM * TC_BK * 2;
+  constexpr int B_BYTES = BN * TC_BK * 2;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int TMEM_COLS = 2 * BN;
   extern __shared__ uint8_t smem_raw[];
   // 128B-swizzled TMA/UMMA tiles need 1024-byte alignment.
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
-  uint64_t* empty_bar = full_bar + Cfg::STAGES;
-  uint64_t* tfull_bar = empty_bar + Cfg::STAGES;
+  uint8_t* staging = smem + p.stages * STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + EPI_WARPS * p.slots * SLOT_BYTES);
+  uint64_t* empty_bar = full_bar + MAX_STAGES;
+  uint64_t* tfull_bar = empty_bar + MAX_STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* ld_bar = tempty_bar + 2;  // [EPI_WARPS][2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ld_bar + 2 * EPI_WARPS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == PRODUCER_WARP && lane == 0) {
     ptx::tma_prefetch_desc(&tmA);
     ptx::tma_prefetch_desc(&tmB);
-    for (int s = 0; s < Cfg::STAGES; ++s) {
+    for (int s = 0; s < p.stages; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
       ptx::mbar_init(&empty_bar[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(&tfull_bar[s], 1);
-      ptx::mbar_init(&tempty_bar[s], 4);
+      ptx::mbar_init(&tempty_bar[s], EPI_WARPS);
     }
+    for (int s = 0; s < 2 * EPI_WARPS; ++s) ptx::mbar_init(&ld_bar[s], 1);
     ptx::fence_barrier_init();
   }
-  if (warp == 1) {
-    ptx::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  if (warp == MMA_WARP) {
+    ptx::tmem_alloc(tmem_slot, TMEM_COLS);
     ptx::tmem_relinquish();
   }
   ptx::tc_fence_before();
@@ -127,7 +172,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int total = p.m_tiles * p.n_tiles * p.splits;
 
-  if (warp == 0) {
+  if (warp == PRODUCER_WARP) {
     // ------------------------------- TMA producer -------------------------------
     if (lane == 0) {
       int stage = 0;
@@ -141,9 +186,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int kc1 = min(p.k_chunks, kc0 + p.chunks_per_split);
         for (int kc = kc0; kc < kc1; ++kc) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
-          ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-          uint8_t* sb = sa + Cfg::A_BYTES;
+          ptx::mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+          uint8_t* sa = smem + stage * STAGE_BYTES;
+          uint8_t* sb = sa + A_BYTES;
           const int k0 = kc * TC_BK;
           if (!p.a_mn) {
             ptx::tma_load_2d(sa, &tmA, &full_bar[stage], k0, m0);  // box {64 k, 128 rows}
@@ -159,11 +204,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int j = 0; j < BN / 64; ++j)
               ptx::tma_load_2d(sb + j * 8192, &tmB, &full_bar[stage], n0 + 64 * j, k0);
           }
-          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == MMA_WARP) {
     // ------------------------------- MMA issuer -------------------------------
     if (lane == 0) {
       const uint32_t idesc = ptx::umma_idesc_bf16(TC_BM, BN, p.a_mn, p.b_mn);
@@ -186,8 +231,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kc = kc0; kc < kc1; ++kc) {
           ptx::mbar_wait(&full_bar[stage], phase);
           ptx::tc_fence_after();
-          const uint32_t sa = ptx::smem_u32(smem + stage * Cfg::STAGE_BYTES);
-          const uint32_t sb = sa + Cfg::A_BYTES;
+          const uint32_t sa = ptx::smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t sb = sa + A_BYTES;
 #pragma unroll
           for (int k = 0; k < TC_BK / 16; ++k) {
             const uint64_t adesc = ptx::umma_smem_desc(sa + k * a_step, a_lbo, 1024u);
@@ -195,43 +240,132 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             ptx::umma_f16(d_tmem, adesc, bdesc, idesc, (kc > kc0 || k > 0) ? 1u : 0u);
           }
           ptx::umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
-          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
         ptx::umma_commit(&tfull_bar[as]);  // accumulator ready for the epilogue warps
       }
     }
   } else {
     // ------------------------------- epilogue -------------------------------
-    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    const int q = warp & 3;    // TMEM lane quarter this warp may read
+    const int cg = warp >> 2;  // column group: chunks cg, cg+4, ...
+    const GemmEpi& e = p.epi;
+    uint8_t* my_slots = staging + warp * p.slots * SLOT_BYTES;
+    uint64_t* my_ld = ld_bar + 2 * warp;
+    uint32_t ld_phase = 0;  // bit i = parity of my_ld[i]
+    int chunk_ctr = 0;
     int it = 0;
     for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
       const int nt = w % p.n_tiles;
       const int mt = (w / p.n_tiles) % p.m_tiles;
       const int m0 = mt * TC_BM, n0 = nt * BN;
       const int as = it & 1;
-      ptx::mbar_wait(&tfull_bar[as], (it >> 1) & 1);
-      ptx::tc_fence_after();
-      const int m = m0 + q * 32 + lane;
+      const int mrow0 = m0 + q * 32;
+      const int m = mrow0 + lane;
       const uint32_t t0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
+      bool waited = false;
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 16) {
-        if (n0 + c >= p.N) break;
-        float v[16];
-        ptx::tmem_ld16(t0 + c, v);
-        if (m < p.M) epi_row16<TO>(p.epi, m, n0 + c, v, p.vec_ok);
+      for (int c = cg; c < BN / CH; c += 4) {
+        const int n0c = n0 + c * CH;
+        if (n0c >= p.N) break;
+        uint8_t* s0 = nullptr;
+        uint8_t* s1 = nullptr;
+        int pr = 0;
+        if (p.slots) {
+          pr = chunk_ctr & 1;
+          ++chunk_ctr;
+          s0 = my_slots + (p.slots == 4 ? 2 * pr : pr) * SLOT_BYTES;
+          s1 = s0 + SLOT_BYTES;
+          // the stores issued two chunks ago from this slot pair must have finished reading smem
+          if (lane == 0) ptx::bulk_wait_read<1>();
+          __syncwarp();
+          if (p.epi_load && lane == 0) {
+            ptx::mbar_arrive_expect_tx(&my_ld[pr], SLOT_BYTES);
+            ptx::tma_load_2d(s0, &tmL, &my_ld[pr], n0c, mrow0);
+          }
+        }
+        if (!waited) {
+          ptx::mbar_wait(&tfull_bar[as], (it >> 1) & 1);
+          ptx::tc_fence_after();
+          waited = true;
+        }
+        float v[32];
+        ptx::tmem_ld32(t0 + c * CH, v);
+        if (!p.slots) {
+          if (m < p.M) {
+            epi_row16<TO>(e, m, n0c, v, p.vec_ok);
+            epi_row16<TO>(e, m, n0c + 16, v + 16, p.vec_ok);
+          }
+          continue;
+        }
+        // ---- staged epilogue (bf16 tensors, TMA in/out) ----
+        if (e.bias) {
+          if (n0c + CH <= p.N) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(e.bias + n0c) + i);
+              v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (n0c + i < p.N) v[i] += __ldg(e.bias + n0c + i);
+          }
+        }
+        if (e.pre_out) stage_write_row(s1, lane, v);
+        if (e.act != OGV_ACT_NONE) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = act_apply(e.act, v[i]);
+        }
+        if (p.epi_load) {
+          ptx::mbar_wait(&my_ld[pr], (ld_phase >> pr) & 1u);
+          ld_phase ^= 1u << pr;
+          float r[32];
+          stage_read_row(s0, lane, r);
+          if (p.epi_load == 2) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] *= act_grad(e.dact, r[i]);
+            if (e.row_scale) {
+              const float rs = m < p.M ? e.row_scale[m / e.rows_per_scale] : 0.f;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] *= rs;
+            }
+          } else {
+            const float rs = (e.row_scale && m < p.M) ? e.row_scale[m / e.rows_per_scale] : 1.f;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = fmaf(v[i], rs, r[i]);
+          }
+          __syncwarp();  // every lane has read its residual row before anyone overwrites the slot
+        } else if (e.row_scale) {
+          const float rs = m < p.M ? e.row_scale[m / e.rows_per_scale] : 0.f;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] *= rs;
+        }
+        stage_write_row(s0, lane, v);
+        ptx::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          ptx::tma_store_2d(&tmD, s0, n0c, mrow0);
+          if (e.pre_out) ptx::tma_store_2d(&tmP, s1, n0c, mrow0);
+          ptx::bulk_commit();
+        }
+      }
+      if (!waited) {  // warps without a chunk in this tile still pace themselves on the accumulator
+        ptx::mbar_wait(&tfull_bar[as], (it >> 1) & 1);
       }
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tempty_bar[as]);
     }
+    if (p.slots && lane == 0) ptx::bulk_wait<0>();
   }
 
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == MMA_WARP) {
     __syncwarp();
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    ptx::tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -251,8 +385,9 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// 2-D bf16 tensor map: inner (contiguous) extent `inner`, outer extent `outer`, outer stride in elements.
-int make_tmap(CUtensorMap* tm, const void* ptr, long long inner, long long outer, long long ld, int box_outer) {
+// 2-D bf16 tensor map: inner (contiguous) extent `inner`, outer extent `outer`, outer stride `ld` elements.
+int make_tmap(CUtensorMap* tm, const void* ptr, long long inner, long long outer, long long ld, int box_inner,
+              int box_outer, CUtensorMapSwizzle swz) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) {
     ogv_set_error("cuTensorMapEncodeTiled entry point not available");
@@ -260,14 +395,14 @@ int make_tmap(CUtensorMap* tm, const void* ptr, long long inner, long long outer
   }
   cuuint64_t gdim[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
   cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {64u, (cuuint32_t)box_outer};
+  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
   cuuint32_t estr[2] = {1u, 1u};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    ogv_set_error("cuTensorMapEncodeTiled failed (%d) inner=%lld outer=%lld ld=%lld box_outer=%d ptr=%p", (int)r,
-                  inner, outer, ld, box_outer, ptr);
+    ogv_set_error("cuTensorMapEncodeTiled failed (%d) inner=%lld outer=%lld ld=%lld box=%dx%d ptr=%p", (int)r, inner,
+                  outer, ld, box_inner, box_outer, ptr);
     return OGV_ERR_CUDA;
   }
   return OGV_OK;
@@ -280,22 +415,35 @@ int operand_major(long long rs, long long cs) {
   return -1;
 }
 
+bool tma_ok(const void* ptr, long long ld) {
+  return ptr != nullptr && (reinterpret_cast<uintptr_t>(ptr) % 16 == 0) && (ld % 8 == 0);
+}
+
 template <int BN, typename TO>
-int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, cudaStream_t stream) {
-  using Cfg = TcCfg<BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg::SMEM_BYTES);
-    if (e != cudaSuccess) {
-      ogv_set_error("gemm_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+int launch_tc(const CUtensorMap* tms, TcParams& p, cudaStream_t stream) {
+  constexpr int STAGE_BYTES = TC_BM * TC_BK * 2 + BN * TC_BK * 2;
+  const int staging = EPI_WARPS * p.slots * SLOT_BYTES;
+  int stages = (SMEM_LIMIT - 1024 - BAR_BYTES - staging) / STAGE_BYTES;
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  if (stages < 2) {
+    ogv_set_error("gemm_tc: shared memory budget leaves %d pipeline stages", stages);
+    return OGV_ERR_UNSUPPORTED;
+  }
+  p.stages = stages;
+  const int smem_bytes = stages * STAGE_BYTES + staging + BAR_BYTES + 1024;
+  static int attr_bytes = 0;
+  if (attr_bytes < smem_bytes) {
+    cudaError_t err = cudaFuncSetAttribute(gemm_tc_kernel<BN, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           SMEM_LIMIT);
+    if (err != cudaSuccess) {
+      ogv_set_error("gemm_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(err));
       return OGV_ERR_CUDA;
     }
-    attr_set = true;
+    attr_bytes = SMEM_LIMIT;
   }
   int total = p.m_tiles * p.n_tiles * p.splits;
   int grid = total < ogv_num_sms() ? total : ogv_num_sms();
-  gemm_tc_kernel<BN, TO><<<grid, TC_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  gemm_tc_kernel<BN, TO><<<grid, TC_THREADS, smem_bytes, stream>>>(tms[0], tms[1], tms[2], tms[3], tms[4], p);
   return ogv_check_launch("gemm_tc");
 }
 
@@ -328,6 +476,10 @@ int ogv_gemm_tc(const ogv_gemm_args& a, cudaStream_t stream) {
     ogv_set_error("gemm_tc: unsupported problem: %s", why);
     return OGV_ERR_UNSUPPORTED;
   }
+  if (a.out_dtype != OGV_BF16 && a.out_dtype != OGV_F32) {
+    ogv_set_error("gemm_tc: bad out dtype %d", a.out_dtype);
+    return OGV_ERR_ARG;
+  }
   TcParams p;
   p.M = a.M; p.N = a.N; p.K = a.K;
   p.a_mn = operand_major(a.a_rs, a.a_cs);
@@ -341,31 +493,41 @@ int ogv_gemm_tc(const ogv_gemm_args& a, cudaStream_t stream) {
   p.chunks_per_split = ogv_ceil_div(p.k_chunks, split);
   p.splits = ogv_ceil_div(p.k_chunks, p.chunks_per_split);
   p.epi = make_epi(a);
-  // vector epilogue needs 8-element alignment of every [M,N] tensor it touches
-  const int esz = a.out_dtype == OGV_BF16 ? 2 : 4;
+  p.stages = 0;
+
+  // staged (TMA) epilogue: bf16 tensors, 16-byte aligned rows, at most one epilogue input operand
+  const bool obf = a.out_dtype == OGV_BF16;
+  const bool staged = obf && !a.accumulate && tma_ok(a.D, a.ldd) && (!a.pre_out || tma_ok(a.pre_out, a.ld_pre)) &&
+                      (!a.residual || tma_ok(a.residual, a.ld_res)) && (!a.dact_src || tma_ok(a.dact_src, a.ld_dact)) &&
+                      !(a.residual && a.dact_src);
+  p.slots = staged ? (a.pre_out ? 4 : 2) : 0;
+  p.epi_load = staged ? (a.residual ? 1 : (a.dact_src ? 2 : 0)) : 0;
+  const int esz = obf ? 2 : 4;
   auto ok = [&](const void* ptr, long long ld) {
-    return ptr == nullptr || ((reinterpret_cast<uintptr_t>(ptr) % 16 == 0) && ((ld * esz) % 16 == 0) && (ld % 8 == 0 || esz == 4));
+    return ptr == nullptr || ((reinterpret_cast<uintptr_t>(ptr) % 16 == 0) && ((ld * esz) % 16 == 0));
   };
   p.vec_ok = (a.accumulate || ok(a.D, a.ldd)) && ok(a.pre_out, a.ld_pre) && ok(a.dact_src, a.ld_dact) &&
              ok(a.residual, a.ld_res);
 
-  CUtensorMap tmA, tmB;
+  CUtensorMap tms[5];
   int rc;
-  if (!p.a_mn) rc = make_tmap(&tmA, a.A, a.K, a.M, a.a_rs, TC_BM);
-  else rc = make_tmap(&tmA, a.A, a.M, a.K, a.a_cs, 64);
+  if (!p.a_mn) rc = make_tmap(&tms[0], a.A, a.K, a.M, a.a_rs, 64, TC_BM, CU_TENSOR_MAP_SWIZZLE_128B);
+  else rc = make_tmap(&tms[0], a.A, a.M, a.K, a.a_cs, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
-  if (!p.b_mn) rc = make_tmap(&tmB, a.B, a.K, a.N, a.b_rs, BN);
-  else rc = make_tmap(&tmB, a.B, a.N, a.K, a.b_cs, 64);
+  if (!p.b_mn) rc = make_tmap(&tms[1], a.B, a.K, a.N, a.b_rs, 64, BN, CU_TENSOR_MAP_SWIZZLE_128B);
+  else rc = make_tmap(&tms[1], a.B, a.N, a.K, a.b_cs, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
-
-  const bool obf = a.out_dtype == OGV_BF16;
-  if (a.out_dtype != OGV_BF16 && a.out_dtype != OGV_F32) {
-    ogv_set_error("gemm_tc: bad out dtype %d", a.out_dtype);
-    return OGV_ERR_ARG;
+  tms[2] = tms[0]; tms[3] = tms[0]; tms[4] = tms[0];  // placeholders, never dereferenced when unused
+  if (staged) {
+    if ((rc = make_tmap(&tms[2], a.D, a.N, a.M, a.ldd, CH, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+    if (a.pre_out && (rc = make_tmap(&tms[3], a.pre_out, a.N, a.M, a.ld_pre, CH, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+    if (a.residual && (rc = make_tmap(&tms[4], a.residual, a.N, a.M, a.ld_res, CH, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+    if (a.dact_src && (rc = make_tmap(&tms[4], a.dact_src, a.N, a.M, a.ld_dact, CH, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
   }
+
   switch (BN) {
-    case 64: return obf ? launch_tc<64, bf16>(tmA, tmB, p, stream) : launch_tc<64, float>(tmA, tmB, p, stream);
-    case 128: return obf ? launch_tc<128, bf16>(tmA, tmB, p, stream) : launch_tc<128, float>(tmA, tmB, p, stream);
-    default: return obf ? launch_tc<256, bf16>(tmA, tmB, p, stream) : launch_tc<256, float>(tmA, tmB, p, stream);
+    case 64: return obf ? launch_tc<64, bf16>(tms, p, stream) : launch_tc<64, float>(tms, p, stream);
+    case 128: return obf ? launch_tc<128, bf16>(tms, p, stream) : launch_tc<128, float>(tms, p, stream);
+    default: return obf ? launch_tc<256, bf16>(tms, p, stream) : launch_tc<256, float>(tms, p, stream);
   }
 }

@@ -105,8 +105,8 @@ __global__ void ga_fwd_kernel(const T* __restrict__ qkv, T* __restrict__ out, fl
   for (int j = 0; j < G.N; ++j) {
     const float s = ga_dot<HD>(q, Kp + j * LD) * G.scale;
     const float mn = fmaxf(mx, s);
-    const float corr = expf(mx - mn);
-    const float p = expf(s - mn);
+    const float corr = __expf(mx - mn);
+    const float p = __expf(s - mn);
     l = l * corr + p;
     if (MODE == 0) {
 #pragma unroll
@@ -128,7 +128,7 @@ __global__ void ga_fwd_kernel(const T* __restrict__ qkv, T* __restrict__ out, fl
   } else {
     // probs layout [B*g*g, heads, N, N]; pr = group*heads + head
     float* dst = probs + (pr * G.N + n) * G.N;
-    for (int j = 0; j < G.N; ++j) dst[j] = expf(ga_dot<HD>(q, Kp + j * LD) * G.scale - mx) * inv;
+    for (int j = 0; j < G.N; ++j) dst[j] = __expf(ga_dot<HD>(q, Kp + j * LD) * G.scale - mx) * inv;
   }
 }
 
@@ -173,8 +173,8 @@ __global__ void ga_bwd_kernel(const T* __restrict__ qkv, const T* __restrict__ d
     for (int j = 0; j < G.N; ++j) {
       const float s = ga_dot<HD>(a, Kp + j * LD) * G.scale;
       const float mn = fmaxf(mx, s);
-      const float corr = expf(mx - mn);
-      const float p = expf(s - mn);
+      const float corr = __expf(mx - mn);
+      const float p = __expf(s - mn);
       l = l * corr + p;
       dacc = dacc * corr + p * ga_dot<HD>(b, Vp + j * LD);
       mx = mn;
@@ -195,7 +195,7 @@ __global__ void ga_bwd_kernel(const T* __restrict__ qkv, const T* __restrict__ d
     for (int d = 0; d < HD; ++d) dq[d] = 0.f;
     for (int j = 0; j < G.N; ++j) {
       const float s = ga_dot<HD>(a, Kp + j * LD) * G.scale;
-      const float p = expf(s - mx) * inv;
+      const float p = __expf(s - mx) * inv;
       const float dS = p * (ga_dot<HD>(b, Vp + j * LD) - Di) * G.scale;
 #pragma unroll
       for (int d = 0; d < HD; d += 4) {
@@ -220,7 +220,7 @@ __global__ void ga_bwd_kernel(const T* __restrict__ qkv, const T* __restrict__ d
     const float* Dp = sD + pl * G.N;
     for (int i = 0; i < G.N; ++i) {
       const float s = ga_dot<HD>(a, Qp + i * LD) * G.scale;
-      const float p = expf(s - Mp[i]) * Lp[i];
+      const float p = __expf(s - Mp[i]) * Lp[i];
       const float dS = p * (ga_dot<HD>(b, Gp + i * LD) - Dp[i]) * G.scale;
 #pragma unroll
       for (int d = 0; d < HD; d += 4) {
@@ -291,10 +291,12 @@ int ga_launch_bwd(const void* qkv, const void* dout, void* dqkv, const GaGeom& G
     case 16: { constexpr int HD = 16; __VA_ARGS__; }                                             \
     case 24: { constexpr int HD = 24; __VA_ARGS__; }                                             \
     case 32: { constexpr int HD = 32; __VA_ARGS__; }                                             \
+    case 40: { constexpr int HD = 40; __VA_ARGS__; }                                             \
+    case 56: { constexpr int HD = 56; __VA_ARGS__; }                                             \
     case 48: { constexpr int HD = 48; __VA_ARGS__; }                                             \
     case 64: { constexpr int HD = 64; __VA_ARGS__; }                                             \
     default:                                                                                     \
-      ogv_set_error("grid_attn: head_dim %d not in {4,8,16,24,32,48,64}", hd);                   \
+      ogv_set_error("grid_attn: head_dim %d not in {4,8,16,24,32,40,48,56,64}", hd);                   \
       return OGV_ERR_UNSUPPORTED;                                                                \
   }
 

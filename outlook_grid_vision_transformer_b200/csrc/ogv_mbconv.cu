@@ -111,7 +111,7 @@ __device__ __forceinline__ void dw_decode_tile(const DwGeom& g, long long t, int
 // forward: d_pre[p,c] = sum_t w[c,t] * act(scale1*e_pre + shift1)[p + d_t, c]; stats of d_pre
 // ------------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(DW_THREADS) dwconv_fwd_kernel(const T* __restrict__ e_pre,
+__global__ void __launch_bounds__(DW_THREADS, 2) dwconv_fwd_kernel(const T* __restrict__ e_pre,
                                                                 const float* __restrict__ scale1,
                                                                 const float* __restrict__ shift1,
                                                                 const float* __restrict__ wgt, T* __restrict__ d_pre,
@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(DW_THREADS) dwconv_fwd_kernel(const T* __restr
 //           dw[c,t] += sum_p e_act[p] * G[p - d_t];  dbeta1 += du1; dgamma1 += du1 * xhat1
 // ------------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(DW_THREADS) dwconv_bwd_kernel(
+__global__ void __launch_bounds__(DW_THREADS, 2) dwconv_bwd_kernel(
     const T* __restrict__ dd_pre, const T* __restrict__ e_pre, const float* __restrict__ scale1,
     const float* __restrict__ shift1, const float* __restrict__ mean1, const float* __restrict__ rstd1,
     const float* __restrict__ wgt, T* __restrict__ du1, float* __restrict__ dwgt, float* __restrict__ dgamma1,
@@ -439,7 +439,7 @@ __device__ __forceinline__ void dw_bn2_du(const T* dd_act, const T* d_pre, const
 }
 
 template <typename T>
-__global__ void dw_bn2_bwd_reduce_kernel(const T* __restrict__ dd_act, const T* __restrict__ d_pre,
+__global__ void __launch_bounds__(COLREDUCE_THREADS) dw_bn2_bwd_reduce_kernel(const T* __restrict__ dd_act, const T* __restrict__ d_pre,
                                          const float* __restrict__ gate, const float* __restrict__ dpool,
                                          const float* __restrict__ scale2, const float* __restrict__ shift2,
                                          const float* __restrict__ mean2, const float* __restrict__ rstd2,

@@ -182,7 +182,7 @@ struct ColSumF {
 };
 
 template <typename T>
-__global__ void colsum_kernel(const T* __restrict__ x, long long ld, float* __restrict__ out, long long M, int nv) {
+__global__ void __launch_bounds__(COLREDUCE_THREADS) colsum_kernel(const T* __restrict__ x, long long ld, float* __restrict__ out, long long M, int nv) {
   float acc[1][8];
   colreduce_init(acc);
   COLREDUCE_LOOP(M, nv, row, cv) {
@@ -196,7 +196,7 @@ __global__ void colsum_kernel(const T* __restrict__ x, long long ld, float* __re
 }
 
 template <typename T>
-__global__ void colstats_kernel(const T* __restrict__ x, long long ld, float* __restrict__ sum,
+__global__ void __launch_bounds__(COLREDUCE_THREADS) colstats_kernel(const T* __restrict__ x, long long ld, float* __restrict__ sum,
                                 float* __restrict__ sumsq, long long M, int nv) {
   float acc[2][8];
   colreduce_init(acc);

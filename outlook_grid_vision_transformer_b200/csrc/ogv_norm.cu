@@ -7,34 +7,58 @@
 
 namespace {
 
-// ------------------------------------------------------------------ LayerNorm: one warp per row
-template <typename T, int MAXV>
+// ------------------------------------------------------------------ LayerNorm
+// A row (C channels = nv 16-byte vectors) is owned by a group of G lanes, VPL vectors per lane, so
+// that all 32 lanes of a warp move data even at C = 64 (G = 8 -> 4 rows per warp).
+template <int G>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <typename T, int G, int VPL>
 __global__ void __launch_bounds__(256) ln_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
                                                      const float* __restrict__ beta, T* __restrict__ y,
                                                      float* __restrict__ mean_out, float* __restrict__ rstd_out,
                                                      long long M, int C, float eps) {
+  constexpr int RPW = 32 / G;  // rows per warp
   const int lane = threadIdx.x & 31;
+  const int gl = lane % G, gr = lane / G;
   const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = (gridDim.x * (long long)blockDim.x) >> 5;
   const int nv = C >> 3;
   const float inv_c = 1.f / (float)C;
-  for (long long row = warp0; row < M; row += nwarps) {
-    float v[MAXV][8];
+  float g[VPL][8], b[VPL][8];
+#pragma unroll
+  for (int j = 0; j < VPL; ++j) {
+    const int idx = gl + G * j;
+    if (idx < nv) {
+      ld8(gamma + idx * 8, g[j]);
+      ld8(beta + idx * 8, b[j]);
+    }
+  }
+  for (long long base = warp0 * RPW; base < M; base += nwarps * RPW) {
+    const long long row = base + gr;
+    const bool rv = row < M;
+    float v[VPL][8];
     float s = 0.f;
 #pragma unroll
-    for (int j = 0; j < MAXV; ++j) {
-      int idx = lane + 32 * j;
-      if (idx < nv) {
+    for (int j = 0; j < VPL; ++j) {
+      const int idx = gl + G * j;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[j][i] = 0.f;
+      if (rv && idx < nv) {
         ld8(x + row * C + idx * 8, v[j]);
 #pragma unroll
         for (int i = 0; i < 8; ++i) s += v[j][i];
       }
     }
-    const float mean = warp_sum(s) * inv_c;
+    const float mean = group_sum<G>(s) * inv_c;
     float q = 0.f;
 #pragma unroll
-    for (int j = 0; j < MAXV; ++j) {
-      int idx = lane + 32 * j;
+    for (int j = 0; j < VPL; ++j) {
+      const int idx = gl + G * j;
       if (idx < nv) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -43,57 +67,61 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const T* __restrict__ x, co
         }
       }
     }
-    const float rstd = 1.f / sqrtf(warp_sum(q) * inv_c + eps);
+    const float rstd = 1.f / sqrtf(group_sum<G>(q) * inv_c + eps);
 #pragma unroll
-    for (int j = 0; j < MAXV; ++j) {
-      int idx = lane + 32 * j;
-      if (idx < nv) {
-        float g[8], b[8], o[8];
-        ld8(gamma + idx * 8, g);
-        ld8(beta + idx * 8, b);
+    for (int j = 0; j < VPL; ++j) {
+      const int idx = gl + G * j;
+      if (rv && idx < nv) {
+        float o[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] = (v[j][i] - mean) * rstd * g[i] + b[i];
+        for (int i = 0; i < 8; ++i) o[i] = (v[j][i] - mean) * rstd * g[j][i] + b[j][i];
         st8(y + row * C + idx * 8, o);
       }
     }
-    if (lane == 0) {
+    if (rv && gl == 0) {
       if (mean_out) mean_out[row] = mean;
       if (rstd_out) rstd_out[row] = rstd;
     }
   }
 }
 
-template <typename T, int MAXV>
-__global__ void __launch_bounds__(256) ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+template <typename T, int G, int VPL>
+__global__ void __launch_bounds__(512) ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
                                                      const float* __restrict__ gamma, const float* __restrict__ mean,
                                                      const float* __restrict__ rstd, const T* __restrict__ dres,
                                                      T* __restrict__ dx, float* __restrict__ dgamma,
                                                      float* __restrict__ dbeta, long long M, int C) {
+  constexpr int RPW = 32 / G;
   __shared__ float sg[1024];
   __shared__ float sb[1024];
   for (int i = threadIdx.x; i < C; i += blockDim.x) { sg[i] = 0.f; sb[i] = 0.f; }
   __syncthreads();
   const int lane = threadIdx.x & 31;
+  const int gl = lane % G, gr = lane / G;
   const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = (gridDim.x * (long long)blockDim.x) >> 5;
   const int nv = C >> 3;
   const float inv_c = 1.f / (float)C;
-  float ag[MAXV][8], ab[MAXV][8], gm[MAXV][8];
+  float ag[VPL][8], ab[VPL][8], gm[VPL][8];
 #pragma unroll
-  for (int j = 0; j < MAXV; ++j) {
-    int idx = lane + 32 * j;
+  for (int j = 0; j < VPL; ++j) {
+    const int idx = gl + G * j;
 #pragma unroll
     for (int i = 0; i < 8; ++i) { ag[j][i] = 0.f; ab[j][i] = 0.f; gm[j][i] = 0.f; }
     if (idx < nv) ld8(gamma + idx * 8, gm[j]);
   }
-  for (long long row = warp0; row < M; row += nwarps) {
-    const float mu = mean[row], rs = rstd[row];
-    float g[MAXV][8], xh[MAXV][8];
+  for (long long base = warp0 * RPW; base < M; base += nwarps * RPW) {
+    const long long row = base + gr;
+    const bool rv = row < M;
+    const float mu = rv ? mean[row] : 0.f, rs = rv ? rstd[row] : 0.f;
+    float gg[VPL][8], xh[VPL][8];
     float c1 = 0.f, c2 = 0.f;
 #pragma unroll
-    for (int j = 0; j < MAXV; ++j) {
-      int idx = lane + 32 * j;
-      if (idx < nv) {
+    for (int j = 0; j < VPL; ++j) {
+      const int idx = gl + G * j;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { gg[j][i] = 0.f; xh[j][i] = 0.f; }
+      if (rv && idx < nv) {
         float d[8], xv[8];
         ld8(dy + row * C + idx * 8, d);
         ld8(x + row * C + idx * 8, xv);
@@ -102,21 +130,21 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const T* __restrict__ dy, c
           xh[j][i] = (xv[i] - mu) * rs;
           ag[j][i] += d[i] * xh[j][i];
           ab[j][i] += d[i];
-          g[j][i] = d[i] * gm[j][i];
-          c1 += g[j][i];
-          c2 += g[j][i] * xh[j][i];
+          gg[j][i] = d[i] * gm[j][i];
+          c1 += gg[j][i];
+          c2 += gg[j][i] * xh[j][i];
         }
       }
     }
-    c1 = warp_sum(c1) * inv_c;
-    c2 = warp_sum(c2) * inv_c;
+    c1 = group_sum<G>(c1) * inv_c;
+    c2 = group_sum<G>(c2) * inv_c;
 #pragma unroll
-    for (int j = 0; j < MAXV; ++j) {
-      int idx = lane + 32 * j;
-      if (idx < nv) {
+    for (int j = 0; j < VPL; ++j) {
+      const int idx = gl + G * j;
+      if (rv && idx < nv) {
         float o[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] = rs * (g[j][i] - c1 - xh[j][i] * c2);
+        for (int i = 0; i < 8; ++i) o[i] = rs * (gg[j][i] - c1 - xh[j][i] * c2);
         if (dres) {
           float r[8];
           ld8(dres + row * C + idx * 8, r);
@@ -127,14 +155,21 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const T* __restrict__ dy, c
       }
     }
   }
+  // fold the RPW row-groups of the warp, then one shared-memory atomic per channel per warp
 #pragma unroll
-  for (int j = 0; j < MAXV; ++j) {
-    int idx = lane + 32 * j;
-    if (idx < nv) {
+  for (int j = 0; j < VPL; ++j) {
+    const int idx = gl + G * j;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        atomicAdd(&sg[idx * 8 + i], ag[j][i]);
-        atomicAdd(&sb[idx * 8 + i], ab[j][i]);
+    for (int i = 0; i < 8; ++i) {
+      float a = ag[j][i], b = ab[j][i];
+#pragma unroll
+      for (int o = 16; o >= G; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+      }
+      if (gr == 0 && idx < nv) {
+        atomicAdd(&sg[idx * 8 + i], a);
+        atomicAdd(&sb[idx * 8 + i], b);
       }
     }
   }
@@ -144,6 +179,16 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const T* __restrict__ dy, c
     if (dbeta) atomicAdd(dbeta + i, sb[i]);
   }
 }
+
+#define LN_DISPATCH(C, CALL)                                  \
+  do {                                                        \
+    if ((C) <= 32) { constexpr int G = 4, VPL = 1; CALL; }    \
+    else if ((C) <= 64) { constexpr int G = 8, VPL = 1; CALL; }  \
+    else if ((C) <= 128) { constexpr int G = 16, VPL = 1; CALL; } \
+    else if ((C) <= 256) { constexpr int G = 32, VPL = 1; CALL; } \
+    else if ((C) <= 512) { constexpr int G = 32, VPL = 2; CALL; } \
+    else { constexpr int G = 32, VPL = 4; CALL; }             \
+  } while (0)
 
 // ------------------------------------------------------------------ BatchNorm
 __global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* __restrict__ sumsq,
@@ -198,7 +243,7 @@ __global__ void bn_apply_kernel(const T* __restrict__ x, const float* __restrict
 }
 
 template <typename T>
-__global__ void bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+__global__ void __launch_bounds__(COLREDUCE_THREADS) bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x,
                                      const float* __restrict__ mean, const float* __restrict__ rstd,
                                      float* __restrict__ dgamma, float* __restrict__ dbeta, long long M, int nv) {
   float acc[2][8];
@@ -261,14 +306,13 @@ extern "C" int ogv_layernorm_fwd(const void* x, const float* gamma, const float*
   OGV_REQUIRE(x && gamma && beta && y, "layernorm_fwd: null pointer");
   OGV_REQUIRE(C > 0 && C % 8 == 0 && C <= 1024, "layernorm_fwd: C=%d must be a multiple of 8 and <= 1024", C);
   if (M == 0) return OGV_OK;
-  int grid = flat_grid(M * 32, 256);
+  const int ln_g = C <= 32 ? 4 : (C <= 64 ? 8 : (C <= 128 ? 16 : 32));
+  int grid = flat_grid(M * ln_g, 256);
   cudaStream_t st = (cudaStream_t)stream;
   OGV_DISPATCH_DTYPE(dtype, T, {
     const T* xp = reinterpret_cast<const T*>(x);
     T* yp = reinterpret_cast<T*>(y);
-    if (C <= 256) ln_fwd_kernel<T, 1><<<grid, 256, 0, st>>>(xp, gamma, beta, yp, mean, rstd, M, C, eps);
-    else if (C <= 512) ln_fwd_kernel<T, 2><<<grid, 256, 0, st>>>(xp, gamma, beta, yp, mean, rstd, M, C, eps);
-    else ln_fwd_kernel<T, 4><<<grid, 256, 0, st>>>(xp, gamma, beta, yp, mean, rstd, M, C, eps);
+    LN_DISPATCH(C, (ln_fwd_kernel<T, G, VPL><<<grid, 256, 0, st>>>(xp, gamma, beta, yp, mean, rstd, M, C, eps)));
     return ogv_check_launch("layernorm_fwd");
   });
 }
@@ -279,8 +323,9 @@ extern "C" int ogv_layernorm_bwd(const void* dy, const void* x, const float* gam
   OGV_REQUIRE(dy && x && gamma && mean && rstd && dx, "layernorm_bwd: null pointer");
   OGV_REQUIRE(C > 0 && C % 8 == 0 && C <= 1024, "layernorm_bwd: C=%d must be a multiple of 8 and <= 1024", C);
   if (M == 0) return OGV_OK;
-  long long want = (M * 32 + 255) / 256;
-  long long cap = (long long)ogv_num_sms() * 4;  // few CTAs: one dgamma/dbeta flush per CTA
+  const int ln_g = C <= 32 ? 4 : (C <= 64 ? 8 : (C <= 128 ? 16 : 32));
+  long long want = (M * ln_g + 511) / 512;
+  long long cap = (long long)ogv_num_sms() * 2;  // few fat CTAs: one dgamma/dbeta atomic flush per CTA  // few CTAs: one dgamma/dbeta flush per CTA
   int grid = (int)(want < cap ? want : cap);
   cudaStream_t st = (cudaStream_t)stream;
   OGV_DISPATCH_DTYPE(dtype, T, {
@@ -288,9 +333,7 @@ extern "C" int ogv_layernorm_bwd(const void* dy, const void* x, const float* gam
     const T* xp = reinterpret_cast<const T*>(x);
     const T* rp = reinterpret_cast<const T*>(dres);
     T* dxp = reinterpret_cast<T*>(dx);
-    if (C <= 256) ln_bwd_kernel<T, 1><<<grid, 256, 0, st>>>(dyp, xp, gamma, mean, rstd, rp, dxp, dgamma, dbeta, M, C);
-    else if (C <= 512) ln_bwd_kernel<T, 2><<<grid, 256, 0, st>>>(dyp, xp, gamma, mean, rstd, rp, dxp, dgamma, dbeta, M, C);
-    else ln_bwd_kernel<T, 4><<<grid, 256, 0, st>>>(dyp, xp, gamma, mean, rstd, rp, dxp, dgamma, dbeta, M, C);
+    LN_DISPATCH(C, (ln_bwd_kernel<T, G, VPL><<<grid, 512, 0, st>>>(dyp, xp, gamma, mean, rstd, rp, dxp, dgamma, dbeta, M, C)));
     return ogv_check_launch("layernorm_bwd");
   });
 }

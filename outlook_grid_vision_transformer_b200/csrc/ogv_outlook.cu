@@ -16,7 +16,7 @@ __device__ __forceinline__ void softmax9(const float (&l)[9], float (&a)[9]) {
   float s = 0.f;
 #pragma unroll
   for (int t = 0; t < 9; ++t) {
-    a[t] = expf(l[t] - mx);
+    a[t] = __expf(l[t] - mx);
     s += a[t];
   }
   float inv = 1.f / s;

@@ -8,13 +8,17 @@ struct ColReduceCfg {
   int grid, block;
 };
 
-// nv = channel vectors (8 channels each) per row; block = nv * k threads with k = floor(256 / nv).
+// nv = channel vectors (8 channels each) per row; block = nv * k threads with k = floor(T / nv),
+// T = COLREDUCE_THREADS.  Few, fat CTAs (2 per SM): every CTA ends with one atomicAdd per channel on
+// the SAME few cache lines, and same-line atomics serialise in L2 -- with 8 CTAs/SM that tail cost
+// more than the streaming pass itself.
+constexpr int COLREDUCE_THREADS = 512;
 static inline bool colreduce_config(long long M, int nv, ColReduceCfg* cfg) {
   if (nv < 1 || nv > 256) return false;
-  int k = 256 / nv;
+  int k = COLREDUCE_THREADS / nv;
   cfg->block = nv * k;
   long long blocks = (M + k - 1) / k;
-  long long cap = (long long)ogv_num_sms() * 8;
+  long long cap = (long long)ogv_num_sms() * 2;
   cfg->grid = (int)(blocks < cap ? blocks : cap);
   if (cfg->grid < 1) cfg->grid = 1;
   return true;
@@ -23,6 +27,7 @@ static inline bool colreduce_config(long long M, int nv, ColReduceCfg* cfg) {
 #define COLREDUCE_LOOP(M, nv, row, cv)                                                \
   const int cv = threadIdx.x % (nv);                                                  \
   const long long _cr_stride = (long long)gridDim.x * (blockDim.x / (nv));            \
+  _Pragma("unroll 4")                                                                 \
   for (long long row = (long long)blockIdx.x * (blockDim.x / (nv)) + threadIdx.x / (nv); row < (M); \
        row += _cr_stride)
 
@@ -37,7 +42,7 @@ __device__ __forceinline__ void colreduce_init(float (&acc)[Q][8]) {
 // outs[q][c] += column sums; every thread of the CTA must call this (it synchronises).
 template <int Q>
 __device__ __forceinline__ void colreduce_finish(float (&acc)[Q][8], float* const (&outs)[Q], int nv) {
-  __shared__ float red[256 * 9];
+  __shared__ float red[COLREDUCE_THREADS * 9];
   const int k = blockDim.x / nv;
 #pragma unroll
   for (int q = 0; q < Q; ++q) {

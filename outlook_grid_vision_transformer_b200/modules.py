@@ -63,6 +63,9 @@ except TypeError:  # pragma: no cover - older torch
     _NEW_AUTOCAST_API = False
 
 
+FORCE_PREP = False  # set while a CUDA graph is being captured: the casts must be graph nodes
+
+
 class _Prep:
     """Cache of compute-dtype weight copies, invalidated by parameter version / storage / dtype."""
 
@@ -72,7 +75,7 @@ class _Prep:
 
     def get(self, params, dtype, build):
         key = (dtype,) + tuple((p.data_ptr(), p._version) if p is not None else None for p in params)
-        if key != self._key:
+        if FORCE_PREP or key != self._key:
             self._val = build()
             self._key = key
         return self._val

@@ -20,6 +20,10 @@ def pytest_collection_modifyitems(config, items):
     except Exception:  # pragma: no cover
         has_gpu = False
     if has_gpu:
+        # fp32 parity is owed to true fp32: the out-of-scope cuDNN/cuBLAS layers (stem, downsample,
+        # classifier) must not silently run TF32 (torch default: cudnn.allow_tf32 = True)
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
         return
     skip = pytest.mark.skip(reason="no CUDA device in this container")
     for item in items:

@@ -95,3 +95,21 @@ def assert_close(a, b, rtol, what="", atol=1e-12):
         i = torch.nonzero(bad)[0].tolist()
         raise AssertionError(f"{what}: {int(bad.sum())}/{bad.numel()} elements outside rtol={rtol}; "
                              f"max_rel_err={max_rel_err(a, b):.3e}; first at {i}: got {a[tuple(i)]:.6g} want {b[tuple(i)]:.6g}")
+
+
+def assert_grad_close_bf16(a, b, rtol, what=""):
+    """bf16 criterion for PARAMETER gradients (sums over B*H*W bf16 products with heavy cancellation,
+    e.g. BatchNorm gamma): normwise relative error <= rtol, at most 1% of the elements outside the
+    elementwise band |a-b| <= rtol*(|b|+max|b|), and no element further than 2.5x that band."""
+    a = a.detach().double().cpu()
+    b = b.detach().double().cpu()
+    assert a.shape == b.shape, f"{what}: shape {tuple(a.shape)} vs {tuple(b.shape)}"
+    assert torch.isfinite(a).all(), f"{what}: non-finite values"
+    scale = b.abs().max() + 1e-3
+    l2 = float((a - b).norm() / (b.norm() + 1e-3 * b.numel() ** 0.5))
+    band = rtol * (b.abs() + scale)
+    out = (a - b).abs() > band
+    worst = float(((a - b).abs() / band).max())
+    assert l2 <= rtol, f"{what}: normwise rel err {l2:.3e} > {rtol}"
+    assert out.float().mean() <= 0.01 and worst <= 2.5, (
+        f"{what}: {int(out.sum())}/{out.numel()} elements outside the rtol={rtol} band, worst {worst:.2f}x")

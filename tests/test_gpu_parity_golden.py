@@ -3,7 +3,7 @@ Tolerances are the north_star's: rtol 1e-3 in fp32, rtol 2e-2 in bf16, for outpu
 import pytest
 import torch
 
-from oracle_cases import assert_close, load_golden, tensor_cases
+from oracle_cases import assert_close, assert_grad_close_bf16, load_golden, tensor_cases
 
 pytestmark = pytest.mark.gpu
 
@@ -37,6 +37,9 @@ def test_cuda_matches_reference_golden(name, dtype):
     assert_close(dx, case["dx"], rtol, f"{name}: dx", atol=1e-6)
     assert set(grads) == set(case["grads"]), f"{name}: parameter-gradient key sets differ"
     for k, g in case["grads"].items():
-        assert_close(grads[k], g, rtol, f"{name}: grad[{k}]", atol=1e-5 if dtype == torch.float32 else 1e-3)
+        if dtype == torch.bfloat16:
+            assert_grad_close_bf16(grads[k], g, rtol, f"{name}: grad[{k}]")
+        else:
+            assert_close(grads[k], g, rtol, f"{name}: grad[{k}]", atol=1e-5)
     for k, v in case["buffers_after"].items():
         assert_close(bufs[k].double(), v.double(), rtol, f"{name}: buffer[{k}]")
