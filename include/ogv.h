@@ -151,13 +151,23 @@ int ogv_bn_act_gate(const void* d_pre, const float* scale2, const float* shift2,
 /* dgate[b,c] = sum_hw dd_act * act(scale2*d_pre+shift2) */
 int ogv_se_bwd_reduce(const void* dd_act, const void* d_pre, const float* scale2, const float* shift2,
                       float* dgate, int B, int HW, int Cm, int act, int dtype, void* stream);
-/* du = (dd_act*gate + dpool/HW) * act'(u), u = scale2*d_pre+shift2.
- * pass 0 (reduce): dbeta2 += sum du ; dgamma2 += sum du*xhat2
- * pass 1 (apply) : dd_pre = gamma2*rstd2*(du - dbeta2/n - xhat2*dgamma2/n) */
-int ogv_dw_bn2_bwd(int pass, const void* dd_act, const void* d_pre, const float* gate, const float* dpool,
-                   const float* scale2, const float* shift2, const float* mean2, const float* rstd2,
-                   const float* gamma2, float* dgamma2, float* dbeta2, void* dd_pre, int B, int HW, int Cm,
-                   int act, int dtype, void* stream);
+/* ONE pass over (dd_act, d_pre) giving every per-(image, channel) sum the SE backward and the BN2
+ * backward reductions need (mbc_conv.py:22-27,61 backward).  With u = scale2*d_pre+shift2, a = act(u),
+ * a' = act'(u), xh = (d_pre-mean2)*rstd2, g = dd_act:   stats[q][b][c], q = 0..4 =
+ *   sum_hw g*a | sum_hw g*a' | sum_hw g*a'*xh | sum_hw a' | sum_hw a'*xh      (stats: [5,B,Cm] fp32)
+ * stats[0] IS dgate (same values as ogv_se_bwd_reduce). */
+int ogv_mbconv_bwd_stats(const void* dd_act, const void* d_pre, const float* scale2, const float* shift2,
+                         const float* mean2, const float* rstd2, float* stats, int B, int HW, int Cm, int act,
+                         int dtype, void* stream);
+/* du = (dd_act*gate + dpool/HW)*a' :  dbeta2[c] += sum_b gate*stats1 + dpool/HW*stats3 ;
+ *                                      dgamma2[c] += sum_b gate*stats2 + dpool/HW*stats4 */
+int ogv_mbconv_bn2_finalize(const float* stats, const float* gate, const float* dpool, float* dgamma2,
+                            float* dbeta2, int B, int HW, int Cm, void* stream);
+/* dd_pre = gamma2*rstd2*(du - dbeta2/n - xhat2*dgamma2/n), du as above, n = B*HW */
+int ogv_dw_bn2_bwd_apply(const void* dd_act, const void* d_pre, const float* gate, const float* dpool,
+                         const float* scale2, const float* shift2, const float* mean2, const float* rstd2,
+                         const float* gamma2, const float* dgamma2, const float* dbeta2, void* dd_pre, int B,
+                         int HW, int Cm, int act, int dtype, void* stream);
 /* Depthwise backward: du1 = corr(dd_pre, w) * act'(u1); dw[c,t] += sum dd_pre[p]*act(u1[p+d_t]);
  * dbeta1 += sum du1 ; dgamma1 += sum du1*xhat1. */
 int ogv_dwconv_bwd(const void* dd_pre, const void* e_pre, const float* scale1, const float* shift1,

@@ -63,7 +63,9 @@ SIGNATURES = {
     "ogv_se_pool": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "ogv_bn_act_gate": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "ogv_se_bwd_reduce": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
-    "ogv_dw_bn2_bwd": [_I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "ogv_mbconv_bwd_stats": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "ogv_mbconv_bn2_finalize": [_P, _P, _P, _P, _P, _I, _I, _I, _P],
+    "ogv_dw_bn2_bwd_apply": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "ogv_dwconv_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "ogv_grid_attn_fwd": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "ogv_grid_attn_bwd": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],

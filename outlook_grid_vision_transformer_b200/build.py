@@ -27,6 +27,8 @@ SOURCES = [
     "ogv_norm.cu",
     "ogv_outlook.cu",
     "ogv_mbconv.cu",
+    "ogv_dwconv.cu",
+    "ogv_tma.cu",
     "ogv_gridattn.cu",
 ]
 

@@ -1,0 +1,736 @@
+// Depthwise 3x3 convolution of MBConv (mbc_conv.py:73-78) with the BatchNorm-affine + activation of
+// the expand stage fused on load and the batch statistics of the output fused on store, and its
+// backward (input gradient with act', filter gradient, BN1 reductions).  Math: SURVEY Appendix A.3/A.4.
+//
+// Structure (both directions): a persistent CTA owns one CC-channel chunk and walks spatial tiles.
+// The halo tile of every step is staged by TMA (cp.async.bulk.tensor.4d over [C, W, H, B]; image
+// borders and ragged edges are the descriptor's zero fill, so there is no address arithmetic or
+// predication on the load side) into a raw slot; a first pass turns it into an fp32 tile (forward:
+// BN1 + activation evaluated ONCE per element -- it is MUFU-bound and the 3x3 stencil would
+// otherwise evaluate it 9 times; backward: plain widening), which frees the raw slot for the TMA
+// load of the next tile while the fp32 stencil (4 channels x R rows per thread, no conversions, no
+// index decoding) runs.  Per-channel statistics and filter-gradient partial sums stay in registers
+// until one flush per CTA.
+#include <stdlib.h>
+
+#include "ogv_common.cuh"
+#include "ogv_ptx.cuh"
+#include "ogv_tma.cuh"
+#include "../../include/ogv.h"
+
+namespace {
+
+constexpr int DW_THREADS = 256;
+constexpr int DW_BUF_POS = 352;  // halo positions per slot (x CC channels): 10 x 34 for 8 x 32 tiles, 3 CTAs/SM forward
+
+struct DwGeom {
+  int B, H, W, Cm;
+  int TH, TW, NI, TH2, TW2;  // tile rows / cols / images, halo extents
+  int tiles_h, tiles_w;
+  int ntiles, nchunks, nworkers;
+  FastDiv d_tw2, d_th2, d_tw;
+  int dbg;  // OGV_DW_DBG bit mask (bottleneck hunting only): 1 skip activation math, 2 skip stencil, 4 skip stores
+};
+
+// tiles: full-width rows of up to 32 columns; several whole images per tile when an image is small.
+int dw_make_geom(int B, int H, int W, int Cm, int CC, int ctas_per_sm, DwGeom* g) {
+  g->B = B; g->H = H; g->W = W; g->Cm = Cm;
+  g->TW = W < 32 ? W : 32;
+  g->TW2 = g->TW + 2;
+  int max_th = DW_BUF_POS / g->TW2 - 2;
+  if (max_th < 1) return -1;
+  g->TH = H < max_th ? H : max_th;
+  if (g->TH >= 4 && g->TH < H) g->TH &= ~3;
+  g->TH2 = g->TH + 2;
+  g->tiles_h = (H + g->TH - 1) / g->TH;
+  g->tiles_w = (W + g->TW - 1) / g->TW;
+  g->NI = 1;
+  if (g->tiles_h == 1 && g->tiles_w == 1) {
+    g->NI = DW_BUF_POS / (g->TH2 * g->TW2);
+    if (g->NI > B) g->NI = B;
+    if (g->NI > 256) g->NI = 256;
+    if (g->NI < 1) g->NI = 1;
+  }
+  long long groups = (B + g->NI - 1) / g->NI;
+  long long nt = groups * g->tiles_h * g->tiles_w;
+  if (nt > 0x7fffffff) return -1;
+  g->ntiles = (int)nt;
+  g->nchunks = (Cm + CC - 1) / CC;
+  long long want = ((long long)ogv_num_sms() * ctas_per_sm + g->nchunks - 1) / g->nchunks;
+  if (want > nt) want = nt;
+  if (want < 1) want = 1;
+  g->nworkers = (int)want;
+  g->d_tw2 = make_fastdiv(g->TW2);
+  g->d_th2 = make_fastdiv(g->TH2);
+  g->d_tw = make_fastdiv(g->TW);
+  {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("OGV_DW_DBG"); dbg = e ? atoi(e) : 0; }
+    g->dbg = dbg;
+  }
+  return 0;
+}
+
+__device__ __forceinline__ void dw_decode_tile(const DwGeom& g, int t, int& b0, int& h0, int& w0) {
+  // t = (grp * tiles_h + th) * tiles_w + tw ; tile counts per image are tiny, grp may be large
+  const int q = t / g.tiles_w;
+  const int tw_i = t - q * g.tiles_w;
+  const int grp = q / g.tiles_h;
+  const int th_i = q - grp * g.tiles_h;
+  b0 = grp * g.NI;
+  h0 = th_i * g.TH;
+  w0 = tw_i * g.TW;
+}
+
+template <typename T>
+int dw_tmap(CUtensorMap* tm, const void* ptr, int dtype, const DwGeom& g, int CC, int halo) {
+  const unsigned long long es = sizeof(T);
+  unsigned long long dims[4] = {(unsigned long long)g.Cm, (unsigned long long)g.W, (unsigned long long)g.H,
+                                (unsigned long long)g.B};
+  unsigned long long str[3] = {g.Cm * es, (unsigned long long)g.W * g.Cm * es, (unsigned long long)g.H * g.W * g.Cm * es};
+  unsigned box[4] = {(unsigned)CC, (unsigned)(g.TW + 2 * halo), (unsigned)(g.TH + 2 * halo), (unsigned)g.NI};
+  return ogv_make_tmap(tm, ptr, dtype, 4, dims, str, box, 0);
+}
+
+// thread -> stencil work mapping.  "Regular" tiles (TW * NTV divides the CTA): a thread keeps one
+// (column x, channel group tv) for the whole kernel and only walks (image, strip) pairs, so the
+// stencil loop carries no index decoding at all.
+struct DwItems {
+  int regular, lanes_per_row, rows_par;
+};
+template <int NTV>
+__host__ __device__ inline DwItems dw_items(int TW) {
+  DwItems m;
+  m.lanes_per_row = TW * NTV;
+  m.regular = (m.lanes_per_row <= DW_THREADS) && (DW_THREADS % m.lanes_per_row == 0);
+  m.rows_par = m.regular ? DW_THREADS / m.lanes_per_row : 1;
+  return m;
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward: d_pre[p,c] = sum_t w[c,t] * act(scale1*e_pre + shift1)[p + d_t, c]; stats of d_pre
+// smem: raw TMA slot (T) | fp32 activated tile | weights | barrier.  Per tile:
+//   wait raw -> BN1+act raw -> fp32 tile (zeros outside the image) -> sync -> TMA(next tile) -> stencil -> sync
+// ------------------------------------------------------------------------------------------------
+template <typename T, int CC, int ACT>
+__global__ void __launch_bounds__(DW_THREADS, 3)
+dwconv_fwd_kernel(const __grid_constant__ CUtensorMap tm_in, const float* __restrict__ scale1,
+                  const float* __restrict__ shift1, const float* __restrict__ wgt, T* __restrict__ d_pre,
+                  float* __restrict__ sum2, float* __restrict__ sumsq2, const DwGeom g) {
+  constexpr int R = 4;                    // output rows per thread item
+  constexpr int NTV = CC / 4;             // 4-channel groups per position (stencil pass)
+  constexpr int AV = 16 / sizeof(T);      // channels per 16-byte vector (activation pass)
+  constexpr int NAV = CC / AV;
+  constexpr int BUF_ELEMS = DW_BUF_POS * CC;
+  extern __shared__ __align__(128) uint8_t dsm[];
+  T* const raw = reinterpret_cast<T*>(dsm);
+  float* const tile = reinterpret_cast<float*>(dsm + BUF_ELEMS * sizeof(T));
+  uint64_t* const bar = reinterpret_cast<uint64_t*>(dsm + BUF_ELEMS * (sizeof(T) + sizeof(float)));
+  __shared__ float s_sum[CC], s_sq[CC];
+  __shared__ __align__(16) float s_w[9][CC];
+
+  const int tid = threadIdx.x;
+  const int chunk = blockIdx.x % g.nchunks;
+  const int worker = blockIdx.x / g.nchunks;
+  const int c0 = chunk * CC;
+  const int tv = tid % NTV;
+  const int c = c0 + tv * 4;
+  const bool cvalid = c < g.Cm;
+  const int av = tid % NAV;
+  const int ca = c0 + av * AV;
+  const bool cavalid = ca < g.Cm;
+
+  if (tid < CC) { s_sum[tid] = 0.f; s_sq[tid] = 0.f; }
+  for (int i = tid; i < 9 * CC; i += DW_THREADS) {
+    const int t9 = i / CC, ch = i - t9 * CC;
+    s_w[t9][ch] = (c0 + ch < g.Cm) ? wgt[(c0 + ch) * 9 + t9] : 0.f;
+  }
+  if (tid == 0) {
+    ptx::tma_prefetch_desc(&tm_in);
+    ptx::mbar_init(&bar[0], 1);
+    ptx::fence_barrier_init();
+  }
+  float st_s[4] = {0.f, 0.f, 0.f, 0.f}, st_q[4] = {0.f, 0.f, 0.f, 0.f};
+  __syncthreads();
+
+  const int TW2 = g.TW2, TH2 = g.TH2;
+  const int npos = g.NI * TH2 * TW2;
+  const uint32_t tx_bytes = (uint32_t)npos * CC * sizeof(T);
+  const int nstrips = (g.TH + R - 1) / R;
+  const DwItems im = dw_items<NTV>(g.TW);
+  const int nrowitems = g.NI * nstrips;               // (image, strip) pairs of a tile
+  const int nitems = nrowitems * g.TW * NTV;          // generic mapping
+  const int x_fixed = (tid % im.lanes_per_row) / NTV;
+  const int sub = tid / im.lanes_per_row;
+
+  int t = worker;
+  if (tid == 0 && t < g.ntiles) {
+    int b0, h0, w0;
+    dw_decode_tile(g, t, b0, h0, w0);
+    ptx::mbar_arrive_expect_tx(&bar[0], tx_bytes);
+    ptx::tma_load_4d(raw, &tm_in, &bar[0], c0, w0 - 1, h0 - 1, b0);
+  }
+  for (int it = 0; t < g.ntiles; t += g.nworkers, ++it) {
+    int b0, h0, w0;
+    dw_decode_tile(g, t, b0, h0, w0);
+    ptx::mbar_wait(&bar[0], it & 1);
+
+    // ---- BN1 + activation ONCE per element: raw (T) -> fp32 tile; positions outside the image -> 0 ----
+    {
+      float sc[AV], sh[AV];
+#pragma unroll
+      for (int k = 0; k < AV; ++k) { sc[k] = 0.f; sh[k] = 0.f; }
+      if (cavalid) {
+        ldv<AV>(scale1 + ca, sc);
+        ldv<AV>(shift1 + ca, sh);
+      }
+#pragma unroll 2
+      for (int pos = tid / NAV; pos < npos; pos += DW_THREADS / NAV) {
+        const int r = fdiv(pos, g.d_tw2);
+        const int col = pos - r * TW2;
+        const int img = fdiv(r, g.d_th2);
+        const int hr = r - img * TH2;
+        const int gh = h0 - 1 + hr, gw = w0 - 1 + col;
+        const bool inside = gh >= 0 && gh < g.H && gw >= 0 && gw < g.W && b0 + img < g.B && cavalid;
+        float v[AV];
+        ldv<AV>(raw + pos * CC + av * AV, v);
+#pragma unroll
+        for (int k = 0; k < AV; ++k) v[k] = inside ? ((g.dbg & 1) ? v[k] : act_apply_t<ACT, FastAct<T>::value>(fmaf(v[k], sc[k], sh[k]))) : 0.f;
+        float* dst = tile + pos * CC + av * AV;
+#pragma unroll
+        for (int k = 0; k < AV; k += 4) *reinterpret_cast<float4*>(dst + k) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
+      }
+    }
+    ptx::fence_proxy_async();  // generic-proxy reads of `raw` precede the next TMA write into it
+    __syncthreads();
+    {
+      const int tn = t + g.nworkers;
+      if (tid == 0 && tn < g.ntiles) {
+        int nb0, nh0, nw0;
+        dw_decode_tile(g, tn, nb0, nh0, nw0);
+        ptx::mbar_arrive_expect_tx(&bar[0], tx_bytes);
+        ptx::tma_load_4d(raw, &tm_in, &bar[0], c0, nw0 - 1, nh0 - 1, nb0);
+      }
+    }
+
+    // ---- 3x3 stencil: item = (img, strip of R rows, column x, 4-channel group) ----
+    if (cvalid && !(g.dbg & 2)) {
+      float w[9][4];
+#pragma unroll
+      for (int t9 = 0; t9 < 9; ++t9) {
+        const float4 wv = *reinterpret_cast<const float4*>(&s_w[t9][tv * 4]);
+        w[t9][0] = wv.x; w[t9][1] = wv.y; w[t9][2] = wv.z; w[t9][3] = wv.w;
+      }
+      const int step = im.regular ? im.rows_par : DW_THREADS;
+      const int last = im.regular ? nrowitems : nitems;
+      for (int s = im.regular ? sub : tid; s < last; s += step) {
+        int x, rowitem;
+        if (im.regular) {
+          x = x_fixed;
+          rowitem = s;
+        } else {
+          const int rest = s / NTV;
+          rowitem = fdiv(rest, g.d_tw);
+          x = rest - rowitem * g.TW;
+        }
+        const int img = rowitem / nstrips;
+        const int r0 = (rowitem - img * nstrips) * R;
+        const int b = b0 + img;
+        if (b >= g.B || w0 + x >= g.W) continue;
+        float acc[R][4];
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) acc[r][k] = 0.f;
+        const float* base = tile + ((img * TH2 + r0) * TW2 + x) * CC + tv * 4;
+#pragma unroll
+        for (int ry = 0; ry < R + 2; ++ry) {  // input row (halo coordinates) r0 + ry
+          if (r0 + ry >= TH2) break;
+          float in[3][4];
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx) {
+            const float4 q = *reinterpret_cast<const float4*>(base + (ry * TW2 + dx) * CC);
+            in[dx][0] = q.x; in[dx][1] = q.y; in[dx][2] = q.z; in[dx][3] = q.w;
+          }
+#pragma unroll
+          for (int ki = 0; ki < 3; ++ki) {
+            const int r = ry - ki;  // output row of the strip that sees this input row through tap row ki
+            if (r >= 0 && r < R) {
+#pragma unroll
+              for (int dx = 0; dx < 3; ++dx)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) acc[r][k] = fmaf(w[ki * 3 + dx][k], in[dx][k], acc[r][k]);
+            }
+          }
+        }
+        T* out = d_pre + (((long long)b * g.H + h0 + r0) * g.W + (w0 + x)) * g.Cm + c;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          if (r0 + r < g.TH && h0 + r0 + r < g.H) {
+            if (!(g.dbg & 4)) stv<4>(out + (long long)r * g.W * g.Cm, acc[r]);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              st_s[k] += acc[r][k];
+              st_q[k] = fmaf(acc[r][k], acc[r][k], st_q[k]);
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();  // fp32 tile is rewritten by the next step
+  }
+  if (cvalid && sum2) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      atomicAdd(&s_sum[tv * 4 + k], st_s[k]);
+      atomicAdd(&s_sq[tv * 4 + k], st_q[k]);
+    }
+  }
+  __syncthreads();
+  if (tid < CC && c0 + tid < g.Cm) {
+    if (sum2) atomicAdd(sum2 + c0 + tid, s_sum[tid]);
+    if (sumsq2) atomicAdd(sumsq2 + c0 + tid, s_sq[tid]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward: de_act[p] = sum_t w[t] * G[p - d_t];  du1 = de_act * act'(u1[p]);
+//           dw[c,t] += sum_p e_act[p] * G[p - d_t];  dbeta1 += du1; dgamma1 += du1 * xhat1
+// G = dd_pre (halo tile), e_pre centre tile -> u1 = scale1*e_pre + shift1.
+// smem: raw G slot (T) | fp32 G tile | raw E slot (T) | barriers.  Per tile:
+//   wait G -> convert G to fp32 -> sync -> TMA(next G) -> wait E -> stencil -> sync -> TMA(next E)
+// ------------------------------------------------------------------------------------------------
+template <typename T, int CC, int ACT>
+__global__ void __launch_bounds__(DW_THREADS, 2)
+dwconv_bwd_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ CUtensorMap tm_e,
+                  const float* __restrict__ scale1, const float* __restrict__ shift1, const float* __restrict__ mean1,
+                  const float* __restrict__ rstd1, const float* __restrict__ wgt, T* __restrict__ du1,
+                  float* __restrict__ dwgt, float* __restrict__ dgamma1, float* __restrict__ dbeta1, const DwGeom g) {
+  constexpr int R = 2;
+  constexpr int NTV = CC / 4;
+  constexpr int AV = 16 / sizeof(T);
+  constexpr int NAV = CC / AV;
+  constexpr int BUF_ELEMS = DW_BUF_POS * CC;
+  extern __shared__ __align__(128) uint8_t dsm[];
+  T* const graw = reinterpret_cast<T*>(dsm);
+  T* const eraw = reinterpret_cast<T*>(dsm + BUF_ELEMS * sizeof(T));
+  float* const gt = reinterpret_cast<float*>(dsm + 2 * BUF_ELEMS * sizeof(T));
+  uint64_t* const bar = reinterpret_cast<uint64_t*>(dsm + BUF_ELEMS * (2 * sizeof(T) + sizeof(float)));
+  __shared__ float s_dw[CC * 9], s_db[CC], s_dg[CC];
+  __shared__ __align__(16) float s_par[4][CC];  // scale1, shift1, mean1, rstd1 of the chunk
+  __shared__ __align__(16) float s_w[9][CC];
+
+  const int tid = threadIdx.x;
+  const int chunk = blockIdx.x % g.nchunks;
+  const int worker = blockIdx.x / g.nchunks;
+  const int c0 = chunk * CC;
+  const int tv = tid % NTV;
+  const int c = c0 + tv * 4;
+  const bool cvalid = c < g.Cm;
+  const int av = tid % NAV;
+
+  for (int i = tid; i < CC * 9; i += DW_THREADS) {
+    s_dw[i] = 0.f;
+    const int t9 = i / CC, ch = i - t9 * CC;
+    s_w[t9][ch] = (c0 + ch < g.Cm) ? wgt[(c0 + ch) * 9 + t9] : 0.f;
+  }
+  if (tid < CC) {
+    s_db[tid] = 0.f;
+    s_dg[tid] = 0.f;
+    const bool ok = c0 + tid < g.Cm;
+    s_par[0][tid] = ok ? scale1[c0 + tid] : 0.f;
+    s_par[1][tid] = ok ? shift1[c0 + tid] : 0.f;
+    s_par[2][tid] = ok ? mean1[c0 + tid] : 0.f;
+    s_par[3][tid] = ok ? rstd1[c0 + tid] : 0.f;
+  }
+  if (tid == 0) {
+    ptx::tma_prefetch_desc(&tm_g);
+    ptx::tma_prefetch_desc(&tm_e);
+    ptx::mbar_init(&bar[0], 1);
+    ptx::mbar_init(&bar[1], 1);
+    ptx::fence_barrier_init();
+  }
+  float dwa[9][4];
+#pragma unroll
+  for (int t9 = 0; t9 < 9; ++t9)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) dwa[t9][k] = 0.f;
+  float a_db[4] = {0.f, 0.f, 0.f, 0.f}, a_dg[4] = {0.f, 0.f, 0.f, 0.f};
+  __syncthreads();
+
+  const int TW2 = g.TW2, TH2 = g.TH2;
+  const int npos = g.NI * TH2 * TW2;
+  const uint32_t g_bytes = (uint32_t)npos * CC * sizeof(T);
+  const uint32_t e_bytes = (uint32_t)(g.NI * g.TH * g.TW) * CC * sizeof(T);
+  const int nstrips = (g.TH + R - 1) / R;
+  const DwItems im = dw_items<NTV>(g.TW);
+  const int nrowitems = g.NI * nstrips;
+  const int nitems = nrowitems * g.TW * NTV;
+  const int x_fixed = (tid % im.lanes_per_row) / NTV;
+  const int sub = tid / im.lanes_per_row;
+
+  int t = worker;
+  if (tid == 0 && t < g.ntiles) {
+    int b0, h0, w0;
+    dw_decode_tile(g, t, b0, h0, w0);
+    ptx::mbar_arrive_expect_tx(&bar[0], g_bytes);
+    ptx::tma_load_4d(graw, &tm_g, &bar[0], c0, w0 - 1, h0 - 1, b0);
+    ptx::mbar_arrive_expect_tx(&bar[1], e_bytes);
+    ptx::tma_load_4d(eraw, &tm_e, &bar[1], c0, w0, h0, b0);
+  }
+  for (int it = 0; t < g.ntiles; t += g.nworkers, ++it) {
+    int b0, h0, w0;
+    dw_decode_tile(g, t, b0, h0, w0);
+    const int tn = t + g.nworkers;
+    int nb0 = 0, nh0 = 0, nw0 = 0;
+    if (tn < g.ntiles) dw_decode_tile(g, tn, nb0, nh0, nw0);
+
+    // ---- gradient halo tile: raw (T) -> fp32 (TMA zero fill already handled the borders) ----
+    ptx::mbar_wait(&bar[0], it & 1);
+#pragma unroll 4
+    for (int i = tid; i < npos * NAV; i += DW_THREADS) {
+      float v[AV];
+      ldv<AV>(graw + i * AV, v);
+#pragma unroll
+      for (int k = 0; k < AV; k += 4)
+        *reinterpret_cast<float4*>(gt + i * AV + k) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
+    }
+    (void)av;
+    ptx::fence_proxy_async();
+    __syncthreads();
+    if (tid == 0 && tn < g.ntiles) {
+      ptx::mbar_arrive_expect_tx(&bar[0], g_bytes);
+      ptx::tma_load_4d(graw, &tm_g, &bar[0], c0, nw0 - 1, nh0 - 1, nb0);
+    }
+    ptx::mbar_wait(&bar[1], it & 1);
+
+    if (cvalid) {
+      float w[9][4];
+#pragma unroll
+      for (int t9 = 0; t9 < 9; ++t9) {
+        const float4 wv = *reinterpret_cast<const float4*>(&s_w[t9][tv * 4]);
+        w[t9][0] = wv.x; w[t9][1] = wv.y; w[t9][2] = wv.z; w[t9][3] = wv.w;
+      }
+      const int step = im.regular ? im.rows_par : DW_THREADS;
+      const int last = im.regular ? nrowitems : nitems;
+      for (int s = im.regular ? sub : tid; s < last; s += step) {
+        int x, rowitem;
+        if (im.regular) {
+          x = x_fixed;
+          rowitem = s;
+        } else {
+          const int rest = s / NTV;
+          rowitem = fdiv(rest, g.d_tw);
+          x = rest - rowitem * g.TW;
+        }
+        const int img = rowitem / nstrips;
+        const int r0 = (rowitem - img * nstrips) * R;
+        const int b = b0 + img;
+        if (b >= g.B || w0 + x >= g.W) continue;
+        float de[R][4], ea[R][4], da[R][4];
+        bool rvalid[R];
+        const T* ep = eraw + ((img * g.TH + r0) * g.TW + x) * CC + tv * 4;
+        {
+          const float4 sc = *reinterpret_cast<const float4*>(&s_par[0][tv * 4]);
+          const float4 sh = *reinterpret_cast<const float4*>(&s_par[1][tv * 4]);
+          const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            rvalid[r] = (r0 + r < g.TH) && (h0 + r0 + r < g.H);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { de[r][k] = 0.f; ea[r][k] = 0.f; da[r][k] = 0.f; }
+            if (rvalid[r]) {
+              float ev[4];
+              ldv<4>(ep + r * g.TW * CC, ev);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) act_both_t<ACT, FastAct<T>::value>(fmaf(ev[k], scv[k], shv[k]), &ea[r][k], &da[r][k]);
+            }
+          }
+        }
+        const float* base = gt + ((img * TH2 + r0) * TW2 + x) * CC + tv * 4;
+#pragma unroll
+        for (int ry = 0; ry < R + 2; ++ry) {  // gradient row (halo coords) r0 + ry  <->  image row h0 + r0 + ry - 1
+          if (r0 + ry >= TH2) break;
+          float gr[3][4];
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx) {
+            const float4 q = *reinterpret_cast<const float4*>(base + (ry * TW2 + dx) * CC);
+            gr[dx][0] = q.x; gr[dx][1] = q.y; gr[dx][2] = q.z; gr[dx][3] = q.w;
+          }
+          // output row r sits at halo row r0 + r + 1; gradient row offset (ry - 1) - r = -(ki - 1)
+#pragma unroll
+          for (int ki = 0; ki < 3; ++ki) {
+            const int r = ry - 1 + (ki - 1);
+            if (r >= 0 && r < R) {
+#pragma unroll
+              for (int dx = 0; dx < 3; ++dx) {
+                const int tt = ki * 3 + (2 - dx);  // gradient column offset dx - 1 = -(kj - 1)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  de[r][k] = fmaf(w[tt][k], gr[dx][k], de[r][k]);
+                  dwa[tt][k] = fmaf(ea[r][k], gr[dx][k], dwa[tt][k]);
+                }
+              }
+            }
+          }
+        }
+        T* out = du1 + (((long long)b * g.H + h0 + r0) * g.W + (w0 + x)) * g.Cm + c;
+        const float4 mu = *reinterpret_cast<const float4*>(&s_par[2][tv * 4]);
+        const float4 rs = *reinterpret_cast<const float4*>(&s_par[3][tv * 4]);
+        const float muv[4] = {mu.x, mu.y, mu.z, mu.w}, rsv[4] = {rs.x, rs.y, rs.z, rs.w};
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          if (rvalid[r]) {
+            float o[4], ev[4];
+            ldv<4>(ep + r * g.TW * CC, ev);  // re-read (smem) instead of carrying xhat through the stencil
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              o[k] = de[r][k] * da[r][k];
+              a_db[k] += o[k];
+              a_dg[k] = fmaf(o[k], (ev[k] - muv[k]) * rsv[k], a_dg[k]);
+            }
+            stv<4>(out + (long long)r * g.W * g.Cm, o);
+          }
+        }
+      }
+    }
+    ptx::fence_proxy_async();
+    __syncthreads();
+    if (tid == 0 && tn < g.ntiles) {
+      ptx::mbar_arrive_expect_tx(&bar[1], e_bytes);
+      ptx::tma_load_4d(eraw, &tm_e, &bar[1], c0, nw0, nh0, nb0);
+    }
+  }
+  if (cvalid) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      atomicAdd(&s_db[tv * 4 + k], a_db[k]);
+      atomicAdd(&s_dg[tv * 4 + k], a_dg[k]);
+#pragma unroll
+      for (int t9 = 0; t9 < 9; ++t9) atomicAdd(&s_dw[(tv * 4 + k) * 9 + t9], dwa[t9][k]);
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < CC * 9; i += DW_THREADS)
+    if (c0 + i / 9 < g.Cm) atomicAdd(dwgt + (long long)c0 * 9 + i, s_dw[i]);
+  if (tid < CC && c0 + tid < g.Cm) {
+    atomicAdd(dbeta1 + c0 + tid, s_db[tid]);
+    atomicAdd(dgamma1 + c0 + tid, s_dg[tid]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward, register-window variant.  lane = 4 consecutive channels, warp = 128 channels of one
+// (image, band of RR output rows); the warp sweeps x = 0..W-1 holding the 3 x (RR+2) x 4 window of
+// ACTIVATED inputs in registers, so there is no shared-memory staging, no barrier and no tile
+// bookkeeping: every step is (RR+2) coalesced 256-byte row loads, (RR+2)*4 activations, RR*36 FMAs and
+// RR coalesced stores.  Halo rows are re-read by the neighbouring band (same CTA -> L1/L2 hits).
+// ------------------------------------------------------------------------------------------------
+template <typename T, int ACT, int RR>
+__global__ void __launch_bounds__(256, 2)
+dwconv_fwd_sweep_kernel(const T* __restrict__ e_pre, const float* __restrict__ scale1, const float* __restrict__ shift1,
+                        const float* __restrict__ wgt, T* __restrict__ d_pre, float* __restrict__ sum2,
+                        float* __restrict__ sumsq2, int B, int H, int W, int Cm, int bands_per_img, int nbands) {
+  constexpr int NR = RR + 2;
+  __shared__ float s_red[2][8][128];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = (blockIdx.y * 32 + lane) * 4;
+  const bool cvalid = c < Cm;
+  float w[9][4], sc[4], sh[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    sc[k] = cvalid ? scale1[c + k] : 0.f;
+    sh[k] = cvalid ? shift1[c + k] : 0.f;
+#pragma unroll
+    for (int t9 = 0; t9 < 9; ++t9) w[t9][k] = cvalid ? wgt[(c + k) * 9 + t9] : 0.f;
+  }
+  float st_s[4] = {0.f, 0.f, 0.f, 0.f}, st_q[4] = {0.f, 0.f, 0.f, 0.f};
+  const long long rowpitch = (long long)W * Cm;
+
+  for (int item = blockIdx.x * 8 + warp; item < nbands && cvalid; item += gridDim.x * 8) {
+    const int b = item / bands_per_img;
+    const int r0 = (item - b * bands_per_img) * RR;
+    const T* in0 = e_pre + ((long long)b * H + (r0 - 1)) * rowpitch + c;   // halo row 0, column 0
+    T* out0 = d_pre + ((long long)b * H + r0) * rowpitch + c;
+    bool rv[NR];
+#pragma unroll
+    for (int i = 0; i < NR; ++i) rv[i] = (r0 - 1 + i >= 0) && (r0 - 1 + i < H);
+    float win[3][NR][4];
+    // load + activate one column of the window (zeros outside the image)
+    auto load_col = [&](float (&col)[NR][4], int x) {
+      const bool xv = x < W;
+#pragma unroll
+      for (int i = 0; i < NR; ++i) {
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        const bool ok = xv && rv[i];
+        if (ok) ldv<4>(in0 + (long long)i * rowpitch + (long long)x * Cm, v);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) col[i][k] = ok ? act_apply_t<ACT, FastAct<T>::value>(fmaf(v[k], sc[k], sh[k])) : 0.f;
+      }
+    };
+    auto step = [&](const float (&L)[NR][4], const float (&M)[NR][4], const float (&Rc)[NR][4], int x) {
+      float acc[RR][4];
+#pragma unroll
+      for (int r = 0; r < RR; ++r)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float a = 0.f;
+#pragma unroll
+          for (int ki = 0; ki < 3; ++ki) {
+            a = fmaf(w[ki * 3 + 0][k], L[r + ki][k], a);
+            a = fmaf(w[ki * 3 + 1][k], M[r + ki][k], a);
+            a = fmaf(w[ki * 3 + 2][k], Rc[r + ki][k], a);
+          }
+          acc[r][k] = a;
+        }
+#pragma unroll
+      for (int r = 0; r < RR; ++r) {
+        if (r0 + r < H) {
+          stv<4>(out0 + (long long)r * rowpitch + (long long)x * Cm, acc[r]);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            st_s[k] += acc[r][k];
+            st_q[k] = fmaf(acc[r][k], acc[r][k], st_q[k]);
+          }
+        }
+      }
+    };
+#pragma unroll
+    for (int i = 0; i < NR; ++i)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) win[0][i][k] = 0.f;
+    load_col(win[1], 0);
+    for (int x = 0; x < W; x += 3) {
+      load_col(win[2], x + 1);
+      step(win[0], win[1], win[2], x);
+      if (x + 1 < W) {
+        load_col(win[0], x + 2);
+        step(win[1], win[2], win[0], x + 1);
+      }
+      if (x + 2 < W) {
+        load_col(win[1], x + 3);
+        step(win[2], win[0], win[1], x + 2);
+      }
+    }
+  }
+  // per-channel statistics: fold the 8 warps of the CTA, then one atomic per channel per CTA
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    s_red[0][warp][lane * 4 + k] = st_s[k];
+    s_red[1][warp][lane * 4 + k] = st_q[k];
+  }
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int ch = blockIdx.y * 128 + threadIdx.x;
+    if (ch < Cm) {
+      float a = 0.f, q = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { a += s_red[0][j][threadIdx.x]; q += s_red[1][j][threadIdx.x]; }
+      if (sum2) atomicAdd(sum2 + ch, a);
+      if (sumsq2) atomicAdd(sumsq2 + ch, q);
+    }
+  }
+}
+
+// opt in to the dynamic shared memory and report how many CTAs of this kernel are resident per SM:
+// the persistent grid is sized to exactly one wave (a second, partly filled wave would idle SMs).
+template <typename K>
+int dw_smem_optin(K kernel, int bytes, int* ctas_per_sm) {
+  static int cached_bytes = -1, cached_occ = 0;  // one instance per kernel instantiation
+  if (cached_bytes != bytes) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) {
+      ogv_set_error("dwconv: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+      return OGV_ERR_CUDA;
+    }
+    int occ = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, DW_THREADS, bytes);
+    if (e != cudaSuccess || occ < 1) occ = 1;
+    cached_occ = occ;
+    cached_bytes = bytes;
+  }
+  *ctas_per_sm = cached_occ;
+  return OGV_OK;
+}
+
+template <typename T>
+constexpr int dw_cc() { return 64 / (int)sizeof(T); }  // 64-byte channel chunk per position
+
+}  // namespace
+
+extern "C" int ogv_dwconv_fwd(const void* e_pre, const float* scale1, const float* shift1, const float* w,
+                              void* d_pre, float* sum2, float* sumsq2, int B, int H, int W, int Cm, int act,
+                              int dtype, void* stream) {
+  OGV_REQUIRE(e_pre && scale1 && shift1 && w && d_pre, "dwconv_fwd: null pointer");
+  OGV_REQUIRE(Cm > 0 && Cm % 8 == 0 && H > 0 && W > 0, "dwconv_fwd: channels must be a multiple of 8");
+  OGV_REQUIRE((reinterpret_cast<uintptr_t>(e_pre) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_pre) & 15) == 0,
+              "dwconv_fwd: tensors must be 16-byte aligned");
+  if (B == 0) return OGV_OK;
+  static int variant = -1;  // OGV_DW_FWD=tile selects the TMA-tiled kernel (A/B measurements)
+  if (variant < 0) {
+    const char* e = getenv("OGV_DW_FWD");
+    variant = (e && e[0] == 't') ? 1 : 0;
+  }
+  if (variant == 0) {
+    constexpr int RR = 2;
+    const int bands = (H + RR - 1) / RR;
+    const long long nb = (long long)B * bands;
+    OGV_REQUIRE(nb < 0x7fffffffLL, "dwconv_fwd: too many row bands");
+    const int ychunks = ogv_ceil_div(Cm, 128);
+    long long gx = (nb + 7) / 8;
+    const long long cap = ((long long)ogv_num_sms() * 2 + ychunks - 1) / ychunks * 4;  // a few waves of 2 CTAs/SM
+    if (gx > cap) gx = cap;
+    OGV_DISPATCH_DTYPE(dtype, T, {
+      OGV_DISPATCH_ACT(act, ACT, {
+        dwconv_fwd_sweep_kernel<T, ACT, RR><<<dim3((unsigned)gx, ychunks), 256, 0, (cudaStream_t)stream>>>(
+            reinterpret_cast<const T*>(e_pre), scale1, shift1, w, reinterpret_cast<T*>(d_pre), sum2, sumsq2, B, H, W,
+            Cm, bands, (int)nb);
+      });
+      return ogv_check_launch("dwconv_fwd");
+    });
+  }
+  OGV_DISPATCH_DTYPE(dtype, T, {
+    constexpr int CC = dw_cc<T>();
+    const int smem = DW_BUF_POS * CC * (int)(sizeof(T) + sizeof(float)) + 64;
+    OGV_DISPATCH_ACT(act, ACT, {
+      int occ = 1;
+      if (int rc = dw_smem_optin(dwconv_fwd_kernel<T, CC, ACT>, smem, &occ)) return rc;
+      DwGeom g;
+      if (dw_make_geom(B, H, W, Cm, CC, occ, &g)) { ogv_set_error("dwconv_fwd: cannot tile %dx%d", H, W); return OGV_ERR_UNSUPPORTED; }
+      CUtensorMap tm;
+      if (int rc = dw_tmap<T>(&tm, e_pre, dtype, g, CC, 1)) return rc;
+      dwconv_fwd_kernel<T, CC, ACT><<<g.nchunks * g.nworkers, DW_THREADS, smem, (cudaStream_t)stream>>>(
+          tm, scale1, shift1, w, reinterpret_cast<T*>(d_pre), sum2, sumsq2, g);
+    });
+    return ogv_check_launch("dwconv_fwd");
+  });
+}
+
+extern "C" int ogv_dwconv_bwd(const void* dd_pre, const void* e_pre, const float* scale1, const float* shift1,
+                              const float* mean1, const float* rstd1, const float* w, void* du1, float* dw,
+                              float* dgamma1, float* dbeta1, int B, int H, int W, int Cm, int act, int dtype,
+                              void* stream) {
+  OGV_REQUIRE(dd_pre && e_pre && scale1 && shift1 && mean1 && rstd1 && w && du1 && dw && dgamma1 && dbeta1,
+              "dwconv_bwd: null pointer");
+  OGV_REQUIRE(Cm > 0 && Cm % 8 == 0 && H > 0 && W > 0, "dwconv_bwd: channels must be a multiple of 8");
+  OGV_REQUIRE((reinterpret_cast<uintptr_t>(dd_pre) & 15) == 0 && (reinterpret_cast<uintptr_t>(e_pre) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(du1) & 15) == 0,
+              "dwconv_bwd: tensors must be 16-byte aligned");
+  if (B == 0) return OGV_OK;
+  OGV_DISPATCH_DTYPE(dtype, T, {
+    constexpr int CC = dw_cc<T>();
+    const int smem = DW_BUF_POS * CC * (int)(2 * sizeof(T) + sizeof(float)) + 64;
+    OGV_DISPATCH_ACT(act, ACT, {
+      int occ = 1;
+      if (int rc = dw_smem_optin(dwconv_bwd_kernel<T, CC, ACT>, smem, &occ)) return rc;
+      DwGeom g;
+      if (dw_make_geom(B, H, W, Cm, CC, occ, &g)) { ogv_set_error("dwconv_bwd: cannot tile %dx%d", H, W); return OGV_ERR_UNSUPPORTED; }
+      CUtensorMap tmg, tme;
+      if (int rc = dw_tmap<T>(&tmg, dd_pre, dtype, g, CC, 1)) return rc;
+      if (int rc = dw_tmap<T>(&tme, e_pre, dtype, g, CC, 0)) return rc;
+      dwconv_bwd_kernel<T, CC, ACT><<<g.nchunks * g.nworkers, DW_THREADS, smem, (cudaStream_t)stream>>>(
+          tmg, tme, scale1, shift1, mean1, rstd1, w, reinterpret_cast<T*>(du1), dw, dgamma1, dbeta1, g);
+    });
+    return ogv_check_launch("dwconv_bwd");
+  });
+}

@@ -59,15 +59,11 @@ __device__ __forceinline__ void epi_row16(const GemmEpi& e, int m, int n0, const
         for (int i = 0; i < 8; ++i) x[i] += __ldg(e.bias + n + i);
       }
       if (e.pre_out) st8(reinterpret_cast<TO*>(e.pre_out) + (long long)m * e.ld_pre + n, x);
-      if (e.act != OGV_ACT_NONE) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) x[i] = act_apply(e.act, x[i]);
-      }
+      if (e.act != OGV_ACT_NONE) act_apply_n<8, FastAct<TO>::value>(e.act, x);
       if (e.dact_src) {
         float d[8];
         ld8(reinterpret_cast<const TO*>(e.dact_src) + (long long)m * e.ld_dact + n, d);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) x[i] *= act_grad(e.dact, d[i]);
+        act_grad_mul_n<8, FastAct<TO>::value>(e.dact, x, d);
       }
       if (e.row_scale) {
 #pragma unroll
@@ -313,18 +309,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
         if (e.pre_out) stage_write_row(s1, lane, v);
-        if (e.act != OGV_ACT_NONE) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = act_apply(e.act, v[i]);
-        }
+        if (e.act != OGV_ACT_NONE) act_apply_n<32, FastAct<TO>::value>(e.act, v);
         if (p.epi_load) {
           ptx::mbar_wait(&my_ld[pr], (ld_phase >> pr) & 1u);
           ld_phase ^= 1u << pr;
           float r[32];
           stage_read_row(s0, lane, r);
           if (p.epi_load == 2) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] *= act_grad(e.dact, r[i]);
+            act_grad_mul_n<32, FastAct<TO>::value>(e.dact, v, r);
             if (e.row_scale) {
               const float rs = m < p.M ? e.row_scale[m / e.rows_per_scale] : 0.f;
 #pragma unroll

@@ -349,16 +349,19 @@ class MBConvFn(torch.autograd.Function):
         d_pre = ops.dwconv_fwd(e_pre, s1[2], s1[3], wdw2, s2[0] if training else None, s2[1] if training else None,
                                g.B, g.H, g.W, act)
         ops.bn_finalize(s2[0], s2[1], g2, b2, rm2, rv2, s2[2], s2[3], s2[4], s2[5], M, eps, mom, training)
-        # squeeze-excite (tiny fp32 products, B rows)
+        # squeeze-excite on [B, Cm] rows: bf16 compute -> tcgen05 engine (the reference's autocast runs these 1x1
+        # convs in bf16 too); fp32 compute -> fp32 FFMA engine.  The gate itself is always produced in fp32.
         pool = ops.se_pool(d_pre, s2[2], s2[3], g.B, g.P, act)
-        s1_pre = _empty((g.B, Cs), x, torch.float32)
-        s1a = _empty((g.B, Cs), x, torch.float32)
-        sw1m = sw1.detach().reshape(Cs, Cm)
-        sw2m = sw2.detach().reshape(Cm, Cs)
-        ops.gemm(pool, sw1m, s1a, bias=sb1, pre_out=s1_pre, act=act, engine=ENGINE_SIMT)
+        ps1: PreparedLinear = meta["pse1"]
+        ps2: PreparedLinear = meta["pse2"]
+        cdt = x.dtype
+        pool_c = pool if cdt == torch.float32 else ops.cast(pool, cdt)
+        s1_pre = _empty((g.B, Cs), x, cdt)
+        s1a = _empty((g.B, Cs), x, cdt)
+        ops.gemm(pool_c, ps1.w, s1a, bias=sb1, pre_out=s1_pre, act=act)
         gate_pre = _empty((g.B, Cm), x, torch.float32)
         gate = _empty((g.B, Cm), x, torch.float32)
-        ops.gemm(s1a, sw2m, gate, bias=sb2, pre_out=gate_pre, act="sigmoid", engine=ENGINE_SIMT)
+        ops.gemm(s1a, ps2.w, gate, bias=sb2, pre_out=gate_pre, act="sigmoid")
         d_act = ops.bn_act_gate(d_pre, s2[2], s2[3], gate, g.B, g.P, act)
         # project
         o_pre = _empty((M, C), x)
@@ -369,7 +372,7 @@ class MBConvFn(torch.autograd.Function):
         y = ops.bn_apply(o_pre, s3[2], s3[3], x if meta["use_res"] else None)
         ctx.meta = meta
         ctx.wdw2 = wdw2
-        ctx.save_for_backward(x, e_pre, d_pre, d_act, o_pre, st, pool, s1_pre, s1a, gate_pre, gate, g1, g2, g3, sw1, sw2)
+        ctx.save_for_backward(x, e_pre, d_pre, d_act, o_pre, st, pool_c, s1_pre, s1a, gate_pre, gate, g1, g2, g3, sw1, sw2)
         return y
 
     @staticmethod
@@ -408,23 +411,25 @@ class MBConvFn(torch.autograd.Function):
         dd_act = _empty((M, Cm), x)
         ops.gemm(do_pre, ppj.wt, dd_act)
         ops.wgrad(do_pre, d_act, dWp)
-        # squeeze-excite backward
-        dgate = ops.se_bwd_reduce(dd_act, d_pre, s2[2], s2[3], g.B, g.P, act)
-        dgate_pre = ops.mul_dact(dgate, gate_pre, "sigmoid")
-        sw1m = sw1.detach().reshape(Cs, Cm)
-        sw2m = sw2.detach().reshape(Cm, Cs)
-        ds1_pre = _empty((g.B, Cs), x, torch.float32)
-        ops.gemm(dgate_pre, sw2m.t(), ds1_pre, dact_src=s1_pre, dact=act, engine=ENGINE_SIMT)
-        ops.wgrad(dgate_pre, s1a, dsw2, engine=ENGINE_SIMT)
+        # squeeze-excite + BN2 backward: one pass over (dd_act, d_pre) yields dgate and the per-image pieces of
+        # the BN2 reductions; the tiny SE products then give dpool, and a [B, Cm] kernel finishes dgamma2 / dbeta2
+        stats = ops.mbconv_bwd_stats(dd_act, d_pre, s2[2], s2[3], s2[4], s2[5], g.B, g.P, act)
+        dgate_pre = ops.mul_dact(stats[0], gate_pre, "sigmoid")
+        ps1: PreparedLinear = meta["pse1"]
+        ps2: PreparedLinear = meta["pse2"]
+        cdt = x.dtype
+        dgate_c = dgate_pre if cdt == torch.float32 else ops.cast(dgate_pre, cdt)
+        ds1_pre = _empty((g.B, Cs), x, cdt)
+        ops.gemm(dgate_c, ps2.wt, ds1_pre, dact_src=s1_pre, dact=act)
+        ops.wgrad(dgate_c, s1a, dsw2)
         ops.colsum(dgate_pre, dsb2)
         dpool = _empty((g.B, Cm), x, torch.float32)
-        ops.gemm(ds1_pre, sw1m.t(), dpool, engine=ENGINE_SIMT)
-        ops.wgrad(ds1_pre, pool, dsw1, engine=ENGINE_SIMT)
+        ops.gemm(ds1_pre, ps1.wt, dpool)
+        ops.wgrad(ds1_pre, pool, dsw1)
         ops.colsum(ds1_pre, dsb1)
-        # BN2 + activation backward (two passes over the wide tensor)
-        dd_pre = _empty((M, Cm), x)
-        ops.dw_bn2_bwd(0, dd_act, d_pre, gate, dpool, s2[2], s2[3], s2[4], s2[5], g2, dg2, db2, None, g.B, g.P, act)
-        ops.dw_bn2_bwd(1, dd_act, d_pre, gate, dpool, s2[2], s2[3], s2[4], s2[5], g2, dg2, db2, dd_pre, g.B, g.P, act)
+        ops.mbconv_bn2_finalize(stats, gate, dpool, dg2, db2, g.B, g.P)
+        dd_pre = ops.dw_bn2_bwd_apply(dd_act, d_pre, gate, dpool, s2[2], s2[3], s2[4], s2[5], g2, dg2, db2, g.B, g.P,
+                                      act)
         # depthwise backward (+ activation derivative, + BN1 reductions)
         du1 = ops.dwconv_bwd(dd_pre, e_pre, s1[2], s1[3], s1[4], s1[5], ctx.wdw2, dwdw, dg1, db1, g.B, g.H, g.W, act)
         de_pre = ops.bn_bwd_apply(du1, e_pre, s1[4], s1[5], g1, dg1, db1)
@@ -437,9 +442,9 @@ class MBConvFn(torch.autograd.Function):
                 dg3, db3, None)
 
 
-def mbconv(x, we, g1, b1, wdw, g2, b2, sw1, sb1, sw2, sb2, wp, g3, b3, *, pe, pp, geom: Geom, act: str, training: bool,
-           running, bn_eps: float, bn_momentum: float, use_res: bool) -> Tensor:
-    meta = dict(pe=pe, pp=pp, geom=geom, act=act, training=training, running=running, bn_eps=bn_eps,
+def mbconv(x, we, g1, b1, wdw, g2, b2, sw1, sb1, sw2, sb2, wp, g3, b3, *, pe, pp, pse1, pse2, geom: Geom, act: str,
+           training: bool, running, bn_eps: float, bn_momentum: float, use_res: bool) -> Tensor:
+    meta = dict(pe=pe, pp=pp, pse1=pse1, pse2=pse2, geom=geom, act=act, training=training, running=running, bn_eps=bn_eps,
                 bn_momentum=bn_momentum, use_res=use_res, we_shape=tuple(we.shape), wdw_shape=tuple(wdw.shape),
                 sw1_shape=tuple(sw1.shape), sw2_shape=tuple(sw2.shape), wp_shape=tuple(wp.shape))
     return MBConvFn.apply(x, we, g1, b1, wdw, g2, b2, sw1, sb1, sw2, sb2, wp, g3, b3, meta)

@@ -357,12 +357,15 @@ class MBConv(nn.Module):
         we, wp = self.expand[0].weight, self.project[0].weight
         pe = _prep_attr(self, "expand").get([we], dtype, lambda: OF.prepare_linear(we, dtype))
         pp = _prep_attr(self, "project").get([wp], dtype, lambda: OF.prepare_linear(wp, dtype))
-        return pe, pp
+        w1, w2 = self.se.fc1.weight, self.se.fc2.weight
+        ps1 = _prep_attr(self, "se1").get([w1], dtype, lambda: OF.prepare_linear(w1, dtype))
+        ps2 = _prep_attr(self, "se2").get([w2], dtype, lambda: OF.prepare_linear(w2, dtype))
+        return pe, pp, ps1, ps2
 
     def rows_forward(self, rows: Tensor, geom: Geom) -> Tensor:
         self._check_supported()
         bn1, bn2, bn3 = self.expand[1], self.depthwise[1], self.project[1]
-        pe, pp = self._prepared(rows.dtype)
+        pe, pp, ps1, ps2 = self._prepared(rows.dtype)
         training = self.training and bn1.track_running_stats is not None
         if self.training:
             for bn in (bn1, bn2, bn3):
@@ -373,7 +376,7 @@ class MBConv(nn.Module):
                    bn3.running_var)
         return OF.mbconv(rows, self.expand[0].weight, bn1.weight, bn1.bias, self.depthwise[0].weight, bn2.weight,
                          bn2.bias, self.se.fc1.weight, self.se.fc1.bias, self.se.fc2.weight, self.se.fc2.bias,
-                         self.project[0].weight, bn3.weight, bn3.bias, pe=pe, pp=pp, geom=geom,
+                         self.project[0].weight, bn3.weight, bn3.bias, pe=pe, pp=pp, pse1=ps1, pse2=ps2, geom=geom,
                          act=_act_name(self.depthwise[2]), training=training, running=running, bn_eps=bn1.eps,
                          bn_momentum=mom, use_res=self.use_res)
 

@@ -152,7 +152,8 @@ def gemm(A: Tensor, B: Tensor, D: Tensor, *, bias: Optional[Tensor] = None, pre_
         PROFILER.cur_bytes = A.element_size() * (M * K + N * K) + D.element_size() * M * N * (1 + extra)
         PROFILER.cur_flops = 2 * M * N * K
         kind = "wgrad" if accumulate else ("bwd" if dact_src is not None else "fwd")
-        PROFILER.cur_label = f"ogv_gemm[{kind} {M}x{N}x{K} {'bf16' if A.dtype == torch.bfloat16 else 'f32'}]"
+        flags = "".join(ch for ch, t in (("b", bias), ("p", pre_out), ("a", act), ("s", row_scale), ("r", residual)) if t is not None)
+        PROFILER.cur_label = f"ogv_gemm[{kind} {M}x{N}x{K} {'bf16' if A.dtype == torch.bfloat16 else 'f32'} {flags}]"
     _call("ogv_gemm", ctypes.byref(a), engine, _stream())
     return D
 
@@ -202,6 +203,13 @@ def cast_transpose(src: Tensor, dst: Optional[Tensor], dst_t: Optional[Tensor]) 
     _call("ogv_cast_transpose", _p(src), _p(dst), dst.stride(0) if dst is not None else 0, _p(dst_t),
                                         dst_t.stride(0) if dst_t is not None else 0, rows, cols, dtype_code(ref),
                                         _stream())
+
+
+def cast(src: Tensor, dtype: torch.dtype) -> Tensor:
+    """fp32 [rows, cols] -> compute-dtype copy (ogv_cast_transpose without the transposed output)."""
+    dst = torch.empty(src.shape, device=src.device, dtype=dtype)
+    cast_transpose(src.contiguous(), dst, None)
+    return dst
 
 
 def rowscale(x: Tensor, scale: Tensor, rows_per_scale: int) -> Tensor:
@@ -341,11 +349,26 @@ def se_bwd_reduce(dd_act, d_pre, scale2, shift2, B, HW, act: str) -> Tensor:
     return dgate
 
 
-def dw_bn2_bwd(pass_: int, dd_act, d_pre, gate, dpool, scale2, shift2, mean2, rstd2, gamma2, dgamma2, dbeta2, dd_pre,
-               B, HW, act: str) -> None:
-    _call("ogv_dw_bn2_bwd", pass_, _p(dd_act), _p(d_pre), _p(gate), _p(dpool), _p(scale2), _p(shift2),
-                                    _p(mean2), _p(rstd2), _p(gamma2), _p(dgamma2), _p(dbeta2), _p(dd_pre), B, HW,
-                                    d_pre.shape[1], ACT[act], dtype_code(d_pre), _stream())
+def mbconv_bwd_stats(dd_act, d_pre, scale2, shift2, mean2, rstd2, B, HW, act: str) -> Tensor:
+    """-> stats [5, B, Cm] fp32 (stats[0] = dgate); see include/ogv.h."""
+    stats = torch.empty((5, B, d_pre.shape[1]), device=d_pre.device, dtype=torch.float32)
+    _call("ogv_mbconv_bwd_stats", _p(dd_act), _p(d_pre), _p(scale2), _p(shift2), _p(mean2), _p(rstd2), _p(stats), B,
+          HW, d_pre.shape[1], ACT[act], dtype_code(d_pre), _stream())
+    return stats
+
+
+def mbconv_bn2_finalize(stats, gate, dpool, dgamma2, dbeta2, B, HW) -> None:
+    _call("ogv_mbconv_bn2_finalize", _p(stats), _p(gate), _p(dpool), _p(dgamma2), _p(dbeta2), B, HW, gate.shape[1],
+          _stream())
+
+
+def dw_bn2_bwd_apply(dd_act, d_pre, gate, dpool, scale2, shift2, mean2, rstd2, gamma2, dgamma2, dbeta2, B, HW,
+                     act: str) -> Tensor:
+    dd_pre = torch.empty_like(d_pre)
+    _call("ogv_dw_bn2_bwd_apply", _p(dd_act), _p(d_pre), _p(gate), _p(dpool), _p(scale2), _p(shift2), _p(mean2),
+          _p(rstd2), _p(gamma2), _p(dgamma2), _p(dbeta2), _p(dd_pre), B, HW, d_pre.shape[1], ACT[act],
+          dtype_code(d_pre), _stream())
+    return dd_pre
 
 
 # --------------------------------------------------------------------------------- grid attention

@@ -162,7 +162,7 @@ def _dw_ref(e_pre, sc, sh, w, B, H, W):
 
 @pytest.mark.parametrize("dt", DT, ids=IDS)
 @pytest.mark.parametrize("B,H,W,Cm", [(3, 8, 8, 32), (2, 32, 32, 64), (5, 4, 4, 96), (2, 16, 16, 40), (1, 5, 7, 96),
-                                      (2, 64, 64, 32)])
+                                      (2, 64, 64, 32), (300, 32, 32, 32)])
 def test_dwconv_fwd_bwd(B, H, W, Cm, dt):
     from outlook_grid_vision_transformer_b200 import ops
     torch.manual_seed(B + H + Cm)
@@ -179,8 +179,9 @@ def test_dwconv_fwd_bwd(B, H, W, Cm, dt):
     s2, q2 = torch.zeros(Cm, device=DEV), torch.zeros(Cm, device=DEV)
     d = ops.dwconv_fwd(dev(e_pre), dev(sc), dev(sh), dev(w), s2, q2, B, H, W, "silu")
     close(d, dr.detach(), tol(dt), "dw fwd")
-    close(s2, d.double().sum(0), 1e-3, "dw stats sum")
-    close(q2, (d.double() ** 2).sum(0), 1e-3, "dw stats sumsq")
+    # statistics are accumulated from the fp32 results before they are rounded for storage
+    close(s2, dr.detach().sum(0), 1e-3 if dt == torch.float32 else 5e-3, "dw stats sum")
+    close(q2, (dr.detach() ** 2).sum(0), 1e-3 if dt == torch.float32 else 5e-3, "dw stats sumsq")
     # backward: du1 = dL/d(u1) where u1 = sc*e_pre+sh  ->  dL/de_pre = du1 * sc
     dw_, dg1, db1 = torch.zeros(Cm, 9, device=DEV), torch.zeros(Cm, device=DEV), torch.zeros(Cm, device=DEV)
     du1 = ops.dwconv_bwd(dev(g), dev(e_pre), dev(sc), dev(sh), dev(mean1), dev(rstd1), dev(w), dw_, dg1, db1, B, H, W,
@@ -194,10 +195,11 @@ def test_dwconv_fwd_bwd(B, H, W, Cm, dt):
 
 
 @pytest.mark.parametrize("dt", DT, ids=IDS)
-def test_se_and_bn2_kernels(dt):
+@pytest.mark.parametrize("Cm", [40, 264])
+def test_se_and_bn2_kernels(Cm, dt):
     from outlook_grid_vision_transformer_b200 import ops
     torch.manual_seed(4)
-    B, HW, Cm = 3, 20, 40
+    B, HW, Cm = 3, 20, Cm
     M = B * HW
     d_pre = torch.randn(M, Cm).to(dt)
     sc, sh = torch.rand(Cm) + 0.5, torch.randn(Cm) * 0.2
@@ -219,12 +221,13 @@ def test_se_and_bn2_kernels(dt):
     du = dd.reshape(M, Cm) * dsilu
     xh = (dD - mean2.double()) * rstd2.double()
     dg2, db2 = torch.zeros(Cm, device=DEV), torch.zeros(Cm, device=DEV)
-    args = (dev(dd_act), dev(d_pre), dev(gate), dev(dpool), dev(sc), dev(sh), dev(mean2), dev(rstd2), dev(gamma2))
-    ops.dw_bn2_bwd(0, *args, dg2, db2, None, B, HW, "silu")
+    stats = ops.mbconv_bwd_stats(dev(dd_act), dev(d_pre), dev(sc), dev(sh), dev(mean2), dev(rstd2), B, HW, "silu")
+    close(stats[0], (dd_act.double().reshape(B, HW, Cm) * act).sum(1), tol(dt), "bwd_stats dgate")
+    ops.mbconv_bn2_finalize(stats, dev(gate), dev(dpool), dg2, db2, B, HW)
     close(db2, du.sum(0), tol(dt), "bn2 dbeta")
     close(dg2, (du * xh).sum(0), tol(dt), "bn2 dgamma")
-    out = torch.empty(M, Cm, device=DEV, dtype=dt)
-    ops.dw_bn2_bwd(1, *args, dg2, db2, out, B, HW, "silu")
+    out = ops.dw_bn2_bwd_apply(dev(dd_act), dev(d_pre), dev(gate), dev(dpool), dev(sc), dev(sh), dev(mean2),
+                               dev(rstd2), dev(gamma2), dg2, db2, B, HW, "silu")
     want = gamma2.double() * rstd2.double() * (du - du.sum(0) / M - xh * (du * xh).sum(0) / M)
     close(out, want, tol(dt) * 2, "bn2 dx")
 
