@@ -37,6 +37,7 @@ extern "C" {
 #define OGV_ACT_SILU 2
 #define OGV_ACT_SIGMOID 3
 #define OGV_ACT_RELU 4
+#define OGV_ACT_MUL 5 /* `dact` only: multiply by dact_src itself (a derivative saved by the forward pass) */
 
 #define OGV_ENGINE_AUTO 0
 #define OGV_ENGINE_SIMT 1 /* fp32 FFMA tiles (exact-fp32 parity mode, debugging) */
@@ -55,7 +56,7 @@ int ogv_sm_count(void);
  *   forward : A = activations [M,K] (a_cs=1), B = weight [N,K] (b_cs=1)
  *   dgrad   : A = dY [M,N'],  B = W^T [K',N'] (pre-transposed copy, b_cs=1)
  *   wgrad   : A(m,k) = dY[k, m] (a_rs=1), B(n,k) = X[k, n] (b_rs=1), reduction over rows
- * epilogue order: v = acc (+bias[n]); pre_out[m,n] = v; v = act(v); v *= act'(dact_src[m,n]);
+ * epilogue order: v = acc (+bias[n]); pre_out[m,n] = v (or act'(v) if pre_out_grad); v = act(v); v *= act'(dact_src[m,n]);
  *                 v *= row_scale[m / rows_per_scale]; v += residual[m,n]; D[m,n] = v (or += v).
  * ------------------------------------------------------------------------------------------- */
 typedef struct ogv_gemm_args {
@@ -83,6 +84,8 @@ typedef struct ogv_gemm_args {
   int split_k;    /* >=1; >1 requires accumulate */
   float* col_sum;   /* optional [N]: += sum_m of stored value (BatchNorm batch statistics) */
   float* col_sumsq; /* optional [N]: += sum_m of stored value^2 */
+  int pre_out_grad; /* 1: pre_out receives act'(v) instead of v, so that the backward pass multiplies by it
+                       (dact = OGV_ACT_MUL) without re-evaluating a transcendental */
 } ogv_gemm_args;
 
 int ogv_gemm(const ogv_gemm_args* args, int engine, void* stream);
@@ -98,6 +101,9 @@ int ogv_cast_transpose(const float* src, void* dst, long long ld_dst, void* dst_
 /* y = x * scale[row / rows_per_scale]  (DropPath, Outlook_Block.py:15-22) */
 int ogv_rowscale(const void* x, const float* scale, void* y, long long rows, int cols, int rows_per_scale,
                  int dtype, void* stream);
+/* y = x * scale[row / rows_per_scale] and out[n] += sum_m y[m,n] in one pass (DropPath backward + bias gradient) */
+int ogv_rowscale_colsum(const void* x, const float* scale, void* y, float* out, long long rows, int cols,
+                        int rows_per_scale, int dtype, void* stream);
 /* out[n] += sum_m x[m,n]  (bias gradients) */
 int ogv_colsum(const void* x, long long ld, float* out, long long M, int N, int dtype, void* stream);
 /* out = a * act'(pre) elementwise, n elements (SE gate backward) */

@@ -45,6 +45,9 @@ def main():
             g = case["grads"][k].double()
             noise[k] = float((p.grad.double() - g).norm() / (g.norm() + 1e-3 * g.numel() ** 0.5))
         noise["__y__"] = float((y.double() - case["y"]).norm() / case["y"].norm())
+        noise["__dx__"] = float((x.grad.double() - case["dx"].double()).norm() / case["dx"].double().norm())
+        dxe = (x.grad.double() - case["dx"].double()).abs() / (case["dx"].double().abs() + case["dx"].double().abs().max())
+        noise["__dx_max_band__"] = float(dxe.max())  # worst elementwise error in units of (|b| + max|b|)
         out[name] = noise
         worst = sorted(noise.items(), key=lambda kv: -kv[1])[:5]
         print(name, "worst:", worst)

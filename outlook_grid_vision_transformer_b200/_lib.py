@@ -11,7 +11,7 @@ _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "libogvit.so"
 
 F32, BF16 = 0, 1
-ACT = {None: 0, "none": 0, "gelu": 1, "silu": 2, "sigmoid": 3, "relu": 4}
+ACT = {None: 0, "none": 0, "gelu": 1, "silu": 2, "sigmoid": 3, "relu": 4, "mul": 5}
 ENGINE_AUTO, ENGINE_SIMT, ENGINE_TC = 0, 1, 2
 
 
@@ -32,6 +32,7 @@ class GemmArgs(Structure):
         ("residual", c_void_p), ("ld_res", c_longlong),
         ("accumulate", c_int), ("split_k", c_int),
         ("col_sum", c_void_p), ("col_sumsq", c_void_p),
+        ("pre_out_grad", c_int),
     ]
 
 
@@ -47,6 +48,7 @@ SIGNATURES = {
     "ogv_nhwc_to_nchw": [_P, _P, _I, _I, _I, _I, _P],
     "ogv_cast_transpose": [_P, _P, _L, _P, _L, _I, _I, _I, _P],
     "ogv_rowscale": [_P, _P, _P, _L, _I, _I, _I, _P],
+    "ogv_rowscale_colsum": [_P, _P, _P, _P, _L, _I, _I, _I, _P],
     "ogv_colsum": [_P, _L, _P, _L, _I, _I, _P],
     "ogv_mul_dact": [_P, _P, _P, _L, _I, _I, _P],
     "ogv_add": [_P, _P, _P, _L, _I, _P],

@@ -22,6 +22,7 @@ typedef __nv_bfloat16 bf16;
 #define OGV_ACT_SILU 2
 #define OGV_ACT_SIGMOID 3
 #define OGV_ACT_RELU 4
+#define OGV_ACT_MUL 5
 
 void ogv_set_error(const char* fmt, ...);
 int ogv_check_launch(const char* what);
@@ -178,6 +179,7 @@ __device__ __forceinline__ float act_grad(int act, float x) {
     case OGV_ACT_SILU: return dsilu_f(x);
     case OGV_ACT_SIGMOID: { float s = sigmoid_f(x); return s * (1.f - s); }
     case OGV_ACT_RELU: return x > 0.f ? 1.f : 0.f;
+    case OGV_ACT_MUL: return x;
     default: return 1.f;
   }
 }
@@ -200,10 +202,14 @@ __device__ __forceinline__ float silu_fast(float x) {
   const float h = 0.5f * x;
   return fmaf(h, tanh_approx(h), h);
 }
+// Derivatives feed cancellation-heavy reductions (BatchNorm gamma / beta gradients), where the x-correlated
+// 2^-11 error of tanh.approx shows up as a bias: the backward kernels keep the 2-MUFU sigmoid (ex2 + rcp,
+// rel. error ~1e-7) -- same ALU count, one more MUFU op.
 __device__ __forceinline__ void silu_both_fast(float x, float* a, float* da) {
-  const float s = sigmoid_fast(x);
-  *a = x * s;
-  *da = s * fmaf(x, 1.f - s, 1.f);
+  const float s = sigmoid_f(x);
+  const float v = x * s;
+  *a = v;
+  *da = fmaf(v, 1.f - s, s);
 }
 constexpr float kGeluC1 = 1.12777659f, kGeluC3 = 0.1047942f, kGeluC5 = -0.0020293f;
 __device__ __forceinline__ float gelu_fast(float x) {
@@ -325,7 +331,28 @@ template <int N, bool FAST = false> __device__ __forceinline__ void act_grad_mul
 #pragma unroll
       for (int i = 0; i < N; ++i) v[i] = src[i] > 0.f ? v[i] : 0.f;
       break;
+    case OGV_ACT_MUL:
+#pragma unroll
+      for (int i = 0; i < N; ++i) v[i] *= src[i];
+      break;
     default: break;
+  }
+}
+// v <- act(v), d <- act'(v) with the switch hoisted out of the element loop
+template <int N, bool FAST = false> __device__ __forceinline__ void act_both_n(int act, float (&v)[N], float (&d)[N]) {
+  switch (act) {
+    case OGV_ACT_GELU:
+#pragma unroll
+      for (int i = 0; i < N; ++i) { if (FAST) gelu_both_fast(v[i], &v[i], &d[i]); else act_both(OGV_ACT_GELU, v[i], &v[i], &d[i]); }
+      break;
+    case OGV_ACT_SILU:
+#pragma unroll
+      for (int i = 0; i < N; ++i) { if (FAST) silu_both_fast(v[i], &v[i], &d[i]); else act_both(OGV_ACT_SILU, v[i], &v[i], &d[i]); }
+      break;
+    default:
+#pragma unroll
+      for (int i = 0; i < N; ++i) act_both(act, v[i], &v[i], &d[i]);
+      break;
   }
 }
 

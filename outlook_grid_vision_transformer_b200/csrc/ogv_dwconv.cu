@@ -270,8 +270,9 @@ dwconv_fwd_kernel(const __grid_constant__ CUtensorMap tm_in, const float* __rest
             if (!(g.dbg & 4)) stv<4>(out + (long long)r * g.W * g.Cm, acc[r]);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              st_s[k] += acc[r][k];
-              st_q[k] = fmaf(acc[r][k], acc[r][k], st_q[k]);
+              const float sv = round_to<T>(acc[r][k]);  // statistics of the values as stored
+              st_s[k] += sv;
+              st_q[k] = fmaf(sv, sv, st_q[k]);
             }
           }
         }
@@ -589,8 +590,11 @@ dwconv_fwd_sweep_kernel(const T* __restrict__ e_pre, const float* __restrict__ s
           stv<4>(out0 + (long long)r * rowpitch + (long long)x * Cm, acc[r]);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            st_s[k] += acc[r][k];
-            st_q[k] = fmaf(acc[r][k], acc[r][k], st_q[k]);
+            // statistics of the values AS STORED: BatchNorm's backward sums (sum xhat = 0, sum xhat^2 = n) only
+            // cancel exactly if mean / variance describe the tensor the later passes actually read
+            const float sv = round_to<T>(acc[r][k]);
+            st_s[k] += sv;
+            st_q[k] = fmaf(sv, sv, st_q[k]);
           }
         }
       }

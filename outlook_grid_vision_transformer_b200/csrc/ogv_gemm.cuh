@@ -20,6 +20,7 @@ struct GemmEpi {
   int accumulate;
   float* col_sum;
   float* col_sumsq;
+  int pre_out_grad;
   int M, N;
 };
 
@@ -28,7 +29,7 @@ static inline GemmEpi make_epi(const ogv_gemm_args& a) {
   e.D = a.D; e.ldd = a.ldd; e.bias = a.bias; e.pre_out = a.pre_out; e.ld_pre = a.ld_pre; e.act = a.act;
   e.dact_src = a.dact_src; e.ld_dact = a.ld_dact; e.dact = a.dact; e.row_scale = a.row_scale;
   e.rows_per_scale = a.rows_per_scale > 0 ? a.rows_per_scale : 1; e.residual = a.residual; e.ld_res = a.ld_res;
-  e.accumulate = a.accumulate; e.col_sum = a.col_sum; e.col_sumsq = a.col_sumsq; e.M = a.M; e.N = a.N;
+  e.accumulate = a.accumulate; e.col_sum = a.col_sum; e.col_sumsq = a.col_sumsq; e.pre_out_grad = a.pre_out_grad; e.M = a.M; e.N = a.N;
   return e;
 }
 
@@ -36,7 +37,8 @@ static inline GemmEpi make_epi(const ogv_gemm_args& a) {
 template <typename TO>
 __device__ __forceinline__ float epi_scalar(const GemmEpi& e, int m, int n, float v) {
   if (e.bias) v += e.bias[n];
-  if (e.pre_out) st1(reinterpret_cast<TO*>(e.pre_out) + (long long)m * e.ld_pre + n, v);
+  if (e.pre_out)
+    st1(reinterpret_cast<TO*>(e.pre_out) + (long long)m * e.ld_pre + n, e.pre_out_grad ? act_grad(e.act, v) : v);
   v = act_apply(e.act, v);
   if (e.dact_src) v *= act_grad(e.dact, ld1(reinterpret_cast<const TO*>(e.dact_src) + (long long)m * e.ld_dact + n));
   if (e.row_scale) v *= e.row_scale[m / e.rows_per_scale];

@@ -38,6 +38,8 @@ struct TcParams {
   int slots;        // staging slots per epilogue warp (0: direct epilogue, 2, or 4 with pre_out)
   int epi_load;     // 0 none, 1 residual, 2 dact_src -- operand fetched by TMA into the staging slot
   int vec_ok;       // direct epilogue may use 8-wide vector accesses
+  int col_stats;    // staged epilogue also accumulates per-column sum (and sum of squares) of the stored values
+  int n_pad;        // n_tiles * BN: extent of the per-CTA column accumulators in shared memory
   GemmEpi epi;
 };
 
@@ -58,8 +60,14 @@ __device__ __forceinline__ void epi_row16(const GemmEpi& e, int m, int n0, const
 #pragma unroll
         for (int i = 0; i < 8; ++i) x[i] += __ldg(e.bias + n + i);
       }
-      if (e.pre_out) st8(reinterpret_cast<TO*>(e.pre_out) + (long long)m * e.ld_pre + n, x);
-      if (e.act != OGV_ACT_NONE) act_apply_n<8, FastAct<TO>::value>(e.act, x);
+      if (e.pre_out && e.pre_out_grad) {
+        float d[8];
+        act_both_n<8, FastAct<TO>::value>(e.act, x, d);
+        st8(reinterpret_cast<TO*>(e.pre_out) + (long long)m * e.ld_pre + n, d);
+      } else {
+        if (e.pre_out) st8(reinterpret_cast<TO*>(e.pre_out) + (long long)m * e.ld_pre + n, x);
+        if (e.act != OGV_ACT_NONE) act_apply_n<8, FastAct<TO>::value>(e.act, x);
+      }
       if (e.dact_src) {
         float d[8];
         ld8(reinterpret_cast<const TO*>(e.dact_src) + (long long)m * e.ld_dact + n, d);
@@ -120,6 +128,30 @@ __device__ __forceinline__ void stage_read_row(const uint8_t* slot, int row, flo
   }
 }
 
+// Column sums of a warp's 32 x 32 chunk (lane = row, v[j] = column j): butterfly exchange in which
+// every step halves the columns a lane is responsible for; lane l ends up with the sum of column l.
+__device__ __forceinline__ float warp_colsum32(const float (&v)[32], int lane) {
+  float t[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const bool up = lane & 16;
+    const float keep = up ? v[i + 16] : v[i];
+    const float send = up ? v[i] : v[i + 16];
+    t[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int off = 8; off >= 1; off >>= 1) {
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const bool up = lane & off;
+      const float keep = up ? t[i + off] : t[i];
+      const float send = up ? t[i] : t[i + off];
+      t[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return t[0];
+}
+
 template <int BN, typename TO>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -139,6 +171,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tempty_bar = tfull_bar + 2;
   uint64_t* ld_bar = tempty_bar + 2;  // [EPI_WARPS][2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ld_bar + 2 * EPI_WARPS);
+  float* colacc = reinterpret_cast<float*>(tmem_slot + 4);  // [2][n_pad] when p.col_stats
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -161,6 +194,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     ptx::tmem_alloc(tmem_slot, TMEM_COLS);
     ptx::tmem_relinquish();
   }
+  if (p.col_stats)
+    for (int i = threadIdx.x; i < 2 * p.n_pad; i += TC_THREADS) colacc[i] = 0.f;
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -308,8 +343,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               if (n0c + i < p.N) v[i] += __ldg(e.bias + n0c + i);
           }
         }
-        if (e.pre_out) stage_write_row(s1, lane, v);
-        if (e.act != OGV_ACT_NONE) act_apply_n<32, FastAct<TO>::value>(e.act, v);
+        if (e.pre_out && e.pre_out_grad) {
+          float d[32];
+          act_both_n<32, FastAct<TO>::value>(e.act, v, d);
+          stage_write_row(s1, lane, d);
+        } else {
+          if (e.pre_out) stage_write_row(s1, lane, v);
+          if (e.act != OGV_ACT_NONE) act_apply_n<32, FastAct<TO>::value>(e.act, v);
+        }
         if (p.epi_load) {
           ptx::mbar_wait(&my_ld[pr], (ld_phase >> pr) & 1u);
           ld_phase ^= 1u << pr;
@@ -333,6 +374,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] *= rs;
         }
+        if (p.col_stats) {
+          float u[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) u[i] = m < p.M ? round_to<bf16>(v[i]) : 0.f;  // statistics of the STORED values
+          const float cs = warp_colsum32(u, lane);
+          if (n0c + lane < p.N) atomicAdd(&colacc[n0c + lane], cs);
+          if (e.col_sumsq) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) u[i] *= u[i];
+            const float cq = warp_colsum32(u, lane);
+            if (n0c + lane < p.N) atomicAdd(&colacc[p.n_pad + n0c + lane], cq);
+          }
+        }
         stage_write_row(s0, lane, v);
         ptx::fence_proxy_async();
         __syncwarp();
@@ -354,6 +408,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   ptx::tc_fence_before();
   __syncthreads();
+  if (p.col_stats) {  // one global atomic per column per CTA
+    for (int i = threadIdx.x; i < p.N; i += TC_THREADS) {
+      if (p.epi.col_sum) atomicAdd(p.epi.col_sum + i, colacc[i]);
+      if (p.epi.col_sumsq) atomicAdd(p.epi.col_sumsq + i, colacc[p.n_pad + i]);
+    }
+  }
   if (warp == MMA_WARP) {
     __syncwarp();
     ptx::tc_fence_after();
@@ -415,14 +475,15 @@ template <int BN, typename TO>
 int launch_tc(const CUtensorMap* tms, TcParams& p, cudaStream_t stream) {
   constexpr int STAGE_BYTES = TC_BM * TC_BK * 2 + BN * TC_BK * 2;
   const int staging = EPI_WARPS * p.slots * SLOT_BYTES;
-  int stages = (SMEM_LIMIT - 1024 - BAR_BYTES - staging) / STAGE_BYTES;
+  const int colbytes = p.col_stats ? 2 * p.n_pad * 4 : 0;
+  int stages = (SMEM_LIMIT - 1024 - BAR_BYTES - staging - colbytes) / STAGE_BYTES;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages < 2) {
     ogv_set_error("gemm_tc: shared memory budget leaves %d pipeline stages", stages);
     return OGV_ERR_UNSUPPORTED;
   }
   p.stages = stages;
-  const int smem_bytes = stages * STAGE_BYTES + staging + BAR_BYTES + 1024;
+  const int smem_bytes = stages * STAGE_BYTES + staging + BAR_BYTES + colbytes + 1024;
   static int attr_bytes = 0;
   if (attr_bytes < smem_bytes) {
     cudaError_t err = cudaFuncSetAttribute(gemm_tc_kernel<BN, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -456,7 +517,13 @@ bool ogv_gemm_tc_supported(const ogv_gemm_args& a, const char** why) {
   if (a_ld % 8 || b_ld % 8) return fail("leading dimension not a multiple of 8 elements (16 B)");
   if ((reinterpret_cast<uintptr_t>(a.A) & 15) || (reinterpret_cast<uintptr_t>(a.B) & 15))
     return fail("operand base not 16-byte aligned");
-  if (a.col_sum || a.col_sumsq) return fail("column statistics not fused in the tcgen05 epilogue");
+  if (a.col_sum || a.col_sumsq) {
+    // fused only in the staged (bf16, TMA-store) epilogue
+    if (!a.col_sum) return fail("col_sumsq needs col_sum");
+    if (a.out_dtype != OGV_BF16 || a.accumulate) return fail("column statistics need a bf16, non-accumulating output");
+    if ((reinterpret_cast<uintptr_t>(a.D) & 15) || (a.ldd % 8)) return fail("column statistics need a TMA-storable output");
+    if (a.N > 4096) return fail("column statistics: N too large");
+  }
   if (a.split_k > 1 && !a.accumulate) return fail("split_k>1 needs accumulate");
   if (a.accumulate && a.out_dtype != OGV_F32) return fail("accumulate needs fp32 output");
   return true;
@@ -493,6 +560,12 @@ int ogv_gemm_tc(const ogv_gemm_args& a, cudaStream_t stream) {
                       (!a.residual || tma_ok(a.residual, a.ld_res)) && (!a.dact_src || tma_ok(a.dact_src, a.ld_dact)) &&
                       !(a.residual && a.dact_src);
   p.slots = staged ? (a.pre_out ? 4 : 2) : 0;
+  p.col_stats = (a.col_sum != nullptr) ? 1 : 0;
+  p.n_pad = p.n_tiles * BN;
+  if (p.col_stats && !staged) {
+    ogv_set_error("gemm_tc: column statistics requested on a problem without a staged epilogue");
+    return OGV_ERR_UNSUPPORTED;
+  }
   p.epi_load = staged ? (a.residual ? 1 : (a.dact_src ? 2 : 0)) : 0;
   const int esz = obf ? 2 : 4;
   auto ok = [&](const void* ptr, long long ld) {

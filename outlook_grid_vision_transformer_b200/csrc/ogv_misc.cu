@@ -195,6 +195,30 @@ __global__ void __launch_bounds__(COLREDUCE_THREADS) colsum_kernel(const T* __re
   colreduce_finish<1>(acc, outs, nv);
 }
 
+// y = x * scale[row / rows_per_scale] and out[n] += sum_m y[m,n] in one pass (DropPath backward feeding
+// the bias gradient of the branch's last linear layer).
+template <typename T>
+__global__ void __launch_bounds__(COLREDUCE_THREADS) rowscale_colsum_kernel(const T* __restrict__ x,
+                                                                            const float* __restrict__ scale,
+                                                                            T* __restrict__ y, float* __restrict__ out,
+                                                                            long long M, int nv, unsigned rows_per_scale) {
+  float acc[1][8];
+  colreduce_init(acc);
+  COLREDUCE_LOOP(M, nv, row, cv) {
+    float v[8];
+    ld8(x + (row * nv + cv) * 8, v);
+    const float s = scale[(unsigned)row / rows_per_scale];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      v[i] *= s;
+      acc[0][i] += v[i];
+    }
+    st8(y + (row * nv + cv) * 8, v);
+  }
+  float* outs[1] = {out};
+  colreduce_finish<1>(acc, outs, nv);
+}
+
 template <typename T>
 __global__ void __launch_bounds__(COLREDUCE_THREADS) colstats_kernel(const T* __restrict__ x, long long ld, float* __restrict__ sum,
                                 float* __restrict__ sumsq, long long M, int nv) {
@@ -246,6 +270,20 @@ extern "C" int ogv_rowscale(const void* x, const float* scale, void* y, long lon
                                                                reinterpret_cast<T*>(y), nvec, cols / 8,
                                                                rows_per_scale);
     return ogv_check_launch("rowscale");
+  });
+}
+
+extern "C" int ogv_rowscale_colsum(const void* x, const float* scale, void* y, float* out, long long rows, int cols,
+                                   int rows_per_scale, int dtype, void* stream) {
+  OGV_REQUIRE(x && y && scale && out && cols % 8 == 0 && rows_per_scale > 0, "rowscale_colsum: bad args (cols %% 8 == 0)");
+  OGV_REQUIRE(rows < 0x7fffffffLL, "rowscale_colsum: too many rows");
+  if (rows == 0 || cols == 0) return OGV_OK;
+  ColReduceCfg cfg;
+  if (!colreduce_config(rows, cols / 8, &cfg)) { ogv_set_error("rowscale_colsum: cols=%d too wide", cols); return OGV_ERR_UNSUPPORTED; }
+  OGV_DISPATCH_DTYPE(dtype, T, {
+    rowscale_colsum_kernel<T><<<cfg.grid, cfg.block, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const T*>(x), scale, reinterpret_cast<T*>(y), out, rows, cols / 8, (unsigned)rows_per_scale);
+    return ogv_check_launch("rowscale_colsum");
   });
 }
 

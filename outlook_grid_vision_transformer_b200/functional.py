@@ -60,6 +60,14 @@ def prepare_linear(weight: Tensor, dtype: torch.dtype, out_rows: Optional[int] =
     return PreparedLinear(w, wt)
 
 
+def _scaled_grad(dy: Tensor, scale: Optional[Tensor], rows_per_sample: int, dbias: Tensor) -> Tensor:
+    """gy = dy * per-sample DropPath scale, and dbias += colsum(gy) -- one pass when a scale is present."""
+    if scale is None:
+        ops.colsum(dy, dbias)
+        return dy
+    return ops.rowscale_colsum(dy, scale, rows_per_sample, dbias)
+
+
 def _zeros(shape, like: Tensor) -> Tensor:
     return torch.zeros(shape, device=like.device, dtype=torch.float32)
 
@@ -85,9 +93,11 @@ class MlpBranchFn(torch.autograd.Function):
             xn, mean, rstd = ops.layernorm_fwd(x, ln_w, ln_b, meta["eps"])
         else:
             xn, mean, rstd = x, None, None
+        # the forward epilogue saves act'(z) (it has the transcendental in hand), so the backward epilogue is a
+        # plain multiply instead of a second erf/exp evaluation per element
         z = _empty((M, Hd), x)
         h = _empty((M, Hd), x)
-        ops.gemm(xn, p1.w, h, bias=b1, pre_out=z, act=act)
+        ops.gemm(xn, p1.w, h, bias=b1, pre_out=z, act=act, pre_out_grad=True)
         y = _empty((M, C), x)
         ops.gemm(h, p2.w, y, bias=b2, row_scale=scale, rows_per_scale=P, residual=x if with_res else None)
         ctx.meta = meta
@@ -105,7 +115,6 @@ class MlpBranchFn(torch.autograd.Function):
         dy = dy.contiguous()
         M, C = x.shape
         Hd = p1.w.shape[0]
-        gy = ops.rowscale(dy, scale, P) if scale is not None else dy
         # one zeroed fp32 arena for all parameter gradients of the branch
         arena = _zeros(Hd * C * 2 + Hd + C + 2 * C, x)
         o = 0
@@ -115,11 +124,11 @@ class MlpBranchFn(torch.autograd.Function):
         db2 = arena[o:o + C]; o += C
         dg = arena[o:o + C]; o += C
         dbt = arena[o:o + C]; o += C
-        # fc2 backward (+ activation derivative fused into the dgrad epilogue)
+        gy = _scaled_grad(dy, scale, P, db2)
+        # fc2 backward (+ activation derivative and the fc1 bias gradient fused into the dgrad epilogue)
         dz = _empty((M, Hd), x)
-        ops.gemm(gy, p2.wt, dz, dact_src=z, dact=act)
+        ops.gemm(gy, p2.wt, dz, dact_src=z, dact="mul", col_sum=db1)
         ops.wgrad(gy, h, dW2)
-        ops.colsum(gy, db2)
         # fc1 backward
         dxn = _empty((M, C), x)
         if with_ln:
@@ -127,7 +136,6 @@ class MlpBranchFn(torch.autograd.Function):
         else:
             ops.gemm(dz, p1.wt, dxn, residual=dy if with_res else None)
         ops.wgrad(dz, xn, dW1)
-        ops.colsum(dz, db1)
         if with_ln:
             dx = ops.layernorm_bwd(dxn, x, ln_w, mean, rstd, dy if with_res else None, dg, dbt)
             return dx, dg, dbt, dW1.view(meta["w1_shape"]), db1, dW2.view(meta["w2_shape"]), db2, None, None
@@ -185,7 +193,6 @@ class OutlookBranchFn(torch.autograd.Function):
         M, C = x.shape
         npad = pva.w.shape[0]
         nl = 9 * heads
-        gy = ops.rowscale(dy, scale, g.P) if scale is not None else dy
         arena = _zeros(npad * C + C * C + npad + C + 2 * C, x)
         o = 0
         dWva = arena[o:o + npad * C].view(npad, C); o += npad * C
@@ -194,10 +201,10 @@ class OutlookBranchFn(torch.autograd.Function):
         dbp = arena[o:o + C]; o += C
         dg = arena[o:o + C]; o += C
         dbt = arena[o:o + C]; o += C
+        gy = _scaled_grad(dy, scale, g.P, dbp)
         dyc = _empty((M, C), x)
         ops.gemm(gy, pp.wt, dyc)
         ops.wgrad(gy, yc, dWp)
-        ops.colsum(gy, dbp)
         dva = ops.outlook_core_bwd(va, dyc, g.B, g.H, g.W, C, heads)
         dxn = _empty((M, C), x)
         if with_ln:
@@ -281,7 +288,6 @@ class GridBranchFn(torch.autograd.Function):
         with_ln = ln_w is not None
         dy = dy.contiguous()
         M, C = x.shape
-        gy = ops.rowscale(dy, scale, g.P) if scale is not None else dy
         arena = _zeros(3 * C * C + C * C + 3 * C + C + 2 * C, x)
         off = 0
         dWq = arena[off:off + 3 * C * C].view(3 * C, C); off += 3 * C * C
@@ -290,10 +296,10 @@ class GridBranchFn(torch.autograd.Function):
         dbp = arena[off:off + C]; off += C
         dg = arena[off:off + C]; off += C
         dbt = arena[off:off + C]; off += C
+        gy = _scaled_grad(dy, scale, g.P, dbp)
         do = _empty((M, C), x)
         ops.gemm(gy, pp.wt, do)
         ops.wgrad(gy, o, dWp)
-        ops.colsum(gy, dbp)
         dqkv = ops.grid_attn_bwd(qkv, do, g.B, g.H, g.W, C, heads, gs)
         dxn = _empty((M, C), x)
         if with_ln:
@@ -340,9 +346,8 @@ class MBConvFn(torch.autograd.Function):
         s3 = carve(12 * Cm, C)
         # expand
         e_pre = _empty((M, Cm), x)
-        ops.gemm(x, pe.w, e_pre)
-        if training:
-            ops.colstats(e_pre, s1[0], s1[1])
+        # BatchNorm batch statistics come out of the GEMM epilogue (no extra pass over the wide tensor)
+        ops.gemm(x, pe.w, e_pre, col_sum=s1[0] if training else None, col_sumsq=s1[1] if training else None)
         ops.bn_finalize(s1[0], s1[1], g1, b1, rm1, rv1, s1[2], s1[3], s1[4], s1[5], M, eps, mom, training)
         # depthwise (BN1 + act on load, BN2 statistics on store)
         wdw2 = wdw.detach().reshape(Cm, 9).contiguous()
@@ -365,9 +370,7 @@ class MBConvFn(torch.autograd.Function):
         d_act = ops.bn_act_gate(d_pre, s2[2], s2[3], gate, g.B, g.P, act)
         # project
         o_pre = _empty((M, C), x)
-        ops.gemm(d_act, ppj.w, o_pre)
-        if training:
-            ops.colstats(o_pre, s3[0], s3[1])
+        ops.gemm(d_act, ppj.w, o_pre, col_sum=s3[0] if training else None, col_sumsq=s3[1] if training else None)
         ops.bn_finalize(s3[0], s3[1], g3, b3, rm3, rv3, s3[2], s3[3], s3[4], s3[5], M, eps, mom, training)
         y = ops.bn_apply(o_pre, s3[2], s3[3], x if meta["use_res"] else None)
         ctx.meta = meta

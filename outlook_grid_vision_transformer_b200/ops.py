@@ -112,8 +112,10 @@ def _rows(t: Tensor, name: str) -> None:
 def gemm(A: Tensor, B: Tensor, D: Tensor, *, bias: Optional[Tensor] = None, pre_out: Optional[Tensor] = None,
          act: Optional[str] = None, dact_src: Optional[Tensor] = None, dact: Optional[str] = None,
          row_scale: Optional[Tensor] = None, rows_per_scale: int = 1, residual: Optional[Tensor] = None,
-         accumulate: bool = False, split_k: int = 1, engine: int = ENGINE_AUTO) -> Tensor:
-    """D[m,n] = epi(sum_k A[m,k] * B[n,k]); A:[M,K], B:[N,K] (any strides), D:[M,N] row-major."""
+         accumulate: bool = False, split_k: int = 1, engine: int = ENGINE_AUTO, col_sum: Optional[Tensor] = None,
+         col_sumsq: Optional[Tensor] = None, pre_out_grad: bool = False) -> Tensor:
+    """D[m,n] = epi(sum_k A[m,k] * B[n,k]); A:[M,K], B:[N,K] (any strides), D:[M,N] row-major.
+    col_sum / col_sumsq (fp32 [N]) are accumulated (+=) with the per-column sum / sum of squares of D."""
     _require_cuda(A, B, D, bias, pre_out, dact_src, row_scale, residual)
     if A.dim() != 2 or B.dim() != 2 or D.dim() != 2:
         raise ValueError("gemm operands must be 2-D")
@@ -131,6 +133,8 @@ def gemm(A: Tensor, B: Tensor, D: Tensor, *, bias: Optional[Tensor] = None, pre_
                 raise ValueError(f"gemm: {name} must match D in dtype and shape")
     _f32(bias, "bias")
     _f32(row_scale, "row_scale")
+    _f32(col_sum, "col_sum")
+    _f32(col_sumsq, "col_sumsq")
     a = GemmArgs()
     a.A, a.a_rs, a.a_cs = A.data_ptr(), A.stride(0), A.stride(1)
     a.B, a.b_rs, a.b_cs = B.data_ptr(), B.stride(0), B.stride(1)
@@ -146,7 +150,9 @@ def gemm(A: Tensor, B: Tensor, D: Tensor, *, bias: Optional[Tensor] = None, pre_
     a.rows_per_scale = int(rows_per_scale)
     a.residual, a.ld_res = (residual.data_ptr(), residual.stride(0)) if residual is not None else (None, 0)
     a.accumulate, a.split_k = int(accumulate), int(split_k)
-    a.col_sum, a.col_sumsq = None, None
+    a.col_sum = col_sum.data_ptr() if col_sum is not None else None
+    a.col_sumsq = col_sumsq.data_ptr() if col_sumsq is not None else None
+    a.pre_out_grad = int(bool(pre_out_grad))
     if PROFILER.enabled:
         extra = sum(1 for t in (pre_out, dact_src, residual) if t is not None)
         PROFILER.cur_bytes = A.element_size() * (M * K + N * K) + D.element_size() * M * N * (1 + extra)
@@ -218,6 +224,17 @@ def rowscale(x: Tensor, scale: Tensor, rows_per_scale: int) -> Tensor:
     y = torch.empty_like(x)
     _call("ogv_rowscale", _p(x), _p(scale), _p(y), x.shape[0], x.shape[1], rows_per_scale, dtype_code(x),
                                   _stream())
+    return y
+
+
+def rowscale_colsum(x: Tensor, scale: Tensor, rows_per_scale: int, out: Tensor) -> Tensor:
+    """-> y = x * scale[row // rows_per_scale];  out[n] += sum_m y[m,n]  (one pass)."""
+    _require_cuda(x, scale, out)
+    _f32(scale, "scale")
+    _f32(out, "out")
+    y = torch.empty_like(x)
+    _call("ogv_rowscale_colsum", _p(x), _p(scale), _p(y), _p(out), x.shape[0], x.shape[1], rows_per_scale,
+          dtype_code(x), _stream())
     return y
 
 

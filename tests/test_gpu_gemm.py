@@ -92,6 +92,19 @@ def test_gemm_epilogue(engine_name):
     zp = pre.double().cpu()
     dgelu = 0.5 * (1 + torch.erf(zp / 2 ** 0.5)) + zp * torch.exp(-0.5 * zp * zp) / (2 * torch.pi) ** 0.5
     _check(D2, _ref(G, B) * dgelu, tol, "dact epilogue")
+    # saved-derivative form: forward stores act'(z), backward multiplies by it
+    gp = torch.empty((M, N), device=DEV, dtype=dt)
+    D3 = torch.empty((M, N), device=DEV, dtype=dt)
+    ops.gemm(A, B, D3, bias=bias, pre_out=gp, act="gelu", pre_out_grad=True, engine=eng)
+    torch.cuda.synchronize()
+    dz = 0.5 * (1 + torch.erf(z / 2 ** 0.5)) + z * torch.exp(-0.5 * z * z) / (2 * torch.pi) ** 0.5
+    _check(D3, torch.nn.functional.gelu(z), tol, "gelu output (saved-derivative form)")
+    _check(gp, dz, tol, "saved gelu'")
+    s1 = torch.zeros(N, device=DEV)
+    ops.gemm(G, B, D2, dact_src=gp, dact="mul", col_sum=s1, engine=eng)
+    torch.cuda.synchronize()
+    _check(D2, _ref(G, B) * gp.double().cpu(), tol, "mul epilogue")
+    _check(s1, D2.double().cpu().sum(0), 5e-3, "mul epilogue col_sum")
 
 
 @pytest.mark.parametrize("M,N,K,ta,tb", [(100, 70, 33, False, False), (64, 64, 1000, True, True), (130, 20, 77, False, True)])
@@ -119,3 +132,33 @@ def test_tc_gemm_large_multi_tile_persistent():
     want = (A.float() @ B.float().t())
     err = (D.float() - want).abs().max() / want.abs().max()
     assert err < 1e-2, f"rel err {err:.3e}"
+
+
+@pytest.mark.parametrize("M,N,K", [(1000, 256, 64), (50000, 512, 128), (777, 82 * 0 + 88, 64), (300, 1536, 384)])
+@pytest.mark.parametrize("engine_name", ["tc", "simt"])
+def test_gemm_column_statistics(M, N, K, engine_name):
+    """BatchNorm batch statistics / bias gradients out of the GEMM epilogue: col_sum, col_sumsq of D."""
+    from outlook_grid_vision_transformer_b200 import ops
+    torch.manual_seed(M + N)
+    dt = torch.bfloat16 if engine_name == "tc" else torch.float32
+    eng = ops.ENGINE_TC if engine_name == "tc" else ops.ENGINE_SIMT
+    if engine_name == "simt" and M > 2000:
+        pytest.skip("large case is for the persistent tcgen05 kernel")
+    A = torch.randn(M, K, device=DEV).to(dt)
+    B = (torch.randn(N, K, device=DEV) * 0.3).to(dt)
+    bias = torch.randn(N, device=DEV)
+    D = torch.empty((M, N), device=DEV, dtype=dt)
+    s = torch.full((N,), 1.0, device=DEV)      # accumulated INTO (+=): starts at 1
+    q = torch.full((N,), 2.0, device=DEV)
+    ops.gemm(A, B, D, bias=bias, col_sum=s, col_sumsq=q, engine=eng)
+    torch.cuda.synchronize()
+    z = _ref(A, B) + bias.double().cpu()
+    _check(D, z, 1e-2 if dt == torch.bfloat16 else 1e-5, "D")
+    Dd = D.double().cpu()                      # statistics describe the tensor as stored
+    _check(s - 1.0, Dd.sum(0), 2e-3, "col_sum")
+    _check(q - 2.0, (Dd * Dd).sum(0), 2e-3, "col_sumsq")
+    # sum only (bias gradient of a dgrad output)
+    s2 = torch.zeros(N, device=DEV)
+    ops.gemm(A, B, D, col_sum=s2, engine=eng)
+    torch.cuda.synchronize()
+    _check(s2, D.double().cpu().sum(0), 2e-3, "col_sum only")

@@ -44,12 +44,20 @@ def test_cuda_matches_reference_golden(name, dtype):
     y, dx, grads, bufs = run_product(case, dtype)
     rtol = RTOL[dtype]
     assert_close(y, case["y"], rtol, f"{name}: forward")
-    assert_close(dx, case["dx"], rtol, f"{name}: dx", atol=1e-6)
+    # whole-model bf16 input gradient: the reference's own bf16 run deviates from its fp64 result by
+    # `__dx_max_band__` (in units of |b| + max|b|); allow 1.6x that, like the parameter gradients below
+    dx_tol = rtol
+    if dtype == torch.bfloat16:
+        dx_tol = max(rtol, 1.6 * REF_BF16_NOISE.get(name, {}).get("__dx_max_band__", 0.0))
+    assert_close(dx, case["dx"], dx_tol, f"{name}: dx", atol=1e-6)
     assert set(grads) == set(case["grads"]), f"{name}: parameter-gradient key sets differ"
     for k, g in case["grads"].items():
         if dtype == torch.bfloat16:
-            tol = max(rtol, 1.6 * REF_BF16_NOISE.get(name, {}).get(k, 0.0))
-            assert_grad_close_bf16(grads[k], g, tol, f"{name}: grad[{k}]")
+            noise = REF_BF16_NOISE.get(name, {}).get(k)
+            tol = max(rtol, 1.6 * (noise or 0.0))
+            # whole-model case: the per-parameter noise floor is a normwise figure, so only the normwise
+            # criterion is applied there; module / block cases also check the elementwise band
+            assert_grad_close_bf16(grads[k], g, tol, f"{name}: grad[{k}]", elementwise=noise is None)
         else:
             assert_close(grads[k], g, rtol, f"{name}: grad[{k}]", atol=1e-5)
     for k, v in case["buffers_after"].items():
