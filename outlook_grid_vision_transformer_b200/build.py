@@ -58,7 +58,8 @@ def needs_build() -> bool:
 
 def _compile_one(src: str, verbose: bool) -> Path:
     obj = BUILD_DIR / (Path(src).stem + ".o")
-    cmd = [_nvcc(), *NVCC_FLAGS, "-c", str(CSRC / src), "-o", str(obj)]
+    extra = os.environ.get("OGV_NVCC_EXTRA", "").split()  # e.g. -DOGV_EPI_WARPS=16 for A/B measurements
+    cmd = [_nvcc(), *NVCC_FLAGS, *extra, "-c", str(CSRC / src), "-o", str(obj)]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     res = subprocess.run(cmd, capture_output=True, text=True)

@@ -20,7 +20,13 @@ namespace {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;  // 64 bf16 = one 128-byte swizzle row
-constexpr int EPI_WARPS = 16;
+// 16 epilogue warps (4 per scheduler, 96 registers each).  Measured against 8 warps x 168 registers
+// (-DOGV_EPI_WARPS=8, no spills): plain-store GEMMs gain ~8 % with 8, the GELU / saved-derivative epilogues
+// lose ~10 % (they are ALU-bound and want the warps); the sum over the model's shapes is a wash.
+#ifndef OGV_EPI_WARPS
+#define OGV_EPI_WARPS 16
+#endif
+constexpr int EPI_WARPS = OGV_EPI_WARPS;
 constexpr int TC_THREADS = (EPI_WARPS + 2) * 32;
 constexpr int PRODUCER_WARP = EPI_WARPS;
 constexpr int MMA_WARP = EPI_WARPS + 1;
@@ -126,30 +132,6 @@ __device__ __forceinline__ void stage_read_row(const uint8_t* slot, int row, flo
       r[8 * c + 2 * i + 1] = f.y;
     }
   }
-}
-
-// Column sums of a warp's 32 x 32 chunk (lane = row, v[j] = column j): butterfly exchange in which
-// every step halves the columns a lane is responsible for; lane l ends up with the sum of column l.
-__device__ __forceinline__ float warp_colsum32(const float (&v)[32], int lane) {
-  float t[16];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const bool up = lane & 16;
-    const float keep = up ? v[i + 16] : v[i];
-    const float send = up ? v[i] : v[i + 16];
-    t[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-  }
-#pragma unroll
-  for (int off = 8; off >= 1; off >>= 1) {
-#pragma unroll
-    for (int i = 0; i < off; ++i) {
-      const bool up = lane & off;
-      const float keep = up ? t[i + off] : t[i];
-      const float send = up ? t[i] : t[i + off];
-      t[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-    }
-  }
-  return t[0];
 }
 
 template <int BN, typename TO>
@@ -279,7 +261,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else {
     // ------------------------------- epilogue -------------------------------
     const int q = warp & 3;    // TMEM lane quarter this warp may read
-    const int cg = warp >> 2;  // column group: chunks cg, cg+4, ...
+    const int cg = warp >> 2;  // column group: chunks cg, cg + EPI_WARPS/4, ...
     const GemmEpi& e = p.epi;
     uint8_t* my_slots = staging + warp * p.slots * SLOT_BYTES;
     uint64_t* my_ld = ld_bar + 2 * warp;
@@ -296,7 +278,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t t0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
       bool waited = false;
 #pragma unroll 1
-      for (int c = cg; c < BN / CH; c += 4) {
+      for (int c = cg; c < BN / CH; c += EPI_WARPS / 4) {
         const int n0c = n0 + c * CH;
         if (n0c >= p.N) break;
         uint8_t* s0 = nullptr;
@@ -374,19 +356,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] *= rs;
         }
-        if (p.col_stats) {
-          float u[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) u[i] = m < p.M ? round_to<bf16>(v[i]) : 0.f;  // statistics of the STORED values
-          const float cs = warp_colsum32(u, lane);
-          if (n0c + lane < p.N) atomicAdd(&colacc[n0c + lane], cs);
-          if (e.col_sumsq) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) u[i] *= u[i];
-            const float cq = warp_colsum32(u, lane);
-            if (n0c + lane < p.N) atomicAdd(&colacc[p.n_pad + n0c + lane], cq);
-          }
-        }
         stage_write_row(s0, lane, v);
         ptx::fence_proxy_async();
         __syncwarp();
@@ -394,6 +363,37 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           ptx::tma_store_2d(&tmD, s0, n0c, mrow0);
           if (e.pre_out) ptx::tma_store_2d(&tmP, s1, n0c, mrow0);
           ptx::bulk_commit();
+        }
+        if (p.col_stats) {
+          // column statistics of the chunk AS STORED, read back from the staged tile (12 -> 3.5 instructions per
+          // element vs. a register butterfly): lanes 0-15 walk the even rows, lanes 16-31 the odd rows, each
+          // lane owning the column pair (2j, 2j+1); every warp load is two conflict-free 64-byte rows.
+          const int rows_valid = min(32, p.M - mrow0);
+          const int j = lane & 15;
+          float sa = 0.f, sb = 0.f, qa = 0.f, qb = 0.f;
+#pragma unroll 8
+          for (int i = 0; i < 16; ++i) {
+            const int row = 2 * i + (lane >> 4);
+            if (row < rows_valid) {
+              const uint32_t off = row * 64 + (((uint32_t)(j >> 2) ^ ((row >> 1) & 3)) << 4) + (j & 3) * 4;
+              const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(s0 + off));
+              sa += f.x; sb += f.y;
+              qa = fmaf(f.x, f.x, qa); qb = fmaf(f.y, f.y, qb);
+            }
+          }
+          sa += __shfl_xor_sync(0xffffffffu, sa, 16);
+          sb += __shfl_xor_sync(0xffffffffu, sb, 16);
+          qa += __shfl_xor_sync(0xffffffffu, qa, 16);
+          qb += __shfl_xor_sync(0xffffffffu, qb, 16);
+          if (lane < 16) {
+            const int ca = n0c + 2 * j;
+            if (ca < p.N) atomicAdd(&colacc[ca], sa);
+            if (ca + 1 < p.N) atomicAdd(&colacc[ca + 1], sb);
+            if (e.col_sumsq) {
+              if (ca < p.N) atomicAdd(&colacc[p.n_pad + ca], qa);
+              if (ca + 1 < p.N) atomicAdd(&colacc[p.n_pad + ca + 1], qb);
+            }
+          }
         }
       }
       if (!waited) {  // warps without a chunk in this tile still pace themselves on the accumulator

@@ -72,6 +72,15 @@ def main():
         rows.append(dict(kernel=full, ms=ms, GBps=gbs, frac=gbs / hbm, TFLOPs=flops / ms / 1e9))
         print(f"{full:34s} {ms * 1e3:9.1f} us  {gbs:8.1f} GB/s  {100 * gbs / hbm:5.1f}% HBM  {flops / ms / 1e9:7.1f} TF/s", flush=True)
 
+    # box-to-box variation is +-20 %: print this box's raw stream rates next to the kernel numbers
+    n_ref = 1 << 28
+    xr = torch.empty(n_ref, device=dev, dtype=dt)
+    yr = torch.empty(n_ref, device=dev, dtype=dt)
+    ms = timeit(lambda: yr.copy_(xr), 10)
+    print(f"[box] copy (read+write) {2 * n_ref * 2 / ms / 1e6:7.0f} GB/s", end="   ")
+    ms = timeit(lambda: xr.fill_(1.0), 10)
+    print(f"fill (write only) {n_ref * 2 / ms / 1e6:7.0f} GB/s   (MEASURED_PEAKS hbm {hbm:.0f})", flush=True)
+    del xr, yr
     for s in [int(x) for x in a.stages.split(",")]:
         st = STAGES[s]
         C, H, W = st["C"], st["H"], st["H"]
