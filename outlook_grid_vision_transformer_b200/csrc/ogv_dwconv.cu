@@ -388,15 +388,16 @@ dwconv_bwd_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constan
 
     // ---- gradient halo tile: raw (T) -> fp32 (TMA zero fill already handled the borders) ----
     ptx::mbar_wait(&bar[0], it & 1);
+    // 4 elements per thread: 8-byte loads / 16-byte stores with consecutive lanes on consecutive addresses,
+    // both conflict-free (8 elements per thread made every float4 store 2-way bank conflicted)
 #pragma unroll 4
-    for (int i = tid; i < npos * NAV; i += DW_THREADS) {
-      float v[AV];
-      ldv<AV>(graw + i * AV, v);
-#pragma unroll
-      for (int k = 0; k < AV; k += 4)
-        *reinterpret_cast<float4*>(gt + i * AV + k) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
+    for (int i = tid; i < npos * NTV; i += DW_THREADS) {
+      float v[4];
+      ldv<4>(graw + i * 4, v);
+      *reinterpret_cast<float4*>(gt + i * 4) = make_float4(v[0], v[1], v[2], v[3]);
     }
     (void)av;
+    (void)NAV;
     ptx::fence_proxy_async();
     __syncthreads();
     if (tid == 0 && tn < g.ntiles) {

@@ -241,6 +241,361 @@ __global__ void ga_bwd_kernel(const T* __restrict__ qkv, const T* __restrict__ d
   }
 }
 
+// =================================================================================================
+// Tensor-core path (bf16, N <= 16 tokens per group): the thread-per-row kernels above spend 9*N FMAs per
+// element with one shared-memory operand fetch per 4 FMAs -- they are LDS-issue bound, not memory bound.
+// Here a WARP owns 16 query rows (= 16/N whole problems) and runs every contraction as
+// mma.sync.m16n8k16 (bf16 x bf16 -> fp32) on fragments fetched with ldmatrix: S = Q K^T, O = P V, and
+// in backward dP = dO V^T, dQ = dS K, dK = dS^T Q, dV = P^T dO.  Problems smaller than the 16-row tile
+// share it block-diagonally (cross-problem scores are masked to -inf).  P and dS are rounded to bf16
+// before their second contraction, which is what the reference does under autocast.  (tcgen05 needs
+// 64/128-row tiles and TMEM round trips; at N = 4..16 and 0.5-2 % of the model FLOPs the warp-level
+// MMA is the right-sized tensor-core instruction.)
+// =================================================================================================
+constexpr int MA_WARPS = 4;
+
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"((uint32_t)__cvta_generic_to_shared(p)));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"((uint32_t)__cvta_generic_to_shared(p)));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// A fragment of the 16 x 16 tile at (0, k0) of a row-major [16][ld] bf16 array
+__device__ __forceinline__ void frag_a(uint32_t (&a)[4], const bf16* t, int ld, int k0, int lane) {
+  ldsm_x4(a, t + (lane & 15) * ld + k0 + (lane >> 4) * 8);
+}
+// A fragment of X^T for a row-major [16][ld] X (A[m][k] = X[k][m]), 16 x 16
+__device__ __forceinline__ void frag_a_t(uint32_t (&a)[4], const bf16* t, int ld, int lane) {
+  ldsm_x4_t(a, t + ((lane & 7) + (lane >> 4) * 8) * ld + ((lane >> 3) & 1) * 8);
+}
+// B fragments (two n-tiles n0..n0+15) of the k-step k0 for an operand stored [n][k] row-major (e.g. K for Q K^T)
+__device__ __forceinline__ void frag_b_nk(uint32_t (&b)[4], const bf16* t, int ld, int n0, int k0, int lane) {
+  ldsm_x4(b, t + (n0 + (lane & 7) + (lane >> 4) * 8) * ld + k0 + ((lane >> 3) & 1) * 8);
+}
+// B fragments (two n-tiles n0..n0+15) of the k-step k0 for an operand stored [k][n] row-major (e.g. V for P V)
+__device__ __forceinline__ void frag_b_kn(uint32_t (&b)[4], const bf16* t, int ld, int n0, int k0, int lane) {
+  ldsm_x4_t(b, t + (k0 + (lane & 7) + ((lane >> 3) & 1) * 8) * ld + n0 + (lane >> 4) * 8);
+}
+
+struct MaGeom {
+  int B, H, W, C, heads, g, Hg, Wg, N;
+  int P16;           // problems per 16-row tile
+  long long nprob, ntiles;
+  int hd;
+  float scale;
+};
+
+// Row bookkeeping of a tile, computed ONCE per warp: lane l holds the global row index (or -1 past the
+// last problem) and head of tile-row (l & 15); the copy loops fetch them with a shuffle.  32-bit
+// arithmetic (the host checks that problem and row counts fit).
+struct MaRows {
+  int m, head;
+};
+__device__ __forceinline__ MaRows ma_rows(const MaGeom& G, long long t, int lane) {
+  const int r = lane & 15;
+  const int pr = (int)t * G.P16 + r / G.N;
+  MaRows o;
+  o.m = -1;
+  o.head = 0;
+  if (pr < (int)G.nprob) {
+    const int n = r % G.N;
+    o.head = pr % G.heads;
+    const int grp = pr / G.heads;
+    const int gj = grp % G.g;
+    const int gq = grp / G.g;
+    const int gi = gq % G.g;
+    const int b = gq / G.g;
+    o.m = (b * G.H + (n / G.Wg) * G.g + gi) * G.W + (n % G.Wg) * G.g + gj;
+  }
+  return o;
+}
+
+// stage 16 rows x hd columns (zero padded to HDP, zero rows for inactive entries) of a [M, ld] tensor
+template <int HDP>
+__device__ __forceinline__ void ma_load_tile(bf16* __restrict__ dst, const bf16* __restrict__ src, long long ld,
+                                             int col0, const MaGeom& G, const MaRows& R, int lane) {
+  constexpr int LD = HDP + 8;
+  constexpr int CPR = HDP / 8;  // 16-byte chunks per row
+  static_assert((16 * CPR) % 32 == 0, "whole warps of chunks");
+#pragma unroll
+  for (int i0 = 0; i0 < 16 * CPR; i0 += 32) {
+    const int i = i0 + lane;
+    const int r = i / CPR, ch = i - r * CPR;
+    const int m = __shfl_sync(0xffffffffu, R.m, r);
+    const int head = __shfl_sync(0xffffffffu, R.head, r);
+    uint4 u = make_uint4(0u, 0u, 0u, 0u);
+    if (m >= 0 && ch * 8 < G.hd) u = *reinterpret_cast<const uint4*>(src + (long long)m * ld + col0 + head * G.hd + ch * 8);
+    *reinterpret_cast<uint4*>(dst + r * LD + ch * 8) = u;
+  }
+}
+// write 16 rows x hd columns from a staged [16][HDP+8] tile
+template <int HDP>
+__device__ __forceinline__ void ma_store_tile(const bf16* __restrict__ srcT, bf16* __restrict__ dst, long long ld,
+                                              int col0, const MaGeom& G, const MaRows& R, int lane) {
+  constexpr int LD = HDP + 8;
+  constexpr int CPR = HDP / 8;
+#pragma unroll
+  for (int i0 = 0; i0 < 16 * CPR; i0 += 32) {
+    const int i = i0 + lane;
+    const int r = i / CPR, ch = i - r * CPR;
+    const int m = __shfl_sync(0xffffffffu, R.m, r);
+    const int head = __shfl_sync(0xffffffffu, R.head, r);
+    if (m >= 0 && ch * 8 < G.hd)
+      *reinterpret_cast<uint4*>(dst + (long long)m * ld + col0 + head * G.hd + ch * 8) =
+          *reinterpret_cast<const uint4*>(srcT + r * LD + ch * 8);
+  }
+}
+// C fragments (n-tiles of 8 columns) -> staged bf16 tile
+template <int NT>
+__device__ __forceinline__ void ma_frags_to_tile(bf16* tile, int ld, const float (&c)[NT][4], int lane) {
+  const int g = lane >> 2, q = lane & 3;
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+    *reinterpret_cast<uint32_t*>(tile + g * ld + nt * 8 + q * 2) = pack_bf16(c[nt][0], c[nt][1]);
+    *reinterpret_cast<uint32_t*>(tile + (g + 8) * ld + nt * 8 + q * 2) = pack_bf16(c[nt][2], c[nt][3]);
+  }
+}
+
+// S = scale * Q K^T with the block-diagonal mask, then row softmax in place; returns P in s[2][4] (two n-tiles)
+template <int HDP>
+__device__ __forceinline__ void ma_scores_softmax(float (&s)[2][4], const bf16* sQ, const bf16* sK, const MaGeom& G,
+                                                  int lane) {
+  constexpr int LD = HDP + 8;
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) s[nt][i] = 0.f;
+#pragma unroll
+  for (int k0 = 0; k0 < HDP; k0 += 16) {
+    uint32_t a[4], b[4];
+    frag_a(a, sQ, LD, k0, lane);
+    frag_b_nk(b, sK, LD, 0, k0, lane);
+    mma_bf16_16816(s[0], a, b[0], b[1]);
+    mma_bf16_16816(s[1], a, b[2], b[3]);
+  }
+  const int g = lane >> 2, q = lane & 3;
+  // rows g (elements 0,1) and g+8 (elements 2,3); columns nt*8 + q*2 + {0,1}
+  float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int row = g + (i >> 1) * 8, col = nt * 8 + q * 2 + (i & 1);
+      const bool same = ((row ^ col) & ~(G.N - 1)) == 0;  // N is a power of two: same block of N
+      s[nt][i] = same ? s[nt][i] * G.scale : -INFINITY;
+      mx[i >> 1] = fmaxf(mx[i >> 1], s[nt][i]);
+    }
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 1));
+    mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 2));
+  }
+  float sum[2] = {0.f, 0.f};
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      s[nt][i] = __expf(s[nt][i] - mx[i >> 1]);  // exp(-inf) = 0 for masked entries
+      sum[i >> 1] += s[nt][i];
+    }
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    sum[h] += __shfl_xor_sync(0xffffffffu, sum[h], 1);
+    sum[h] += __shfl_xor_sync(0xffffffffu, sum[h], 2);
+    sum[h] = 1.f / sum[h];
+  }
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) s[nt][i] *= sum[i >> 1];
+}
+
+template <int HDP>
+__global__ void __launch_bounds__(MA_WARPS * 32) ma_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out,
+                                                               const MaGeom G) {
+  constexpr int LD = HDP + 8;
+  constexpr int NTO = HDP / 8;
+  __shared__ __align__(16) bf16 smem[MA_WARPS][3][16 * LD];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long t = (long long)blockIdx.x * MA_WARPS + warp;
+  if (t >= G.ntiles) return;
+  bf16* sQ = smem[warp][0];
+  bf16* sK = smem[warp][1];
+  bf16* sV = smem[warp][2];
+  const MaRows R = ma_rows(G, t, lane);
+  ma_load_tile<HDP>(sQ, qkv, 3LL * G.C, 0, G, R, lane);
+  ma_load_tile<HDP>(sK, qkv, 3LL * G.C, G.C, G, R, lane);
+  ma_load_tile<HDP>(sV, qkv, 3LL * G.C, 2 * G.C, G, R, lane);
+  __syncwarp();
+  float p[2][4];
+  ma_scores_softmax<HDP>(p, sQ, sK, G, lane);
+  // O = P V : P (16 x 16) is one k-step; its A fragment comes straight from the score accumulators
+  const uint32_t pa[4] = {pack_bf16(p[0][0], p[0][1]), pack_bf16(p[0][2], p[0][3]), pack_bf16(p[1][0], p[1][1]),
+                          pack_bf16(p[1][2], p[1][3])};
+  float o[NTO][4];
+#pragma unroll
+  for (int nt = 0; nt < NTO; ++nt)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[nt][i] = 0.f;
+#pragma unroll
+  for (int n0 = 0; n0 < HDP; n0 += 16) {
+    uint32_t b[4];
+    frag_b_kn(b, sV, LD, n0, 0, lane);
+    mma_bf16_16816(o[n0 / 8], pa, b[0], b[1]);
+    mma_bf16_16816(o[n0 / 8 + 1], pa, b[2], b[3]);
+  }
+  __syncwarp();  // all lanes are done reading sQ through ldmatrix
+  ma_frags_to_tile<NTO>(sQ, LD, o, lane);
+  __syncwarp();
+  ma_store_tile<HDP>(sQ, out, G.C, 0, G, R, lane);
+}
+
+template <int HDP>
+__global__ void __launch_bounds__(MA_WARPS * 32) ma_bwd_kernel(const bf16* __restrict__ qkv,
+                                                               const bf16* __restrict__ dout,
+                                                               bf16* __restrict__ dqkv, const MaGeom G) {
+  constexpr int LD = HDP + 8;
+  constexpr int NTO = HDP / 8;
+  constexpr int LDP = 24;  // pitch of the 16 x 16 P / dS tiles
+  __shared__ __align__(16) bf16 smem[MA_WARPS][4][16 * LD];
+  __shared__ __align__(16) bf16 smemP[MA_WARPS][2][16 * LDP];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long t = (long long)blockIdx.x * MA_WARPS + warp;
+  if (t >= G.ntiles) return;
+  bf16* sQ = smem[warp][0];
+  bf16* sK = smem[warp][1];
+  bf16* sV = smem[warp][2];
+  bf16* sG = smem[warp][3];
+  bf16* sP = smemP[warp][0];
+  bf16* sS = smemP[warp][1];
+  const MaRows R = ma_rows(G, t, lane);
+  ma_load_tile<HDP>(sQ, qkv, 3LL * G.C, 0, G, R, lane);
+  ma_load_tile<HDP>(sK, qkv, 3LL * G.C, G.C, G, R, lane);
+  ma_load_tile<HDP>(sV, qkv, 3LL * G.C, 2 * G.C, G, R, lane);
+  ma_load_tile<HDP>(sG, dout, G.C, 0, G, R, lane);
+  __syncwarp();
+  float p[2][4];
+  ma_scores_softmax<HDP>(p, sQ, sK, G, lane);
+  // dP = dO V^T
+  float dp[2][4];
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) dp[nt][i] = 0.f;
+#pragma unroll
+  for (int k0 = 0; k0 < HDP; k0 += 16) {
+    uint32_t a[4], b[4];
+    frag_a(a, sG, LD, k0, lane);
+    frag_b_nk(b, sV, LD, 0, k0, lane);
+    mma_bf16_16816(dp[0], a, b[0], b[1]);
+    mma_bf16_16816(dp[1], a, b[2], b[3]);
+  }
+  // D_i = sum_j P_ij dP_ij ;  dS = P (dP - D) * scale   (masked entries have P = 0)
+  float D[2] = {0.f, 0.f};
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) D[i >> 1] = fmaf(p[nt][i], dp[nt][i], D[i >> 1]);
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    D[h] += __shfl_xor_sync(0xffffffffu, D[h], 1);
+    D[h] += __shfl_xor_sync(0xffffffffu, D[h], 2);
+  }
+  float ds[2][4];
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) ds[nt][i] = p[nt][i] * (dp[nt][i] - D[i >> 1]) * G.scale;
+  ma_frags_to_tile<2>(sP, LDP, p, lane);
+  ma_frags_to_tile<2>(sS, LDP, ds, lane);
+  __syncwarp();
+  float acc[NTO][4];
+  // dQ = dS K
+  {
+    const uint32_t a[4] = {pack_bf16(ds[0][0], ds[0][1]), pack_bf16(ds[0][2], ds[0][3]), pack_bf16(ds[1][0], ds[1][1]),
+                           pack_bf16(ds[1][2], ds[1][3])};
+#pragma unroll
+    for (int nt = 0; nt < NTO; ++nt)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
+#pragma unroll
+    for (int n0 = 0; n0 < HDP; n0 += 16) {
+      uint32_t b[4];
+      frag_b_kn(b, sK, LD, n0, 0, lane);
+      mma_bf16_16816(acc[n0 / 8], a, b[0], b[1]);
+      mma_bf16_16816(acc[n0 / 8 + 1], a, b[2], b[3]);
+    }
+  }
+  float acck[NTO][4], accv[NTO][4];
+  {
+    uint32_t at[4], pt[4];
+    frag_a_t(at, sS, LDP, lane);  // dS^T
+    frag_a_t(pt, sP, LDP, lane);  // P^T
+#pragma unroll
+    for (int nt = 0; nt < NTO; ++nt)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { acck[nt][i] = 0.f; accv[nt][i] = 0.f; }
+#pragma unroll
+    for (int n0 = 0; n0 < HDP; n0 += 16) {
+      uint32_t bq[4], bg[4];
+      frag_b_kn(bq, sQ, LD, n0, 0, lane);
+      frag_b_kn(bg, sG, LD, n0, 0, lane);
+      mma_bf16_16816(acck[n0 / 8], at, bq[0], bq[1]);       // dK = dS^T Q
+      mma_bf16_16816(acck[n0 / 8 + 1], at, bq[2], bq[3]);
+      mma_bf16_16816(accv[n0 / 8], pt, bg[0], bg[1]);       // dV = P^T dO
+      mma_bf16_16816(accv[n0 / 8 + 1], pt, bg[2], bg[3]);
+    }
+  }
+  __syncwarp();  // every ldmatrix of the input tiles has completed: reuse them as output staging
+  ma_frags_to_tile<NTO>(sQ, LD, acc, lane);
+  ma_frags_to_tile<NTO>(sK, LD, acck, lane);
+  ma_frags_to_tile<NTO>(sV, LD, accv, lane);
+  __syncwarp();
+  ma_store_tile<HDP>(sQ, dqkv, 3LL * G.C, 0, G, R, lane);
+  ma_store_tile<HDP>(sK, dqkv, 3LL * G.C, G.C, G, R, lane);
+  ma_store_tile<HDP>(sV, dqkv, 3LL * G.C, 2 * G.C, G, R, lane);
+}
+
+// eligibility: bf16, N divides 16, head_dim <= 64 and a multiple of 4 with 16-byte aligned head starts
+bool ma_geom(int B, int H, int W, int C, int heads, int g, int dtype, MaGeom* G, int* hdp) {
+  if (dtype != OGV_BF16) return false;
+  const int Hg = H / g, Wg = W / g, N = Hg * Wg, hd = C / heads;
+  if (N < 1 || N > 16 || (16 % N) != 0) return false;
+  if (hd > 64 || (hd % 8) != 0 || (C % 8) != 0) return false;
+  G->B = B; G->H = H; G->W = W; G->C = C; G->heads = heads; G->g = g; G->Hg = Hg; G->Wg = Wg; G->N = N;
+  G->P16 = 16 / N;
+  G->nprob = (long long)B * g * g * heads;
+  G->ntiles = (G->nprob + G->P16 - 1) / G->P16;
+  G->hd = hd;
+  G->scale = 1.f / sqrtf((float)hd);
+  *hdp = (hd + 15) / 16 * 16;
+  // 32-bit row / problem arithmetic in the kernels
+  return G->nprob + 16 < 0x7fffffffLL && (long long)B * H * W < 0x7fffffffLL;
+}
+
+#define MA_DISPATCH_HDP(hdp, ...)                          \
+  switch (hdp) {                                           \
+    case 16: { constexpr int HDP = 16; __VA_ARGS__; } break; \
+    case 32: { constexpr int HDP = 32; __VA_ARGS__; } break; \
+    case 48: { constexpr int HDP = 48; __VA_ARGS__; } break; \
+    default: { constexpr int HDP = 64; __VA_ARGS__; } break; \
+  }
+
 int ga_geom(int B, int H, int W, int C, int heads, int g, GaGeom* G, int* threads) {
   if (g <= 0 || heads <= 0 || C <= 0 || H <= 0 || W <= 0) { ogv_set_error("grid_attn: non-positive dims"); return OGV_ERR_ARG; }
   if (H % g || W % g) { ogv_set_error("grid_attn: H and W must be divisible by grid_size (H=%d W=%d g=%d)", H, W, g); return OGV_ERR_ARG; }
@@ -310,6 +665,16 @@ extern "C" int ogv_grid_attn_fwd(const void* qkv, void* out, int B, int H, int W
   if (int rc = ga_geom(B, H, W, C, heads, g, &G, &threads)) return rc;
   if (B == 0) return OGV_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  {
+    MaGeom Mg;
+    int hdp;
+    if (ma_geom(B, H, W, C, heads, g, dtype, &Mg, &hdp)) {
+      const unsigned grid = (unsigned)((Mg.ntiles + MA_WARPS - 1) / MA_WARPS);
+      MA_DISPATCH_HDP(hdp, (ma_fwd_kernel<HDP><<<grid, MA_WARPS * 32, 0, st>>>(reinterpret_cast<const bf16*>(qkv),
+                                                                             reinterpret_cast<bf16*>(out), Mg)));
+      return ogv_check_launch("grid_attn_fwd(mma)");
+    }
+  }
   OGV_DISPATCH_DTYPE(dtype, T, GA_DISPATCH_HD(C / heads, return (ga_launch_fwd<T, HD, 0>(qkv, out, nullptr, G, threads, st))));
 }
 
@@ -332,5 +697,16 @@ extern "C" int ogv_grid_attn_bwd(const void* qkv, const void* dout, void* dqkv, 
   if (int rc = ga_geom(B, H, W, C, heads, g, &G, &threads)) return rc;
   if (B == 0) return OGV_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  {
+    MaGeom Mg;
+    int hdp;
+    if (ma_geom(B, H, W, C, heads, g, dtype, &Mg, &hdp)) {
+      const unsigned grid = (unsigned)((Mg.ntiles + MA_WARPS - 1) / MA_WARPS);
+      MA_DISPATCH_HDP(hdp, (ma_bwd_kernel<HDP><<<grid, MA_WARPS * 32, 0, st>>>(
+                               reinterpret_cast<const bf16*>(qkv), reinterpret_cast<const bf16*>(dout),
+                               reinterpret_cast<bf16*>(dqkv), Mg)));
+      return ogv_check_launch("grid_attn_bwd(mma)");
+    }
+  }
   OGV_DISPATCH_DTYPE(dtype, T, GA_DISPATCH_HD(C / heads, return (ga_launch_bwd<T, HD>(qkv, dout, dqkv, G, threads, st))));
 }
