@@ -314,8 +314,31 @@ def run_ours(args):
                 roof = {"bound": "tensor", "achieved": tfs, "peak": peaks["tc"], "unit": "TFLOP/s", "frac": tfs / peaks["tc"]}
             else:
                 roof = {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"]}
-            roof.update({"traffic": None, "kernel": name, "avg_us": per_ms * 1e3, "share_of_ogv_time": k["ms"] / tot,
-                         "peak_source": peaks["src"], "ogv_kernel_ms_per_step": tot / nprof})
+            # DRAM traffic per launch of this kernel from the committed ncu --set full capture (profiles/), if any
+            traffic = None
+            tpath = ROOT / "profiles" / "traffic.json"
+            if tpath.exists():
+                try:
+                    traffic = json.loads(tpath.read_text()).get(name, {}).get("dram_bytes_per_launch")
+                except Exception:
+                    traffic = None
+            # context: a write-only stream on this part tops out well below the copy figure used as `peak`
+            nfill = 1 << 28
+            buf = torch.empty(nfill, device=dev, dtype=torch.bfloat16)
+            for _ in range(3):
+                buf.fill_(1.0)
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            for _ in range(10):
+                buf.fill_(1.0)
+            f1.record()
+            torch.cuda.synchronize()
+            fill_gbs = nfill * 2 * 10 / (f0.elapsed_time(f1) * 1e-3) / 1e9
+            del buf
+            roof.update({"traffic": traffic, "kernel": name, "avg_us": per_ms * 1e3, "share_of_ogv_time": k["ms"] / tot,
+                         "algorithmic_bytes_per_launch": k["bytes"] / k["calls"],
+                         "peak_source": peaks["src"], "ogv_kernel_ms_per_step": tot / nprof,
+                         "hbm_write_only_gbs_this_box": fill_gbs})
             try:
                 outp = ROOT / "gpurun_out"
                 outp.mkdir(exist_ok=True)

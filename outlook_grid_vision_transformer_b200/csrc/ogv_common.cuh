@@ -106,6 +106,12 @@ __device__ __forceinline__ void ldv(const T* p, float (&v)[VEC]) {
     const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
     float2 f0 = __bfloat1622float2(h[0]), f1 = __bfloat1622float2(h[1]);
     v[0] = f0.x; v[1] = f0.y; v[2] = f1.x; v[3] = f1.y;
+  } else if constexpr (VEC == 2 && sizeof(T) == 2) {
+    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p));
+    v[0] = f.x; v[1] = f.y;
+  } else if constexpr (VEC == 2 && sizeof(T) == 4) {
+    const float2 f = *reinterpret_cast<const float2*>(p);
+    v[0] = f.x; v[1] = f.y;
   } else {
 #pragma unroll
     for (int i = 0; i < VEC; ++i) v[i] = ld1(p + i);
@@ -123,6 +129,10 @@ __device__ __forceinline__ void stv(T* p, const float (&v)[VEC]) {
     h[0] = __floats2bfloat162_rn(v[0], v[1]);
     h[1] = __floats2bfloat162_rn(v[2], v[3]);
     *reinterpret_cast<uint2*>(p) = u;
+  } else if constexpr (VEC == 2 && sizeof(T) == 2) {
+    *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(v[0], v[1]);
+  } else if constexpr (VEC == 2 && sizeof(T) == 4) {
+    *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]);
   } else {
 #pragma unroll
     for (int i = 0; i < VEC; ++i) st1(p + i, v[i]);
