@@ -376,7 +376,13 @@ def run_ours(args):
         }
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # Tear-down of a process group whose collectives were captured into a CUDA graph has been seen to
+        # block in destroy_process_group(); every rank has its result out, so synchronise and leave hard.
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():
