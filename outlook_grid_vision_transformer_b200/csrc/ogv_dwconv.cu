@@ -666,11 +666,11 @@ constexpr int dw_cc() { return 64 / (int)sizeof(T); }  // 64-byte channel chunk 
 extern "C" int ogv_dwconv_fwd(const void* e_pre, const float* scale1, const float* shift1, const float* w,
                               void* d_pre, float* sum2, float* sumsq2, int B, int H, int W, int Cm, int act,
                               int dtype, void* stream) {
+  if (B == 0) return OGV_OK;
   OGV_REQUIRE(e_pre && scale1 && shift1 && w && d_pre, "dwconv_fwd: null pointer");
   OGV_REQUIRE(Cm > 0 && Cm % 8 == 0 && H > 0 && W > 0, "dwconv_fwd: channels must be a multiple of 8");
   OGV_REQUIRE((reinterpret_cast<uintptr_t>(e_pre) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_pre) & 15) == 0,
               "dwconv_fwd: tensors must be 16-byte aligned");
-  if (B == 0) return OGV_OK;
   static int variant = -1;  // OGV_DW_FWD=tile selects the TMA-tiled kernel (A/B measurements)
   if (variant < 0) {
     const char* e = getenv("OGV_DW_FWD");
@@ -715,13 +715,13 @@ extern "C" int ogv_dwconv_bwd(const void* dd_pre, const void* e_pre, const float
                               const float* mean1, const float* rstd1, const float* w, void* du1, float* dw,
                               float* dgamma1, float* dbeta1, int B, int H, int W, int Cm, int act, int dtype,
                               void* stream) {
+  if (B == 0) return OGV_OK;
   OGV_REQUIRE(dd_pre && e_pre && scale1 && shift1 && mean1 && rstd1 && w && du1 && dw && dgamma1 && dbeta1,
               "dwconv_bwd: null pointer");
   OGV_REQUIRE(Cm > 0 && Cm % 8 == 0 && H > 0 && W > 0, "dwconv_bwd: channels must be a multiple of 8");
   OGV_REQUIRE((reinterpret_cast<uintptr_t>(dd_pre) & 15) == 0 && (reinterpret_cast<uintptr_t>(e_pre) & 15) == 0 &&
                   (reinterpret_cast<uintptr_t>(du1) & 15) == 0,
               "dwconv_bwd: tensors must be 16-byte aligned");
-  if (B == 0) return OGV_OK;
   OGV_DISPATCH_DTYPE(dtype, T, {
     constexpr int CC = dw_cc<T>();
     const int smem = DW_BUF_POS * CC * (int)(2 * sizeof(T) + sizeof(float)) + 64;

@@ -659,11 +659,11 @@ int ga_launch_bwd(const void* qkv, const void* dout, void* dqkv, const GaGeom& G
 
 extern "C" int ogv_grid_attn_fwd(const void* qkv, void* out, int B, int H, int W, int C, int heads, int g,
                                  int dtype, void* stream) {
+  if (B == 0) return OGV_OK;
   OGV_REQUIRE(qkv && out, "grid_attn_fwd: null pointer");
   GaGeom G;
   int threads;
   if (int rc = ga_geom(B, H, W, C, heads, g, &G, &threads)) return rc;
-  if (B == 0) return OGV_OK;
   cudaStream_t st = (cudaStream_t)stream;
   {
     MaGeom Mg;
@@ -680,22 +680,22 @@ extern "C" int ogv_grid_attn_fwd(const void* qkv, void* out, int B, int H, int W
 
 extern "C" int ogv_grid_attn_probs(const void* qkv, float* attn, int B, int H, int W, int C, int heads, int g,
                                    int dtype, void* stream) {
+  if (B == 0) return OGV_OK;
   OGV_REQUIRE(qkv && attn, "grid_attn_probs: null pointer");
   GaGeom G;
   int threads;
   if (int rc = ga_geom(B, H, W, C, heads, g, &G, &threads)) return rc;
-  if (B == 0) return OGV_OK;
   cudaStream_t st = (cudaStream_t)stream;
   OGV_DISPATCH_DTYPE(dtype, T, GA_DISPATCH_HD(C / heads, return (ga_launch_fwd<T, HD, 1>(qkv, nullptr, attn, G, threads, st))));
 }
 
 extern "C" int ogv_grid_attn_bwd(const void* qkv, const void* dout, void* dqkv, int B, int H, int W, int C,
                                  int heads, int g, int dtype, void* stream) {
+  if (B == 0) return OGV_OK;
   OGV_REQUIRE(qkv && dout && dqkv, "grid_attn_bwd: null pointer");
   GaGeom G;
   int threads;
   if (int rc = ga_geom(B, H, W, C, heads, g, &G, &threads)) return rc;
-  if (B == 0) return OGV_OK;
   cudaStream_t st = (cudaStream_t)stream;
   {
     MaGeom Mg;

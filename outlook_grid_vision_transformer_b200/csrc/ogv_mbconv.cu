@@ -270,8 +270,8 @@ inline int img_row_splits(int B, int nvb, int HW) {
 
 extern "C" int ogv_se_pool(const void* d_pre, const float* scale2, const float* shift2, float* pool, int B, int HW,
                            int Cm, int act, int dtype, void* stream) {
-  OGV_REQUIRE(d_pre && scale2 && shift2 && pool && Cm % 8 == 0 && HW > 0, "se_pool: bad args");
   if (B == 0) return OGV_OK;
+  OGV_REQUIRE(d_pre && scale2 && shift2 && pool && Cm % 8 == 0 && HW > 0, "se_pool: bad args");
   dim3 grid(B, ogv_ceil_div(Cm / 8, 32));
   OGV_DISPATCH_DTYPE(dtype, T, {
     OGV_DISPATCH_ACT(act, ACT, {
@@ -284,8 +284,8 @@ extern "C" int ogv_se_pool(const void* d_pre, const float* scale2, const float* 
 
 extern "C" int ogv_se_bwd_reduce(const void* dd_act, const void* d_pre, const float* scale2, const float* shift2,
                                  float* dgate, int B, int HW, int Cm, int act, int dtype, void* stream) {
-  OGV_REQUIRE(dd_act && d_pre && scale2 && shift2 && dgate && Cm % 8 == 0 && HW > 0, "se_bwd_reduce: bad args");
   if (B == 0) return OGV_OK;
+  OGV_REQUIRE(dd_act && d_pre && scale2 && shift2 && dgate && Cm % 8 == 0 && HW > 0, "se_bwd_reduce: bad args");
   dim3 grid(B, ogv_ceil_div(Cm / 8, 32));
   OGV_DISPATCH_DTYPE(dtype, T, {
     OGV_DISPATCH_ACT(act, ACT, {
@@ -299,9 +299,9 @@ extern "C" int ogv_se_bwd_reduce(const void* dd_act, const void* d_pre, const fl
 extern "C" int ogv_mbconv_bwd_stats(const void* dd_act, const void* d_pre, const float* scale2, const float* shift2,
                                     const float* mean2, const float* rstd2, float* stats, int B, int HW, int Cm,
                                     int act, int dtype, void* stream) {
+  if (B == 0) return OGV_OK;
   OGV_REQUIRE(dd_act && d_pre && scale2 && shift2 && mean2 && rstd2 && stats && Cm % 8 == 0 && HW > 0,
               "mbconv_bwd_stats: bad args");
-  if (B == 0) return OGV_OK;
   dim3 grid(B, ogv_ceil_div(Cm / 8, 32));
   OGV_DISPATCH_DTYPE(dtype, T, {
     OGV_DISPATCH_ACT(act, ACT, {
@@ -315,8 +315,8 @@ extern "C" int ogv_mbconv_bwd_stats(const void* dd_act, const void* d_pre, const
 
 extern "C" int ogv_mbconv_bn2_finalize(const float* stats, const float* gate, const float* dpool, float* dgamma2,
                                        float* dbeta2, int B, int HW, int Cm, void* stream) {
-  OGV_REQUIRE(stats && gate && dpool && dgamma2 && dbeta2 && Cm > 0 && HW > 0, "mbconv_bn2_finalize: bad args");
   if (B == 0) return OGV_OK;
+  OGV_REQUIRE(stats && gate && dpool && dgamma2 && dbeta2 && Cm > 0 && HW > 0, "mbconv_bn2_finalize: bad args");
   mbconv_bn2_finalize_kernel<<<ogv_ceil_div(Cm, 32), dim3(32, 32), 0, (cudaStream_t)stream>>>(
       stats, gate, dpool, dgamma2, dbeta2, B, Cm, 1.f / (float)HW);
   return ogv_check_launch("mbconv_bn2_finalize");
@@ -324,8 +324,8 @@ extern "C" int ogv_mbconv_bn2_finalize(const float* stats, const float* gate, co
 
 extern "C" int ogv_bn_act_gate(const void* d_pre, const float* scale2, const float* shift2, const float* gate,
                                void* d_act, int B, int HW, int Cm, int act, int dtype, void* stream) {
-  OGV_REQUIRE(d_pre && scale2 && shift2 && gate && d_act && Cm % 8 == 0 && HW > 0, "bn_act_gate: bad args");
   if (B == 0) return OGV_OK;
+  OGV_REQUIRE(d_pre && scale2 && shift2 && gate && d_act && Cm % 8 == 0 && HW > 0, "bn_act_gate: bad args");
   const int nvb = ogv_ceil_div(Cm / 8, 32);
   dim3 grid(B, nvb, img_row_splits(B, nvb, HW));
   OGV_DISPATCH_DTYPE(dtype, T, {
@@ -341,11 +341,11 @@ extern "C" int ogv_dw_bn2_bwd_apply(const void* dd_act, const void* d_pre, const
                                     const float* scale2, const float* shift2, const float* mean2, const float* rstd2,
                                     const float* gamma2, const float* dgamma2, const float* dbeta2, void* dd_pre,
                                     int B, int HW, int Cm, int act, int dtype, void* stream) {
+  if (B == 0) return OGV_OK;
   OGV_REQUIRE(dd_act && d_pre && gate && dpool && scale2 && shift2 && mean2 && rstd2 && gamma2 && dgamma2 && dbeta2 &&
                   dd_pre,
               "dw_bn2_bwd_apply: null pointer");
   OGV_REQUIRE(Cm % 8 == 0 && HW > 0, "dw_bn2_bwd_apply: channels must be a multiple of 8");
-  if (B == 0) return OGV_OK;
   const int nvb = ogv_ceil_div(Cm / 8, 32);
   dim3 grid(B, nvb, img_row_splits(B, nvb, HW));
   OGV_DISPATCH_DTYPE(dtype, T, {

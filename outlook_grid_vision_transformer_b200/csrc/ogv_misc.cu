@@ -53,10 +53,10 @@ extern "C" int ogv_gemm(const ogv_gemm_args* args, int engine, void* stream) {
   if (!args) { ogv_set_error("ogv_gemm: null args"); return OGV_ERR_ARG; }
   const ogv_gemm_args& a = *args;
   OGV_REQUIRE(a.M >= 0 && a.N >= 0 && a.K >= 0, "ogv_gemm: negative extent");
+  if (a.M == 0 || a.N == 0) return OGV_OK;  // empty problem: nothing to do (operands may legitimately be null)
   OGV_REQUIRE(a.A && a.B && a.D, "ogv_gemm: null operand");
   OGV_REQUIRE(!(a.split_k > 1 && !a.accumulate), "ogv_gemm: split_k>1 requires accumulate");
   OGV_REQUIRE(!(a.accumulate && a.out_dtype != OGV_F32), "ogv_gemm: accumulate requires fp32 output");
-  if (a.M == 0 || a.N == 0) return OGV_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (engine == OGV_ENGINE_AUTO) {
     static int force_simt = -1;
@@ -275,9 +275,9 @@ extern "C" int ogv_rowscale(const void* x, const float* scale, void* y, long lon
 
 extern "C" int ogv_rowscale_colsum(const void* x, const float* scale, void* y, float* out, long long rows, int cols,
                                    int rows_per_scale, int dtype, void* stream) {
+  if (rows == 0 || cols == 0) return OGV_OK;
   OGV_REQUIRE(x && y && scale && out && cols % 8 == 0 && rows_per_scale > 0, "rowscale_colsum: bad args (cols %% 8 == 0)");
   OGV_REQUIRE(rows < 0x7fffffffLL, "rowscale_colsum: too many rows");
-  if (rows == 0 || cols == 0) return OGV_OK;
   ColReduceCfg cfg;
   if (!colreduce_config(rows, cols / 8, &cfg)) { ogv_set_error("rowscale_colsum: cols=%d too wide", cols); return OGV_ERR_UNSUPPORTED; }
   OGV_DISPATCH_DTYPE(dtype, T, {
@@ -289,8 +289,8 @@ extern "C" int ogv_rowscale_colsum(const void* x, const float* scale, void* y, f
 
 extern "C" int ogv_mul_dact(const void* a, const void* pre, void* out, long long n, int act, int dtype,
                             void* stream) {
-  OGV_REQUIRE(a && pre && out, "mul_dact: null");
   if (n == 0) return OGV_OK;
+  OGV_REQUIRE(a && pre && out, "mul_dact: null");
   int grid = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
   OGV_DISPATCH_DTYPE(dtype, T, {
     mul_dact_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const T*>(a),
@@ -301,8 +301,8 @@ extern "C" int ogv_mul_dact(const void* a, const void* pre, void* out, long long
 }
 
 extern "C" int ogv_add(const void* a, const void* b, void* y, long long n, int dtype, void* stream) {
-  OGV_REQUIRE(a && b && y, "add: null");
   if (n == 0) return OGV_OK;
+  OGV_REQUIRE(a && b && y, "add: null");
   int grid = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
   OGV_DISPATCH_DTYPE(dtype, T, {
     add_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const T*>(a),
@@ -314,8 +314,8 @@ extern "C" int ogv_add(const void* a, const void* b, void* y, long long n, int d
 extern "C" int ogv_adamw(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1,
                          float beta2, float eps, float weight_decay, float bias_c1, float bias_c2, float grad_scale,
                          void* stream) {
-  OGV_REQUIRE(p && g && m && v, "adamw: null");
   if (n == 0) return OGV_OK;
+  OGV_REQUIRE(p && g && m && v, "adamw: null");
   int grid = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
   adamw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bias_c1,
                                                        bias_c2, grad_scale);
@@ -323,8 +323,8 @@ extern "C" int ogv_adamw(float* p, const float* g, float* m, float* v, long long
 }
 
 extern "C" int ogv_colsum(const void* x, long long ld, float* out, long long M, int N, int dtype, void* stream) {
-  OGV_REQUIRE(x && out && N % 8 == 0 && ld % 8 == 0, "colsum: N and ld must be multiples of 8");
   if (M == 0 || N == 0) return OGV_OK;
+  OGV_REQUIRE(x && out && N % 8 == 0 && ld % 8 == 0, "colsum: N and ld must be multiples of 8");
   ColReduceCfg cfg;
   if (!colreduce_config(M, N / 8, &cfg)) { ogv_set_error("colsum: N=%d too wide", N); return OGV_ERR_UNSUPPORTED; }
   OGV_DISPATCH_DTYPE(dtype, T, {
@@ -336,8 +336,8 @@ extern "C" int ogv_colsum(const void* x, long long ld, float* out, long long M, 
 
 extern "C" int ogv_colstats(const void* x, long long ld, float* sum, float* sumsq, long long M, int N, int dtype,
                             void* stream) {
-  OGV_REQUIRE(x && sum && sumsq && N % 8 == 0 && ld % 8 == 0, "colstats: N and ld must be multiples of 8");
   if (M == 0 || N == 0) return OGV_OK;
+  OGV_REQUIRE(x && sum && sumsq && N % 8 == 0 && ld % 8 == 0, "colstats: N and ld must be multiples of 8");
   ColReduceCfg cfg;
   if (!colreduce_config(M, N / 8, &cfg)) { ogv_set_error("colstats: N=%d too wide", N); return OGV_ERR_UNSUPPORTED; }
   OGV_DISPATCH_DTYPE(dtype, T, {

@@ -303,9 +303,9 @@ inline int flat_grid(long long n, int threads) {
 
 extern "C" int ogv_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean,
                                  float* rstd, long long M, int C, float eps, int dtype, void* stream) {
+  if (M == 0) return OGV_OK;
   OGV_REQUIRE(x && gamma && beta && y, "layernorm_fwd: null pointer");
   OGV_REQUIRE(C > 0 && C % 8 == 0 && C <= 1024, "layernorm_fwd: C=%d must be a multiple of 8 and <= 1024", C);
-  if (M == 0) return OGV_OK;
   const int ln_g = C <= 32 ? 4 : (C <= 64 ? 8 : (C <= 128 ? 16 : 32));
   int grid = flat_grid(M * ln_g, 256);
   cudaStream_t st = (cudaStream_t)stream;
@@ -320,9 +320,9 @@ extern "C" int ogv_layernorm_fwd(const void* x, const float* gamma, const float*
 extern "C" int ogv_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean,
                                  const float* rstd, const void* dres, void* dx, float* dgamma, float* dbeta,
                                  long long M, int C, int dtype, void* stream) {
+  if (M == 0) return OGV_OK;
   OGV_REQUIRE(dy && x && gamma && mean && rstd && dx, "layernorm_bwd: null pointer");
   OGV_REQUIRE(C > 0 && C % 8 == 0 && C <= 1024, "layernorm_bwd: C=%d must be a multiple of 8 and <= 1024", C);
-  if (M == 0) return OGV_OK;
   const int ln_g = C <= 32 ? 4 : (C <= 64 ? 8 : (C <= 128 ? 16 : 32));
   long long want = (M * ln_g + 511) / 512;
   long long cap = (long long)ogv_num_sms() * 2;  // few fat CTAs: one dgamma/dbeta atomic flush per CTA  // few CTAs: one dgamma/dbeta flush per CTA
@@ -366,8 +366,8 @@ extern "C" int ogv_bn_apply(const void* x, const float* scale, const float* shif
 
 extern "C" int ogv_bn_bwd_reduce(const void* dy, const void* x, const float* mean, const float* rstd, float* dgamma,
                                  float* dbeta, long long M, int C, int dtype, void* stream) {
-  OGV_REQUIRE(dy && x && mean && rstd && dgamma && dbeta && C % 8 == 0, "bn_bwd_reduce: bad args");
   if (M == 0) return OGV_OK;
+  OGV_REQUIRE(dy && x && mean && rstd && dgamma && dbeta && C % 8 == 0, "bn_bwd_reduce: bad args");
   ColReduceCfg cfg;
   if (!colreduce_config(M, C / 8, &cfg)) { ogv_set_error("bn_bwd_reduce: C=%d too wide", C); return OGV_ERR_UNSUPPORTED; }
   OGV_DISPATCH_DTYPE(dtype, T, {

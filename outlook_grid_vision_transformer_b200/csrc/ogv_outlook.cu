@@ -275,10 +275,10 @@ int ol_optin(K kernel, size_t bytes) {
 
 extern "C" int ogv_outlook_core_fwd(const void* va, long long ld_va, void* y, int B, int H, int W, int C, int heads,
                                     int dtype, void* stream) {
+  if ((long long)B * H * W == 0) return OGV_OK;
   OGV_REQUIRE(va && y, "outlook_core_fwd: null pointer");
   OGV_REQUIRE(heads > 0 && C > 0 && C % heads == 0, "outlook_core_fwd: dim must be divisible by num_heads");
   OGV_REQUIRE(ld_va >= C + 9 * heads, "outlook_core_fwd: ld_va=%lld < C+9*heads", ld_va);
-  if ((long long)B * H * W == 0) return OGV_OK;
   OlGeom g;
   const int vec = pick_vec(C, C / heads, ld_va);
   if (ol_geom(B, H, W, C, heads, ld_va, vec, &g)) { ogv_set_error("outlook_core_fwd: image %dx%d too wide", H, W); return OGV_ERR_UNSUPPORTED; }
@@ -296,10 +296,10 @@ extern "C" int ogv_outlook_core_fwd(const void* va, long long ld_va, void* y, in
 
 extern "C" int ogv_outlook_core_bwd(const void* va, long long ld_va, const void* dy, void* dva, int B, int H, int W,
                                     int C, int heads, int dtype, void* stream) {
+  if ((long long)B * H * W == 0) return OGV_OK;
   OGV_REQUIRE(va && dy && dva, "outlook_core_bwd: null pointer");
   OGV_REQUIRE(heads > 0 && C > 0 && C % heads == 0, "outlook_core_bwd: dim must be divisible by num_heads");
   OGV_REQUIRE(ld_va >= C + 9 * heads, "outlook_core_bwd: ld_va=%lld < C+9*heads", ld_va);
-  if ((long long)B * H * W == 0) return OGV_OK;
   OlGeom g;
   const int vec = pick_vec(C, C / heads, ld_va);
   if (ol_geom(B, H, W, C, heads, ld_va, vec, &g)) { ogv_set_error("outlook_core_bwd: image %dx%d too wide", H, W); return OGV_ERR_UNSUPPORTED; }

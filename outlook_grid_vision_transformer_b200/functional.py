@@ -346,8 +346,12 @@ class MBConvFn(torch.autograd.Function):
         s3 = carve(12 * Cm, C)
         # expand
         e_pre = _empty((M, Cm), x)
-        # BatchNorm batch statistics come out of the GEMM epilogue (no extra pass over the wide tensor)
-        ops.gemm(x, pe.w, e_pre, col_sum=s1[0] if training else None, col_sumsq=s1[1] if training else None)
+        # BN1 batch statistics: a separate streaming pass.  Fusing them into this GEMM's epilogue was measured
+        # SLOWER (358 us vs 192 + 107 us at stage 0): the epilogue warps of a C -> 4C GEMM are its critical path.
+        # (The narrow project GEMM below does take its statistics from the epilogue.)
+        ops.gemm(x, pe.w, e_pre)
+        if training:
+            ops.colstats(e_pre, s1[0], s1[1])
         ops.bn_finalize(s1[0], s1[1], g1, b1, rm1, rv1, s1[2], s1[3], s1[4], s1[5], M, eps, mom, training)
         # depthwise (BN1 + act on load, BN2 statistics on store)
         wdw2 = wdw.detach().reshape(Cm, 9).contiguous()

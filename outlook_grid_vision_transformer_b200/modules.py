@@ -67,15 +67,22 @@ FORCE_PREP = False  # set while a CUDA graph is being captured: the casts must b
 
 
 class _Prep:
-    """Cache of compute-dtype weight copies, invalidated by parameter version / storage / dtype."""
+    """Compute-dtype weight copies (what autocast's weight cast produces).  In training mode they are
+    re-derived on EVERY forward: an optimizer may update the fp32 master weights without touching the
+    tensor version counter (torch's fused AdamW does), so no cache key is trustworthy there -- the casts
+    are a few microseconds per layer.  In eval mode the copies are cached, keyed by storage / version / dtype."""
 
     def __init__(self):
         self._key = None
         self._val = None
 
-    def get(self, params, dtype, build):
+    def get(self, training, params, dtype, build):
+        if training or FORCE_PREP:
+            self._key = None  # the optimizer step that follows makes this copy stale: never reuse it
+            self._val = build()
+            return self._val
         key = (dtype,) + tuple((p.data_ptr(), p._version) if p is not None else None for p in params)
-        if FORCE_PREP or key != self._key:
+        if key != self._key:
             self._val = build()
             self._key = key
         return self._val
@@ -130,8 +137,8 @@ class MLP2d(nn.Module):
         self.drop2 = nn.Dropout(drop)
 
     def _prepared(self, dtype):
-        p1 = _prep_attr(self, "fc1").get([self.fc1.weight], dtype, lambda: OF.prepare_linear(self.fc1.weight, dtype))
-        p2 = _prep_attr(self, "fc2").get([self.fc2.weight], dtype, lambda: OF.prepare_linear(self.fc2.weight, dtype))
+        p1 = _prep_attr(self, "fc1").get(self.training, [self.fc1.weight], dtype, lambda: OF.prepare_linear(self.fc1.weight, dtype))
+        p2 = _prep_attr(self, "fc2").get(self.training, [self.fc2.weight], dtype, lambda: OF.prepare_linear(self.fc2.weight, dtype))
         return p1, p2
 
     def _check_dropout(self):
@@ -181,9 +188,9 @@ class OutlookAttention2d(nn.Module):
 
     def _prepared(self, dtype):
         pva, bva = _prep_attr(self, "va").get(
-            [self.v.weight, self.v.bias, self.attn.weight, self.attn.bias], dtype,
+            self.training, [self.v.weight, self.v.bias, self.attn.weight, self.attn.bias], dtype,
             lambda: OF.prepare_outlook_va(self.v.weight, self.v.bias, self.attn.weight, self.attn.bias, dtype))
-        pp = _prep_attr(self, "proj").get([self.proj.weight], dtype, lambda: OF.prepare_linear(self.proj.weight, dtype))
+        pp = _prep_attr(self, "proj").get(self.training, [self.proj.weight], dtype, lambda: OF.prepare_linear(self.proj.weight, dtype))
         return pva, bva, pp
 
     def rows_forward(self, rows: Tensor, geom: Geom, ln: Optional[nn.LayerNorm], scale: Optional[Tensor],
@@ -355,11 +362,11 @@ class MBConv(nn.Module):
 
     def _prepared(self, dtype):
         we, wp = self.expand[0].weight, self.project[0].weight
-        pe = _prep_attr(self, "expand").get([we], dtype, lambda: OF.prepare_linear(we, dtype))
-        pp = _prep_attr(self, "project").get([wp], dtype, lambda: OF.prepare_linear(wp, dtype))
+        pe = _prep_attr(self, "expand").get(self.training, [we], dtype, lambda: OF.prepare_linear(we, dtype))
+        pp = _prep_attr(self, "project").get(self.training, [wp], dtype, lambda: OF.prepare_linear(wp, dtype))
         w1, w2 = self.se.fc1.weight, self.se.fc2.weight
-        ps1 = _prep_attr(self, "se1").get([w1], dtype, lambda: OF.prepare_linear(w1, dtype))
-        ps2 = _prep_attr(self, "se2").get([w2], dtype, lambda: OF.prepare_linear(w2, dtype))
+        ps1 = _prep_attr(self, "se1").get(self.training, [w1], dtype, lambda: OF.prepare_linear(w1, dtype))
+        ps2 = _prep_attr(self, "se2").get(self.training, [w2], dtype, lambda: OF.prepare_linear(w2, dtype))
         return pe, pp, ps1, ps2
 
     def rows_forward(self, rows: Tensor, geom: Geom) -> Tensor:
@@ -466,8 +473,8 @@ class MultiHeadSelfAttention(nn.Module):
         self.proj_drop = nn.Dropout(cfg.proj_drop)
 
     def _prepared(self, dtype):
-        pq = _prep_attr(self, "qkv").get([self.qkv.weight], dtype, lambda: OF.prepare_linear(self.qkv.weight, dtype))
-        pp = _prep_attr(self, "proj").get([self.proj.weight], dtype, lambda: OF.prepare_linear(self.proj.weight, dtype))
+        pq = _prep_attr(self, "qkv").get(self.training, [self.qkv.weight], dtype, lambda: OF.prepare_linear(self.qkv.weight, dtype))
+        pp = _prep_attr(self, "proj").get(self.training, [self.proj.weight], dtype, lambda: OF.prepare_linear(self.proj.weight, dtype))
         return pq, pp
 
     def _capture(self):

@@ -138,3 +138,20 @@ def test_state_dict_matches_golden_reference_keys():
     model = og.build_model(case["model_cfg"])
     assert list(model.state_dict().keys()) == list(case["state"].keys())
     model.load_state_dict(case["state"], strict=True)
+
+
+def test_weight_copies_are_rebuilt_every_training_forward():
+    """torch's fused AdamW updates parameters without bumping their version counter, so in training mode the
+    compute-dtype weight copies must never come from a cache (regression: stale bf16 weights after opt.step())."""
+    from outlook_grid_vision_transformer_b200.modules import _Prep
+    w = torch.nn.Parameter(torch.zeros(2, 2))
+    calls = []
+    prep = _Prep()
+    build = lambda: calls.append(1) or len(calls)  # noqa: E731
+    assert prep.get(True, [w], torch.bfloat16, build) == 1
+    assert prep.get(True, [w], torch.bfloat16, build) == 2      # training: always fresh
+    assert prep.get(False, [w], torch.bfloat16, build) == 3     # eval: first call after the mode switch rebuilds ...
+    assert prep.get(False, [w], torch.bfloat16, build) == 3     # ... then hits the cache
+    with torch.no_grad():
+        w.add_(1.0)                                             # versioned in-place update invalidates it
+    assert prep.get(False, [w], torch.bfloat16, build) == 4

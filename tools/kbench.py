@@ -144,6 +144,10 @@ def main():
         out_c = torch.empty(M, C, device=dev, dtype=dt)
         run("gemm fc1+gelu (z,h)", s, lambda: ops.gemm(x, w1, h, bias=b1, pre_out=z, act="gelu"), nbytes(x, z, h), 2 * M * Cm * C)
         run("gemm expand (plain)", s, lambda: ops.gemm(x, w1, h), nbytes(x, h), 2 * M * Cm * C)
+        cs, cq = torch.zeros(Cm, **f32), torch.zeros(Cm, **f32)
+        run("gemm expand +colstats", s, lambda: ops.gemm(x, w1, h, col_sum=cs, col_sumsq=cq), nbytes(x, h), 2 * M * Cm * C)
+        run("gemm dgrad mul +colsum", s, lambda: ops.gemm(dy, w1, h, dact_src=z, dact="mul", col_sum=cs), nbytes(dy, z, h), 2 * M * Cm * C)
+        run("gemm fc1+gelu (g',h)", s, lambda: ops.gemm(x, w1, h, bias=b1, pre_out=z, act="gelu", pre_out_grad=True), nbytes(x, z, h), 2 * M * Cm * C)
         run("gemm fc2+res", s, lambda: ops.gemm(wide, w1t, out_c, bias=bC, residual=x), nbytes(wide, x, out_c), 2 * M * Cm * C)
         run("gemm project (plain)", s, lambda: ops.gemm(wide, w1t, out_c), nbytes(wide, out_c), 2 * M * Cm * C)
         run("gemm dgrad fc2 (gelu')", s, lambda: ops.gemm(dy, w1, h, dact_src=z, dact="gelu"), nbytes(dy, z, h), 2 * M * Cm * C)
