@@ -23,19 +23,24 @@ ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 
 from src.Model_A_OutGridNet import MaxOutNet  # noqa: E402
+from src.Model_B_OutGridNet import OutlookerFrontGridNet  # noqa: E402
 from src.stage_config import StageCfg  # noqa: E402
 
 
 def main():
     cases = torch.load(ROOT / "tests" / "golden" / "outgrid_golden.pt", map_location="cpu", weights_only=False)
     out = {}
-    for name in ("model_a_tiny",):
+    for name in ("model_a_tiny", "model_b_tiny_eval"):
         case = cases[name]
         mcfg = case["model_cfg"]
         stages = [StageCfg(**dict(s, drop_path=0.0)) for s in mcfg["stages"]]
-        m = MaxOutNet(num_classes=mcfg["num_classes"], stages=stages, stem_dim=mcfg["stem_dim"], dpr_max=0.0)
+        if str(mcfg.get("type", "model_a")).lower() in ("b", "model_b"):
+            m = OutlookerFrontGridNet(num_classes=mcfg["num_classes"], stages=stages, stem_dim=mcfg["stem_dim"],
+                                      outlooker_front_depth=int(mcfg.get("outlooker_front_depth", 2)), dpr_max=0.0)
+        else:
+            m = MaxOutNet(num_classes=mcfg["num_classes"], stages=stages, stem_dim=mcfg["stem_dim"], dpr_max=0.0)
         m.load_state_dict({k: v.float() if v.is_floating_point() else v for k, v in case["state"].items()}, strict=True)
-        m.train()
+        m.train(bool(case["training"]))
         x = case["x"].float().clone().requires_grad_(True)
         with torch.autocast("cpu", dtype=torch.bfloat16):
             y = m(x)

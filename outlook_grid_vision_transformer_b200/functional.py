@@ -385,8 +385,6 @@ class MBConvFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         meta = ctx.meta
-        if not meta["training"]:
-            raise NotImplementedError("MBConv backward in eval mode (running-statistics BatchNorm) is not implemented")
         (x, e_pre, d_pre, d_act, o_pre, st, pool, s1_pre, s1a, gate_pre, gate, g1, g2, g3, sw1, sw2) = ctx.saved_tensors
         pe: PreparedLinear = meta["pe"]
         ppj: PreparedLinear = meta["pp"]
@@ -412,8 +410,14 @@ class MBConvFn(torch.autograd.Function):
         dWe, dg1, db1, dwdw, dg2, db2, dsw1, dsb1, dsw2, dsb2, dWp, dg3, db3 = sl
         dWe = dWe.view(Cm, C); dsw1 = dsw1.view(Cs, Cm); dsw2 = dsw2.view(Cm, Cs); dWp = dWp.view(C, Cm)
         # BN3 backward
+        # eval mode (running statistics): mean / variance are constants, so the batch-coupling terms of the
+        # BatchNorm backward vanish -- same kernels, zero vectors in place of (dgamma, dbeta) in the apply steps;
+        # the parameter gradients dgamma / dbeta themselves are unchanged.
+        training = meta["training"]
+        zC = None if training else _zeros(C, x)
+        zM = None if training else _zeros(Cm, x)
         ops.bn_bwd_reduce(dy, o_pre, s3[4], s3[5], dg3, db3)
-        do_pre = ops.bn_bwd_apply(dy, o_pre, s3[4], s3[5], g3, dg3, db3)
+        do_pre = ops.bn_bwd_apply(dy, o_pre, s3[4], s3[5], g3, dg3 if training else zC, db3 if training else zC)
         # project backward
         dd_act = _empty((M, Cm), x)
         ops.gemm(do_pre, ppj.wt, dd_act)
@@ -435,11 +439,11 @@ class MBConvFn(torch.autograd.Function):
         ops.wgrad(ds1_pre, pool, dsw1)
         ops.colsum(ds1_pre, dsb1)
         ops.mbconv_bn2_finalize(stats, gate, dpool, dg2, db2, g.B, g.P)
-        dd_pre = ops.dw_bn2_bwd_apply(dd_act, d_pre, gate, dpool, s2[2], s2[3], s2[4], s2[5], g2, dg2, db2, g.B, g.P,
-                                      act)
+        dd_pre = ops.dw_bn2_bwd_apply(dd_act, d_pre, gate, dpool, s2[2], s2[3], s2[4], s2[5], g2,
+                                      dg2 if training else zM, db2 if training else zM, g.B, g.P, act)
         # depthwise backward (+ activation derivative, + BN1 reductions)
         du1 = ops.dwconv_bwd(dd_pre, e_pre, s1[2], s1[3], s1[4], s1[5], ctx.wdw2, dwdw, dg1, db1, g.B, g.H, g.W, act)
-        de_pre = ops.bn_bwd_apply(du1, e_pre, s1[4], s1[5], g1, dg1, db1)
+        de_pre = ops.bn_bwd_apply(du1, e_pre, s1[4], s1[5], g1, dg1 if training else zM, db1 if training else zM)
         # expand backward (+ skip-connection gradient)
         dx = _empty((M, C), x)
         ops.gemm(de_pre, pe.wt, dx, residual=dy if meta["use_res"] else None)
