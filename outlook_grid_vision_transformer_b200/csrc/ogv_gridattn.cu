@@ -253,6 +253,8 @@ __global__ void ga_bwd_kernel(const T* __restrict__ qkv, const T* __restrict__ d
 // MMA is the right-sized tensor-core instruction.)
 // =================================================================================================
 constexpr int MA_WARPS = 4;
+template <typename K>
+int ga_optin(K kernel, size_t bytes);
 
 __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
@@ -301,19 +303,21 @@ struct MaGeom {
 };
 
 // Row bookkeeping of a tile, computed ONCE per warp: lane l holds the global row index (or -1 past the
-// last problem) and head of tile-row (l & 15); the copy loops fetch them with a shuffle.  32-bit
-// arithmetic (the host checks that problem and row counts fit).
+// last problem) and head of tile-row (l & 15); the copy loops fetch them with a shuffle.  Tile rows are
+// numbered problem-major: row gr = t*16 + r belongs to problem gr / N, token gr % N (for N < 16 a tile
+// holds 16/N whole problems, for N = 16*WP a problem spans WP consecutive tiles).  32-bit arithmetic
+// (the host checks that problem and row counts fit).
 struct MaRows {
   int m, head;
 };
 __device__ __forceinline__ MaRows ma_rows(const MaGeom& G, long long t, int lane) {
-  const int r = lane & 15;
-  const int pr = (int)t * G.P16 + r / G.N;
+  const int gr = (int)t * 16 + (lane & 15);
+  const int pr = gr / G.N;
   MaRows o;
   o.m = -1;
   o.head = 0;
   if (pr < (int)G.nprob) {
-    const int n = r % G.N;
+    const int n = gr - pr * G.N;
     o.head = pr % G.heads;
     const int grp = pr / G.heads;
     const int gj = grp % G.g;
@@ -371,32 +375,37 @@ __device__ __forceinline__ void ma_frags_to_tile(bf16* tile, int ld, const float
   }
 }
 
-// S = scale * Q K^T with the block-diagonal mask, then row softmax in place; returns P in s[2][4] (two n-tiles)
-template <int HDP>
-__device__ __forceinline__ void ma_scores_softmax(float (&s)[2][4], const bf16* sQ, const bf16* sK, const MaGeom& G,
+// S = scale * Q K^T for this warp's 16 query rows against NKT key tiles (8 keys each), masked
+// block-diagonally when several problems share the tile (N < 16), then row softmax in place -> P.
+template <int HDP, int NKT>
+__device__ __forceinline__ void ma_scores_softmax(float (&s)[NKT][4], const bf16* sQ, const bf16* sK, const MaGeom& G,
                                                   int lane) {
   constexpr int LD = HDP + 8;
 #pragma unroll
-  for (int nt = 0; nt < 2; ++nt)
+  for (int nt = 0; nt < NKT; ++nt)
 #pragma unroll
     for (int i = 0; i < 4; ++i) s[nt][i] = 0.f;
 #pragma unroll
   for (int k0 = 0; k0 < HDP; k0 += 16) {
-    uint32_t a[4], b[4];
+    uint32_t a[4];
     frag_a(a, sQ, LD, k0, lane);
-    frag_b_nk(b, sK, LD, 0, k0, lane);
-    mma_bf16_16816(s[0], a, b[0], b[1]);
-    mma_bf16_16816(s[1], a, b[2], b[3]);
+#pragma unroll
+    for (int n2 = 0; n2 < NKT / 2; ++n2) {
+      uint32_t b[4];
+      frag_b_nk(b, sK, LD, n2 * 16, k0, lane);
+      mma_bf16_16816(s[2 * n2], a, b[0], b[1]);
+      mma_bf16_16816(s[2 * n2 + 1], a, b[2], b[3]);
+    }
   }
   const int g = lane >> 2, q = lane & 3;
   // rows g (elements 0,1) and g+8 (elements 2,3); columns nt*8 + q*2 + {0,1}
   float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
-  for (int nt = 0; nt < 2; ++nt)
+  for (int nt = 0; nt < NKT; ++nt)
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int row = g + (i >> 1) * 8, col = nt * 8 + q * 2 + (i & 1);
-      const bool same = ((row ^ col) & ~(G.N - 1)) == 0;  // N is a power of two: same block of N
+      const bool same = NKT > 2 || ((row ^ col) & ~(G.N - 1)) == 0;  // N < 16 is a power of two: same block of N
       s[nt][i] = same ? s[nt][i] * G.scale : -INFINITY;
       mx[i >> 1] = fmaxf(mx[i >> 1], s[nt][i]);
     }
@@ -407,7 +416,7 @@ __device__ __forceinline__ void ma_scores_softmax(float (&s)[2][4], const bf16* 
   }
   float sum[2] = {0.f, 0.f};
 #pragma unroll
-  for (int nt = 0; nt < 2; ++nt)
+  for (int nt = 0; nt < NKT; ++nt)
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       s[nt][i] = __expf(s[nt][i] - mx[i >> 1]);  // exp(-inf) = 0 for masked entries
@@ -420,172 +429,213 @@ __device__ __forceinline__ void ma_scores_softmax(float (&s)[2][4], const bf16* 
     sum[h] = 1.f / sum[h];
   }
 #pragma unroll
-  for (int nt = 0; nt < 2; ++nt)
+  for (int nt = 0; nt < NKT; ++nt)
 #pragma unroll
     for (int i = 0; i < 4; ++i) s[nt][i] *= sum[i >> 1];
 }
 
-template <int HDP>
+// acc[16 x HDP] += A[16 x 16*KS] * X[16*KS x HDP], A given as accumulator-layout fragments c[2*KS][4] (rounded to
+// bf16), X stored row-major [k][n] in shared memory
+template <int HDP, int NKT>
+__device__ __forceinline__ void ma_mm_frag_kn(float (&acc)[HDP / 8][4], const float (&c)[NKT][4], const bf16* sX,
+                                              int lane) {
+  constexpr int LD = HDP + 8;
+#pragma unroll
+  for (int ks = 0; ks < NKT / 2; ++ks) {
+    const uint32_t a[4] = {pack_bf16(c[2 * ks][0], c[2 * ks][1]), pack_bf16(c[2 * ks][2], c[2 * ks][3]),
+                           pack_bf16(c[2 * ks + 1][0], c[2 * ks + 1][1]), pack_bf16(c[2 * ks + 1][2], c[2 * ks + 1][3])};
+#pragma unroll
+    for (int n0 = 0; n0 < HDP; n0 += 16) {
+      uint32_t b[4];
+      frag_b_kn(b, sX, LD, n0, ks * 16, lane);
+      mma_bf16_16816(acc[n0 / 8], a, b[0], b[1]);
+      mma_bf16_16816(acc[n0 / 8 + 1], a, b[2], b[3]);
+    }
+  }
+}
+
+// Shared memory of a CTA: 4 tiles of 16 rows each for Q | K | V (| dO), indexed by warp; a problem with
+// N = 16*WP tokens owns WP consecutive, WP-aligned tiles, so its K / V rows are contiguous.
+template <int HDP, int NKT>
 __global__ void __launch_bounds__(MA_WARPS * 32) ma_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out,
                                                                const MaGeom G) {
   constexpr int LD = HDP + 8;
   constexpr int NTO = HDP / 8;
-  __shared__ __align__(16) bf16 smem[MA_WARPS][3][16 * LD];
+  constexpr int WP = NKT / 2;  // warps (16-row tiles) per problem
+  extern __shared__ __align__(16) uint8_t ma_sm[];
+  bf16* const base = reinterpret_cast<bf16*>(ma_sm);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long t = (long long)blockIdx.x * MA_WARPS + warp;
-  if (t >= G.ntiles) return;
-  bf16* sQ = smem[warp][0];
-  bf16* sK = smem[warp][1];
-  bf16* sV = smem[warp][2];
-  const MaRows R = ma_rows(G, t, lane);
-  ma_load_tile<HDP>(sQ, qkv, 3LL * G.C, 0, G, R, lane);
-  ma_load_tile<HDP>(sK, qkv, 3LL * G.C, G.C, G, R, lane);
-  ma_load_tile<HDP>(sV, qkv, 3LL * G.C, 2 * G.C, G, R, lane);
-  __syncwarp();
-  float p[2][4];
-  ma_scores_softmax<HDP>(p, sQ, sK, G, lane);
-  // O = P V : P (16 x 16) is one k-step; its A fragment comes straight from the score accumulators
-  const uint32_t pa[4] = {pack_bf16(p[0][0], p[0][1]), pack_bf16(p[0][2], p[0][3]), pack_bf16(p[1][0], p[1][1]),
-                          pack_bf16(p[1][2], p[1][3])};
+  const bool active = t < G.ntiles;
+  bf16* sQ = base + (0 * MA_WARPS + warp) * 16 * LD;
+  bf16* sK = base + (1 * MA_WARPS + (warp / WP) * WP) * 16 * LD;  // first key row of this warp's problem
+  bf16* sV = base + (2 * MA_WARPS + (warp / WP) * WP) * 16 * LD;
+  MaRows R;
+  R.m = -1; R.head = 0;
+  if (active) {
+    R = ma_rows(G, t, lane);
+    ma_load_tile<HDP>(sQ, qkv, 3LL * G.C, 0, G, R, lane);
+    ma_load_tile<HDP>(base + (1 * MA_WARPS + warp) * 16 * LD, qkv, 3LL * G.C, G.C, G, R, lane);
+    ma_load_tile<HDP>(base + (2 * MA_WARPS + warp) * 16 * LD, qkv, 3LL * G.C, 2 * G.C, G, R, lane);
+  }
+  if (WP > 1) __syncthreads(); else __syncwarp();
+  if (!active) return;
+  float p[NKT][4];
+  ma_scores_softmax<HDP, NKT>(p, sQ, sK, G, lane);
   float o[NTO][4];
 #pragma unroll
   for (int nt = 0; nt < NTO; ++nt)
 #pragma unroll
     for (int i = 0; i < 4; ++i) o[nt][i] = 0.f;
-#pragma unroll
-  for (int n0 = 0; n0 < HDP; n0 += 16) {
-    uint32_t b[4];
-    frag_b_kn(b, sV, LD, n0, 0, lane);
-    mma_bf16_16816(o[n0 / 8], pa, b[0], b[1]);
-    mma_bf16_16816(o[n0 / 8 + 1], pa, b[2], b[3]);
-  }
-  __syncwarp();  // all lanes are done reading sQ through ldmatrix
+  ma_mm_frag_kn<HDP, NKT>(o, p, sV, lane);  // O = P V
+  __syncwarp();  // all lanes are done reading sQ through ldmatrix (only this warp reads its Q tile)
   ma_frags_to_tile<NTO>(sQ, LD, o, lane);
   __syncwarp();
   ma_store_tile<HDP>(sQ, out, G.C, 0, G, R, lane);
 }
 
-template <int HDP>
+template <int HDP, int NKT>
 __global__ void __launch_bounds__(MA_WARPS * 32) ma_bwd_kernel(const bf16* __restrict__ qkv,
                                                                const bf16* __restrict__ dout,
                                                                bf16* __restrict__ dqkv, const MaGeom G) {
   constexpr int LD = HDP + 8;
   constexpr int NTO = HDP / 8;
-  constexpr int LDP = 24;  // pitch of the 16 x 16 P / dS tiles
-  __shared__ __align__(16) bf16 smem[MA_WARPS][4][16 * LD];
-  __shared__ __align__(16) bf16 smemP[MA_WARPS][2][16 * LDP];
+  constexpr int WP = NKT / 2;
+  constexpr int LDP = NKT * 8 + 8;  // pitch of the P / dS tiles ([16 query rows][keys of the problem])
+  extern __shared__ __align__(16) uint8_t ma_sm[];
+  bf16* const base = reinterpret_cast<bf16*>(ma_sm);
+  bf16* const baseP = base + 4 * MA_WARPS * 16 * LD;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long t = (long long)blockIdx.x * MA_WARPS + warp;
-  if (t >= G.ntiles) return;
-  bf16* sQ = smem[warp][0];
-  bf16* sK = smem[warp][1];
-  bf16* sV = smem[warp][2];
-  bf16* sG = smem[warp][3];
-  bf16* sP = smemP[warp][0];
-  bf16* sS = smemP[warp][1];
-  const MaRows R = ma_rows(G, t, lane);
-  ma_load_tile<HDP>(sQ, qkv, 3LL * G.C, 0, G, R, lane);
-  ma_load_tile<HDP>(sK, qkv, 3LL * G.C, G.C, G, R, lane);
-  ma_load_tile<HDP>(sV, qkv, 3LL * G.C, 2 * G.C, G, R, lane);
-  ma_load_tile<HDP>(sG, dout, G.C, 0, G, R, lane);
-  __syncwarp();
-  float p[2][4];
-  ma_scores_softmax<HDP>(p, sQ, sK, G, lane);
-  // dP = dO V^T
-  float dp[2][4];
-#pragma unroll
-  for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-    for (int i = 0; i < 4; ++i) dp[nt][i] = 0.f;
-#pragma unroll
-  for (int k0 = 0; k0 < HDP; k0 += 16) {
-    uint32_t a[4], b[4];
-    frag_a(a, sG, LD, k0, lane);
-    frag_b_nk(b, sV, LD, 0, k0, lane);
-    mma_bf16_16816(dp[0], a, b[0], b[1]);
-    mma_bf16_16816(dp[1], a, b[2], b[3]);
+  const bool active = t < G.ntiles;
+  const int w0 = (warp / WP) * WP;  // first tile of this warp's problem
+  const int sb = warp - w0;         // this warp's 16-row block inside the problem
+  bf16* sQ = base + (0 * MA_WARPS + warp) * 16 * LD;
+  bf16* sKo = base + (1 * MA_WARPS + warp) * 16 * LD;  // own tiles (loads / output staging)
+  bf16* sVo = base + (2 * MA_WARPS + warp) * 16 * LD;
+  bf16* sG = base + (3 * MA_WARPS + warp) * 16 * LD;
+  bf16* sQp = base + (0 * MA_WARPS + w0) * 16 * LD;    // whole problem (N rows)
+  bf16* sKp = base + (1 * MA_WARPS + w0) * 16 * LD;
+  bf16* sVp = base + (2 * MA_WARPS + w0) * 16 * LD;
+  bf16* sGp = base + (3 * MA_WARPS + w0) * 16 * LD;
+  bf16* sP = baseP + (0 * MA_WARPS + warp) * 16 * LDP;  // own query rows
+  bf16* sS = baseP + (1 * MA_WARPS + warp) * 16 * LDP;
+  bf16* sPp = baseP + (0 * MA_WARPS + w0) * 16 * LDP;   // whole problem
+  bf16* sSp = baseP + (1 * MA_WARPS + w0) * 16 * LDP;
+  MaRows R;
+  R.m = -1; R.head = 0;
+  if (active) {
+    R = ma_rows(G, t, lane);
+    ma_load_tile<HDP>(sQ, qkv, 3LL * G.C, 0, G, R, lane);
+    ma_load_tile<HDP>(sKo, qkv, 3LL * G.C, G.C, G, R, lane);
+    ma_load_tile<HDP>(sVo, qkv, 3LL * G.C, 2 * G.C, G, R, lane);
+    ma_load_tile<HDP>(sG, dout, G.C, 0, G, R, lane);
   }
-  // D_i = sum_j P_ij dP_ij ;  dS = P (dP - D) * scale   (masked entries have P = 0)
-  float D[2] = {0.f, 0.f};
-#pragma unroll
-  for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-    for (int i = 0; i < 4; ++i) D[i >> 1] = fmaf(p[nt][i], dp[nt][i], D[i >> 1]);
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    D[h] += __shfl_xor_sync(0xffffffffu, D[h], 1);
-    D[h] += __shfl_xor_sync(0xffffffffu, D[h], 2);
-  }
-  float ds[2][4];
-#pragma unroll
-  for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-    for (int i = 0; i < 4; ++i) ds[nt][i] = p[nt][i] * (dp[nt][i] - D[i >> 1]) * G.scale;
-  ma_frags_to_tile<2>(sP, LDP, p, lane);
-  ma_frags_to_tile<2>(sS, LDP, ds, lane);
-  __syncwarp();
+  if (WP > 1) __syncthreads(); else __syncwarp();
   float acc[NTO][4];
-  // dQ = dS K
-  {
-    const uint32_t a[4] = {pack_bf16(ds[0][0], ds[0][1]), pack_bf16(ds[0][2], ds[0][3]), pack_bf16(ds[1][0], ds[1][1]),
-                           pack_bf16(ds[1][2], ds[1][3])};
+  if (active) {
+    // ---- query role: P, dP, dS for this warp's 16 query rows against all keys of the problem ----
+    float p[NKT][4];
+    ma_scores_softmax<HDP, NKT>(p, sQ, sKp, G, lane);
+    float dp[NKT][4];
+#pragma unroll
+    for (int nt = 0; nt < NKT; ++nt)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) dp[nt][i] = 0.f;
+#pragma unroll
+    for (int k0 = 0; k0 < HDP; k0 += 16) {  // dP = dO V^T
+      uint32_t a[4];
+      frag_a(a, sG, LD, k0, lane);
+#pragma unroll
+      for (int n2 = 0; n2 < NKT / 2; ++n2) {
+        uint32_t b[4];
+        frag_b_nk(b, sVp, LD, n2 * 16, k0, lane);
+        mma_bf16_16816(dp[2 * n2], a, b[0], b[1]);
+        mma_bf16_16816(dp[2 * n2 + 1], a, b[2], b[3]);
+      }
+    }
+    // D_i = sum_j P_ij dP_ij ;  dS = P (dP - D) * scale   (masked entries have P = 0)
+    float D[2] = {0.f, 0.f};
+#pragma unroll
+    for (int nt = 0; nt < NKT; ++nt)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) D[i >> 1] = fmaf(p[nt][i], dp[nt][i], D[i >> 1]);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      D[h] += __shfl_xor_sync(0xffffffffu, D[h], 1);
+      D[h] += __shfl_xor_sync(0xffffffffu, D[h], 2);
+    }
+#pragma unroll
+    for (int nt = 0; nt < NKT; ++nt)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) dp[nt][i] = p[nt][i] * (dp[nt][i] - D[i >> 1]) * G.scale;  // dp now holds dS
+    ma_frags_to_tile<NKT>(sP, LDP, p, lane);
+    ma_frags_to_tile<NKT>(sS, LDP, dp, lane);
 #pragma unroll
     for (int nt = 0; nt < NTO; ++nt)
 #pragma unroll
       for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
-#pragma unroll
-    for (int n0 = 0; n0 < HDP; n0 += 16) {
-      uint32_t b[4];
-      frag_b_kn(b, sK, LD, n0, 0, lane);
-      mma_bf16_16816(acc[n0 / 8], a, b[0], b[1]);
-      mma_bf16_16816(acc[n0 / 8 + 1], a, b[2], b[3]);
-    }
+    ma_mm_frag_kn<HDP, NKT>(acc, dp, sKp, lane);  // dQ = dS K
   }
+  if (WP > 1) __syncthreads(); else __syncwarp();  // P / dS of every query block of the problem are staged
   float acck[NTO][4], accv[NTO][4];
-  {
-    uint32_t at[4], pt[4];
-    frag_a_t(at, sS, LDP, lane);  // dS^T
-    frag_a_t(pt, sP, LDP, lane);  // P^T
+  if (active) {
+    // ---- key role: this warp's 16 keys against all query rows of the problem ----
 #pragma unroll
     for (int nt = 0; nt < NTO; ++nt)
 #pragma unroll
       for (int i = 0; i < 4; ++i) { acck[nt][i] = 0.f; accv[nt][i] = 0.f; }
 #pragma unroll
-    for (int n0 = 0; n0 < HDP; n0 += 16) {
-      uint32_t bq[4], bg[4];
-      frag_b_kn(bq, sQ, LD, n0, 0, lane);
-      frag_b_kn(bg, sG, LD, n0, 0, lane);
-      mma_bf16_16816(acck[n0 / 8], at, bq[0], bq[1]);       // dK = dS^T Q
-      mma_bf16_16816(acck[n0 / 8 + 1], at, bq[2], bq[3]);
-      mma_bf16_16816(accv[n0 / 8], pt, bg[0], bg[1]);       // dV = P^T dO
-      mma_bf16_16816(accv[n0 / 8 + 1], pt, bg[2], bg[3]);
+    for (int qb = 0; qb < WP; ++qb) {  // query block qb: rows [16 qb, 16 qb + 16) of the problem
+      uint32_t at[4], pt[4];
+      frag_a_t(at, sSp + qb * 16 * LDP + sb * 16, LDP, lane);  // (dS^T)[own keys][query block]
+      frag_a_t(pt, sPp + qb * 16 * LDP + sb * 16, LDP, lane);  // (P^T)
+#pragma unroll
+      for (int n0 = 0; n0 < HDP; n0 += 16) {
+        uint32_t bq[4], bg[4];
+        frag_b_kn(bq, sQp, LD, n0, qb * 16, lane);
+        frag_b_kn(bg, sGp, LD, n0, qb * 16, lane);
+        mma_bf16_16816(acck[n0 / 8], at, bq[0], bq[1]);      // dK = dS^T Q
+        mma_bf16_16816(acck[n0 / 8 + 1], at, bq[2], bq[3]);
+        mma_bf16_16816(accv[n0 / 8], pt, bg[0], bg[1]);      // dV = P^T dO
+        mma_bf16_16816(accv[n0 / 8 + 1], pt, bg[2], bg[3]);
+      }
     }
   }
-  __syncwarp();  // every ldmatrix of the input tiles has completed: reuse them as output staging
+  if (WP > 1) __syncthreads(); else __syncwarp();  // every ldmatrix of the input tiles has completed: reuse them
+  if (!active) return;
   ma_frags_to_tile<NTO>(sQ, LD, acc, lane);
-  ma_frags_to_tile<NTO>(sK, LD, acck, lane);
-  ma_frags_to_tile<NTO>(sV, LD, accv, lane);
+  ma_frags_to_tile<NTO>(sKo, LD, acck, lane);
+  ma_frags_to_tile<NTO>(sVo, LD, accv, lane);
   __syncwarp();
   ma_store_tile<HDP>(sQ, dqkv, 3LL * G.C, 0, G, R, lane);
-  ma_store_tile<HDP>(sK, dqkv, 3LL * G.C, G.C, G, R, lane);
-  ma_store_tile<HDP>(sV, dqkv, 3LL * G.C, 2 * G.C, G, R, lane);
+  ma_store_tile<HDP>(sKo, dqkv, 3LL * G.C, G.C, G, R, lane);
+  ma_store_tile<HDP>(sVo, dqkv, 3LL * G.C, 2 * G.C, G, R, lane);
 }
 
-// eligibility: bf16, N divides 16, head_dim <= 64 and a multiple of 4 with 16-byte aligned head starts
-bool ma_geom(int B, int H, int W, int C, int heads, int g, int dtype, MaGeom* G, int* hdp) {
+// eligibility: bf16; N divides 16, or N in {32, 64}; head_dim <= 64, a multiple of 8
+bool ma_geom(int B, int H, int W, int C, int heads, int g, int dtype, MaGeom* G, int* hdp, int* nkt) {
   if (dtype != OGV_BF16) return false;
   const int Hg = H / g, Wg = W / g, N = Hg * Wg, hd = C / heads;
-  if (N < 1 || N > 16 || (16 % N) != 0) return false;
+  if (N < 1) return false;
+  if (N <= 16) {
+    if ((16 % N) != 0) return false;
+    *nkt = 2;
+  } else if (N == 32 || N == 64) {
+    *nkt = N / 8;
+  } else {
+    return false;
+  }
   if (hd > 64 || (hd % 8) != 0 || (C % 8) != 0) return false;
   G->B = B; G->H = H; G->W = W; G->C = C; G->heads = heads; G->g = g; G->Hg = Hg; G->Wg = Wg; G->N = N;
-  G->P16 = 16 / N;
+  G->P16 = N <= 16 ? 16 / N : 1;
   G->nprob = (long long)B * g * g * heads;
-  G->ntiles = (G->nprob + G->P16 - 1) / G->P16;
+  G->ntiles = N <= 16 ? (G->nprob + G->P16 - 1) / G->P16 : G->nprob * (N / 16);
   G->hd = hd;
   G->scale = 1.f / sqrtf((float)hd);
   *hdp = (hd + 15) / 16 * 16;
   // 32-bit row / problem arithmetic in the kernels
-  return G->nprob + 16 < 0x7fffffffLL && (long long)B * H * W < 0x7fffffffLL;
+  return G->ntiles * 16 + 16 < 0x7fffffffLL && (long long)B * H * W < 0x7fffffffLL;
 }
 
 #define MA_DISPATCH_HDP(hdp, ...)                          \
@@ -595,6 +645,32 @@ bool ma_geom(int B, int H, int W, int C, int heads, int g, int dtype, MaGeom* G,
     case 48: { constexpr int HDP = 48; __VA_ARGS__; } break; \
     default: { constexpr int HDP = 64; __VA_ARGS__; } break; \
   }
+#define MA_DISPATCH_NKT(nkt, ...)                          \
+  switch (nkt) {                                           \
+    case 2: { constexpr int NKT = 2; __VA_ARGS__; } break; \
+    case 4: { constexpr int NKT = 4; __VA_ARGS__; } break; \
+    default: { constexpr int NKT = 8; __VA_ARGS__; } break; \
+  }
+
+template <int HDP, int NKT>
+int ma_launch_fwd(const void* qkv, void* out, const MaGeom& Mg, cudaStream_t st) {
+  const size_t smem = (size_t)3 * MA_WARPS * 16 * (HDP + 8) * sizeof(bf16);
+  if (int rc = ga_optin(ma_fwd_kernel<HDP, NKT>, smem)) return rc;
+  const unsigned grid = (unsigned)((Mg.ntiles + MA_WARPS - 1) / MA_WARPS);
+  ma_fwd_kernel<HDP, NKT><<<grid, MA_WARPS * 32, smem, st>>>(reinterpret_cast<const bf16*>(qkv),
+                                                            reinterpret_cast<bf16*>(out), Mg);
+  return ogv_check_launch("grid_attn_fwd(mma)");
+}
+template <int HDP, int NKT>
+int ma_launch_bwd(const void* qkv, const void* dout, void* dqkv, const MaGeom& Mg, cudaStream_t st) {
+  const size_t smem = ((size_t)4 * MA_WARPS * 16 * (HDP + 8) + (size_t)2 * MA_WARPS * 16 * (NKT * 8 + 8)) * sizeof(bf16);
+  if (int rc = ga_optin(ma_bwd_kernel<HDP, NKT>, smem)) return rc;
+  const unsigned grid = (unsigned)((Mg.ntiles + MA_WARPS - 1) / MA_WARPS);
+  ma_bwd_kernel<HDP, NKT><<<grid, MA_WARPS * 32, smem, st>>>(reinterpret_cast<const bf16*>(qkv),
+                                                            reinterpret_cast<const bf16*>(dout),
+                                                            reinterpret_cast<bf16*>(dqkv), Mg);
+  return ogv_check_launch("grid_attn_bwd(mma)");
+}
 
 int ga_geom(int B, int H, int W, int C, int heads, int g, GaGeom* G, int* threads) {
   if (g <= 0 || heads <= 0 || C <= 0 || H <= 0 || W <= 0) { ogv_set_error("grid_attn: non-positive dims"); return OGV_ERR_ARG; }
@@ -667,12 +743,9 @@ extern "C" int ogv_grid_attn_fwd(const void* qkv, void* out, int B, int H, int W
   cudaStream_t st = (cudaStream_t)stream;
   {
     MaGeom Mg;
-    int hdp;
-    if (ma_geom(B, H, W, C, heads, g, dtype, &Mg, &hdp)) {
-      const unsigned grid = (unsigned)((Mg.ntiles + MA_WARPS - 1) / MA_WARPS);
-      MA_DISPATCH_HDP(hdp, (ma_fwd_kernel<HDP><<<grid, MA_WARPS * 32, 0, st>>>(reinterpret_cast<const bf16*>(qkv),
-                                                                             reinterpret_cast<bf16*>(out), Mg)));
-      return ogv_check_launch("grid_attn_fwd(mma)");
+    int hdp, nkt;
+    if (ma_geom(B, H, W, C, heads, g, dtype, &Mg, &hdp, &nkt)) {
+      MA_DISPATCH_HDP(hdp, MA_DISPATCH_NKT(nkt, return (ma_launch_fwd<HDP, NKT>(qkv, out, Mg, st))));
     }
   }
   OGV_DISPATCH_DTYPE(dtype, T, GA_DISPATCH_HD(C / heads, return (ga_launch_fwd<T, HD, 0>(qkv, out, nullptr, G, threads, st))));
@@ -699,13 +772,9 @@ extern "C" int ogv_grid_attn_bwd(const void* qkv, const void* dout, void* dqkv, 
   cudaStream_t st = (cudaStream_t)stream;
   {
     MaGeom Mg;
-    int hdp;
-    if (ma_geom(B, H, W, C, heads, g, dtype, &Mg, &hdp)) {
-      const unsigned grid = (unsigned)((Mg.ntiles + MA_WARPS - 1) / MA_WARPS);
-      MA_DISPATCH_HDP(hdp, (ma_bwd_kernel<HDP><<<grid, MA_WARPS * 32, 0, st>>>(
-                               reinterpret_cast<const bf16*>(qkv), reinterpret_cast<const bf16*>(dout),
-                               reinterpret_cast<bf16*>(dqkv), Mg)));
-      return ogv_check_launch("grid_attn_bwd(mma)");
+    int hdp, nkt;
+    if (ma_geom(B, H, W, C, heads, g, dtype, &Mg, &hdp, &nkt)) {
+      MA_DISPATCH_HDP(hdp, MA_DISPATCH_NKT(nkt, return (ma_launch_bwd<HDP, NKT>(qkv, dout, dqkv, Mg, st))));
     }
   }
   OGV_DISPATCH_DTYPE(dtype, T, GA_DISPATCH_HD(C / heads, return (ga_launch_bwd<T, HD>(qkv, dout, dqkv, G, threads, st))));

@@ -262,7 +262,8 @@ def _ga_ref(qkv, B, H, W, C, heads, g):
 @pytest.mark.parametrize("dt", DT, ids=IDS)
 @pytest.mark.parametrize("B,H,W,C,heads,g", [(2, 8, 8, 16, 4, 2), (2, 32, 32, 64, 2, 8), (3, 16, 16, 128, 4, 8),
                                              (2, 8, 8, 48, 2, 8), (2, 4, 4, 384, 6, 2), (1, 64, 64, 64, 2, 8),
-                                             (2, 8, 16, 80, 2, 4)])
+                                             (2, 8, 16, 80, 2, 4), (1, 32, 64, 64, 2, 8), (3, 64, 64, 128, 2, 8),
+                                             (1, 16, 32, 48, 2, 4)])
 def test_grid_attention_fwd_bwd(B, H, W, C, heads, g, dt):
     from outlook_grid_vision_transformer_b200 import ops
     torch.manual_seed(C + g)
