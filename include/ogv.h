@@ -98,6 +98,11 @@ int ogv_nhwc_to_nchw(const void* src, void* dst, int B, int C, int HW, int dtype
  * dst_t[c*ld_dst_t + r] (what torch.autocast's weight cast does per step; autocast.py:60-66). */
 int ogv_cast_transpose(const float* src, void* dst, long long ld_dst, void* dst_t, long long ld_dst_t,
                        int rows, int cols, int dtype, void* stream);
+/* fp32 [rows, cols] -> three bf16 planes (hi, hi, lo) [pattern 0] or (hi, lo, hi) [pattern 1], `plane_stride` dst
+ * elements apart: the operands of the "bf16 x 3" tensor-core emulation of an fp32 GEMM (a*b ~= a_hi*b_hi +
+ * a_hi*b_lo + a_lo*b_hi over a 3x longer reduction axis; relative error ~2^-17).  Used for the fp32 parity mode. */
+int ogv_split3(const float* src, long long ld_src, void* dst, long long ld_dst, long long plane_stride, long long rows,
+               int cols, int pattern, void* stream);
 /* y = x * scale[row / rows_per_scale]  (DropPath, Outlook_Block.py:15-22) */
 int ogv_rowscale(const void* x, const float* scale, void* y, long long rows, int cols, int rows_per_scale,
                  int dtype, void* stream);

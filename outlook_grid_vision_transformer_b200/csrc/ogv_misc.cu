@@ -129,6 +129,34 @@ __global__ void cast_transpose_kernel(const float* __restrict__ src, T* __restri
   }
 }
 
+// fp32 -> three bf16 planes for the "bf16 x 3" tensor-core emulation of an fp32 product:
+//   a = hi + lo (+ 2^-17 a),  a*b ~= a_hi*b_hi + a_hi*b_lo + a_lo*b_hi   (every bf16 product is exact in fp32)
+// pattern 0 writes (hi, hi, lo), pattern 1 writes (hi, lo, hi), so that the element-wise product of a pattern-0
+// and a pattern-1 operand along a 3x longer reduction axis is exactly that sum.  plane_stride = distance between
+// planes in dst elements (cols: planes side by side in a [rows, 3*cols] matrix; rows*ld_dst: stacked).
+__global__ void split3_kernel(const float* __restrict__ src, long long ld_src, bf16* __restrict__ dst, long long ld_dst,
+                              long long plane_stride, long long rows, int cols, int pattern) {
+  // one thread per 8 consecutive columns (cols % 8 == 0): two 16-byte loads, three 16-byte stores
+  const unsigned vpr = (unsigned)cols >> 3;
+  const long long nvec = rows * vpr;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    const unsigned r = (unsigned)i / vpr;  // host guarantees rows * cols / 8 < 2^32
+    const unsigned c = ((unsigned)i - r * vpr) << 3;
+    float a[8];
+    ld8(src + (long long)r * ld_src + c, a);
+    float hi[8], lo[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      hi[k] = round_to<bf16>(a[k]);
+      lo[k] = a[k] - hi[k];
+    }
+    bf16* o = dst + (long long)r * ld_dst + c;
+    st8(o, hi);
+    st8(o + plane_stride, pattern == 0 ? hi : lo);
+    st8(o + 2 * plane_stride, pattern == 0 ? lo : hi);
+  }
+}
+
 template <typename T>
 __global__ void rowscale_kernel(const T* __restrict__ x, const float* __restrict__ scale, T* __restrict__ y,
                                 long long nvec, int vec_per_row, int rows_per_scale) {
@@ -257,6 +285,23 @@ extern "C" int ogv_cast_transpose(const float* src, void* dst, long long ld_dst,
         src, reinterpret_cast<T*>(dst), ld_dst, reinterpret_cast<T*>(dst_t), ld_dst_t, rows, cols);
     return ogv_check_launch("cast_transpose");
   });
+}
+
+extern "C" int ogv_split3(const float* src, long long ld_src, void* dst, long long ld_dst, long long plane_stride,
+                          long long rows, int cols, int pattern, void* stream) {
+  if (rows == 0 || cols == 0) return OGV_OK;
+  OGV_REQUIRE(src && dst && (pattern == 0 || pattern == 1), "split3: bad args");
+  OGV_REQUIRE(cols % 8 == 0 && ld_src % 4 == 0 && ld_dst % 8 == 0 && plane_stride % 8 == 0 &&
+                  (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0,
+              "split3: rows must be 16-byte aligned and cols a multiple of 8");
+  const long long n = rows * (cols / 8);
+  OGV_REQUIRE(n < 0xffffffffLL, "split3: tensor too large");
+  long long blocks = (n + 255) / 256;
+  const long long cap = (long long)ogv_num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  split3_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(src, ld_src, reinterpret_cast<bf16*>(dst), ld_dst,
+                                                              plane_stride, rows, cols, pattern);
+  return ogv_check_launch("split3");
 }
 
 extern "C" int ogv_rowscale(const void* x, const float* scale, void* y, long long rows, int cols,

@@ -7,6 +7,7 @@ from __future__ import annotations
 
 import ctypes
 import math
+import os
 from typing import Optional
 
 import torch
@@ -109,6 +110,29 @@ def _rows(t: Tensor, name: str) -> None:
 
 
 # ------------------------------------------------------------------------------------------- GEMM
+# fp32 compute mode: run the product on the tcgen05 engine as three bf16 planes per operand (error ~2^-17 per
+# product, three times the tensor work of a bf16 GEMM, still memory bound) instead of the FFMA engine.
+# OGV_FP32_EXACT=1 keeps every fp32 product on the FFMA engine.
+FP32_ON_TENSOR_CORES = os.environ.get("OGV_FP32_EXACT", "0") != "1"
+
+
+def _split3(t: Tensor, pattern: int) -> Optional[Tensor]:
+    """2-D fp32 operand [R, K] of a GEMM (K = reduction axis) -> bf16 operand with a 3x longer reduction axis and
+    the same majorness, or None when the layout cannot be expressed."""
+    R, K = t.shape
+    if t.data_ptr() % 16:
+        return None
+    if t.stride(1) == 1 and K % 8 == 0 and t.stride(0) % 4 == 0:      # K-major: planes side by side -> [R, 3K]
+        dst = torch.empty((R, 3 * K), device=t.device, dtype=torch.bfloat16)
+        _call("ogv_split3", _p(t), t.stride(0), _p(dst), 3 * K, K, R, K, pattern, _stream())
+        return dst
+    if t.stride(0) == 1 and R % 8 == 0 and t.stride(1) % 4 == 0:      # MN-major view of a row-major [K, R] tensor: planes stacked -> [3K, R]
+        base = torch.empty((3 * K, R), device=t.device, dtype=torch.bfloat16)
+        _call("ogv_split3", _p(t), t.stride(1), _p(base), R, K * R, K, R, pattern, _stream())
+        return base.t()
+    return None
+
+
 def gemm(A: Tensor, B: Tensor, D: Tensor, *, bias: Optional[Tensor] = None, pre_out: Optional[Tensor] = None,
          act: Optional[str] = None, dact_src: Optional[Tensor] = None, dact: Optional[str] = None,
          row_scale: Optional[Tensor] = None, rows_per_scale: int = 1, residual: Optional[Tensor] = None,
@@ -135,6 +159,19 @@ def gemm(A: Tensor, B: Tensor, D: Tensor, *, bias: Optional[Tensor] = None, pre_
     _f32(row_scale, "row_scale")
     _f32(col_sum, "col_sum")
     _f32(col_sumsq, "col_sumsq")
+    if (FP32_ON_TENSOR_CORES and engine == ENGINE_AUTO and A.dtype == torch.float32 and D.dtype == torch.float32
+            and K >= 8 and M >= 64 and not (accumulate and col_sum is not None)):
+        A3, B3 = _split3(A, 0), _split3(B, 1)
+        if A3 is not None and B3 is not None:
+            gemm(A3, B3, D, bias=bias, pre_out=pre_out, act=act, dact_src=dact_src, dact=dact,
+                 row_scale=row_scale, rows_per_scale=rows_per_scale, residual=residual, accumulate=accumulate,
+                 split_k=split_k, engine=ENGINE_AUTO, pre_out_grad=pre_out_grad)
+            # column statistics of an fp32 output: one more streaming pass (the fused form needs a bf16 output)
+            if col_sum is not None and col_sumsq is not None:
+                colstats(D, col_sum, col_sumsq)
+            elif col_sum is not None:
+                colsum(D, col_sum)
+            return D
     a = GemmArgs()
     a.A, a.a_rs, a.a_cs = A.data_ptr(), A.stride(0), A.stride(1)
     a.B, a.b_rs, a.b_cs = B.data_ptr(), B.stride(0), B.stride(1)

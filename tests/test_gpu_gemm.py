@@ -162,3 +162,28 @@ def test_gemm_column_statistics(M, N, K, engine_name):
     ops.gemm(A, B, D, col_sum=s2, engine=eng)
     torch.cuda.synchronize()
     _check(s2, D.double().cpu().sum(0), 2e-3, "col_sum only")
+
+
+@pytest.mark.parametrize("M,N,K", [(1000, 192, 48), (4096, 64, 256), (300, 88, 64)])
+def test_fp32_gemm_on_tensor_cores_bf16x3(M, N, K):
+    """fp32 operands, engine AUTO: three bf16 planes per operand on the tcgen05 engine (a*b ~= hi*hi + hi*lo + lo*hi).
+    Error budget 2^-17 per product -> well inside the fp32 parity tolerance (1e-3); forward, dgrad-with-view and
+    wgrad forms."""
+    from outlook_grid_vision_transformer_b200 import ops
+    torch.manual_seed(K + N)
+    A = torch.randn(M, K, device=DEV)
+    W = torch.randn(N, K, device=DEV) * 0.2
+    bias = torch.randn(N, device=DEV)
+    D = torch.empty(M, N, device=DEV)
+    ops.gemm(A, W, D, bias=bias)
+    _check(D, _ref(A, W) + bias.double().cpu(), 5e-5, "fp32 forward (bf16x3)")
+    G = torch.randn(M, N, device=DEV)
+    dA = torch.empty(M, K, device=DEV)
+    ops.gemm(G, W.t(), dA)                      # dgrad with the un-transposed weight (MN-major view)
+    _check(dA, G.double().cpu() @ W.double().cpu(), 5e-5, "fp32 dgrad (bf16x3)")
+    dW = torch.zeros(N, K, device=DEV)
+    ops.wgrad(G, A, dW)
+    _check(dW, G.double().cpu().t() @ A.double().cpu(), 5e-5, "fp32 wgrad (bf16x3)")
+    s = torch.zeros(N, device=DEV)
+    ops.gemm(A, W, D, col_sum=s)
+    _check(s, _ref(A, W).sum(0), 1e-4, "fp32 col_sum after bf16x3 product")
