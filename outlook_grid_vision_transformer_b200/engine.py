@@ -17,10 +17,14 @@ from . import modules as _modules
 class TrainStep:
     def __init__(self, model: torch.nn.Module, optimizer: torch.optim.Optimizer, loss_fn: Callable,
                  example_x: torch.Tensor, example_y: torch.Tensor, *, autocast_bf16: bool = True,
-                 grad_sync=None, use_graph: bool = True, warmup: int = 3):
+                 grad_sync=None, use_graph: bool = True, warmup: int = 3, grad_clip_norm: Optional[float] = None):
         self.model, self.opt, self.loss_fn = model, optimizer, loss_fn
         self.autocast_bf16 = autocast_bf16
         self.grad_sync = grad_sync
+        # global gradient-norm clipping like the reference loop (one_epoch_train.py:121-122,141-142), but with the
+        # norm kept on the device: no float(gnorm) host sync, so the step stays graph-capturable
+        self.grad_clip_norm = grad_clip_norm
+        self._params = [p for p in model.parameters() if p.requires_grad]
         self.x = example_x.clone()
         self.y = example_y.clone()
         self.loss = None
@@ -37,6 +41,8 @@ class TrainStep:
         loss.backward()
         if self.grad_sync is not None:
             self.grad_sync.finish()
+        if self.grad_clip_norm is not None:
+            torch.nn.utils.clip_grad_norm_(self._params, self.grad_clip_norm, foreach=True)
         self.opt.step()
         return loss.detach()
 
