@@ -41,21 +41,23 @@ class _Profiler:
 
     def __init__(self):
         self.enabled = False
-        self.records = []     # (label, start_event, end_event, bytes, flops)
+        self.records = []     # (label, start_event, end_event, bytes, flops, cuda kernel)
         self.cur_bytes = 0
         self.cur_flops = 0
         self.cur_label = None
+        self.cur_kernel = None  # name of the CUDA kernel behind the call when one label covers several
 
     def start(self):
         self.enabled, self.records, self.cur_bytes, self.cur_flops, self.cur_label = True, [], 0, 0, None
+        self.cur_kernel = None
 
     def stop(self):
         """-> {label: dict(ms, calls, bytes, flops)} (synchronises)."""
         self.enabled = False
         torch.cuda.synchronize()
         out = {}
-        for label, e0, e1, nbytes, flops in self.records:
-            d = out.setdefault(label, dict(ms=0.0, calls=0, bytes=0, flops=0))
+        for label, e0, e1, nbytes, flops, kern in self.records:
+            d = out.setdefault(label, dict(ms=0.0, calls=0, bytes=0, flops=0, cuda_kernel=kern or label))
             d["ms"] += e0.elapsed_time(e1)
             d["calls"] += 1
             d["bytes"] += nbytes
@@ -81,14 +83,14 @@ def _call(name: str, *args) -> None:
     fn = getattr(_lib.lib(), name)
     if PROFILER.enabled:
         label = PROFILER.cur_label or name
-        nbytes, flops = PROFILER.cur_bytes, PROFILER.cur_flops
-        PROFILER.cur_bytes, PROFILER.cur_flops, PROFILER.cur_label = 0, 0, None
+        nbytes, flops, kern = PROFILER.cur_bytes, PROFILER.cur_flops, PROFILER.cur_kernel
+        PROFILER.cur_bytes, PROFILER.cur_flops, PROFILER.cur_label, PROFILER.cur_kernel = 0, 0, None, None
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
         e0.record()
         rc = fn(*args)
         e1.record()
-        PROFILER.records.append((label, e0, e1, nbytes, flops))
+        PROFILER.records.append((label, e0, e1, nbytes, flops, kern))
     else:
         rc = fn(*args)
     LAUNCHES += 1
@@ -197,6 +199,11 @@ def gemm(A: Tensor, B: Tensor, D: Tensor, *, bias: Optional[Tensor] = None, pre_
         kind = "wgrad" if accumulate else ("bwd" if dact_src is not None else "fwd")
         flags = "".join(ch for ch, t in (("b", bias), ("p", pre_out), ("a", act), ("s", row_scale), ("r", residual)) if t is not None)
         PROFILER.cur_label = f"ogv_gemm[{kind} {M}x{N}x{K} {'bf16' if A.dtype == torch.bfloat16 else 'f32'} {flags}]"
+        if A.dtype == torch.bfloat16 and engine != ENGINE_SIMT:
+            bn = 64 if N <= 64 else (128 if N <= 128 else 256)
+            PROFILER.cur_kernel = f"gemm_tc_kernel<{bn}, {'__nv_bfloat16' if D.dtype == torch.bfloat16 else 'float'}>"
+        else:
+            PROFILER.cur_kernel = "gemm_simt_kernel"
     _call("ogv_gemm", ctypes.byref(a), engine, _stream())
     return D
 
