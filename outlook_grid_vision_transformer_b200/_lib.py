@@ -91,7 +91,8 @@ def lib() -> ctypes.CDLL:
         _build.build(force=os.environ.get("OGV_REBUILD") == "1")
     if not LIB_PATH.exists():
         raise RuntimeError(f"{LIB_PATH} is missing: the CUDA extension is required, there is no CPU fallback")
-    handle = ctypes.CDLL(str(LIB_PATH))
+    # OGV_LIB: load another build of the SAME library (A/B measurements of a kernel change on one box)
+    handle = ctypes.CDLL(os.environ.get("OGV_LIB") or str(LIB_PATH))
     for name, argtypes in SIGNATURES.items():
         fn = getattr(handle, name)  # AttributeError = header/library mismatch: fail loudly
         fn.argtypes = argtypes

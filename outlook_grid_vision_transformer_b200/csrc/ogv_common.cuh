@@ -140,6 +140,59 @@ __device__ __forceinline__ void stv(T* p, const float (&v)[VEC]) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// packed fp32x2 arithmetic (sm_100: FFMA2 / FMUL2 / FADD2 -- two IEEE round-to-nearest fp32 operations per
+// issue slot).  Results are bit-identical to the scalar forms; the gain is issue bandwidth in the
+// instruction-bound stencil and epilogue loops.  A pair lives in one 64-bit register (element 0 in the
+// low half = the lower address of a float2), so 8- and 16-byte loads deliver pairs without any packing.
+// -DOGV_PACKED_F32=0 builds the scalar forms (A/B measurements).
+// ---------------------------------------------------------------------------------------------
+#ifndef OGV_PACKED_F32
+#define OGV_PACKED_F32 1
+#endif
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpk2(f32x2 p, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(p));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+#if OGV_PACKED_F32
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+#else
+  float a0, a1, b0, b1, c0, c1;
+  unpk2(a, a0, a1); unpk2(b, b0, b1); unpk2(c, c0, c1);
+  return pk2(fmaf(a0, b0, c0), fmaf(a1, b1, c1));
+#endif
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+#if OGV_PACKED_F32
+  f32x2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+#else
+  float a0, a1, b0, b1;
+  unpk2(a, a0, a1); unpk2(b, b0, b1);
+  return pk2(a0 * b0, a1 * b1);
+#endif
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+#if OGV_PACKED_F32
+  f32x2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+#else
+  float a0, a1, b0, b1;
+  unpk2(a, a0, a1); unpk2(b, b0, b1);
+  return pk2(a0 + b0, a1 + b1);
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------
 // activations (exact erf GELU, SiLU, sigmoid) and their derivatives w.r.t. the pre-activation
 // ---------------------------------------------------------------------------------------------
 // Transcendentals are MUFU-throughput bound on the wide (4C) tensors, so the fast hardware paths are
@@ -364,6 +417,89 @@ template <int N, bool FAST = false> __device__ __forceinline__ void act_both_n(i
       for (int i = 0; i < N; ++i) act_both(act, v[i], &v[i], &d[i]);
       break;
   }
+}
+
+// ---- the same three helpers over packed pairs (v[i] = elements 2i, 2i+1): the bf16-mode GELU forms and the
+// plain multiply run as FFMA2 / FMUL2 (half the issue slots, bit-identical to the scalar forms); everything
+// else unpacks and goes through the scalar helpers. ----
+__device__ __forceinline__ f32x2 splat2(float c) { return pk2(c, c); }
+__device__ __forceinline__ f32x2 tanh_approx2(f32x2 p) {
+  float a, b;
+  unpk2(p, a, b);
+  return pk2(tanh_approx(a), tanh_approx(b));
+}
+__device__ __forceinline__ f32x2 gelu_fast2(f32x2 x) {
+  const f32x2 half = splat2(0.5f);
+  const f32x2 z2 = mul2(mul2(half, x), x);
+  const f32x2 q = fma2(z2, fma2(z2, splat2(kGeluC5), splat2(kGeluC3)), splat2(kGeluC1));
+  const f32x2 t = tanh_approx2(mul2(mul2(x, splat2(0.70710678118654752440f)), q));
+  const f32x2 h = mul2(half, x);
+  return fma2(h, t, h);
+}
+__device__ __forceinline__ void gelu_both_fast2(f32x2 x, f32x2* a, f32x2* da) {
+  const f32x2 half = splat2(0.5f), rs2 = splat2(0.70710678118654752440f);
+  const f32x2 h = mul2(half, x);
+  const f32x2 z2 = mul2(h, x);
+  const f32x2 q = fma2(z2, fma2(z2, splat2(kGeluC5), splat2(kGeluC3)), splat2(kGeluC1));
+  const f32x2 dp = mul2(rs2, fma2(z2, fma2(z2, splat2(5.f * kGeluC5), splat2(3.f * kGeluC3)), splat2(kGeluC1)));
+  const f32x2 t = tanh_approx2(mul2(mul2(x, rs2), q));
+  const f32x2 cdf = fma2(half, t, half);
+  *a = mul2(x, cdf);
+  const f32x2 sech2 = fma2(mul2(t, splat2(-1.f)), t, splat2(1.f));
+  *da = fma2(mul2(h, dp), sech2, cdf);
+}
+template <int N2> __device__ __forceinline__ void unpack_n(const f32x2 (&v)[N2], float (&f)[2 * N2]) {
+#pragma unroll
+  for (int i = 0; i < N2; ++i) unpk2(v[i], f[2 * i], f[2 * i + 1]);
+}
+template <int N2> __device__ __forceinline__ void pack_n(const float (&f)[2 * N2], f32x2 (&v)[N2]) {
+#pragma unroll
+  for (int i = 0; i < N2; ++i) v[i] = pk2(f[2 * i], f[2 * i + 1]);
+}
+template <int N2, bool FAST = false> __device__ __forceinline__ void act_apply_p(int act, f32x2 (&v)[N2]) {
+  if (act == OGV_ACT_NONE) return;
+  if (FAST && act == OGV_ACT_GELU) {
+#pragma unroll
+    for (int i = 0; i < N2; ++i) v[i] = gelu_fast2(v[i]);
+    return;
+  }
+  float f[2 * N2];
+  unpack_n<N2>(v, f);
+  act_apply_n<2 * N2, FAST>(act, f);
+  pack_n<N2>(f, v);
+}
+template <int N2, bool FAST = false> __device__ __forceinline__ void act_grad_mul_p(int act, f32x2 (&v)[N2], const f32x2 (&src)[N2]) {
+  if (act == OGV_ACT_MUL) {
+#pragma unroll
+    for (int i = 0; i < N2; ++i) v[i] = mul2(v[i], src[i]);
+    return;
+  }
+  if (FAST && act == OGV_ACT_GELU) {
+#pragma unroll
+    for (int i = 0; i < N2; ++i) {
+      f32x2 a, d;
+      gelu_both_fast2(src[i], &a, &d);
+      v[i] = mul2(v[i], d);
+    }
+    return;
+  }
+  float f[2 * N2], g[2 * N2];
+  unpack_n<N2>(v, f);
+  unpack_n<N2>(src, g);
+  act_grad_mul_n<2 * N2, FAST>(act, f, g);
+  pack_n<N2>(f, v);
+}
+template <int N2, bool FAST = false> __device__ __forceinline__ void act_both_p(int act, f32x2 (&v)[N2], f32x2 (&d)[N2]) {
+  if (FAST && act == OGV_ACT_GELU) {
+#pragma unroll
+    for (int i = 0; i < N2; ++i) gelu_both_fast2(v[i], &v[i], &d[i]);
+    return;
+  }
+  float f[2 * N2], g[2 * N2];
+  unpack_n<N2>(v, f);
+  act_both_n<2 * N2, FAST>(act, f, g);
+  pack_n<N2>(f, v);
+  pack_n<N2>(g, d);
 }
 
 #define OGV_ACT_CASE_(code, ACT, ...) \

@@ -351,11 +351,11 @@ dwconv_bwd_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constan
     ptx::mbar_init(&bar[1], 1);
     ptx::fence_barrier_init();
   }
-  float dwa[9][4];
+  // channel pairs (k, k+1) ride in one 64-bit register: the 18 FMAs per element issue as 9 FFMA2
+  // (measured -7 % on this kernel; the same change on the forward sweep was +3 %: its pack moves outweigh the gain)
+  f32x2 dwa[9][2];
 #pragma unroll
-  for (int t9 = 0; t9 < 9; ++t9)
-#pragma unroll
-    for (int k = 0; k < 4; ++k) dwa[t9][k] = 0.f;
+  for (int t9 = 0; t9 < 9; ++t9) dwa[t9][0] = dwa[t9][1] = 0ull;
   float a_db[4] = {0.f, 0.f, 0.f, 0.f}, a_dg[4] = {0.f, 0.f, 0.f, 0.f};
   __syncthreads();
 
@@ -407,11 +407,11 @@ dwconv_bwd_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constan
     ptx::mbar_wait(&bar[1], it & 1);
 
     if (cvalid) {
-      float w[9][4];
+      f32x2 w[9][2];
 #pragma unroll
       for (int t9 = 0; t9 < 9; ++t9) {
-        const float4 wv = *reinterpret_cast<const float4*>(&s_w[t9][tv * 4]);
-        w[t9][0] = wv.x; w[t9][1] = wv.y; w[t9][2] = wv.z; w[t9][3] = wv.w;
+        const ulonglong2 wv = *reinterpret_cast<const ulonglong2*>(&s_w[t9][tv * 4]);
+        w[t9][0] = wv.x; w[t9][1] = wv.y;
       }
       const int step = im.regular ? im.rows_par : DW_THREADS;
       const int last = im.regular ? nrowitems : nitems;
@@ -429,7 +429,8 @@ dwconv_bwd_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constan
         const int r0 = (rowitem - img * nstrips) * R;
         const int b = b0 + img;
         if (b >= g.B || w0 + x >= g.W) continue;
-        float de[R][4], ea[R][4], da[R][4];
+        f32x2 de[R][2], ea[R][2];
+        float da[R][4];
         bool rvalid[R];
         const T* ep = eraw + ((img * g.TH + r0) * g.TW + x) * CC + tv * 4;
         {
@@ -439,13 +440,16 @@ dwconv_bwd_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constan
 #pragma unroll
           for (int r = 0; r < R; ++r) {
             rvalid[r] = (r0 + r < g.TH) && (h0 + r0 + r < g.H);
+            de[r][0] = de[r][1] = ea[r][0] = ea[r][1] = 0ull;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) { de[r][k] = 0.f; ea[r][k] = 0.f; da[r][k] = 0.f; }
+            for (int k = 0; k < 4; ++k) da[r][k] = 0.f;
             if (rvalid[r]) {
-              float ev[4];
+              float ev[4], av4[4];
               ldv<4>(ep + r * g.TW * CC, ev);
 #pragma unroll
-              for (int k = 0; k < 4; ++k) act_both_t<ACT, FastAct<T>::value>(fmaf(ev[k], scv[k], shv[k]), &ea[r][k], &da[r][k]);
+              for (int k = 0; k < 4; ++k) act_both_t<ACT, FastAct<T>::value>(fmaf(ev[k], scv[k], shv[k]), &av4[k], &da[r][k]);
+              ea[r][0] = pk2(av4[0], av4[1]);
+              ea[r][1] = pk2(av4[2], av4[3]);
             }
           }
         }
@@ -453,12 +457,9 @@ dwconv_bwd_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constan
 #pragma unroll
         for (int ry = 0; ry < R + 2; ++ry) {  // gradient row (halo coords) r0 + ry  <->  image row h0 + r0 + ry - 1
           if (r0 + ry >= TH2) break;
-          float gr[3][4];
+          ulonglong2 gr[3];
 #pragma unroll
-          for (int dx = 0; dx < 3; ++dx) {
-            const float4 q = *reinterpret_cast<const float4*>(base + (ry * TW2 + dx) * CC);
-            gr[dx][0] = q.x; gr[dx][1] = q.y; gr[dx][2] = q.z; gr[dx][3] = q.w;
-          }
+          for (int dx = 0; dx < 3; ++dx) gr[dx] = *reinterpret_cast<const ulonglong2*>(base + (ry * TW2 + dx) * CC);
           // output row r sits at halo row r0 + r + 1; gradient row offset (ry - 1) - r = -(ki - 1)
 #pragma unroll
           for (int ki = 0; ki < 3; ++ki) {
@@ -467,11 +468,10 @@ dwconv_bwd_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constan
 #pragma unroll
               for (int dx = 0; dx < 3; ++dx) {
                 const int tt = ki * 3 + (2 - dx);  // gradient column offset dx - 1 = -(kj - 1)
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  de[r][k] = fmaf(w[tt][k], gr[dx][k], de[r][k]);
-                  dwa[tt][k] = fmaf(ea[r][k], gr[dx][k], dwa[tt][k]);
-                }
+                de[r][0] = fma2(w[tt][0], gr[dx].x, de[r][0]);
+                de[r][1] = fma2(w[tt][1], gr[dx].y, de[r][1]);
+                dwa[tt][0] = fma2(ea[r][0], gr[dx].x, dwa[tt][0]);
+                dwa[tt][1] = fma2(ea[r][1], gr[dx].y, dwa[tt][1]);
               }
             }
           }
@@ -483,11 +483,13 @@ dwconv_bwd_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constan
 #pragma unroll
         for (int r = 0; r < R; ++r) {
           if (rvalid[r]) {
-            float o[4], ev[4];
+            float o[4], ev[4], dv[4];
             ldv<4>(ep + r * g.TW * CC, ev);  // re-read (smem) instead of carrying xhat through the stencil
+            unpk2(de[r][0], dv[0], dv[1]);
+            unpk2(de[r][1], dv[2], dv[3]);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              o[k] = de[r][k] * da[r][k];
+              o[k] = dv[k] * da[r][k];
               a_db[k] += o[k];
               a_dg[k] = fmaf(o[k], (ev[k] - muv[k]) * rsv[k], a_dg[k]);
             }
@@ -508,8 +510,14 @@ dwconv_bwd_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constan
     for (int k = 0; k < 4; ++k) {
       atomicAdd(&s_db[tv * 4 + k], a_db[k]);
       atomicAdd(&s_dg[tv * 4 + k], a_dg[k]);
+    }
 #pragma unroll
-      for (int t9 = 0; t9 < 9; ++t9) atomicAdd(&s_dw[(tv * 4 + k) * 9 + t9], dwa[t9][k]);
+    for (int t9 = 0; t9 < 9; ++t9) {
+      float d4[4];
+      unpk2(dwa[t9][0], d4[0], d4[1]);
+      unpk2(dwa[t9][1], d4[2], d4[3]);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) atomicAdd(&s_dw[(tv * 4 + k) * 9 + t9], d4[k]);
     }
   }
   __syncthreads();

@@ -45,6 +45,7 @@ struct TcParams {
   int epi_load;     // 0 none, 1 residual, 2 dact_src -- operand fetched by TMA into the staging slot
   int vec_ok;       // direct epilogue may use 8-wide vector accesses
   int col_stats;    // staged epilogue also accumulates per-column sum (and sum of squares) of the stored values
+  int plain;        // staged epilogue with no bias / activation / operand / scale / statistics: convert and store
   int n_pad;        // n_tiles * BN: extent of the per-CTA column accumulators in shared memory
   GemmEpi epi;
 };
@@ -118,6 +119,33 @@ __device__ __forceinline__ void stage_write_row(uint8_t* slot, int row, const fl
 #pragma unroll
     for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[8 * c + 2 * i], v[8 * c + 2 * i + 1]);
     *reinterpret_cast<uint4*>(slot + sw64(row, c)) = u;
+  }
+}
+// packed-pair forms (element pairs (2i, 2i+1) in one 64-bit register, see ogv_common.cuh)
+__device__ __forceinline__ void stage_write_row(uint8_t* slot, int row, const f32x2 (&v)[16]) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint4 u;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float lo, hi;
+      unpk2(v[4 * c + i], lo, hi);
+      h[i] = __floats2bfloat162_rn(lo, hi);
+    }
+    *reinterpret_cast<uint4*>(slot + sw64(row, c)) = u;
+  }
+}
+__device__ __forceinline__ void stage_read_row(const uint8_t* slot, int row, f32x2 (&r)[16]) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint4 u = *reinterpret_cast<const uint4*>(slot + sw64(row, c));
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __bfloat1622float2(h[i]);
+      r[4 * c + i] = pk2(f.x, f.y);
+    }
   }
 }
 __device__ __forceinline__ void stage_read_row(const uint8_t* slot, int row, float (&r)[32]) {
@@ -312,51 +340,66 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           continue;
         }
         // ---- staged epilogue (bf16 tensors, TMA in/out) ----
+        if (p.plain) {  // convert and store, nothing else (expand / project / dgrad without a fused derivative)
+          stage_write_row(s0, lane, v);
+          ptx::fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            ptx::tma_store_2d(&tmD, s0, n0c, mrow0);
+            ptx::bulk_commit();
+          }
+          continue;
+        }
+        // fused epilogues work on element pairs: FADD2 / FMUL2 / FFMA2
+        f32x2 v2[16];
+        pack_n<16>(v, v2);
         if (e.bias) {
           if (n0c + CH <= p.N) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(e.bias + n0c) + i);
-              v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
+              const ulonglong2 b4 = __ldg(reinterpret_cast<const ulonglong2*>(e.bias + n0c) + i);
+              v2[2 * i] = add2(v2[2 * i], b4.x);
+              v2[2 * i + 1] = add2(v2[2 * i + 1], b4.y);
             }
           } else {
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (n0c + i < p.N) v[i] += __ldg(e.bias + n0c + i);
+            for (int i = 0; i < 16; ++i)
+              v2[i] = add2(v2[i], pk2(n0c + 2 * i < p.N ? __ldg(e.bias + n0c + 2 * i) : 0.f,
+                                      n0c + 2 * i + 1 < p.N ? __ldg(e.bias + n0c + 2 * i + 1) : 0.f));
           }
         }
         if (e.pre_out && e.pre_out_grad) {
-          float d[32];
-          act_both_n<32, FastAct<TO>::value>(e.act, v, d);
-          stage_write_row(s1, lane, d);
+          f32x2 d2[16];
+          act_both_p<16, FastAct<TO>::value>(e.act, v2, d2);
+          stage_write_row(s1, lane, d2);
         } else {
-          if (e.pre_out) stage_write_row(s1, lane, v);
-          if (e.act != OGV_ACT_NONE) act_apply_n<32, FastAct<TO>::value>(e.act, v);
+          if (e.pre_out) stage_write_row(s1, lane, v2);
+          act_apply_p<16, FastAct<TO>::value>(e.act, v2);
         }
         if (p.epi_load) {
           ptx::mbar_wait(&my_ld[pr], (ld_phase >> pr) & 1u);
           ld_phase ^= 1u << pr;
-          float r[32];
-          stage_read_row(s0, lane, r);
+          f32x2 r2[16];
+          stage_read_row(s0, lane, r2);
           if (p.epi_load == 2) {
-            act_grad_mul_n<32, FastAct<TO>::value>(e.dact, v, r);
+            act_grad_mul_p<16, FastAct<TO>::value>(e.dact, v2, r2);
             if (e.row_scale) {
-              const float rs = m < p.M ? e.row_scale[m / e.rows_per_scale] : 0.f;
+              const f32x2 rs = splat2(m < p.M ? e.row_scale[m / e.rows_per_scale] : 0.f);
 #pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] *= rs;
+              for (int i = 0; i < 16; ++i) v2[i] = mul2(v2[i], rs);
             }
           } else {
-            const float rs = (e.row_scale && m < p.M) ? e.row_scale[m / e.rows_per_scale] : 1.f;
+            const f32x2 rs = splat2((e.row_scale && m < p.M) ? e.row_scale[m / e.rows_per_scale] : 1.f);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = fmaf(v[i], rs, r[i]);
+            for (int i = 0; i < 16; ++i) v2[i] = fma2(v2[i], rs, r2[i]);
           }
           __syncwarp();  // every lane has read its residual row before anyone overwrites the slot
         } else if (e.row_scale) {
-          const float rs = m < p.M ? e.row_scale[m / e.rows_per_scale] : 0.f;
+          const f32x2 rs = splat2(m < p.M ? e.row_scale[m / e.rows_per_scale] : 0.f);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] *= rs;
+          for (int i = 0; i < 16; ++i) v2[i] = mul2(v2[i], rs);
         }
-        stage_write_row(s0, lane, v);
+        stage_write_row(s0, lane, v2);
         ptx::fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
@@ -567,6 +610,7 @@ int ogv_gemm_tc(const ogv_gemm_args& a, cudaStream_t stream) {
     return OGV_ERR_UNSUPPORTED;
   }
   p.epi_load = staged ? (a.residual ? 1 : (a.dact_src ? 2 : 0)) : 0;
+  p.plain = staged && !p.col_stats && !p.epi_load && !a.pre_out && !a.bias && !a.row_scale && a.act == OGV_ACT_NONE;
   const int esz = obf ? 2 : 4;
   auto ok = [&](const void* ptr, long long ld) {
     return ptr == nullptr || ((reinterpret_cast<uintptr_t>(ptr) % 16 == 0) && ((ld * esz) % 16 == 0));
