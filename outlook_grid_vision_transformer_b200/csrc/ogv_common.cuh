@@ -93,6 +93,32 @@ __device__ __forceinline__ void st8(bf16* p, const float (&v)[8]) {
   *reinterpret_cast<uint4*>(p) = u;
 }
 
+// 8 elements kept in their storage format (4 registers for bf16): streaming kernels issue the loads of several
+// rows up front and convert a row only when they get to it, so bytes in flight cost half the registers.
+template <typename T> struct Raw8;
+template <> struct Raw8<float> { float4 a, b; };
+template <> struct Raw8<bf16> { uint4 u; };
+__device__ __forceinline__ void raw8_zero(Raw8<float>& r) { r.a = make_float4(0.f, 0.f, 0.f, 0.f); r.b = r.a; }
+__device__ __forceinline__ void raw8_zero(Raw8<bf16>& r) { r.u = make_uint4(0u, 0u, 0u, 0u); }
+__device__ __forceinline__ void ld_raw8(const float* p, Raw8<float>& r) {
+  r.a = *reinterpret_cast<const float4*>(p);
+  r.b = *reinterpret_cast<const float4*>(p + 4);
+}
+__device__ __forceinline__ void ld_raw8(const bf16* p, Raw8<bf16>& r) { r.u = *reinterpret_cast<const uint4*>(p); }
+__device__ __forceinline__ void cvt_raw8(const Raw8<float>& r, float (&v)[8]) {
+  v[0] = r.a.x; v[1] = r.a.y; v[2] = r.a.z; v[3] = r.a.w;
+  v[4] = r.b.x; v[5] = r.b.y; v[6] = r.b.z; v[7] = r.b.w;
+}
+__device__ __forceinline__ void cvt_raw8(const Raw8<bf16>& r, float (&v)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r.u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __bfloat1622float2(h[i]);
+    v[2 * i] = f.x;
+    v[2 * i + 1] = f.y;
+  }
+}
+
 // VEC-wide generic versions (VEC in {1,2,4,8}); alignment = VEC*sizeof(T).
 template <int VEC, typename T>
 __device__ __forceinline__ void ldv(const T* p, float (&v)[VEC]) {

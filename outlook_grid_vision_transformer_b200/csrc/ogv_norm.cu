@@ -5,6 +5,20 @@
 #include "ogv_reduce.cuh"
 #include "../../include/ogv.h"
 
+// row-groups in flight per warp iteration (U) and resident CTAs per SM the kernels are compiled for
+#ifndef LN_FWD_U
+#define LN_FWD_U 2
+#endif
+#ifndef LN_BWD_U
+#define LN_BWD_U 2
+#endif
+#ifndef LN_FWD_MINB
+#define LN_FWD_MINB 4
+#endif
+#ifndef LN_BWD_MINB
+#define LN_BWD_MINB 2
+#endif
+
 namespace {
 
 // ------------------------------------------------------------------ LayerNorm
@@ -17,12 +31,14 @@ __device__ __forceinline__ float group_sum(float v) {
   return v;
 }
 
-template <typename T, int G, int VPL>
-__global__ void __launch_bounds__(256) ln_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
+// U row-groups per warp iteration: the loads of all U rows are issued first (kept in storage format), then the
+// rows are normalised one after the other -- bytes in flight per SM, not arithmetic, bound these kernels.
+template <typename T, int G, int VPL, int U>
+__global__ void __launch_bounds__(256, VPL == 1 ? LN_FWD_MINB : 1) ln_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
                                                      const float* __restrict__ beta, T* __restrict__ y,
                                                      float* __restrict__ mean_out, float* __restrict__ rstd_out,
                                                      long long M, int C, float eps) {
-  constexpr int RPW = 32 / G;  // rows per warp
+  constexpr int RPW = 32 / G;  // rows per warp and row-group
   const int lane = threadIdx.x & 31;
   const int gl = lane % G, gr = lane / G;
   const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
@@ -38,59 +54,67 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const T* __restrict__ x, co
       ld8(beta + idx * 8, b[j]);
     }
   }
-  for (long long base = warp0 * RPW; base < M; base += nwarps * RPW) {
-    const long long row = base + gr;
-    const bool rv = row < M;
-    float v[VPL][8];
-    float s = 0.f;
+  for (long long base = warp0 * (RPW * U); base < M; base += nwarps * (RPW * U)) {
+    Raw8<T> rx[U][VPL];
 #pragma unroll
-    for (int j = 0; j < VPL; ++j) {
-      const int idx = gl + G * j;
+    for (int u = 0; u < U; ++u) {
+      const long long row = base + u * RPW + gr;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[j][i] = 0.f;
-      if (rv && idx < nv) {
-        ld8(x + row * C + idx * 8, v[j]);
+      for (int j = 0; j < VPL; ++j) {
+        const int idx = gl + G * j;
+        raw8_zero(rx[u][j]);
+        if (row < M && idx < nv) ld_raw8(x + row * C + idx * 8, rx[u][j]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long row = base + u * RPW + gr;
+      const bool rv = row < M;
+      float v[VPL][8];
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < VPL; ++j) {
+        cvt_raw8(rx[u][j], v[j]);
 #pragma unroll
         for (int i = 0; i < 8; ++i) s += v[j][i];
       }
-    }
-    const float mean = group_sum<G>(s) * inv_c;
-    float q = 0.f;
+      const float mean = group_sum<G>(s) * inv_c;
+      float q = 0.f;
 #pragma unroll
-    for (int j = 0; j < VPL; ++j) {
-      const int idx = gl + G * j;
-      if (idx < nv) {
+      for (int j = 0; j < VPL; ++j) {
+        const int idx = gl + G * j;
+        if (idx < nv) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float d = v[j][i] - mean;
-          q += d * d;
+          for (int i = 0; i < 8; ++i) {
+            float d = v[j][i] - mean;
+            q += d * d;
+          }
         }
       }
-    }
-    const float rstd = 1.f / sqrtf(group_sum<G>(q) * inv_c + eps);
+      const float rstd = 1.f / sqrtf(group_sum<G>(q) * inv_c + eps);
 #pragma unroll
-    for (int j = 0; j < VPL; ++j) {
-      const int idx = gl + G * j;
-      if (rv && idx < nv) {
-        float o[8];
+      for (int j = 0; j < VPL; ++j) {
+        const int idx = gl + G * j;
+        if (rv && idx < nv) {
+          float o[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] = (v[j][i] - mean) * rstd * g[j][i] + b[j][i];
-        st8(y + row * C + idx * 8, o);
+          for (int i = 0; i < 8; ++i) o[i] = (v[j][i] - mean) * rstd * g[j][i] + b[j][i];
+          st8(y + row * C + idx * 8, o);
+        }
       }
-    }
-    if (rv && gl == 0) {
-      if (mean_out) mean_out[row] = mean;
-      if (rstd_out) rstd_out[row] = rstd;
+      if (rv && gl == 0) {
+        if (mean_out) mean_out[row] = mean;
+        if (rstd_out) rstd_out[row] = rstd;
+      }
     }
   }
 }
 
-template <typename T, int G, int VPL>
-__global__ void __launch_bounds__(512) ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
-                                                     const float* __restrict__ gamma, const float* __restrict__ mean,
-                                                     const float* __restrict__ rstd, const T* __restrict__ dres,
-                                                     T* __restrict__ dx, float* __restrict__ dgamma,
-                                                     float* __restrict__ dbeta, long long M, int C) {
+template <typename T, int G, int VPL, int U>
+__global__ void __launch_bounds__(256, VPL == 1 ? LN_BWD_MINB : 1)
+ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ gamma,
+              const float* __restrict__ mean, const float* __restrict__ rstd, const T* __restrict__ dres,
+              T* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta, long long M, int C) {
   constexpr int RPW = 32 / G;
   __shared__ float sg[1024];
   __shared__ float sb[1024];
@@ -110,24 +134,43 @@ __global__ void __launch_bounds__(512) ln_bwd_kernel(const T* __restrict__ dy, c
     for (int i = 0; i < 8; ++i) { ag[j][i] = 0.f; ab[j][i] = 0.f; gm[j][i] = 0.f; }
     if (idx < nv) ld8(gamma + idx * 8, gm[j]);
   }
-  for (long long base = warp0 * RPW; base < M; base += nwarps * RPW) {
-    const long long row = base + gr;
-    const bool rv = row < M;
-    const float mu = rv ? mean[row] : 0.f, rs = rv ? rstd[row] : 0.f;
-    float gg[VPL][8], xh[VPL][8];
-    float c1 = 0.f, c2 = 0.f;
+  for (long long base = warp0 * (RPW * U); base < M; base += nwarps * (RPW * U)) {
+    // every load of the U rows (gradient, input, residual gradient, row statistics) is in flight before any use
+    Raw8<T> rd[U][VPL], rx[U][VPL], rr[U][VPL];
+    float mu[U], rs[U];
 #pragma unroll
-    for (int j = 0; j < VPL; ++j) {
-      const int idx = gl + G * j;
+    for (int u = 0; u < U; ++u) {
+      const long long row = base + u * RPW + gr;
+      const bool rv = row < M;
+      mu[u] = rv ? mean[row] : 0.f;
+      rs[u] = rv ? rstd[row] : 0.f;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { gg[j][i] = 0.f; xh[j][i] = 0.f; }
-      if (rv && idx < nv) {
+      for (int j = 0; j < VPL; ++j) {
+        const int idx = gl + G * j;
+        raw8_zero(rd[u][j]);
+        raw8_zero(rx[u][j]);
+        raw8_zero(rr[u][j]);
+        if (rv && idx < nv) {
+          ld_raw8(dy + row * C + idx * 8, rd[u][j]);
+          ld_raw8(x + row * C + idx * 8, rx[u][j]);
+          if (dres) ld_raw8(dres + row * C + idx * 8, rr[u][j]);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long row = base + u * RPW + gr;
+      const bool rv = row < M;
+      float gg[VPL][8], xh[VPL][8];
+      float c1 = 0.f, c2 = 0.f;
+#pragma unroll
+      for (int j = 0; j < VPL; ++j) {
         float d[8], xv[8];
-        ld8(dy + row * C + idx * 8, d);
-        ld8(x + row * C + idx * 8, xv);
+        cvt_raw8(rd[u][j], d);  // zeros outside the row / beyond C: no contribution below
+        cvt_raw8(rx[u][j], xv);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          xh[j][i] = (xv[i] - mu) * rs;
+          xh[j][i] = (xv[i] - mu[u]) * rs[u];
           ag[j][i] += d[i] * xh[j][i];
           ab[j][i] += d[i];
           gg[j][i] = d[i] * gm[j][i];
@@ -135,23 +178,18 @@ __global__ void __launch_bounds__(512) ln_bwd_kernel(const T* __restrict__ dy, c
           c2 += gg[j][i] * xh[j][i];
         }
       }
-    }
-    c1 = group_sum<G>(c1) * inv_c;
-    c2 = group_sum<G>(c2) * inv_c;
+      c1 = group_sum<G>(c1) * inv_c;
+      c2 = group_sum<G>(c2) * inv_c;
 #pragma unroll
-    for (int j = 0; j < VPL; ++j) {
-      const int idx = gl + G * j;
-      if (rv && idx < nv) {
-        float o[8];
+      for (int j = 0; j < VPL; ++j) {
+        const int idx = gl + G * j;
+        if (rv && idx < nv) {
+          float o[8], r[8];
+          cvt_raw8(rr[u][j], r);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] = rs * (gg[j][i] - c1 - xh[j][i] * c2);
-        if (dres) {
-          float r[8];
-          ld8(dres + row * C + idx * 8, r);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) o[i] += r[i];
+          for (int i = 0; i < 8; ++i) o[i] = rs[u] * (gg[j][i] - c1 - xh[j][i] * c2) + r[i];
+          st8(dx + row * C + idx * 8, o);
         }
-        st8(dx + row * C + idx * 8, o);
       }
     }
   }
@@ -180,14 +218,14 @@ __global__ void __launch_bounds__(512) ln_bwd_kernel(const T* __restrict__ dy, c
   }
 }
 
-#define LN_DISPATCH(C, CALL)                                  \
+#define LN_DISPATCH(C, ...)                                  \
   do {                                                        \
-    if ((C) <= 32) { constexpr int G = 4, VPL = 1; CALL; }    \
-    else if ((C) <= 64) { constexpr int G = 8, VPL = 1; CALL; }  \
-    else if ((C) <= 128) { constexpr int G = 16, VPL = 1; CALL; } \
-    else if ((C) <= 256) { constexpr int G = 32, VPL = 1; CALL; } \
-    else if ((C) <= 512) { constexpr int G = 32, VPL = 2; CALL; } \
-    else { constexpr int G = 32, VPL = 4; CALL; }             \
+    if ((C) <= 32) { constexpr int G = 4, VPL = 1; __VA_ARGS__; }    \
+    else if ((C) <= 64) { constexpr int G = 8, VPL = 1; __VA_ARGS__; }  \
+    else if ((C) <= 128) { constexpr int G = 16, VPL = 1; __VA_ARGS__; } \
+    else if ((C) <= 256) { constexpr int G = 32, VPL = 1; __VA_ARGS__; } \
+    else if ((C) <= 512) { constexpr int G = 32, VPL = 2; __VA_ARGS__; } \
+    else { constexpr int G = 32, VPL = 4; __VA_ARGS__; }             \
   } while (0)
 
 // ------------------------------------------------------------------ BatchNorm
@@ -307,12 +345,15 @@ extern "C" int ogv_layernorm_fwd(const void* x, const float* gamma, const float*
   OGV_REQUIRE(x && gamma && beta && y, "layernorm_fwd: null pointer");
   OGV_REQUIRE(C > 0 && C % 8 == 0 && C <= 1024, "layernorm_fwd: C=%d must be a multiple of 8 and <= 1024", C);
   const int ln_g = C <= 32 ? 4 : (C <= 64 ? 8 : (C <= 128 ? 16 : 32));
-  int grid = flat_grid(M * ln_g, 256);
   cudaStream_t st = (cudaStream_t)stream;
   OGV_DISPATCH_DTYPE(dtype, T, {
     const T* xp = reinterpret_cast<const T*>(x);
     T* yp = reinterpret_cast<T*>(y);
-    LN_DISPATCH(C, (ln_fwd_kernel<T, G, VPL><<<grid, 256, 0, st>>>(xp, gamma, beta, yp, mean, rstd, M, C, eps)));
+    LN_DISPATCH(C, {
+      constexpr int U = LN_FWD_U / VPL > 0 ? LN_FWD_U / VPL : 1;
+      const int grid = flat_grid((M * ln_g + U - 1) / U, 256);
+      ln_fwd_kernel<T, G, VPL, U><<<grid, 256, 0, st>>>(xp, gamma, beta, yp, mean, rstd, M, C, eps);
+    });
     return ogv_check_launch("layernorm_fwd");
   });
 }
@@ -324,16 +365,20 @@ extern "C" int ogv_layernorm_bwd(const void* dy, const void* x, const float* gam
   OGV_REQUIRE(dy && x && gamma && mean && rstd && dx, "layernorm_bwd: null pointer");
   OGV_REQUIRE(C > 0 && C % 8 == 0 && C <= 1024, "layernorm_bwd: C=%d must be a multiple of 8 and <= 1024", C);
   const int ln_g = C <= 32 ? 4 : (C <= 64 ? 8 : (C <= 128 ? 16 : 32));
-  long long want = (M * ln_g + 511) / 512;
-  long long cap = (long long)ogv_num_sms() * 2;  // few fat CTAs: one dgamma/dbeta atomic flush per CTA  // few CTAs: one dgamma/dbeta flush per CTA
-  int grid = (int)(want < cap ? want : cap);
   cudaStream_t st = (cudaStream_t)stream;
   OGV_DISPATCH_DTYPE(dtype, T, {
     const T* dyp = reinterpret_cast<const T*>(dy);
     const T* xp = reinterpret_cast<const T*>(x);
     const T* rp = reinterpret_cast<const T*>(dres);
     T* dxp = reinterpret_cast<T*>(dx);
-    LN_DISPATCH(C, (ln_bwd_kernel<T, G, VPL><<<grid, 512, 0, st>>>(dyp, xp, gamma, mean, rstd, rp, dxp, dgamma, dbeta, M, C)));
+    LN_DISPATCH(C, {
+      constexpr int U = (VPL == 1 && sizeof(T) == 2) ? LN_BWD_U : 1;
+      // one resident wave of grid-striding CTAs: one dgamma / dbeta atomic flush per CTA
+      const long long want = (M * ln_g + 256 * U - 1) / (256 * U);
+      const long long cap = (long long)ogv_num_sms() * (VPL == 1 ? LN_BWD_MINB : 1);
+      const int grid = (int)(want < cap ? want : cap);
+      ln_bwd_kernel<T, G, VPL, U><<<grid, 256, 0, st>>>(dyp, xp, gamma, mean, rstd, rp, dxp, dgamma, dbeta, M, C);
+    });
     return ogv_check_launch("layernorm_bwd");
   });
 }
