@@ -98,6 +98,20 @@ int ogv_nhwc_to_nchw(const void* src, void* dst, int B, int C, int HW, int dtype
  * dst_t[c*ld_dst_t + r] (what torch.autocast's weight cast does per step; autocast.py:60-66). */
 int ogv_cast_transpose(const float* src, void* dst, long long ld_dst, void* dst_t, long long ld_dst_t,
                        int rows, int cols, int dtype, void* stream);
+/* The same cast for MANY weights in one launch (the per-step refresh of every compute-dtype weight copy of a model:
+ * ~120 tiny launches otherwise).  `items` is a DEVICE array of n_items descriptors, caller-owned; item i covers the
+ * 32x32 tiles [tile0_i, tile0_{i+1}) of the batch (tile0 = exclusive prefix sum of ceil(rows/32)*ceil(cols/32)),
+ * total_tiles = the sum.  dst_dtype is per item (OGV_F32 items are plain copies, e.g. concatenated biases). */
+typedef struct ogv_cast_item {
+  const float* src;   /* [rows, cols] fp32, contiguous */
+  void* dst;          /* dst[r*ld_dst + c], or NULL */
+  void* dst_t;        /* dst_t[c*ld_dst_t + r], or NULL */
+  long long ld_dst, ld_dst_t;
+  int rows, cols;
+  int tile0;
+  int dst_dtype;
+} ogv_cast_item;
+int ogv_cast_batch(const ogv_cast_item* items, int n_items, int total_tiles, void* stream);
 /* fp32 [rows, cols] -> three bf16 planes (hi, hi, lo) [pattern 0] or (hi, lo, hi) [pattern 1], `plane_stride` dst
  * elements apart: the operands of the "bf16 x 3" tensor-core emulation of an fp32 GEMM (a*b ~= a_hi*b_hi +
  * a_hi*b_lo + a_lo*b_hi over a 3x longer reduction axis; relative error ~2^-17).  Used for the fp32 parity mode. */

@@ -47,6 +47,7 @@ SIGNATURES = {
     "ogv_nchw_to_nhwc": [_P, _P, _I, _I, _I, _I, _P],
     "ogv_nhwc_to_nchw": [_P, _P, _I, _I, _I, _I, _P],
     "ogv_cast_transpose": [_P, _P, _L, _P, _L, _I, _I, _I, _P],
+    "ogv_cast_batch": [_P, _I, _I, _P],
     "ogv_split3": [_P, _L, _P, _L, _L, _L, _I, _I, _P],
     "ogv_rowscale": [_P, _P, _P, _L, _I, _I, _I, _P],
     "ogv_rowscale_colsum": [_P, _P, _P, _P, _L, _I, _I, _I, _P],

@@ -13,6 +13,13 @@ namespace {
 
 constexpr int IMG_THREADS = 256;
 constexpr int IMG_ROWLANES = 8;
+// rows in flight per thread in the two-operand streaming passes (A/B-tunable)
+#ifndef MBS_U
+#define MBS_U 2
+#endif
+#ifndef DBA_U
+#define DBA_U 4
+#endif
 
 // u = sc*x + sh
 #define OGV_BN_U(k) fmaf(x[k], sc[k], sh[k])
@@ -101,23 +108,37 @@ __global__ void __launch_bounds__(IMG_THREADS) mbconv_bwd_stats_kernel(
     ld8(rstd + cv * 8, rs);
     const T* xp = d_pre + ((long long)b * HW) * Cm + cv * 8;
     const T* gp = dd_act + ((long long)b * HW) * Cm + cv * 8;
-#pragma unroll 2
-    for (int p = ry; p < HW; p += IMG_ROWLANES) {
-      float x[8], g[8];
-      ld8(xp + (long long)p * Cm, x);
-      ld8(gp + (long long)p * Cm, g);
+    constexpr int U = MBS_U;  // rows in flight per thread
+    for (int p0 = ry; p0 < HW; p0 += IMG_ROWLANES * U) {
+      Raw8<T> rx[U], rg[U];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const float u = OGV_BN_U(k);
-        float a, da;
-        act_both_t<ACT, FastAct<T>::value>(u, &a, &da);
-        const float xh = (x[k] - mu[k]) * rs[k];
-        const float gda = g[k] * da;
-        acc[0][k] = fmaf(g[k], a, acc[0][k]);
-        acc[1][k] += gda;
-        acc[2][k] = fmaf(gda, xh, acc[2][k]);
-        acc[3][k] += da;
-        acc[4][k] = fmaf(da, xh, acc[4][k]);
+      for (int u = 0; u < U; ++u) {
+        const int p = p0 + u * IMG_ROWLANES;
+        if (p < HW) {
+          ld_raw8(xp + (long long)p * Cm, rx[u]);
+          ld_raw8(gp + (long long)p * Cm, rg[u]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (p0 + u * IMG_ROWLANES < HW) {
+          float x[8], g[8];
+          cvt_raw8(rx[u], x);
+          cvt_raw8(rg[u], g);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const float uu = OGV_BN_U(k);
+            float a, da;
+            act_both_t<ACT, FastAct<T>::value>(uu, &a, &da);
+            const float xh = (x[k] - mu[k]) * rs[k];
+            const float gda = g[k] * da;
+            acc[0][k] = fmaf(g[k], a, acc[0][k]);
+            acc[1][k] += gda;
+            acc[2][k] = fmaf(gda, xh, acc[2][k]);
+            acc[3][k] += da;
+            acc[4][k] = fmaf(da, xh, acc[4][k]);
+          }
+        }
       }
     }
   }
@@ -241,17 +262,32 @@ __global__ void __launch_bounds__(IMG_THREADS) dw_bn2_bwd_apply_kernel(
   }
   const long long base = ((long long)b * HW) * Cm + cv * 8;
   const int step = IMG_ROWLANES * gridDim.z;
-#pragma unroll 2
-  for (int p = blockIdx.z * IMG_ROWLANES + ry; p < HW; p += step) {
-    float x[8], g[8], o[8];
-    ld8(d_pre + base + (long long)p * Cm, x);
-    ld8(dd_act + base + (long long)p * Cm, g);
+  constexpr int U = DBA_U;  // rows in flight per thread
+  for (int p0 = blockIdx.z * IMG_ROWLANES + ry; p0 < HW; p0 += step * U) {
+    Raw8<T> rx[U], rg[U];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float du = fmaf(g[k], gt[k], dp[k]) * act_grad_t<ACT, FastAct<T>::value>(OGV_BN_U(k));
-      o[k] = fmaf(A[k], du, -fmaf(Cx[k], x[k], Bc[k]));
+    for (int u = 0; u < U; ++u) {
+      const int p = p0 + u * step;
+      if (p < HW) {
+        ld_raw8(d_pre + base + (long long)p * Cm, rx[u]);
+        ld_raw8(dd_act + base + (long long)p * Cm, rg[u]);
+      }
     }
-    st8(dd_pre + base + (long long)p * Cm, o);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int p = p0 + u * step;
+      if (p < HW) {
+        float x[8], g[8], o[8];
+        cvt_raw8(rx[u], x);
+        cvt_raw8(rg[u], g);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float du = fmaf(g[k], gt[k], dp[k]) * act_grad_t<ACT, FastAct<T>::value>(OGV_BN_U(k));
+          o[k] = fmaf(A[k], du, -fmaf(Cx[k], x[k], Bc[k]));
+        }
+        st8(dd_pre + base + (long long)p * Cm, o);
+      }
+    }
   }
 }
 

@@ -129,6 +129,48 @@ __global__ void cast_transpose_kernel(const float* __restrict__ src, T* __restri
   }
 }
 
+// every weight of a model in one launch: CTA t handles 32x32 tile t of the batch; the owning item is found by a
+// binary search over the items' first-tile indices (a few hundred items at most).
+template <typename T>
+__device__ __forceinline__ void cast_tile(const ogv_cast_item& it, int tx, int ty, float (&tile)[32][33]) {
+  T* dst = reinterpret_cast<T*>(it.dst);
+  T* dst_t = reinterpret_cast<T*>(it.dst_t);
+  const int c0 = tx * 32, r0 = ty * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    if (r < it.rows && c < it.cols) {
+      const float v = it.src[(long long)r * it.cols + c];
+      tile[i][threadIdx.x] = v;
+      if (dst) st1(dst + (long long)r * it.ld_dst + c, v);
+    }
+  }
+  __syncthreads();
+  if (dst_t) {
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+      const int c = c0 + i, r = r0 + threadIdx.x;
+      if (r < it.rows && c < it.cols) st1(dst_t + (long long)c * it.ld_dst_t + r, tile[threadIdx.x][i]);
+    }
+  }
+  __syncthreads();
+}
+__global__ void __launch_bounds__(256) cast_batch_kernel(const ogv_cast_item* __restrict__ items, int n_items,
+                                                         int total_tiles) {
+  __shared__ float tile[32][33];
+  for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    int lo = 0, hi = n_items - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (items[mid].tile0 <= t) lo = mid; else hi = mid - 1;
+    }
+    const ogv_cast_item it = items[lo];
+    const int tiles_x = (it.cols + 31) >> 5;
+    const int lt = t - it.tile0;
+    const int ty = lt / tiles_x, tx = lt - ty * tiles_x;
+    if (it.dst_dtype == OGV_BF16) cast_tile<bf16>(it, tx, ty, tile);
+    else cast_tile<float>(it, tx, ty, tile);
+  }
+}
+
 // fp32 -> three bf16 planes for the "bf16 x 3" tensor-core emulation of an fp32 product:
 //   a = hi + lo (+ 2^-17 a),  a*b ~= a_hi*b_hi + a_hi*b_lo + a_lo*b_hi   (every bf16 product is exact in fp32)
 // pattern 0 writes (hi, hi, lo), pattern 1 writes (hi, lo, hi), so that the element-wise product of a pattern-0
@@ -287,6 +329,15 @@ extern "C" int ogv_cast_transpose(const float* src, void* dst, long long ld_dst,
   });
 }
 
+extern "C" int ogv_cast_batch(const ogv_cast_item* items, int n_items, int total_tiles, void* stream) {
+  if (n_items == 0 || total_tiles == 0) return OGV_OK;
+  OGV_REQUIRE(items && n_items > 0 && total_tiles > 0, "cast_batch: bad args");
+  const int cap = ogv_num_sms() * 8;
+  cast_batch_kernel<<<total_tiles < cap ? total_tiles : cap, dim3(32, 8), 0, (cudaStream_t)stream>>>(items, n_items,
+                                                                                                  total_tiles);
+  return ogv_check_launch("cast_batch");
+}
+
 extern "C" int ogv_split3(const float* src, long long ld_src, void* dst, long long ld_dst, long long plane_stride,
                           long long rows, int cols, int pattern, void* stream) {
   if (rows == 0 || cols == 0) return OGV_OK;
@@ -323,9 +374,9 @@ extern "C" int ogv_rowscale_colsum(const void* x, const float* scale, void* y, f
   if (rows == 0 || cols == 0) return OGV_OK;
   OGV_REQUIRE(x && y && scale && out && cols % 8 == 0 && rows_per_scale > 0, "rowscale_colsum: bad args (cols %% 8 == 0)");
   OGV_REQUIRE(rows < 0x7fffffffLL, "rowscale_colsum: too many rows");
-  ColReduceCfg cfg;
-  if (!colreduce_config(rows, cols / 8, &cfg)) { ogv_set_error("rowscale_colsum: cols=%d too wide", cols); return OGV_ERR_UNSUPPORTED; }
   OGV_DISPATCH_DTYPE(dtype, T, {
+    ColReduceCfg cfg;
+    if (!colreduce_config(rows, cols / 8, &cfg, rowscale_colsum_kernel<T>)) { ogv_set_error("rowscale_colsum: cols=%d too wide", cols); return OGV_ERR_UNSUPPORTED; }
     rowscale_colsum_kernel<T><<<cfg.grid, cfg.block, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const T*>(x), scale, reinterpret_cast<T*>(y), out, rows, cols / 8, (unsigned)rows_per_scale);
     return ogv_check_launch("rowscale_colsum");
@@ -370,9 +421,9 @@ extern "C" int ogv_adamw(float* p, const float* g, float* m, float* v, long long
 extern "C" int ogv_colsum(const void* x, long long ld, float* out, long long M, int N, int dtype, void* stream) {
   if (M == 0 || N == 0) return OGV_OK;
   OGV_REQUIRE(x && out && N % 8 == 0 && ld % 8 == 0, "colsum: N and ld must be multiples of 8");
-  ColReduceCfg cfg;
-  if (!colreduce_config(M, N / 8, &cfg)) { ogv_set_error("colsum: N=%d too wide", N); return OGV_ERR_UNSUPPORTED; }
   OGV_DISPATCH_DTYPE(dtype, T, {
+    ColReduceCfg cfg;
+    if (!colreduce_config(M, N / 8, &cfg, colsum_kernel<T>)) { ogv_set_error("colsum: N=%d too wide", N); return OGV_ERR_UNSUPPORTED; }
     colsum_kernel<T><<<cfg.grid, cfg.block, 0, (cudaStream_t)stream>>>(reinterpret_cast<const T*>(x), ld, out, M,
                                                                          N / 8);
     return ogv_check_launch("colsum");
@@ -383,9 +434,9 @@ extern "C" int ogv_colstats(const void* x, long long ld, float* sum, float* sums
                             void* stream) {
   if (M == 0 || N == 0) return OGV_OK;
   OGV_REQUIRE(x && sum && sumsq && N % 8 == 0 && ld % 8 == 0, "colstats: N and ld must be multiples of 8");
-  ColReduceCfg cfg;
-  if (!colreduce_config(M, N / 8, &cfg)) { ogv_set_error("colstats: N=%d too wide", N); return OGV_ERR_UNSUPPORTED; }
   OGV_DISPATCH_DTYPE(dtype, T, {
+    ColReduceCfg cfg;
+    if (!colreduce_config(M, N / 8, &cfg, colstats_kernel<T>)) { ogv_set_error("colstats: N=%d too wide", N); return OGV_ERR_UNSUPPORTED; }
     colstats_kernel<T><<<cfg.grid, cfg.block, 0, (cudaStream_t)stream>>>(reinterpret_cast<const T*>(x), ld, sum,
                                                                            sumsq, M, N / 8);
     return ogv_check_launch("colstats");

@@ -306,17 +306,19 @@ __global__ void __launch_bounds__(COLREDUCE_THREADS) bn_bwd_reduce_kernel(const 
   colreduce_finish<2>(acc, outs, nv);
 }
 
-template <typename T>
-__global__ void bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x,
-                                    const float* __restrict__ mean, const float* __restrict__ rstd,
-                                    const float* __restrict__ gamma, const float* __restrict__ dgamma,
-                                    const float* __restrict__ dbeta, T* __restrict__ dx, long long nvec, int nv,
-                                    float inv_n) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
-    int cv = (int)(i % nv);
-    float d[8], xv[8], mu[8], rs[8], g[8], dg[8], db[8], o[8];
-    ld8(dy + i * 8, d);
-    ld8(x + i * 8, xv);
+// dx = gamma*rstd*(dy - dbeta/n - xhat*dgamma/n).  A thread owns one channel vector (cv) and strides over rows, so
+// the five per-channel parameter vectors are folded ONCE into  dx = A*dy - (Cx*x + Bc)  (they used to be re-read,
+// with a 64-bit modulo, for every 16 bytes of data); U rows are in flight per thread in storage format.
+template <typename T, int U>
+__global__ void __launch_bounds__(COLREDUCE_THREADS)
+bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ mean,
+                    const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ dgamma,
+                    const float* __restrict__ dbeta, T* __restrict__ dx, long long M, int nv, float inv_n) {
+  const int cv = threadIdx.x % nv;
+  const int kk = blockDim.x / nv;
+  float A[8], Bc[8], Cx[8];
+  {
+    float mu[8], rs[8], g[8], dg[8], db[8];
     ld8(mean + cv * 8, mu);
     ld8(rstd + cv * 8, rs);
     ld8(gamma + cv * 8, g);
@@ -324,10 +326,34 @@ __global__ void bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restric
     ld8(dbeta + cv * 8, db);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      float xh = (xv[k] - mu[k]) * rs[k];
-      o[k] = g[k] * rs[k] * (d[k] - db[k] * inv_n - xh * dg[k] * inv_n);
+      A[k] = g[k] * rs[k];
+      Cx[k] = A[k] * rs[k] * dg[k] * inv_n;
+      Bc[k] = A[k] * db[k] * inv_n - Cx[k] * mu[k];
     }
-    st8(dx + i * 8, o);
+  }
+  const long long stride = (long long)gridDim.x * kk;
+  for (long long row0 = (long long)blockIdx.x * kk + threadIdx.x / nv; row0 < M; row0 += stride * U) {
+    Raw8<T> rd[U], rx[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long row = row0 + u * stride;
+      if (row < M) {
+        ld_raw8(dy + (row * nv + cv) * 8, rd[u]);
+        ld_raw8(x + (row * nv + cv) * 8, rx[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long row = row0 + u * stride;
+      if (row < M) {
+        float d[8], xv[8], o[8];
+        cvt_raw8(rd[u], d);
+        cvt_raw8(rx[u], xv);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = fmaf(A[k], d[k], -fmaf(Cx[k], xv[k], Bc[k]));
+        st8(dx + (row * nv + cv) * 8, o);
+      }
+    }
   }
 }
 
@@ -413,9 +439,9 @@ extern "C" int ogv_bn_bwd_reduce(const void* dy, const void* x, const float* mea
                                  float* dbeta, long long M, int C, int dtype, void* stream) {
   if (M == 0) return OGV_OK;
   OGV_REQUIRE(dy && x && mean && rstd && dgamma && dbeta && C % 8 == 0, "bn_bwd_reduce: bad args");
-  ColReduceCfg cfg;
-  if (!colreduce_config(M, C / 8, &cfg)) { ogv_set_error("bn_bwd_reduce: C=%d too wide", C); return OGV_ERR_UNSUPPORTED; }
   OGV_DISPATCH_DTYPE(dtype, T, {
+    ColReduceCfg cfg;
+    if (!colreduce_config(M, C / 8, &cfg, bn_bwd_reduce_kernel<T>)) { ogv_set_error("bn_bwd_reduce: C=%d too wide", C); return OGV_ERR_UNSUPPORTED; }
     bn_bwd_reduce_kernel<T><<<cfg.grid, cfg.block, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const T*>(dy), reinterpret_cast<const T*>(x), mean, rstd, dgamma, dbeta, M, C / 8);
     return ogv_check_launch("bn_bwd_reduce");
@@ -425,13 +451,18 @@ extern "C" int ogv_bn_bwd_reduce(const void* dy, const void* x, const float* mea
 extern "C" int ogv_bn_bwd_apply(const void* dy, const void* x, const float* mean, const float* rstd,
                                 const float* gamma, const float* dgamma, const float* dbeta, void* dx, long long M,
                                 int C, int dtype, void* stream) {
+  if (M == 0) return OGV_OK;
   OGV_REQUIRE(dy && x && mean && rstd && gamma && dgamma && dbeta && dx && C % 8 == 0, "bn_bwd_apply: bad args");
-  long long nvec = M * (C / 8);
-  if (nvec == 0) return OGV_OK;
+  const int nv = C / 8;
+  if (nv > 256) { ogv_set_error("bn_bwd_apply: C=%d too wide", C); return OGV_ERR_UNSUPPORTED; }
+  const int kk = COLREDUCE_THREADS / nv;
+  const long long blocks = (M + kk - 1) / kk;
+  const long long cap = (long long)ogv_num_sms() * 2;  // 2 x 512 threads x 4 rows x 32 B in flight per SM
+  const int grid = (int)(blocks < cap ? blocks : cap);
   OGV_DISPATCH_DTYPE(dtype, T, {
-    bn_bwd_apply_kernel<T><<<flat_grid(nvec, 256), 256, 0, (cudaStream_t)stream>>>(
+    bn_bwd_apply_kernel<T, 4><<<grid, nv * kk, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const T*>(dy), reinterpret_cast<const T*>(x), mean, rstd, gamma, dgamma, dbeta,
-        reinterpret_cast<T*>(dx), nvec, C / 8, 1.f / (float)M);
+        reinterpret_cast<T*>(dx), M, nv, 1.f / (float)M);
     return ogv_check_launch("bn_bwd_apply");
   });
 }

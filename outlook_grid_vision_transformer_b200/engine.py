@@ -35,8 +35,14 @@ class TrainStep:
     # the eager body; also what gets captured
     def _body(self):
         self.opt.zero_grad(set_to_none=True)
-        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.autocast_bf16):
-            logits = self.model(self.x)
+        # every compute-dtype weight copy of the model in one launch (from the second step on; the first step
+        # casts layer by layer and records what to refresh)
+        _modules._BULK_FRESH = _modules.refresh_prepared(self.model)
+        try:
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.autocast_bf16):
+                logits = self.model(self.x)
+        finally:
+            _modules._BULK_FRESH = False
         loss = self.loss_fn(logits.float(), self.y)
         loss.backward()
         if self.grad_sync is not None:
@@ -50,7 +56,7 @@ class TrainStep:
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
-            for _ in range(max(warmup, 1)):
+            for _ in range(max(warmup, 2)):  # >= 2: the bulk weight-refresh table is built (H2D copy) in step 2
                 self._body()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()

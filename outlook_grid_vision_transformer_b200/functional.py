@@ -47,6 +47,17 @@ class PreparedLinear:
         self.wt = wt
 
 
+# When a list, every cast issued by prepare_* below is also recorded as (src, dst, dst_t): modules._Prep keeps the
+# records so that modules.refresh_prepared() can re-run all of a model's casts in ONE launch per step.
+_CAST_LOG: Optional[list] = None
+
+
+def _cast_logged(src: Tensor, dst: Optional[Tensor], dst_t: Optional[Tensor]) -> None:
+    ops.cast_transpose(src, dst, dst_t)
+    if _CAST_LOG is not None:
+        _CAST_LOG.append((src, dst, dst_t))
+
+
 def prepare_linear(weight: Tensor, dtype: torch.dtype, out_rows: Optional[int] = None) -> PreparedLinear:
     """weight: fp32 parameter [out, in(,1,1)].  For fp32 compute the parameter itself is used."""
     w2 = weight.detach().reshape(weight.shape[0], -1)
@@ -54,9 +65,10 @@ def prepare_linear(weight: Tensor, dtype: torch.dtype, out_rows: Optional[int] =
     rows = out_rows or n
     if dtype == torch.float32 and rows == n:
         return PreparedLinear(w2, w2.t())
-    w = torch.zeros((rows, k), device=w2.device, dtype=dtype)
-    wt = torch.zeros((k, rows), device=w2.device, dtype=dtype)
-    ops.cast_transpose(w2.contiguous(), w[:n], wt[:, :n])
+    alloc = torch.empty if rows == n else torch.zeros  # zero fill only where padding rows exist
+    w = alloc((rows, k), device=w2.device, dtype=dtype)
+    wt = alloc((k, rows), device=w2.device, dtype=dtype)
+    _cast_logged(w2.contiguous(), w[:n], wt[:, :n])
     return PreparedLinear(w, wt)
 
 
@@ -230,13 +242,17 @@ def prepare_outlook_va(wv: Tensor, bv: Optional[Tensor], wa: Tensor, ba: Optiona
     npad = (C + nl + 7) // 8 * 8
     w = torch.zeros((npad, C), device=wv.device, dtype=dtype)
     wt = torch.zeros((C, npad), device=wv.device, dtype=dtype)
-    ops.cast_transpose(wv.detach().reshape(C, C).contiguous(), w[:C], wt[:, :C])
-    ops.cast_transpose(wa.detach().reshape(nl, C).contiguous(), w[C:C + nl], wt[:, C:C + nl])
+    _cast_logged(wv.detach().reshape(C, C).contiguous(), w[:C], wt[:, :C])
+    _cast_logged(wa.detach().reshape(nl, C).contiguous(), w[C:C + nl], wt[:, C:C + nl])
     bva = torch.zeros(npad, device=wv.device, dtype=torch.float32)
     if bv is not None:
         bva[:C].copy_(bv.detach())
+        if _CAST_LOG is not None:
+            _CAST_LOG.append((bv.detach().reshape(1, C), bva[:C].reshape(1, C), None))
     if ba is not None:
         bva[C:C + nl].copy_(ba.detach())
+        if _CAST_LOG is not None:
+            _CAST_LOG.append((ba.detach().reshape(1, nl), bva[C:C + nl].reshape(1, nl), None))
     return PreparedLinear(w, wt), bva
 
 

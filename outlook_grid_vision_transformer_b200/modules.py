@@ -69,23 +69,58 @@ FORCE_PREP = False  # set while a CUDA graph is being captured: the casts must b
 class _Prep:
     """Compute-dtype weight copies (what autocast's weight cast produces).  In training mode they are
     re-derived on EVERY forward: an optimizer may update the fp32 master weights without touching the
-    tensor version counter (torch's fused AdamW does), so no cache key is trustworthy there -- the casts
-    are a few microseconds per layer.  In eval mode the copies are cached, keyed by storage / version / dtype."""
+    tensor version counter (torch's fused AdamW does), so no cache key is trustworthy there.  Two ways:
+    per layer (a cast launch per weight, the default), or in bulk -- the casts of the last per-layer build are
+    remembered (`_bulk`), refresh_prepared(model) re-runs all of them in ONE launch at the start of a step and,
+    while `_BULK_FRESH` is set, get() hands out those refreshed buffers.  In eval mode the copies are cached,
+    keyed by storage / version / dtype."""
 
     def __init__(self):
         self._key = None
         self._val = None
+        self._bulk = None  # (key, value, [(src, dst, dst_t), ...]) of the last training-mode build
+
+    @staticmethod
+    def _bulk_key(params, dtype):
+        return (dtype,) + tuple(p.data_ptr() if p is not None else None for p in params)
 
     def get(self, training, params, dtype, build):
         if training or FORCE_PREP:
             self._key = None  # the optimizer step that follows makes this copy stale: never reuse it
-            self._val = build()
-            return self._val
+            if _BULK_FRESH and self._bulk is not None and self._bulk[0] == self._bulk_key(params, dtype):
+                return self._bulk[1]
+            OF._CAST_LOG = log = []
+            try:
+                val = build()
+            finally:
+                OF._CAST_LOG = None
+            self._bulk = (self._bulk_key(params, dtype), val, log) if log else None
+            return val
         key = (dtype,) + tuple((p.data_ptr(), p._version) if p is not None else None for p in params)
         if key != self._key:
             self._val = build()
             self._key = key
         return self._val
+
+
+_BULK_FRESH = False  # set by the train-step executor between refresh_prepared() and the end of the forward pass
+
+
+def refresh_prepared(model: nn.Module) -> bool:
+    """Re-derive every compute-dtype weight copy recorded by the model's training-mode forward in ONE launch
+    (ogv_cast_batch) instead of one launch per weight.  Returns False when there is nothing recorded yet (first
+    step): the caller then leaves `_BULK_FRESH` unset and the layers cast per weight as usual."""
+    preps = [p for m in model.modules() for p in m.__dict__.get("_ogv_prep", {}).values() if p._bulk is not None]
+    if not preps:
+        return False
+    sig = tuple(id(p._bulk) for p in preps)
+    cached = model.__dict__.get("_ogv_cast_batch")
+    if cached is None or cached[0] != sig:
+        triples = [t for p in preps for t in p._bulk[2]]
+        cached = (sig, ops.CastBatch(triples), [p._bulk for p in preps])  # keeps the ids in `sig` alive
+        model.__dict__["_ogv_cast_batch"] = cached
+    cached[1].run()
+    return True
 
 
 def _prep_attr(mod: nn.Module, name: str) -> _Prep:

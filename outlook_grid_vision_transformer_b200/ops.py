@@ -255,6 +255,41 @@ def cast_transpose(src: Tensor, dst: Optional[Tensor], dst_t: Optional[Tensor]) 
                                         _stream())
 
 
+class CastBatch:
+    """Device-resident descriptor table for ogv_cast_batch: every (src fp32 [rows, cols] contiguous, dst, dst_t) cast of
+    a model re-run by ONE launch per step (dst / dst_t: compute-dtype or fp32 2-D views, either may be None)."""
+
+    def __init__(self, triples):
+        import numpy as np
+        rec = np.dtype([("src", "<u8"), ("dst", "<u8"), ("dst_t", "<u8"), ("ld_dst", "<i8"), ("ld_dst_t", "<i8"),
+                        ("rows", "<i4"), ("cols", "<i4"), ("tile0", "<i4"), ("dtype", "<i4")])
+        assert rec.itemsize == 56  # sizeof(ogv_cast_item)
+        arr = np.zeros(len(triples), dtype=rec)
+        tile0 = 0
+        for i, (src, dst, dst_t) in enumerate(triples):
+            _require_cuda(src, dst, dst_t)
+            _f32(src, "src")
+            if src.dim() != 2 or not src.is_contiguous():
+                raise ValueError("cast_batch: src must be a contiguous 2-D fp32 tensor")
+            ref = dst if dst is not None else dst_t
+            for t in (dst, dst_t):
+                if t is not None and (t.dim() != 2 or t.stride(1) != 1 or t.dtype != ref.dtype):
+                    raise ValueError("cast_batch: dst / dst_t must be 2-D row-major views of one dtype")
+            rows, cols = src.shape
+            arr[i] = (src.data_ptr(), dst.data_ptr() if dst is not None else 0,
+                      dst_t.data_ptr() if dst_t is not None else 0, dst.stride(0) if dst is not None else 0,
+                      dst_t.stride(0) if dst_t is not None else 0, rows, cols, tile0, dtype_code(ref))
+            tile0 += ((rows + 31) // 32) * ((cols + 31) // 32)
+        self.n, self.total_tiles = len(triples), tile0
+        self.keep = list(triples)  # the table holds raw pointers: keep the tensors alive
+        dev = triples[0][0].device if triples else "cpu"
+        self.items = torch.from_numpy(arr.view(np.uint8).copy()).to(dev)
+
+    def run(self) -> None:
+        if self.n:
+            _call("ogv_cast_batch", ctypes.c_void_p(self.items.data_ptr()), self.n, self.total_tiles, _stream())
+
+
 def cast(src: Tensor, dtype: torch.dtype) -> Tensor:
     """fp32 [rows, cols] -> compute-dtype copy (ogv_cast_transpose without the transposed output)."""
     dst = torch.empty(src.shape, device=src.device, dtype=dtype)

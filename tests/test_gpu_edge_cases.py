@@ -138,3 +138,65 @@ def test_drop_path_draws_follow_the_reference_order():
     assert len(seen) == 4
     for a, b in zip(seen, want):
         assert torch.equal(a, b)
+
+
+def test_cast_batch_matches_per_weight_casts():
+    """ogv_cast_batch: many (src -> dst, dst_t) casts in one launch == ogv_cast_transpose one by one, including
+    ragged shapes, strided destination views, a missing transposed output and an fp32 copy item."""
+    from outlook_grid_vision_transformer_b200 import ops
+    torch.manual_seed(5)
+    shapes = [(64, 256), (40, 24), (1, 72), (129, 33), (256, 64)]
+    triples, want = [], []
+    for i, (r, c) in enumerate(shapes):
+        src = torch.randn(r, c, device=DEV)
+        big = torch.zeros(r + 3, c + 8, device=DEV, dtype=torch.bfloat16)
+        big_t = torch.zeros(c, r + 8, device=DEV, dtype=torch.bfloat16)
+        dst, dst_t = big[1:r + 1, :c], (big_t[:, :r] if i != 2 else None)
+        triples.append((src, dst, dst_t))
+        a, b = torch.zeros_like(big), torch.zeros_like(big_t)
+        ops.cast_transpose(src, a[1:r + 1, :c], b[:, :r] if i != 2 else None)
+        want.append((big, a, big_t, b))
+    bias = torch.randn(1, 72, device=DEV)
+    cat = torch.zeros(80, device=DEV)
+    triples.append((bias, cat[:72].reshape(1, 72), None))
+    ops.CastBatch(triples).run()
+    for big, a, big_t, b in want:
+        assert torch.equal(big, a) and torch.equal(big_t, b)
+    assert torch.equal(cat[:72], bias[0]) and float(cat[72:].abs().sum()) == 0.0
+
+
+def test_bulk_weight_refresh_equals_per_layer_casts():
+    """TrainStep re-derives all bf16 weight copies in one launch per step (modules.refresh_prepared); a hand-written
+    loop casts per layer.  Same losses step for step -- in particular the copies are never stale after AdamW."""
+    import torch.nn.functional as F
+    import outlook_grid_vision_transformer_b200 as og
+    from outlook_grid_vision_transformer_b200 import modules as M
+    from outlook_grid_vision_transformer_b200.engine import TrainStep
+    cfg = {"type": "model_a", "num_classes": 10, "stem_dim": 16, "dpr_max": 0.0,
+           "stages": [dict(dim=16, depth=1, num_heads=2, grid_size=2, outlook_heads=2),
+                      dict(dim=32, depth=1, num_heads=2, grid_size=2, outlook_heads=2)]}
+    x = torch.randn(4, 3, 8, 8, device=DEV)
+    y = torch.randint(0, 10, (4,), device=DEV)
+    losses = []
+    for bulk in (False, True):
+        torch.manual_seed(11)
+        model = og.build_model(cfg).to(DEV).train()
+        opt = torch.optim.AdamW(model.parameters(), lr=3e-3, fused=True)
+        if bulk:
+            step = TrainStep(model, opt, lambda lg, yy: F.cross_entropy(lg, yy), x, y, autocast_bf16=True, use_graph=False)
+            losses.append([float(step()) for _ in range(5)])
+            assert model.__dict__.get("_ogv_cast_batch") is not None and model.__dict__["_ogv_cast_batch"][1].n > 0
+        else:
+            out = []
+            for _ in range(5):
+                opt.zero_grad(set_to_none=True)
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    lg = model(x)
+                loss = F.cross_entropy(lg.float(), y)
+                loss.backward()
+                opt.step()
+                out.append(float(loss))
+            losses.append(out)
+        assert not M._BULK_FRESH
+    assert losses[0] == pytest.approx(losses[1], rel=2e-3), f"{losses}"
+    assert losses[1][-1] < losses[1][0]
