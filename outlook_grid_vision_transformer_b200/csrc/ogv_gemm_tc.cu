@@ -92,8 +92,8 @@ __device__ __forceinline__ void epi_row16(const GemmEpi& e, int m, int n0, const
       }
       if (e.accumulate) {
         float* d = reinterpret_cast<float*>(e.D) + (long long)m * e.ldd + n;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) atomicAdd(d + i, x[i]);
+        ptx::red_add_v4(d, x[0], x[1], x[2], x[3]);
+        ptx::red_add_v4(d + 4, x[4], x[5], x[6], x[7]);
       } else {
         st8(reinterpret_cast<TO*>(e.D) + (long long)m * e.ldd + n, x);
       }

@@ -67,6 +67,12 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* t
 
 // 4-D tiled TMA load (coordinates innermost first; out-of-range parts of the box are zero-filled and
 // still count towards the mbarrier's transaction bytes).
+// fire-and-forget fp32 reduction of 4 consecutive floats (16-byte aligned): one 16-byte L2 transaction per lane
+// instead of four 4-byte ones (split-K accumulation of weight gradients)
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.v4.f32.add [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int32_t c0,
                                             int32_t c1, int32_t c2, int32_t c3) {
   asm volatile(

@@ -212,8 +212,11 @@ def wgrad(dY: Tensor, X: Tensor, out: Tensor, engine: int = ENGINE_AUTO) -> Tens
     """out[n,k] += sum_m dY[m,n] * X[m,k]   (out fp32, pre-zeroed by the caller)."""
     M, N = dY.shape
     K = X.shape[1]
-    tiles = max(1, math.ceil(N / 128) * math.ceil(K / 128))
-    split = max(1, min(math.ceil(M / 256), (2 * sm_count()) // tiles))
+    # output tiles as the tcgen05 kernel cuts them (128 x 64|128|256); one split-K work item per CTA at most: every
+    # work item ends with a full tile of fp32 reductions into `out`, so more items than CTAs only adds atomics
+    bn = 64 if K <= 64 else (128 if K <= 128 else 256)
+    tiles = max(1, math.ceil(N / 128) * math.ceil(K / bn))
+    split = max(1, min(math.ceil(M / 256), sm_count() // tiles))
     return gemm(dY.t(), X.t(), out, accumulate=True, split_k=split, engine=engine)
 
 
