@@ -119,6 +119,23 @@ __device__ __forceinline__ void cvt_raw8(const Raw8<bf16>& r, float (&v)[8]) {
   }
 }
 
+// 4 elements in storage format (8 bytes of bf16 / 16 bytes of fp32)
+template <typename T> struct Raw4;
+template <> struct Raw4<float> { float4 a; };
+template <> struct Raw4<bf16> { uint2 u; };
+__device__ __forceinline__ void raw4_zero(Raw4<float>& r) { r.a = make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ void raw4_zero(Raw4<bf16>& r) { r.u = make_uint2(0u, 0u); }
+__device__ __forceinline__ void ld_raw4(const float* p, Raw4<float>& r) { r.a = *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void ld_raw4(const bf16* p, Raw4<bf16>& r) { r.u = *reinterpret_cast<const uint2*>(p); }
+__device__ __forceinline__ void cvt_raw4(const Raw4<float>& r, float (&v)[4]) {
+  v[0] = r.a.x; v[1] = r.a.y; v[2] = r.a.z; v[3] = r.a.w;
+}
+__device__ __forceinline__ void cvt_raw4(const Raw4<bf16>& r, float (&v)[4]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r.u);
+  const float2 f0 = __bfloat1622float2(h[0]), f1 = __bfloat1622float2(h[1]);
+  v[0] = f0.x; v[1] = f0.y; v[2] = f1.x; v[3] = f1.y;
+}
+
 // VEC-wide generic versions (VEC in {1,2,4,8}); alignment = VEC*sizeof(T).
 template <int VEC, typename T>
 __device__ __forceinline__ void ldv(const T* p, float (&v)[VEC]) {

@@ -29,6 +29,9 @@ struct DwGeom {
   int tiles_h, tiles_w;
   int ntiles, nchunks, nworkers;
   FastDiv d_tw2, d_th2, d_tw;
+  FastDiv d_tiles_w, d_tiles_h;   // tile decode (valid while ntiles < 65536: `small`)
+  FastDiv d_ns2, d_ns4;           // strips of 2 / 4 output rows per tile (backward / tiled forward)
+  int small;
   int dbg;  // OGV_DW_DBG bit mask (bottleneck hunting only): 1 skip activation math, 2 skip stencil, 4 skip stores
 };
 
@@ -63,6 +66,11 @@ int dw_make_geom(int B, int H, int W, int Cm, int CC, int ctas_per_sm, DwGeom* g
   g->d_tw2 = make_fastdiv(g->TW2);
   g->d_th2 = make_fastdiv(g->TH2);
   g->d_tw = make_fastdiv(g->TW);
+  g->d_tiles_w = make_fastdiv(g->tiles_w);
+  g->d_tiles_h = make_fastdiv(g->tiles_h);
+  g->d_ns2 = make_fastdiv((g->TH + 1) / 2);
+  g->d_ns4 = make_fastdiv((g->TH + 3) / 4);
+  g->small = g->ntiles < 65536;
   {
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("OGV_DW_DBG"); dbg = e ? atoi(e) : 0; }
@@ -73,9 +81,10 @@ int dw_make_geom(int B, int H, int W, int Cm, int CC, int ctas_per_sm, DwGeom* g
 
 __device__ __forceinline__ void dw_decode_tile(const DwGeom& g, int t, int& b0, int& h0, int& w0) {
   // t = (grp * tiles_h + th) * tiles_w + tw ; tile counts per image are tiny, grp may be large
-  const int q = t / g.tiles_w;
+  // (runtime-divisor integer divisions cost ~5 % of the backward kernel's instructions: multiply-high instead)
+  const int q = g.small ? fdiv(t, g.d_tiles_w) : t / g.tiles_w;
   const int tw_i = t - q * g.tiles_w;
-  const int grp = q / g.tiles_h;
+  const int grp = g.small ? fdiv(q, g.d_tiles_h) : q / g.tiles_h;
   const int th_i = q - grp * g.tiles_h;
   b0 = grp * g.NI;
   h0 = th_i * g.TH;
@@ -233,7 +242,7 @@ dwconv_fwd_kernel(const __grid_constant__ CUtensorMap tm_in, const float* __rest
           rowitem = fdiv(rest, g.d_tw);
           x = rest - rowitem * g.TW;
         }
-        const int img = rowitem / nstrips;
+        const int img = fdiv(rowitem, g.d_ns4);
         const int r0 = (rowitem - img * nstrips) * R;
         const int b = b0 + img;
         if (b >= g.B || w0 + x >= g.W) continue;
@@ -425,7 +434,7 @@ dwconv_bwd_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constan
           rowitem = fdiv(rest, g.d_tw);
           x = rest - rowitem * g.TW;
         }
-        const int img = rowitem / nstrips;
+        const int img = fdiv(rowitem, g.d_ns2);
         const int r0 = (rowitem - img * nstrips) * R;
         const int b = b0 + img;
         if (b >= g.B || w0 + x >= g.W) continue;
@@ -477,21 +486,18 @@ dwconv_bwd_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constan
           }
         }
         T* out = du1 + (((long long)b * g.H + h0 + r0) * g.W + (w0 + x)) * g.Cm + c;
-        const float4 mu = *reinterpret_cast<const float4*>(&s_par[2][tv * 4]);
-        const float4 rs = *reinterpret_cast<const float4*>(&s_par[3][tv * 4]);
-        const float muv[4] = {mu.x, mu.y, mu.z, mu.w}, rsv[4] = {rs.x, rs.y, rs.z, rs.w};
 #pragma unroll
         for (int r = 0; r < R; ++r) {
           if (rvalid[r]) {
             float o[4], ev[4], dv[4];
-            ldv<4>(ep + r * g.TW * CC, ev);  // re-read (smem) instead of carrying xhat through the stencil
+            ldv<4>(ep + r * g.TW * CC, ev);  // re-read (smem) instead of carrying it through the stencil
             unpk2(de[r][0], dv[0], dv[1]);
             unpk2(de[r][1], dv[2], dv[3]);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               o[k] = dv[k] * da[r][k];
               a_db[k] += o[k];
-              a_dg[k] = fmaf(o[k], (ev[k] - muv[k]) * rsv[k], a_dg[k]);
+              a_dg[k] = fmaf(o[k], ev[k], a_dg[k]);  // sum o*e; xhat = (e - mean)*rstd is folded in at the end
             }
             stv<4>(out + (long long)r * g.W * g.Cm, o);
           }
@@ -509,7 +515,8 @@ dwconv_bwd_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constan
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       atomicAdd(&s_db[tv * 4 + k], a_db[k]);
-      atomicAdd(&s_dg[tv * 4 + k], a_dg[k]);
+      // sum o*xhat = rstd * (sum o*e - mean * sum o), per thread (a few hundred terms) before the CTA fold
+      atomicAdd(&s_dg[tv * 4 + k], s_par[3][tv * 4 + k] * (a_dg[k] - s_par[2][tv * 4 + k] * a_db[k]));
     }
 #pragma unroll
     for (int t9 = 0; t9 < 9; ++t9) {

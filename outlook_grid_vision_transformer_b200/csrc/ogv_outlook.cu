@@ -85,22 +85,49 @@ __global__ void __launch_bounds__(OL_THREADS) outlook_fwd_kernel(const T* __rest
     const float* a = A_s + (pos * g.heads + fdiv(c, g.d_hd)) * 9;
     const long long m = img + (long long)h * g.W + w;
     const T* vc = va + m * g.ld + c;
+    const bool rok[3] = {h >= 1, true, h + 1 < g.H};
+    const bool cok[3] = {w >= 1, true, w + 1 < g.W};
+    const int ldv_ = (int)g.ld, rowv = g.W * ldv_;
     float v[9][VEC], wt[9];
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
       const int dh = t / 3 - 1, dw = t % 3 - 1;
-      const bool ok = (unsigned)(h + dh) < (unsigned)g.H && (unsigned)(w + dw) < (unsigned)g.W;
-      ldv<VEC>(vc + (ok ? (long long)(dh * g.W + dw) * g.ld : 0), v[t]);
+      const bool ok = rok[dh + 1] && cok[dw + 1];
+      ldv<VEC>(vc + (ok ? dh * rowv + dw * ldv_ : 0), v[t]);
       wt[t] = ok ? a[t] : 0.f;
     }
     float acc[VEC];
+    if constexpr (VEC % 2 == 0) {
+      f32x2 acc2[VEC / 2];
 #pragma unroll
-    for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
+      for (int k = 0; k < VEC / 2; ++k) acc2[k] = 0ull;
 #pragma unroll
-    for (int t = 0; t < 9; ++t)
+      for (int t = 0; t < 9; ++t) {
+        const f32x2 w2 = pk2(wt[t], wt[t]);
 #pragma unroll
-      for (int k = 0; k < VEC; ++k) acc[k] = fmaf(wt[t], v[t][k], acc[k]);
+        for (int k = 0; k < VEC / 2; ++k) acc2[k] = fma2(w2, pk2(v[t][2 * k], v[t][2 * k + 1]), acc2[k]);
+      }
+#pragma unroll
+      for (int k = 0; k < VEC / 2; ++k) unpk2(acc2[k], acc[2 * k], acc[2 * k + 1]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
+#pragma unroll
+      for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) acc[k] = fmaf(wt[t], v[t][k], acc[k]);
+    }
     stv<VEC>(y + m * g.C + c, acc);
+  }
+}
+
+// zero the alignment padding [from, to) of one dva row (a few elements): 4-byte stores where the layout allows
+template <typename T>
+__device__ __forceinline__ void ol_zero_pad(T* row, int from, int to) {
+  if (sizeof(T) == 2 && ((from | to) & 1) == 0 && (reinterpret_cast<uintptr_t>(row) & 3) == 0) {
+    for (int j = from; j < to; j += 2) *reinterpret_cast<uint32_t*>(row + j) = 0u;
+  } else {
+    for (int j = from; j < to; ++j) st1(row + j, 0.f);
   }
 }
 
@@ -148,24 +175,38 @@ __global__ void __launch_bounds__(OL_THREADS) outlook_bwd_kernel(const T* __rest
     const T* gc = dy + m * g.C + c;
     float gctr[VEC], dv[VEC], dA[9];
     ldv<VEC>(gc, gctr);
-#pragma unroll
-    for (int k = 0; k < VEC; ++k) dv[k] = 0.f;
+    // tap validity as 3 row x 3 column flags and 32-bit element offsets (the per-tap 64-bit index arithmetic and
+    // the twice-evaluated bounds checks were over half of this kernel's instructions)
+    const bool rok[3] = {h >= 1, true, h + 1 < g.H};
+    const bool cok[3] = {w >= 1, true, w + 1 < g.W};
+    const int ldv_ = (int)g.ld, rowv = g.W * ldv_, rowg = g.W * g.C;
+    const int hw9 = g.heads * 9, whw9 = g.W * hw9;
+    const int abase = (((h - h_lo) * g.W + w) * g.heads + head) * 9;
     // two batches of unconditional loads: v at p + d_t (for dA), dy at q - d_t (for dv)
     {
       float v[9][VEC];
 #pragma unroll
       for (int t = 0; t < 9; ++t) {
         const int dh = t / 3 - 1, dw = t % 3 - 1;
-        const bool ok = (unsigned)(h + dh) < (unsigned)g.H && (unsigned)(w + dw) < (unsigned)g.W;
-        ldv<VEC>(vc + (ok ? (long long)(dh * g.W + dw) * g.ld : 0), v[t]);
+        const bool ok = rok[dh + 1] && cok[dw + 1];
+        ldv<VEC>(vc + (ok ? dh * rowv + dw * ldv_ : 0), v[t]);
       }
 #pragma unroll
       for (int t = 0; t < 9; ++t) {
         const int dh = t / 3 - 1, dw = t % 3 - 1;
-        const bool ok = (unsigned)(h + dh) < (unsigned)g.H && (unsigned)(w + dw) < (unsigned)g.W;
+        const bool ok = rok[dh + 1] && cok[dw + 1];
         float sdot = 0.f;
+        if constexpr (VEC % 2 == 0) {
+          f32x2 acc2 = 0ull;
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) sdot = fmaf(gctr[k], v[t][k], sdot);
+          for (int k = 0; k < VEC; k += 2) acc2 = fma2(pk2(gctr[k], gctr[k + 1]), pk2(v[t][k], v[t][k + 1]), acc2);
+          float lo, hi;
+          unpk2(acc2, lo, hi);
+          sdot = lo + hi;
+        } else {
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) sdot = fmaf(gctr[k], v[t][k], sdot);
+        }
         dA[t] = ok ? sdot : 0.f;
       }
     }
@@ -174,17 +215,32 @@ __global__ void __launch_bounds__(OL_THREADS) outlook_bwd_kernel(const T* __rest
 #pragma unroll
       for (int t = 0; t < 9; ++t) {
         const int dh = t / 3 - 1, dw = t % 3 - 1;
-        const int hh = h - dh, ww = w - dw;  // source position p = q - d_t used tap t to read q
-        const bool ok = (unsigned)hh < (unsigned)g.H && (unsigned)ww < (unsigned)g.W;
-        ldv<VEC>(gc - (ok ? (long long)(dh * g.W + dw) * g.C : 0), gs_[t]);
-        const int ai = ok ? (((hh - h_lo) * g.W + ww) * g.heads + head) * 9 + t : 0;
-        const float a = A_s[ai];
+        // source position p = q - d_t used tap t to read q
+        const bool ok = rok[1 - dh] && cok[1 - dw];
+        ldv<VEC>(gc - (ok ? dh * rowg + dw * g.C : 0), gs_[t]);
+        const float a = A_s[ok ? abase - dh * whw9 - dw * hw9 + t : 0];
         at[t] = ok ? a : 0.f;
       }
+      if constexpr (VEC % 2 == 0) {
+        f32x2 dv2[VEC / 2];
 #pragma unroll
-      for (int t = 0; t < 9; ++t)
+        for (int k = 0; k < VEC / 2; ++k) dv2[k] = 0ull;
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) dv[k] = fmaf(at[t], gs_[t][k], dv[k]);
+        for (int t = 0; t < 9; ++t) {
+          const f32x2 a2 = pk2(at[t], at[t]);
+#pragma unroll
+          for (int k = 0; k < VEC / 2; ++k) dv2[k] = fma2(a2, pk2(gs_[t][2 * k], gs_[t][2 * k + 1]), dv2[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < VEC / 2; ++k) unpk2(dv2[k], dv[2 * k], dv[2 * k + 1]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) dv[k] = 0.f;
+#pragma unroll
+        for (int t = 0; t < 9; ++t)
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) dv[k] = fmaf(at[t], gs_[t][k], dv[k]);
+      }
     }
     if (valid) stv<VEC>(dva + m * g.ld + c, dv);
     if (SHFL) {
@@ -199,8 +255,7 @@ __global__ void __launch_bounds__(OL_THREADS) outlook_bwd_kernel(const T* __rest
         T* out = dva + m * g.ld + g.C + head * 9;
 #pragma unroll
         for (int t = 0; t < 9; ++t) st1(out + t, a[t] * (dA[t] - dot));
-        if (head == 0)
-          for (int j = g.C + nl; j < g.ld; ++j) st1(dva + m * g.ld + j, 0.f);
+        if (head == 0) ol_zero_pad(dva + m * g.ld, g.C + nl, (int)g.ld);
       }
     } else if (valid) {
       float* dst = dA_s + (pos * g.heads + head) * 9;
@@ -223,8 +278,7 @@ __global__ void __launch_bounds__(OL_THREADS) outlook_bwd_kernel(const T* __rest
     T* out = dva + (img + (long long)r0 * g.W + pos) * g.ld + g.C + head * 9;
 #pragma unroll
     for (int t = 0; t < 9; ++t) st1(out + t, a[t] * (d[t] - dot));
-    if (head == 0)
-      for (int j = g.C + nl; j < g.ld; ++j) st1(dva + (img + (long long)r0 * g.W + pos) * g.ld + j, 0.f);
+    if (head == 0) ol_zero_pad(dva + (img + (long long)r0 * g.W + pos) * g.ld, g.C + nl, (int)g.ld);
   }
 }
 

@@ -1,10 +1,11 @@
 export PYTHONDONTWRITEBYTECODE=1
-sel=colsum,colstats,bn_bwd,se_pool,mbconv_bwd_stats,dw_bn2,rowscale
-OGV_LIB=$PWD/outlook_grid_vision_transformer_b200/_ab/libogvit_base.so python tools/kbench.py --only $sel --stages 0,1,2,3 --reps 30 --out gpurun_out/kb_base.json > /dev/null 2>&1
-python tools/kbench.py --only $sel --stages 0,1,2,3 --reps 30 --out gpurun_out/kb_new.json > /dev/null 2>&1
+sel=dwconv,outlook
+for tag in base v2; do OGV_LIB=$PWD/outlook_grid_vision_transformer_b200/_ab/libogvit_$tag.so python tools/kbench.py --only $sel --stages 0,1,2,3 --reps 20 --out gpurun_out/kb_$tag.json > /dev/null 2>&1; done
+python tools/kbench.py --only $sel --stages 0,1,2,3 --reps 20 --out gpurun_out/kb_new.json > /dev/null 2>&1
 python - <<PY
 import json
-b={r["kernel"]:r["ms"] for r in json.load(open("gpurun_out/kb_base.json"))}
-n={r["kernel"]:r for r in json.load(open("gpurun_out/kb_new.json"))}
-for k in b: print(f"{k:30s} base {b[k]*1e3:8.1f}  new {n[k]['ms']*1e3:8.1f}  {100*(n[k]['ms']/b[k]-1):+6.1f}%   {100*n[k]['frac']:5.1f}% HBM")
+L={t:{r["kernel"]:r for r in json.load(open(f"gpurun_out/kb_{t}.json"))} for t in ("base","v2","new")}
+for k in L["base"]:
+    b=L["base"][k]["ms"]
+    print(f"{k:24s} base {b*1e3:8.1f}  v2 {L['v2'][k]['ms']*1e3:8.1f} ({100*(L['v2'][k]['ms']/b-1):+5.1f}%)  new {L['new'][k]['ms']*1e3:8.1f} ({100*(L['new'][k]['ms']/b-1):+5.1f}%)  {100*L['new'][k]['frac']:5.1f}% HBM")
 PY
