@@ -155,3 +155,55 @@ def test_weight_copies_are_rebuilt_every_training_forward():
     with torch.no_grad():
         w.add_(1.0)                                             # versioned in-place update invalidates it
     assert prep.get(False, [w], torch.bfloat16, build) == 4
+
+
+def test_cast_item_record_matches_the_c_struct(tmp_path):
+    """ops.CastBatch writes ogv_cast_item records with numpy: the field offsets must be the C compiler's."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    root = Path(__file__).resolve().parent.parent
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "ogv.h"\nint main(void){'
+                   'printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(ogv_cast_item), offsetof(ogv_cast_item, src),'
+                   'offsetof(ogv_cast_item, dst), offsetof(ogv_cast_item, dst_t), offsetof(ogv_cast_item, ld_dst),'
+                   'offsetof(ogv_cast_item, ld_dst_t), offsetof(ogv_cast_item, rows), offsetof(ogv_cast_item, cols),'
+                   'offsetof(ogv_cast_item, tile0), offsetof(ogv_cast_item, dst_dtype));return 0;}')
+    exe = tmp_path / "layout"
+    subprocess.run([gcc, "-I", str(root / "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(v) for v in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    assert got == [56, 0, 8, 16, 24, 32, 40, 44, 48, 52]
+
+
+def test_bulk_refreshed_weight_copies_are_handed_out_only_while_fresh():
+    """_Prep in training mode: per-layer rebuild by default; the recorded buffers are reused only between
+    refresh_prepared() and the end of the forward (`_BULK_FRESH`), and never for other parameters / dtypes."""
+    from outlook_grid_vision_transformer_b200 import functional as OF
+    from outlook_grid_vision_transformer_b200 import modules as M
+    w = torch.nn.Parameter(torch.zeros(2, 2))
+    w2 = torch.nn.Parameter(torch.zeros(2, 2))
+    calls = []
+
+    def build():
+        calls.append(1)
+        if OF._CAST_LOG is not None:  # training-mode builds record their casts for refresh_prepared
+            OF._CAST_LOG.append(("src", "dst", None))
+        return len(calls)
+
+    prep = M._Prep()
+    assert prep.get(True, [w], torch.bfloat16, build) == 1
+    assert prep._bulk is not None and prep._bulk[2] == [("src", "dst", None)]
+    assert OF._CAST_LOG is None                                   # the recorder is off outside a build
+    assert prep.get(True, [w], torch.bfloat16, build) == 2        # not fresh: rebuilt
+    M._BULK_FRESH = True
+    try:
+        assert prep.get(True, [w], torch.bfloat16, build) == 2    # fresh: the recorded value, no rebuild
+        assert prep.get(True, [w2], torch.bfloat16, build) == 3   # other parameter storage: rebuilt
+        assert prep.get(True, [w2], torch.float16, build) == 4    # other dtype: rebuilt
+        assert prep.get(False, [w2], torch.float16, build) == 5   # eval mode has its own cache
+        assert prep.get(True, [w2], torch.float16, build) == 4    # ... which does not disturb the bulk record
+    finally:
+        M._BULK_FRESH = False
+    assert prep.get(True, [w2], torch.float16, build) == 6
