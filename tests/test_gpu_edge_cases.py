@@ -195,7 +195,7 @@ def test_bulk_weight_refresh_equals_per_layer_casts():
                 loss = F.cross_entropy(lg.float(), y)
                 loss.backward()
                 opt.step()
-                out.append(float(loss))
+                out.append(float(loss.detach()))
             losses.append(out)
         assert not M._BULK_FRESH
     assert losses[0] == pytest.approx(losses[1], rel=2e-3), f"{losses}"
