@@ -324,3 +324,50 @@ def test_rowscale_colsum_cast_transpose_adamw():
         opt.step()
         ops.adamw(p, g, m, v, 1e-2, 0.9, 0.999, 1e-8, 0.05, step)
     close(p, pr.detach(), 1e-5, "adamw")
+
+
+@pytest.mark.parametrize("C", [64, 128, 384, 1536], ids=lambda c: f"C{c}")
+@pytest.mark.parametrize("dt", DT, ids=IDS)
+def test_column_reductions_and_streaming_passes_at_scale(dt, C):
+    """Many CTAs, every fold path of the column-reduction skeleton (warp-shuffle pre-fold for C = 64 / 128,
+    thread-row fold for C = 384 / 1536), rows that do not divide the per-CTA row count, and the kernels that keep
+    several rows in flight per thread (LayerNorm, BatchNorm backward apply)."""
+    from outlook_grid_vision_transformer_b200 import ops
+    torch.manual_seed(C)
+    M = 20011
+    x = (torch.randn(M, C) * 1.3 + 0.4).to(dt)
+    dy = torch.randn(M, C).to(dt)
+    xd, dyd = x.double(), dy.double()
+    f = lambda *s: torch.zeros(s, device=DEV)  # noqa: E731
+    scale_t = 3e-4 if dt == torch.float32 else 2e-2  # sums of 2e4 terms: relative to the largest column result
+    out = f(C)
+    ops.colsum(dev(x), out)
+    close(out, xd.sum(0), scale_t, "colsum")
+    s, q = f(C), f(C)
+    ops.colstats(dev(x), s, q)
+    close(s, xd.sum(0), scale_t, "colstats sum")
+    close(q, (xd * xd).sum(0), scale_t, "colstats sumsq")
+    mean, var = xd.mean(0), xd.var(0, unbiased=False)
+    rstd = (var + 1e-5).rsqrt()
+    dg, db = f(C), f(C)
+    ops.bn_bwd_reduce(dev(dy), dev(x), dev(mean.float()), dev(rstd.float()), dg, db)
+    xh = (xd - mean) * rstd
+    close(db, dyd.sum(0), scale_t, "bn_bwd_reduce dbeta")
+    close(dg, (dyd * xh).sum(0), scale_t, "bn_bwd_reduce dgamma")
+    g = torch.rand(C).double() + 0.5
+    dx = ops.bn_bwd_apply(dev(dy), dev(x), dev(mean.float()), dev(rstd.float()), dev(g.float()), dg, db)
+    want = g * rstd * (dyd - dyd.sum(0) / M - xh * (dyd * xh).sum(0) / M)
+    close(dx, want, tol(dt) * 2, "bn_bwd_apply")
+    if C <= 1024:
+        w, b = torch.rand(C) + 0.5, torch.randn(C) * 0.1
+        xr = xd.clone().requires_grad_(True)
+        wr, br = w.double().requires_grad_(True), b.double().requires_grad_(True)
+        yr = F.layer_norm(xr, (C,), wr, br, 1e-5)
+        (yr * dyd).sum().backward()
+        y, mu, rs = ops.layernorm_fwd(dev(x), dev(w), dev(b), 1e-5)
+        close(y, yr.detach(), tol(dt), "layernorm fwd")
+        dgam, dbet = f(C), f(C)
+        dxl = ops.layernorm_bwd(dev(dy), dev(x), dev(w), mu, rs, None, dgam, dbet)
+        close(dxl, xr.grad, tol(dt) * 2, "layernorm dx")
+        close(dgam, wr.grad, scale_t, "layernorm dgamma")
+        close(dbet, br.grad, scale_t, "layernorm dbeta")
