@@ -3,6 +3,7 @@
 surface.  All compute runs in libogvit.so (hand-written CUDA, C-ABI in include/ogv.h); there is no
 CPU path and no Triton / torch.compile path.
 """
+from .dropin import find_reference_root, install, uninstall
 from .config import BASELINE_CONFIGS, StageCfg, build_stages, load_yaml
 from .model import (ConvStem, Downsample, DownsampleConfig, MaxOutNet, OutlookerFrontGridNet, build_model,
                     make_dpr)
