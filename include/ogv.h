@@ -213,6 +213,27 @@ int ogv_grid_attn_probs(const void* qkv, float* attn, int B, int H, int W, int C
 int ogv_adamw(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
               float eps, float weight_decay, float bias_c1, float bias_c2, float grad_scale, void* stream);
 
+
+/* ---------------------------------------------------------------------------------------------
+ * Sync-free tail of the train step over FLAT fp32 arenas (parameters, gradients, Adam moments laid out
+ * back to back, every parameter starting on an 8-float granule) -- what lets one captured CUDA graph follow the
+ * reference's per-step host logic (one_epoch_train.py:98-166) without a host sync:
+ *   ogv_sumsq         : out[0] += sum g^2  -- the global gradient norm of clip_grad_norm_ (one_epoch_train.py:141).
+ *   ogv_adamw_flat    : clip + AdamW (train_full_model.py:56-57) in one pass.  hyper (DEVICE fp32[5]) =
+ *                       { lr, 1-beta1^t, 1-beta2^t, grad_scale (1/world), max_norm (<=0: no clip) } is rewritten by the
+ *                       host before every replay, so WarmupCosineLR (warmup.py:29-59) works under graph replay;
+ *                       decay_bits: bit i = granule i takes weight decay (the two param groups of warmup.py:4-26);
+ *                       the update is SKIPPED when *loss or *gnorm_sq is not finite (one_epoch_train.py:99-109) and
+ *                       *skipped is incremented; gnorm_sq / loss / skipped may be null.
+ *   ogv_train_metrics : acc[5] += { loss*B, top-1, top-3, top-5 hits, B } from fp32 logits [B, K] (row stride ld) and
+ *                       int64 labels (metrics.py:7-24, one_epoch_train.py:155-166) -- read back once per epoch. */
+int ogv_sumsq(const float* g, long long n, float* out, void* stream);
+int ogv_adamw_flat(float* p, const float* g, float* m, float* v, const unsigned* decay_bits, long long n,
+                   const float* hyper, const float* gnorm_sq, const float* loss, float beta1, float beta2, float eps,
+                   float weight_decay, float* skipped, void* stream);
+int ogv_train_metrics(const float* logits, long long ld, const long long* labels, int B, int K, const float* loss,
+                      float* acc, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

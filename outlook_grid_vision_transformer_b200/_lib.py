@@ -75,6 +75,9 @@ SIGNATURES = {
     "ogv_grid_attn_bwd": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "ogv_grid_attn_probs": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "ogv_adamw": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _F, _F, _F, _P],
+    "ogv_sumsq": [_P, _L, _P, _P],
+    "ogv_adamw_flat": [_P, _P, _P, _P, _P, _L, _P, _P, _P, _F, _F, _F, _F, _P, _P],
+    "ogv_train_metrics": [_P, _L, _P, _I, _I, _P, _P, _P],
 }
 _RESTYPES = {"ogv_last_error": c_char_p}
 
@@ -89,7 +92,7 @@ def lib() -> ctypes.CDLL:
     if not LIB_PATH.exists() or os.environ.get("OGV_REBUILD") == "1":
         from . import build as _build  # nvcc cross-compiles without a GPU
 
-        _build.build(force=os.environ.get("OGV_REBUILD") == "1")
+        _build.build(force=os.environ.get("OGV_REBUILD") == "1")  # file-locked: one builder across ranks
     if not LIB_PATH.exists():
         raise RuntimeError(f"{LIB_PATH} is missing: the CUDA extension is required, there is no CPU fallback")
     # OGV_LIB: load another build of the SAME library (A/B measurements of a kernel change on one box)

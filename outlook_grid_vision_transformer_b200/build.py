@@ -30,6 +30,7 @@ SOURCES = [
     "ogv_dwconv.cu",
     "ogv_tma.cu",
     "ogv_gridattn.cu",
+    "ogv_optim.cu",
 ]
 
 NVCC_FLAGS = [
@@ -71,17 +72,35 @@ def _compile_one(src: str, verbose: bool) -> Path:
 
 
 def build(force: bool = False, verbose: bool = False) -> Path:
+    """Compile + link in-tree.  Guarded by an exclusive file lock and finished with an atomic rename, so the ranks of a
+    multi-process launch that all find the library missing cannot interleave writes to _build/*.o or load a
+    half-written libogvit.so: the first one builds, the others wait and find it up to date."""
     if not force and not needs_build():
         return LIB_PATH
+    import fcntl
+
     BUILD_DIR.mkdir(exist_ok=True)
+    with open(BUILD_DIR / ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not needs_build():
+                return LIB_PATH
+            return _build_locked(verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(verbose: bool) -> Path:
     with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as pool:
         objs = list(pool.map(lambda s: _compile_one(s, verbose), SOURCES))
-    cmd = [_nvcc(), "-shared", "-o", str(LIB_PATH), *map(str, objs),
+    tmp = LIB_PATH.with_suffix(f".so.tmp{os.getpid()}")
+    cmd = [_nvcc(), "-shared", "-o", str(tmp), *map(str, objs),
            "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC", "-lcudart_static", "-lpthread", "-ldl", "-lrt"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(f"$ {' '.join(cmd)}\n{res.stdout}{res.stderr}\n")
         raise RuntimeError("link of libogvit.so failed")
+    os.replace(tmp, LIB_PATH)
     return LIB_PATH
 
 

@@ -615,7 +615,9 @@ int ogv_gemm_tc(const ogv_gemm_args& a, cudaStream_t stream) {
   auto ok = [&](const void* ptr, long long ld) {
     return ptr == nullptr || ((reinterpret_cast<uintptr_t>(ptr) % 16 == 0) && ((ld * esz) % 16 == 0));
   };
-  p.vec_ok = (a.accumulate || ok(a.D, a.ldd)) && ok(a.pre_out, a.ld_pre) && ok(a.dact_src, a.ld_dact) &&
+  // accumulate: D is fp32 whatever TO is, and red.global.v4.f32 needs 16-byte aligned addresses (D base and ldd*4)
+  const bool acc_ok = (reinterpret_cast<uintptr_t>(a.D) % 16 == 0) && (a.ldd % 4 == 0);
+  p.vec_ok = (a.accumulate ? acc_ok : ok(a.D, a.ldd)) && ok(a.pre_out, a.ld_pre) && ok(a.dact_src, a.ld_dact) &&
              ok(a.residual, a.ld_res);
 
   CUtensorMap tms[5];

@@ -360,7 +360,7 @@ extern "C" int ogv_rowscale(const void* x, const float* scale, void* y, long lon
   OGV_REQUIRE(x && y && scale && cols % 8 == 0 && rows_per_scale > 0, "rowscale: bad args (cols %% 8 == 0)");
   long long nvec = rows * (cols / 8);
   if (nvec == 0) return OGV_OK;
-  int grid = (int)((nvec + 255) / 256 < 148 * 16 ? (nvec + 255) / 256 : 148 * 16);
+  int grid = (int)((nvec + 255) / 256 < ogv_num_sms() * 16 ? (nvec + 255) / 256 : ogv_num_sms() * 16);
   OGV_DISPATCH_DTYPE(dtype, T, {
     rowscale_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const T*>(x), scale,
                                                                reinterpret_cast<T*>(y), nvec, cols / 8,
@@ -387,7 +387,7 @@ extern "C" int ogv_mul_dact(const void* a, const void* pre, void* out, long long
                             void* stream) {
   if (n == 0) return OGV_OK;
   OGV_REQUIRE(a && pre && out, "mul_dact: null");
-  int grid = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
+  int grid = (int)((n + 255) / 256 < ogv_num_sms() * 16 ? (n + 255) / 256 : ogv_num_sms() * 16);
   OGV_DISPATCH_DTYPE(dtype, T, {
     mul_dact_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const T*>(a),
                                                                reinterpret_cast<const T*>(pre),
@@ -399,7 +399,7 @@ extern "C" int ogv_mul_dact(const void* a, const void* pre, void* out, long long
 extern "C" int ogv_add(const void* a, const void* b, void* y, long long n, int dtype, void* stream) {
   if (n == 0) return OGV_OK;
   OGV_REQUIRE(a && b && y, "add: null");
-  int grid = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
+  int grid = (int)((n + 255) / 256 < ogv_num_sms() * 16 ? (n + 255) / 256 : ogv_num_sms() * 16);
   OGV_DISPATCH_DTYPE(dtype, T, {
     add_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const T*>(a),
                                                           reinterpret_cast<const T*>(b), reinterpret_cast<T*>(y), n);
@@ -412,7 +412,7 @@ extern "C" int ogv_adamw(float* p, const float* g, float* m, float* v, long long
                          void* stream) {
   if (n == 0) return OGV_OK;
   OGV_REQUIRE(p && g && m && v, "adamw: null");
-  int grid = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
+  int grid = (int)((n + 255) / 256 < ogv_num_sms() * 16 ? (n + 255) / 256 : ogv_num_sms() * 16);
   adamw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bias_c1,
                                                        bias_c2, grad_scale);
   return ogv_check_launch("adamw");

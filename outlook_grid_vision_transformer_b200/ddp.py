@@ -120,6 +120,95 @@ class BucketedGradAllReduce:
         self._hooks = []
 
 
+class ArenaGradAllReduce:
+    """Gradient all-reduce IN PLACE on slices of engine.FlatState's flat gradient arena: no pack / unpack copies and
+    no scaling pass (the optimizer kernel folds 1/world into its gradient scale, `TrainStep(world=...)`).
+
+    Buckets are contiguous arena slices cut from the END (gradients become ready from the last layer backwards);
+    the bucket that finishes last -- the front of the arena, i.e. the first layers -- is kept small (`tail_bytes`), so
+    the all-reduce that cannot overlap with backward is short.  A bucket is launched on a side stream the moment its
+    last parameter reports in: autograd post-accumulate hooks for the layers torch differentiates (stem, downsample,
+    head), `functional.GRAD_READY` for the fused branches that accumulate into the arena themselves."""
+
+    def __init__(self, flat, bucket_bytes: int = 8 << 20, tail_bytes: int = 1 << 20, process_group=None):
+        from . import functional as _OF
+
+        self.flat, self.group = flat, process_group
+        self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        params, offsets = flat.params, flat.offsets
+        self.buckets = []  # dict(lo, hi, params, pending, work), in launch order (end of the arena first)
+        cur, cur_hi, tail_cut = [], flat.n, False
+        for i in range(len(params) - 1, -1, -1):
+            cur.append(params[i])
+            lo = offsets[i]
+            cut = (cur_hi - lo) * 4 >= bucket_bytes
+            if not tail_cut and 0 < lo * 4 <= tail_bytes:  # what is left in front of here is the short last bucket
+                cut, tail_cut = True, True
+            if cut and i > 0:
+                self.buckets.append(dict(lo=lo, hi=cur_hi, params=cur, pending=len(cur), work=None))
+                cur, cur_hi = [], lo
+        if cur:
+            self.buckets.append(dict(lo=0, hi=cur_hi, params=cur, pending=len(cur), work=None))
+        self._owner = {p: b for b in self.buckets for p in b["params"]}
+        self._comm_stream = None
+        self._hooks = []
+        self._OF = _OF
+        if self.world > 1:
+            for p in params:
+                self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad_ready))
+            _OF.GRAD_READY = self._on_params_ready
+
+    def _on_params_ready(self, plist) -> None:
+        for p in plist:
+            self._on_grad_ready(p)
+
+    def _on_grad_ready(self, p) -> None:
+        b = self._owner.get(p)
+        if b is None:
+            return
+        b["pending"] -= 1
+        if b["pending"] == 0:
+            self._launch(b)
+
+    def _launch(self, b) -> None:
+        buf = self.flat.G[b["lo"]:b["hi"]]
+        if buf.is_cuda:
+            if self._comm_stream is None:
+                self._comm_stream = torch.cuda.Stream(device=buf.device)
+            ready = torch.cuda.Event()
+            ready.record(torch.cuda.current_stream(buf.device))
+            with torch.cuda.stream(self._comm_stream):
+                self._comm_stream.wait_event(ready)
+                b["work"] = dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        else:
+            b["work"] = dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+
+    def finish(self) -> None:
+        """Launch what is still pending (parameters that received no gradient), wait for every bucket, re-arm."""
+        if self.world > 1:
+            for b in self.buckets:
+                if b["work"] is None:
+                    self._launch(b)
+            for b in self.buckets:
+                if self._comm_stream is not None:
+                    with torch.cuda.stream(self._comm_stream):
+                        b["work"].wait()
+                else:
+                    b["work"].wait()
+            if self._comm_stream is not None:
+                torch.cuda.current_stream().wait_stream(self._comm_stream)
+        for b in self.buckets:
+            b["pending"] = len(b["params"])
+            b["work"] = None
+
+    def remove(self) -> None:
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []
+        if self._OF.GRAD_READY == self._on_params_ready:
+            self._OF.GRAD_READY = None
+
+
 def broadcast_parameters(module: torch.nn.Module, src: int = 0, process_group=None) -> None:
     """Make every replica start from rank `src`'s parameters and buffers."""
     if not dist.is_initialized() or dist.get_world_size(process_group) == 1:

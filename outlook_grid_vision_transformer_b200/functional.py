@@ -84,6 +84,32 @@ def _zeros(shape, like: Tensor) -> Tensor:
     return torch.zeros(shape, device=like.device, dtype=torch.float32)
 
 
+# Engine hooks (engine.FlatState / ddp.ArenaGradAllReduce).  With a module in "direct" mode every parameter's .grad is
+# a view of ONE flat fp32 arena that the train step zeroes with a single memset: the backward kernels (all of them
+# accumulate: split-K `red`, column-sum atomics) add straight into those views and the autograd functions return None
+# for the parameters -- no per-branch zero-filled arenas (~190 fill launches per step), no AccumulateGrad copies, no
+# pack / unpack around the gradient all-reduce.
+SCRATCH = None     # object with .take(n) -> zeroed fp32 view or None (pre-zeroed by the step's memset)
+GRAD_READY = None  # callable(list of parameters whose gradients are complete) -- the all-reduce bucket trigger
+
+
+def _scratch_zeros(n: int, like: Tensor) -> Tensor:
+    if SCRATCH is not None:
+        t = SCRATCH.take(n)
+        if t is not None:
+            return t
+    return _zeros(n, like)
+
+
+def _notify(params) -> None:
+    if GRAD_READY is not None:
+        GRAD_READY([p for p in params if p is not None])
+
+
+def _is_direct(meta, params) -> bool:
+    return bool(meta.get("direct")) and all(p is None or p.grad is not None for p in params)
+
+
 def _empty(shape, like: Tensor, dtype=None) -> Tensor:
     return torch.empty(shape, device=like.device, dtype=dtype or like.dtype)
 
@@ -101,6 +127,7 @@ class MlpBranchFn(torch.autograd.Function):
         x = x.contiguous()
         M, C = x.shape
         Hd = p1.w.shape[0]
+        ops.PROFILER.tag = ("K4a" if Hd <= 2 * C else "K4b", "fwd", M, C)
         if with_ln:
             xn, mean, rstd = ops.layernorm_fwd(x, ln_w, ln_b, meta["eps"])
         else:
@@ -113,6 +140,7 @@ class MlpBranchFn(torch.autograd.Function):
         y = _empty((M, C), x)
         ops.gemm(h, p2.w, y, bias=b2, row_scale=scale, rows_per_scale=P, residual=x if with_res else None)
         ctx.meta = meta
+        ctx.params = (ln_w, ln_b, w1, b1, w2, b2)
         ctx.save_for_backward(x, xn, mean, rstd, z, h, ln_w, scale)
         return y
 
@@ -127,15 +155,21 @@ class MlpBranchFn(torch.autograd.Function):
         dy = dy.contiguous()
         M, C = x.shape
         Hd = p1.w.shape[0]
-        # one zeroed fp32 arena for all parameter gradients of the branch
-        arena = _zeros(Hd * C * 2 + Hd + C + 2 * C, x)
-        o = 0
-        dW1 = arena[o:o + Hd * C].view(Hd, C); o += Hd * C
-        dW2 = arena[o:o + C * Hd].view(C, Hd); o += C * Hd
-        db1 = arena[o:o + Hd]; o += Hd
-        db2 = arena[o:o + C]; o += C
-        dg = arena[o:o + C]; o += C
-        dbt = arena[o:o + C]; o += C
+        ops.PROFILER.tag = ("K4a" if Hd <= 2 * C else "K4b", "bwd", M, C)
+        direct = _is_direct(meta, ctx.params)
+        if direct:  # accumulate straight into the parameters' views of the flat gradient arena
+            pl, pb, pw1, pb1, pw2, pb2 = ctx.params
+            dW1, dW2, db1, db2 = pw1.grad.view(Hd, C), pw2.grad.view(C, Hd), pb1.grad, pb2.grad
+            dg, dbt = (pl.grad, pb.grad) if with_ln else (None, None)
+        else:  # one zeroed fp32 arena for all parameter gradients of the branch
+            arena = _zeros(Hd * C * 2 + Hd + C + 2 * C, x)
+            o = 0
+            dW1 = arena[o:o + Hd * C].view(Hd, C); o += Hd * C
+            dW2 = arena[o:o + C * Hd].view(C, Hd); o += C * Hd
+            db1 = arena[o:o + Hd]; o += Hd
+            db2 = arena[o:o + C]; o += C
+            dg = arena[o:o + C]; o += C
+            dbt = arena[o:o + C]; o += C
         gy = _scaled_grad(dy, scale, P, db2)
         # fc2 backward (+ activation derivative and the fc1 bias gradient fused into the dgrad epilogue)
         dz = _empty((M, Hd), x)
@@ -151,15 +185,18 @@ class MlpBranchFn(torch.autograd.Function):
         else:
             ops.gemm(dz, p1.wt, dxn, residual=dy if with_res else None)
         ops.wgrad(dz, xn, dW1)
+        dx = ops.layernorm_bwd(dxn, x, ln_w, mean, rstd, dy if with_res else None, dg, dbt) if with_ln else dxn
+        if direct:
+            _notify(ctx.params)
+            return (dx,) + (None,) * 8
         if with_ln:
-            dx = ops.layernorm_bwd(dxn, x, ln_w, mean, rstd, dy if with_res else None, dg, dbt)
             return dx, dg, dbt, dW1.view(meta["w1_shape"]), db1, dW2.view(meta["w2_shape"]), db2, None, None
         return dxn, None, None, dW1.view(meta["w1_shape"]), db1, dW2.view(meta["w2_shape"]), db2, None, None
 
 
 def mlp_branch(x: Tensor, ln_w, ln_b, w1, b1, w2, b2, scale, *, p1, p2, eps: float, act: str, rows_per_sample: int,
-               with_res: bool) -> Tensor:
-    meta = dict(p1=p1, p2=p2, eps=eps, act=act, rows_per_sample=rows_per_sample, with_res=with_res,
+               with_res: bool, direct: bool = False) -> Tensor:
+    meta = dict(p1=p1, p2=p2, eps=eps, act=act, rows_per_sample=rows_per_sample, with_res=with_res, direct=direct,
                 w1_shape=tuple(w1.shape), w2_shape=tuple(w2.shape))
     return MlpBranchFn.apply(x, ln_w, ln_b, w1, b1, w2, b2, scale, meta)
 
@@ -182,6 +219,7 @@ class OutlookBranchFn(torch.autograd.Function):
         x = x.contiguous()
         M, C = x.shape
         npad = pva.w.shape[0]
+        ops.PROFILER.tag = ("K1", "fwd", M, C, heads)
         if with_ln:
             xn, mean, rstd = ops.layernorm_fwd(x, ln_w, ln_b, meta["eps"])
         else:
@@ -192,6 +230,7 @@ class OutlookBranchFn(torch.autograd.Function):
         y = _empty((M, C), x)
         ops.gemm(yc, pp.w, y, bias=bp, row_scale=scale, rows_per_scale=g.P, residual=x if with_res else None)
         ctx.meta = meta
+        ctx.params = (ln_w, ln_b, wv, bv, wa, ba, wp, bp)
         ctx.save_for_backward(x, xn, mean, rstd, va, yc, ln_w, scale)
         return y
 
@@ -207,15 +246,24 @@ class OutlookBranchFn(torch.autograd.Function):
         dy = dy.contiguous()
         M, C = x.shape
         npad = pva.w.shape[0]
+        ops.PROFILER.tag = ("K1", "bwd", M, C, heads)
         nl = 9 * heads
-        arena = _zeros(npad * C + C * C + npad + C + 2 * C, x)
-        o = 0
-        dWva = arena[o:o + npad * C].view(npad, C); o += npad * C
-        dWp = arena[o:o + C * C].view(C, C); o += C * C
-        dbva = arena[o:o + npad]; o += npad
-        dbp = arena[o:o + C]; o += C
-        dg = arena[o:o + C]; o += C
-        dbt = arena[o:o + C]; o += C
+        flat = meta.get("flat")  # (dWva [npad, C], dbva [npad]) views over (v | attn | pad) in the flat gradient arena
+        direct = _is_direct(meta, ctx.params) and flat is not None
+        if direct:
+            pl, pb, pwv, pbv, pwa, pba, pwp, pbp = ctx.params
+            dWva, dbva = flat
+            dWp, dbp = pwp.grad.view(C, C), pbp.grad
+            dg, dbt = (pl.grad, pb.grad) if with_ln else (None, None)
+        else:
+            arena = _zeros(npad * C + C * C + npad + C + 2 * C, x)
+            o = 0
+            dWva = arena[o:o + npad * C].view(npad, C); o += npad * C
+            dWp = arena[o:o + C * C].view(C, C); o += C * C
+            dbva = arena[o:o + npad]; o += npad
+            dbp = arena[o:o + C]; o += C
+            dg = arena[o:o + C]; o += C
+            dbt = arena[o:o + C]; o += C
         gy = _scaled_grad(dy, scale, g.P, dbp)
         dyc = _empty((M, C), x)
         ops.gemm(gy, pp.wt, dyc)
@@ -228,6 +276,10 @@ class OutlookBranchFn(torch.autograd.Function):
             ops.gemm(dva, pva.wt, dxn, residual=dy if with_res else None)
         ops.wgrad(dva, xn, dWva)
         ops.colsum(dva, dbva)
+        if direct:
+            dx = ops.layernorm_bwd(dxn, x, ln_w, mean, rstd, dy if with_res else None, dg, dbt) if with_ln else dxn
+            _notify(ctx.params)
+            return (dx,) + (None,) * 10
         dwv = dWva[:C].reshape(meta["wv_shape"])
         dwa = dWva[C:C + nl].reshape(meta["wa_shape"])
         dbv = dbva[:C] if meta["has_qkv_bias"] else None
@@ -260,8 +312,8 @@ def prepare_outlook_va(wv: Tensor, bv: Optional[Tensor], wa: Tensor, ba: Optiona
 
 
 def outlook_branch(x, ln_w, ln_b, wv, bv, wa, ba, wp, bp, scale, *, pva, bva, pp, geom: Geom, heads: int, eps: float,
-                   with_res: bool) -> Tensor:
-    meta = dict(pva=pva, bva=bva, pp=pp, geom=geom, heads=heads, eps=eps, with_res=with_res,
+                   with_res: bool, direct: bool = False, flat=None) -> Tensor:
+    meta = dict(pva=pva, bva=bva, pp=pp, geom=geom, heads=heads, eps=eps, with_res=with_res, direct=direct, flat=flat,
                 wv_shape=tuple(wv.shape), wa_shape=tuple(wa.shape), wp_shape=tuple(wp.shape),
                 has_qkv_bias=bv is not None)
     return OutlookBranchFn.apply(x, ln_w, ln_b, wv, bv, wa, ba, wp, bp, scale, meta)
@@ -280,6 +332,7 @@ class GridBranchFn(torch.autograd.Function):
         with_ln = ln_w is not None
         x = x.contiguous()
         M, C = x.shape
+        ops.PROFILER.tag = ("K2", "fwd", M, C, (g.H // gs) * (g.W // gs))
         if with_ln:
             xn, mean, rstd = ops.layernorm_fwd(x, ln_w, ln_b, meta["eps"])
         else:
@@ -293,6 +346,7 @@ class GridBranchFn(torch.autograd.Function):
         y = _empty((M, C), x)
         ops.gemm(o, pp.w, y, bias=bp, row_scale=scale, rows_per_scale=g.P, residual=x if with_res else None)
         ctx.meta = meta
+        ctx.params = (ln_w, ln_b, wqkv, bqkv, wp, bp)
         ctx.save_for_backward(x, xn, mean, rstd, qkv, o, ln_w, scale)
         return y
 
@@ -307,14 +361,21 @@ class GridBranchFn(torch.autograd.Function):
         with_ln = ln_w is not None
         dy = dy.contiguous()
         M, C = x.shape
-        arena = _zeros(3 * C * C + C * C + 3 * C + C + 2 * C, x)
-        off = 0
-        dWq = arena[off:off + 3 * C * C].view(3 * C, C); off += 3 * C * C
-        dWp = arena[off:off + C * C].view(C, C); off += C * C
-        dbq = arena[off:off + 3 * C]; off += 3 * C
-        dbp = arena[off:off + C]; off += C
-        dg = arena[off:off + C]; off += C
-        dbt = arena[off:off + C]; off += C
+        ops.PROFILER.tag = ("K2", "bwd", M, C, (g.H // gs) * (g.W // gs))
+        direct = _is_direct(meta, ctx.params) and meta["has_qkv_bias"]
+        if direct:
+            pl, pb, pwq, pbq, pwp, pbp = ctx.params
+            dWq, dWp, dbq, dbp = pwq.grad.view(3 * C, C), pwp.grad.view(C, C), pbq.grad, pbp.grad
+            dg, dbt = (pl.grad, pb.grad) if with_ln else (None, None)
+        else:
+            arena = _zeros(3 * C * C + C * C + 3 * C + C + 2 * C, x)
+            off = 0
+            dWq = arena[off:off + 3 * C * C].view(3 * C, C); off += 3 * C * C
+            dWp = arena[off:off + C * C].view(C, C); off += C * C
+            dbq = arena[off:off + 3 * C]; off += 3 * C
+            dbp = arena[off:off + C]; off += C
+            dg = arena[off:off + C]; off += C
+            dbt = arena[off:off + C]; off += C
         gy = _scaled_grad(dy, scale, g.P, dbp)
         do = _empty((M, C), x)
         ops.gemm(gy, pp.wt, do)
@@ -327,6 +388,10 @@ class GridBranchFn(torch.autograd.Function):
             ops.gemm(dqkv, pq.wt, dxn, residual=dy if with_res else None)
         ops.wgrad(dqkv, xn, dWq)
         ops.colsum(dqkv, dbq)
+        if direct:
+            dx = ops.layernorm_bwd(dxn, x, ln_w, mean, rstd, dy if with_res else None, dg, dbt) if with_ln else dxn
+            _notify(ctx.params)
+            return (dx,) + (None,) * 8
         dbq_out = dbq if meta["has_qkv_bias"] else None
         if with_ln:
             dx = ops.layernorm_bwd(dxn, x, ln_w, mean, rstd, dy if with_res else None, dg, dbt)
@@ -335,8 +400,8 @@ class GridBranchFn(torch.autograd.Function):
 
 
 def grid_branch(x, ln_w, ln_b, wqkv, bqkv, wp, bp, scale, *, pq, pp, geom: Geom, heads: int, grid: int, eps: float,
-                with_res: bool, capture=None) -> Tensor:
-    meta = dict(pq=pq, pp=pp, geom=geom, heads=heads, grid=grid, eps=eps, with_res=with_res, capture=capture,
+                with_res: bool, capture=None, direct: bool = False) -> Tensor:
+    meta = dict(pq=pq, pp=pp, geom=geom, heads=heads, grid=grid, eps=eps, with_res=with_res, capture=capture, direct=direct,
                 has_qkv_bias=bqkv is not None)
     return GridBranchFn.apply(x, ln_w, ln_b, wqkv, bqkv, wp, bp, scale, meta)
 
@@ -355,9 +420,10 @@ class MBConvFn(torch.autograd.Function):
         x = x.contiguous()
         M, C = x.shape
         Cm = pe.w.shape[0]
+        ops.PROFILER.tag = ("K3", "fwd", M, C)
         Cs = sw1.shape[0]
         # fp32 scratch for the three BatchNorms: [sum, sumsq, scale, shift, mean, rstd] x channels
-        st = _zeros(6 * (2 * Cm + C), x)
+        st = _scratch_zeros(6 * (2 * Cm + C), x)
         def carve(base, n):
             return [st[base + i * n: base + (i + 1) * n] for i in range(6)]
         s1 = carve(0, Cm)
@@ -400,6 +466,7 @@ class MBConvFn(torch.autograd.Function):
         y = ops.bn_apply(o_pre, s3[2], s3[3], x if meta["use_res"] else None)
         ctx.meta = meta
         ctx.wdw2 = wdw2
+        ctx.params = (we, g1, b1, wdw, g2, b2, sw1, sb1, sw2, sb2, wp, g3, b3)
         ctx.save_for_backward(x, e_pre, d_pre, d_act, o_pre, st, pool_c, s1_pre, s1a, gate_pre, gate, g1, g2, g3, sw1, sw2)
         return y
 
@@ -414,6 +481,7 @@ class MBConvFn(torch.autograd.Function):
         dy = dy.contiguous()
         M, C = x.shape
         Cm = pe.w.shape[0]
+        ops.PROFILER.tag = ("K3", "bwd", M, C)
         Cs = sw1.shape[0]
         def carve(base, n):
             return [st[base + i * n: base + (i + 1) * n] for i in range(6)]
@@ -421,13 +489,17 @@ class MBConvFn(torch.autograd.Function):
         s2 = carve(6 * Cm, Cm)
         s3 = carve(12 * Cm, C)
         sizes = [Cm * C, Cm, Cm, Cm * 9, Cm, Cm, Cs * Cm, Cs, Cm * Cs, Cm, C * Cm, C, C]
-        # pad every slice to a multiple of 8 floats so vector loads of the BN partial sums stay aligned
-        offs, tot = [], 0
-        for s in sizes:
-            offs.append(tot)
-            tot += (s + 7) // 8 * 8
-        arena = _zeros(tot, x)
-        sl = [arena[o:o + s] for o, s in zip(offs, sizes)]
+        direct = _is_direct(meta, ctx.params)
+        if direct:  # every parameter starts on an 8-float granule of the flat gradient arena
+            sl = [p.grad.view(-1) for p in ctx.params]
+        else:
+            # pad every slice to a multiple of 8 floats so vector loads of the BN partial sums stay aligned
+            offs, tot = [], 0
+            for s in sizes:
+                offs.append(tot)
+                tot += (s + 7) // 8 * 8
+            arena = _zeros(tot, x)
+            sl = [arena[o:o + s] for o, s in zip(offs, sizes)]
         dWe, dg1, db1, dwdw, dg2, db2, dsw1, dsb1, dsw2, dsb2, dWp, dg3, db3 = sl
         dWe = dWe.view(Cm, C); dsw1 = dsw1.view(Cs, Cm); dsw2 = dsw2.view(Cm, Cs); dWp = dWp.view(C, Cm)
         # BN3 backward
@@ -435,8 +507,8 @@ class MBConvFn(torch.autograd.Function):
         # BatchNorm backward vanish -- same kernels, zero vectors in place of (dgamma, dbeta) in the apply steps;
         # the parameter gradients dgamma / dbeta themselves are unchanged.
         training = meta["training"]
-        zC = None if training else _zeros(C, x)
-        zM = None if training else _zeros(Cm, x)
+        zC = None if training else _scratch_zeros(C, x)
+        zM = None if training else _scratch_zeros(Cm, x)
         ops.bn_bwd_reduce(dy, o_pre, s3[4], s3[5], dg3, db3)
         do_pre = ops.bn_bwd_apply(dy, o_pre, s3[4], s3[5], g3, dg3 if training else zC, db3 if training else zC)
         # project backward
@@ -469,14 +541,18 @@ class MBConvFn(torch.autograd.Function):
         dx = _empty((M, C), x)
         ops.gemm(de_pre, pe.wt, dx, residual=dy if meta["use_res"] else None)
         ops.wgrad(de_pre, x, dWe)
+        if direct:
+            _notify(ctx.params)
+            return (dx,) + (None,) * 14
         return (dx, dWe.view(meta["we_shape"]), dg1, db1, dwdw.view(meta["wdw_shape"]), dg2, db2,
                 dsw1.view(meta["sw1_shape"]), dsb1, dsw2.view(meta["sw2_shape"]), dsb2, dWp.view(meta["wp_shape"]),
                 dg3, db3, None)
 
 
 def mbconv(x, we, g1, b1, wdw, g2, b2, sw1, sb1, sw2, sb2, wp, g3, b3, *, pe, pp, pse1, pse2, geom: Geom, act: str,
-           training: bool, running, bn_eps: float, bn_momentum: float, use_res: bool) -> Tensor:
+           training: bool, running, bn_eps: float, bn_momentum: float, use_res: bool, direct: bool = False) -> Tensor:
     meta = dict(pe=pe, pp=pp, pse1=pse1, pse2=pse2, geom=geom, act=act, training=training, running=running, bn_eps=bn_eps,
+                direct=direct,
                 bn_momentum=bn_momentum, use_res=use_res, we_shape=tuple(we.shape), wdw_shape=tuple(wdw.shape),
                 sw1_shape=tuple(sw1.shape), sw2_shape=tuple(sw2.shape), wp_shape=tuple(wp.shape))
     return MBConvFn.apply(x, we, g1, b1, wdw, g2, b2, sw1, sb1, sw2, sb2, wp, g3, b3, meta)

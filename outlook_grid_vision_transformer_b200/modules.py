@@ -64,6 +64,17 @@ except TypeError:  # pragma: no cover - older torch
 
 
 FORCE_PREP = False  # set while a CUDA graph is being captured: the casts must be graph nodes
+# Bumped by every optimizer update the package performs (engine.TrainStep, eager or graph replay).  Part of the
+# eval-mode cache key below: a fused optimizer (ours, and torch's fused AdamW) updates the fp32 master weights
+# without touching tensor._version, so "same storage, same version" does NOT mean "same values".
+PARAM_GENERATION = 0
+
+
+def note_parameters_updated() -> None:
+    """Call after updating parameters in a way autograd's version counter cannot see (fused / graph-replayed
+    optimizers): invalidates every cached compute-dtype weight copy used by eval-mode forwards."""
+    global PARAM_GENERATION
+    PARAM_GENERATION += 1
 
 
 class _Prep:
@@ -96,7 +107,7 @@ class _Prep:
                 OF._CAST_LOG = None
             self._bulk = (self._bulk_key(params, dtype), val, log) if log else None
             return val
-        key = (dtype,) + tuple((p.data_ptr(), p._version) if p is not None else None for p in params)
+        key = (dtype, PARAM_GENERATION) + tuple((p.data_ptr(), p._version) if p is not None else None for p in params)
         if key != self._key:
             self._val = build()
             self._key = key
@@ -130,10 +141,22 @@ def _prep_attr(mod: nn.Module, name: str) -> _Prep:
     return store[name]
 
 
+# Set by the train-step executor: an iterator over the rows of ONE pre-drawn [n_droppath, B] scale table (a single
+# Bernoulli launch per step instead of four launches per DropPath); rows are consumed in call order.
+DROP_TABLE = None
+
+
+def _direct(mod: nn.Module) -> bool:
+    """Parameter gradients of this module go straight into the engine's flat gradient arena (functional._is_direct)."""
+    return bool(mod.__dict__.get("_ogv_direct", False)) and torch.is_grad_enabled()
+
+
 def _drop_scale(dp: nn.Module, x: Tensor, batch: int) -> Optional[Tensor]:
     """Per-sample stochastic-depth scale, drawn exactly like DropPath.forward (Outlook_Block.py:15-22)."""
     if not isinstance(dp, DropPath) or dp.drop_prob == 0.0 or not dp.training:
         return None
+    if DROP_TABLE is not None:
+        return next(DROP_TABLE)
     keep = 1.0 - dp.drop_prob
     mask = torch.empty((batch, 1, 1, 1), device=x.device, dtype=x.dtype).bernoulli_(keep)
     return (mask.to(torch.float32) / keep).reshape(batch).contiguous()
@@ -187,7 +210,7 @@ class MLP2d(nn.Module):
         return OF.mlp_branch(rows, ln.weight if ln is not None else None, ln.bias if ln is not None else None,
                              self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias, scale, p1=p1, p2=p2,
                              eps=ln.eps if ln is not None else 0.0, act=_act_name(self.act),
-                             rows_per_sample=geom.P, with_res=with_res)
+                             rows_per_sample=geom.P, with_res=with_res, direct=_direct(self))
 
     def forward(self, x):
         rows, geom = OF.to_rows(x)
@@ -239,7 +262,8 @@ class OutlookAttention2d(nn.Module):
         return OF.outlook_branch(rows, ln.weight if ln is not None else None, ln.bias if ln is not None else None,
                                  self.v.weight, self.v.bias, self.attn.weight, self.attn.bias, self.proj.weight,
                                  self.proj.bias, scale, pva=pva, bva=bva, pp=pp, geom=geom, heads=self.num_heads,
-                                 eps=ln.eps if ln is not None else 0.0, with_res=with_res)
+                                 eps=ln.eps if ln is not None else 0.0, with_res=with_res, direct=_direct(self),
+                                 flat=self.__dict__.get("_ogv_flat"))
 
     def forward(self, x: Tensor) -> Tensor:
         rows, geom = OF.to_rows(x)
@@ -409,7 +433,8 @@ class MBConv(nn.Module):
         bn1, bn2, bn3 = self.expand[1], self.depthwise[1], self.project[1]
         pe, pp, ps1, ps2 = self._prepared(rows.dtype)
         training = self.training and bn1.track_running_stats is not None
-        if self.training:
+        if self.training and not self.__dict__.get("_ogv_nbt_shared", False):
+            # (under engine.FlatState the counters of every MBConv are views of one int64 arena bumped once per step)
             for bn in (bn1, bn2, bn3):
                 if bn.num_batches_tracked is not None:
                     bn.num_batches_tracked.add_(1)
@@ -420,7 +445,7 @@ class MBConv(nn.Module):
                          bn2.bias, self.se.fc1.weight, self.se.fc1.bias, self.se.fc2.weight, self.se.fc2.bias,
                          self.project[0].weight, bn3.weight, bn3.bias, pe=pe, pp=pp, pse1=ps1, pse2=ps2, geom=geom,
                          act=_act_name(self.depthwise[2]), training=training, running=running, bn_eps=bn1.eps,
-                         bn_momentum=mom, use_res=self.use_res)
+                         bn_momentum=mom, use_res=self.use_res, direct=_direct(self))
 
     def forward(self, x: Tensor) -> Tensor:
         rows, geom = OF.to_rows(x)
@@ -530,7 +555,7 @@ class MultiHeadSelfAttention(nn.Module):
         return OF.grid_branch(rows, ln.weight if ln is not None else None, ln.bias if ln is not None else None,
                               self.qkv.weight, self.qkv.bias, self.proj.weight, self.proj.bias, scale, pq=pq, pp=pp,
                               geom=geom, heads=self.num_heads, grid=grid, eps=ln.eps if ln is not None else 0.0,
-                              with_res=with_res, capture=self._capture())
+                              with_res=with_res, capture=self._capture(), direct=_direct(self))
 
     def forward(self, x: Tensor) -> Tensor:
         if x.ndim != 3:

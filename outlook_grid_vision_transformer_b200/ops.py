@@ -46,22 +46,31 @@ class _Profiler:
         self.cur_flops = 0
         self.cur_label = None
         self.cur_kernel = None  # name of the CUDA kernel behind the call when one label covers several
+        self.tag = None         # (fused branch, direction, rows M, channels C) the calls belong to; set by functional.py
 
     def start(self):
         self.enabled, self.records, self.cur_bytes, self.cur_flops, self.cur_label = True, [], 0, 0, None
         self.cur_kernel = None
+        self.tag = None
 
     def stop(self):
         """-> {label: dict(ms, calls, bytes, flops)} (synchronises)."""
         self.enabled = False
         torch.cuda.synchronize()
         out = {}
-        for label, e0, e1, nbytes, flops, kern in self.records:
+        self.branches = {}  # tag -> dict(ms, launches, passes): device time per fused branch (SURVEY 8(d) accounting)
+        for label, e0, e1, nbytes, flops, kern, tag in self.records:
+            ms = e0.elapsed_time(e1)
             d = out.setdefault(label, dict(ms=0.0, calls=0, bytes=0, flops=0, cuda_kernel=kern or label))
-            d["ms"] += e0.elapsed_time(e1)
+            d["ms"] += ms
             d["calls"] += 1
             d["bytes"] += nbytes
             d["flops"] += flops
+            if tag is not None:
+                b = self.branches.setdefault(tag, dict(ms=0.0, launches=0, touched_bytes=0))
+                b["ms"] += ms
+                b["launches"] += 1
+                b["touched_bytes"] += nbytes
         self.records = []
         return out
 
@@ -90,7 +99,7 @@ def _call(name: str, *args) -> None:
         e0.record()
         rc = fn(*args)
         e1.record()
-        PROFILER.records.append((label, e0, e1, nbytes, flops, kern))
+        PROFILER.records.append((label, e0, e1, nbytes, flops, kern, PROFILER.tag))
     else:
         rc = fn(*args)
     LAUNCHES += 1
@@ -489,6 +498,43 @@ def grid_attn_probs(qkv: Tensor, B, H, W, C, heads, g) -> Tensor:
     attn = torch.empty((B * g * g, heads, N, N), device=qkv.device, dtype=torch.float32)
     _call("ogv_grid_attn_probs", _p(qkv), _p(attn), B, H, W, C, heads, g, dtype_code(qkv), _stream())
     return attn
+
+
+# ----------------------------------------------------------------------- flat-arena train-step tail
+def sumsq(g: Tensor, out: Tensor) -> None:
+    """out[0] += sum g^2 (g: flat fp32 arena)."""
+    _require_cuda(g, out)
+    _f32(g, "g")
+    _f32(out, "out")
+    _call("ogv_sumsq", _p(g), g.numel(), _p(out), _stream())
+
+
+def adamw_flat(p: Tensor, g: Tensor, m: Tensor, v: Tensor, decay_bits: Tensor, hyper: Tensor, gnorm_sq: Optional[Tensor],
+               loss: Optional[Tensor], beta1: float, beta2: float, eps: float, weight_decay: float,
+               skipped: Optional[Tensor]) -> None:
+    """Clip + AdamW over flat fp32 arenas; lr / bias corrections / 1/world / max_norm come from the DEVICE tensor
+    `hyper` (see include/ogv.h), so the launch is CUDA-graph replayable under a changing schedule."""
+    _require_cuda(p, g, m, v, decay_bits, hyper, gnorm_sq, loss, skipped)
+    for name, t in (("p", p), ("g", g), ("m", m), ("v", v), ("hyper", hyper)):
+        _f32(t, name)
+    if loss is not None and (loss.dtype != torch.float32 or loss.numel() != 1):
+        raise TypeError("adamw_flat: loss must be a single float32 value on the device")
+    if decay_bits.dtype != torch.int32:
+        raise TypeError("adamw_flat: decay_bits must be int32 words")
+    _call("ogv_adamw_flat", _p(p), _p(g), _p(m), _p(v), _p(decay_bits), p.numel(), _p(hyper), _p(gnorm_sq), _p(loss),
+          float(beta1), float(beta2), float(eps), float(weight_decay), _p(skipped), _stream())
+
+
+def train_metrics(logits: Tensor, labels: Tensor, loss: Optional[Tensor], acc: Tensor) -> None:
+    """acc[5] += {loss*B, top-1, top-3, top-5 hits, B} (fp32 logits [B, K], int64 labels)."""
+    _require_cuda(logits, labels, loss, acc)
+    if logits.dtype != torch.float32 or logits.dim() != 2 or logits.stride(1) != 1:
+        raise TypeError("train_metrics: logits must be fp32 [B, K] with unit column stride")
+    if labels.dtype != torch.int64 or not labels.is_contiguous():
+        raise TypeError("train_metrics: labels must be contiguous int64")
+    _f32(acc, "acc")
+    _call("ogv_train_metrics", _p(logits), logits.stride(0), _p(labels), logits.shape[0], logits.shape[1], _p(loss),
+          _p(acc), _stream())
 
 
 # ----------------------------------------------------------------------------------------- AdamW

@@ -97,6 +97,26 @@ def assert_close(a, b, rtol, what="", atol=1e-12):
                              f"max_rel_err={max_rel_err(a, b):.3e}; first at {i}: got {a[tuple(i)]:.6g} want {b[tuple(i)]:.6g}")
 
 
+def assert_close_rms(a, b, rtol, what=""):
+    """Plain elementwise criterion for FORWARD outputs: |a-b| <= rtol*|b| + rtol*rms(b)  (what
+    torch.testing.assert_close(rtol=rtol, atol=rtol*rms) checks; stricter than the tensor-max band of assert_close)."""
+    a = a.detach().double().cpu()
+    b = b.detach().double().cpu()
+    assert a.shape == b.shape, f"{what}: shape {tuple(a.shape)} vs {tuple(b.shape)}"
+    rms = float(b.pow(2).mean().sqrt())
+    bad = (a - b).abs() > rtol * b.abs() + rtol * rms
+    if bad.any():
+        worst = float(((a - b).abs() / (rtol * b.abs() + rtol * rms)).max())
+        raise AssertionError(f"{what}: {int(bad.sum())}/{bad.numel()} elements outside rtol={rtol}, atol=rtol*rms={rtol * rms:.3e} "
+                             f"(worst {worst:.2f}x the band)")
+
+
+def normwise_err(a, b) -> float:
+    a = a.detach().double().cpu()
+    b = b.detach().double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-3 * b.numel() ** 0.5))
+
+
 def assert_grad_close_bf16(a, b, rtol, what="", elementwise=True):
     """bf16 criterion for PARAMETER gradients (sums over B*H*W bf16 products with heavy cancellation,
     e.g. BatchNorm gamma): normwise relative error <= rtol, at most 1% of the elements outside the

@@ -114,3 +114,63 @@ def test_allreduced_grads_equal_mean_of_shard_grads(bucket_bytes):
         for k, v in local[r][1].items():
             torch.testing.assert_close(results[r][1][k], v)
     assert not torch.allclose(results[0][1]["1.running_mean"], results[1][1]["1.running_mean"])
+
+
+# ------------------------------------------------------------------------------------------------
+# the arena form used by engine.TrainStep: all-reduce in place on slices of FlatState's gradient arena
+# ------------------------------------------------------------------------------------------------
+def _arena_worker(rank: int, world: int, port: int, bucket_bytes: int, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from outlook_grid_vision_transformer_b200.ddp import ArenaGradAllReduce
+        from outlook_grid_vision_transformer_b200.engine import FlatState
+
+        net = _net()
+        flat = FlatState(net, scratch_floats=64)
+        sync = ArenaGradAllReduce(flat, bucket_bytes=bucket_bytes, tail_bytes=64)
+        got = []
+        for _ in range(2):
+            flat.zero_grad()
+            x, y = _shard(rank)
+            nn.functional.cross_entropy(net(x), y).backward()
+            sync.finish()
+            # the arena holds the SUM; the optimizer kernel applies 1/world (TrainStep(world=...))
+            got.append({k: (p.grad / world).clone().numpy() for k, p in net.named_parameters()})
+        covered = sorted((b["lo"], b["hi"]) for b in sync.buckets)
+        q.put((rank, got, len(sync.buckets), covered, flat.n))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("bucket_bytes", [128, 8 << 20], ids=["many_buckets", "one_bucket"])
+def test_arena_allreduce_equals_mean_of_shard_grads(bucket_bytes):
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_arena_worker, args=(r, world, port, bucket_bytes, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = {}
+    for _ in range(world):
+        rank, got, nb, covered, n = q.get(timeout=180)
+        results[rank] = (got, nb, covered, n)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    local = {r: _local_grads(r, 2) for r in range(world)}
+    got, nb, covered, n = results[0]
+    if bucket_bytes == 128:
+        assert nb > 2
+    # the buckets tile the arena exactly once
+    assert covered[0][0] == 0 and covered[-1][1] == n and all(a[1] == b[0] for a, b in zip(covered, covered[1:]))
+    for s in range(2):
+        for k in local[0][0][s]:
+            want = sum(local[r][0][s][k] for r in range(world)) / world
+            for r in range(world):
+                torch.testing.assert_close(torch.from_numpy(results[r][0][s][k]), want, rtol=1e-5, atol=1e-6,
+                                           msg=lambda m: f"step {s} rank {r} grad[{k}]: {m}")
+        for r in range(world):  # the never-used parameter keeps a zero gradient
+            assert not results[r][0][s]["unused"].any()

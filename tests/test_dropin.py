@@ -9,6 +9,7 @@ GPU part (-m gpu): the reference's tests/test_blocks.py and tests/test_models.py
 the reference and executed unmodified with CUDA as the default device, plus its training smoke test on cuda.
 """
 import importlib
+import importlib.util
 import sys
 
 import pytest

@@ -1,0 +1,149 @@
+"""-m gpu: whole-model parity from the REAL BASELINE YAMLs.
+
+* cfg 4 (tinyimagenet200_model_a.yaml, 22.5M, 64 px, 200 classes) and cfg 5 (cifar100_model_b.yaml, Model B with
+  its Outlooker front, train AND eval): logits + every parameter gradient against the fp64 oracle, fp32 mode, rtol 1e-3.
+* cfg 2 (14M, 32 px) in bf16 UNDER torch.autocast, the way the train step runs it: logits at rtol 2e-2; every
+  parameter gradient judged normwise at 2e-2 -- or, where a deep gradient cannot meet 2e-2 in bf16 at all, at the
+  deviation the REFERENCE ITSELF shows on the same box under the same CUDA autocast (multiplier 1.0; measured live from
+  baseline/_ref when it travelled, else from the committed tests/golden/ref_bf16_cuda_noise.json).  The measured
+  numbers are written to gpurun_out/bf16_grad_parity_cfg2.json.
+"""
+import importlib
+import json
+import sys
+from pathlib import Path
+
+import pytest
+import torch
+
+from oracle import outgrid_oracle as O
+from oracle_cases import assert_close, assert_close_rms, normwise_err
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def _oracle_model(model, mcfg, x, labels, training):
+    params = {k: (v.detach().double().cpu().clone().requires_grad_("running" not in k) if v.is_floating_point() else v.cpu())
+              for k, v in model.state_dict().items()}
+    logits = O.model_forward(x.double(), params, mcfg, training, {}, None)
+    if training:
+        torch.nn.functional.cross_entropy(logits, labels).backward()
+    return logits.detach(), params
+
+
+@pytest.mark.parametrize("yaml_name,img,B,training", [
+    ("tinyimagenet200_model_a.yaml", 64, 2, True),
+    ("cifar100_model_b.yaml", 32, 2, True),
+    ("cifar100_model_b.yaml", 32, 3, False),
+    ("cifar100_64_model_a.yaml", 64, 1, True),
+], ids=["cfg4_22m_tin64_train", "cfg5_model_b_train", "cfg5_model_b_eval", "cfg3_14m_64_train"])
+def test_model_fp32_matches_oracle(yaml_name, img, B, training):
+    import outlook_grid_vision_transformer_b200 as og
+    from outlook_grid_vision_transformer_b200.config import CONFIG_DIR
+
+    mcfg = dict(og.load_yaml(CONFIG_DIR / yaml_name)["model"], dpr_max=0.0)
+    torch.manual_seed(11)
+    model = og.build_model(mcfg)
+    gen = torch.Generator().manual_seed(12)
+    with torch.no_grad():  # running statistics away from (0, 1) so the eval case exercises them
+        for n, b in model.named_buffers():
+            if n.endswith("running_mean"):
+                b.add_(0.1 * torch.randn(b.shape, generator=gen))
+            elif n.endswith("running_var"):
+                b.mul_(1.0 + 0.2 * torch.rand(b.shape, generator=gen))
+    x = torch.randn(B, 3, img, img, generator=gen)
+    labels = torch.randint(0, mcfg["num_classes"], (B,), generator=gen)
+    logits_o, params = _oracle_model(model, mcfg, x, labels, training)
+    model = model.to(DEV).train(training)
+    xg = x.to(DEV).contiguous(memory_format=torch.channels_last)
+    if training:
+        logits = model(xg)
+        torch.nn.functional.cross_entropy(logits, labels.to(DEV)).backward()
+    else:
+        with torch.no_grad():
+            logits = model(xg)
+    torch.cuda.synchronize()
+    assert_close(logits, logits_o, 1e-3, "logits")
+    assert_close_rms(logits, logits_o, 1e-3, "logits (elementwise)")
+    if training:
+        for k, p in model.named_parameters():
+            assert p.grad is not None, k
+            assert_close(p.grad, params[k].grad, 1e-3, f"grad[{k}]", atol=1e-6)
+
+
+def _reference_bf16_cuda_noise(mcfg, state, x, labels, grads_o):
+    """The unmodified reference under CUDA bf16 autocast on this box -> per-parameter normwise deviation from fp64."""
+    import outlook_grid_vision_transformer_b200 as og
+
+    root = og.find_reference_root()
+    if root is None:
+        return None
+    if str(root) not in sys.path:
+        sys.path.insert(0, str(root))
+    sys.dont_write_bytecode = True
+    og.uninstall()
+    ref = importlib.import_module("scripts.train").build_model(mcfg)
+    ref.load_state_dict(state, strict=True)
+    ref = ref.to(DEV).train()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        lg = ref(x.to(DEV).contiguous(memory_format=torch.channels_last))
+    torch.nn.functional.cross_entropy(lg.float(), labels.to(DEV)).backward()
+    torch.cuda.synchronize()
+    noise = {k: normwise_err(p.grad, grads_o[k]) for k, p in ref.named_parameters()}
+    return noise, lg.detach().float().cpu()
+
+
+def test_cfg2_bf16_autocast_logits_and_grads():
+    import outlook_grid_vision_transformer_b200 as og
+    from outlook_grid_vision_transformer_b200.config import CONFIG_DIR
+
+    mcfg = dict(og.load_yaml(CONFIG_DIR / "cifar100_model_a_14m.yaml")["model"], dpr_max=0.0)
+    torch.manual_seed(21)
+    model = og.build_model(mcfg)
+    gen = torch.Generator().manual_seed(22)
+    B = 4
+    x = torch.randn(B, 3, 32, 32, generator=gen)
+    labels = torch.randint(0, mcfg["num_classes"], (B,), generator=gen)
+    state = {k: v.clone() for k, v in model.state_dict().items()}
+    logits_o, params = _oracle_model(model, mcfg, x, labels, True)
+    grads_o = {k: params[k].grad for k, _ in model.named_parameters()}
+
+    model = model.to(DEV).train()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        logits = model(x.to(DEV).contiguous(memory_format=torch.channels_last))
+    torch.nn.functional.cross_entropy(logits.float(), labels.to(DEV)).backward()
+    torch.cuda.synchronize()
+    ours = {k: normwise_err(p.grad, grads_o[k]) for k, p in model.named_parameters()}
+
+    live = _reference_bf16_cuda_noise(mcfg, state, x, labels, grads_o)
+    committed = ROOT / "tests" / "golden" / "ref_bf16_cuda_noise.json"
+    if live is not None:
+        ref_noise, ref_logits = live
+        src = "reference under CUDA autocast, measured live on this box"
+    elif committed.exists():
+        ref_noise, ref_logits, src = json.loads(committed.read_text())["reference"], None, str(committed.name)
+    else:
+        ref_noise, ref_logits, src = {}, None, "none"
+    out = {"source": src, "ours": ours, "reference": ref_noise,
+           "logits_ours": normwise_err(logits, logits_o),
+           "logits_reference": normwise_err(ref_logits, logits_o) if ref_logits is not None else None}
+    try:
+        (ROOT / "gpurun_out").mkdir(exist_ok=True)
+        (ROOT / "gpurun_out" / "bf16_grad_parity_cfg2.json").write_text(json.dumps(out, indent=1, sort_keys=True))
+    except OSError:
+        pass
+
+    assert_close(logits.float(), logits_o, 2e-2, "logits")
+    assert_close_rms(logits.float(), logits_o, 2e-2, "logits (elementwise)")
+    bad = []
+    for k, e in ours.items():
+        tol = max(2e-2, 1.0 * ref_noise.get(k, 0.0))
+        if not e <= tol:
+            bad.append((k, e, tol))
+    n_plain = sum(1 for e in ours.values() if e <= 2e-2)
+    print(f"cfg2 bf16 autocast: {n_plain}/{len(ours)} parameter gradients within 2e-2 normwise; worst ours "
+          f"{max(ours.values()):.3e}, worst reference {max(ref_noise.values()) if ref_noise else float('nan'):.3e} ({src})")
+    assert not bad, "parameter gradients beyond max(2e-2, reference's own bf16 deviation): " + \
+        ", ".join(f"{k}: {e:.3e} > {t:.3e}" for k, e, t in bad[:8])
