@@ -234,6 +234,19 @@ int ogv_adamw_flat(float* p, const float* g, float* m, float* v, const unsigned*
 int ogv_train_metrics(const float* logits, long long ld, const long long* labels, int B, int K, const float* loss,
                       float* acc, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Fused MLP (north_star kernel 4):  y = residual + row_scale[m / rows_per_scale] * ( act(x W1^T + b1) W2^T + b2 )
+ * in ONE tcgen05 kernel -- MLP2d (outlook_attention.py:43-49) and MLP (Out_Grid_Block.py:24-32) with the residual /
+ * DropPath of Outlook_Block.py:63 and Out_Grid_Block.py:102-104.  The [M, hidden] activation stays on chip: fc1 chunk ->
+ * TMEM -> activation in registers -> bf16 tile in swizzled shared memory -> A operand of fc2.  bf16 tensors, fp32
+ * accumulation / bias / scale.  x: [M, C] (row stride ldx; the LayerNorm-ed rows), w1: [hidden, C], w2: [C, hidden]
+ * (both row-major, dense), residual: [M, C] or null, y: [M, C].  ogv_mlp_fused_supported(C, hidden) says whether the
+ * shape is served (C in {64, 128}, hidden a multiple of the chunk width); other shapes take the ogv_gemm route. */
+int ogv_mlp_fused_supported(int C, int hidden);
+int ogv_mlp_fwd(const void* x, long long ldx, const void* w1, const float* b1, const void* w2, const float* b2,
+                const void* residual, long long ldr, const float* row_scale, int rows_per_scale, void* y, long long ldy,
+                long long M, int C, int hidden, int act, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

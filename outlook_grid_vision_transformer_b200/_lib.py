@@ -78,6 +78,8 @@ SIGNATURES = {
     "ogv_sumsq": [_P, _L, _P, _P],
     "ogv_adamw_flat": [_P, _P, _P, _P, _P, _L, _P, _P, _P, _F, _F, _F, _F, _P, _P],
     "ogv_train_metrics": [_P, _L, _P, _I, _I, _P, _P, _P],
+    "ogv_mlp_fused_supported": [_I, _I],
+    "ogv_mlp_fwd": [_P, _L, _P, _P, _P, _P, _P, _L, _P, _I, _P, _L, _L, _I, _I, _I, _P],
 }
 _RESTYPES = {"ogv_last_error": c_char_p}
 

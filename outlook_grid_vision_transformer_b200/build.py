@@ -31,6 +31,7 @@ SOURCES = [
     "ogv_tma.cu",
     "ogv_gridattn.cu",
     "ogv_optim.cu",
+    "ogv_mlp_fused.cu",
 ]
 
 NVCC_FLAGS = [

@@ -15,6 +15,7 @@
 //   * split-K work items (wgrad) accumulate with fp32 atomics into D (direct, non-TMA epilogue).
 #include "ogv_gemm.cuh"
 #include "ogv_ptx.cuh"
+#include "ogv_stage.cuh"
 
 namespace {
 
@@ -102,63 +103,6 @@ __device__ __forceinline__ void epi_row16(const GemmEpi& e, int m, int n0, const
 #pragma unroll
     for (int j = 0; j < 16; ++j)
       if (n0 + j < e.N) epi_scalar<TO>(e, m, n0 + j, v[j]);
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// staged epilogue helpers: a warp's 32 x 32 bf16 tile in the TMA SWIZZLE_64B layout
-// (byte address bits [4,6) ^= bits [7,9)): conflict-free 16-byte row-owner accesses.
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t sw64(int row, int c16) { return row * 64 + ((c16 ^ ((row >> 1) & 3)) << 4); }
-
-__device__ __forceinline__ void stage_write_row(uint8_t* slot, int row, const float (&v)[32]) {
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    uint4 u;
-    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[8 * c + 2 * i], v[8 * c + 2 * i + 1]);
-    *reinterpret_cast<uint4*>(slot + sw64(row, c)) = u;
-  }
-}
-// packed-pair forms (element pairs (2i, 2i+1) in one 64-bit register, see ogv_common.cuh)
-__device__ __forceinline__ void stage_write_row(uint8_t* slot, int row, const f32x2 (&v)[16]) {
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    uint4 u;
-    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      float lo, hi;
-      unpk2(v[4 * c + i], lo, hi);
-      h[i] = __floats2bfloat162_rn(lo, hi);
-    }
-    *reinterpret_cast<uint4*>(slot + sw64(row, c)) = u;
-  }
-}
-__device__ __forceinline__ void stage_read_row(const uint8_t* slot, int row, f32x2 (&r)[16]) {
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    uint4 u = *reinterpret_cast<const uint4*>(slot + sw64(row, c));
-    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float2 f = __bfloat1622float2(h[i]);
-      r[4 * c + i] = pk2(f.x, f.y);
-    }
-  }
-}
-__device__ __forceinline__ void stage_read_row(const uint8_t* slot, int row, float (&r)[32]) {
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    uint4 u = *reinterpret_cast<const uint4*>(slot + sw64(row, c));
-    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      float2 f = __bfloat1622float2(h[i]);
-      r[8 * c + 2 * i] = f.x;
-      r[8 * c + 2 * i + 1] = f.y;
-    }
   }
 }
 

@@ -467,13 +467,17 @@ class MBConvFn(torch.autograd.Function):
         ctx.meta = meta
         ctx.wdw2 = wdw2
         ctx.params = (we, g1, b1, wdw, g2, b2, sw1, sb1, sw2, sb2, wp, g3, b3)
-        ctx.save_for_backward(x, e_pre, d_pre, d_act, o_pre, st, pool_c, s1_pre, s1a, gate_pre, gate, g1, g2, g3, sw1, sw2)
+        # `st` may be a slice of the engine's flat gradient/scratch arena, whose autograd version counter is bumped by
+        # every in-place accumulation into ANY view of it: keep it out of save_for_backward's version check
+        ctx.st = st
+        ctx.save_for_backward(x, e_pre, d_pre, d_act, o_pre, pool_c, s1_pre, s1a, gate_pre, gate, g1, g2, g3, sw1, sw2)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         meta = ctx.meta
-        (x, e_pre, d_pre, d_act, o_pre, st, pool, s1_pre, s1a, gate_pre, gate, g1, g2, g3, sw1, sw2) = ctx.saved_tensors
+        (x, e_pre, d_pre, d_act, o_pre, pool, s1_pre, s1a, gate_pre, gate, g1, g2, g3, sw1, sw2) = ctx.saved_tensors
+        st = ctx.st
         pe: PreparedLinear = meta["pe"]
         ppj: PreparedLinear = meta["pp"]
         g: Geom = meta["geom"]

@@ -500,6 +500,44 @@ def grid_attn_probs(qkv: Tensor, B, H, W, C, heads, g) -> Tensor:
     return attn
 
 
+# -------------------------------------------------------------------------------------- fused MLP
+def mlp_fused_supported(C: int, hidden: int, dtype: torch.dtype) -> bool:
+    return dtype == torch.bfloat16 and bool(_lib.lib().ogv_mlp_fused_supported(int(C), int(hidden)))
+
+
+def mlp_fwd(x: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor, *, act: str, residual: Optional[Tensor] = None,
+            row_scale: Optional[Tensor] = None, rows_per_scale: int = 1) -> Tensor:
+    """y = residual + row_scale * (act(x w1^T + b1) w2^T + b2) in one kernel; the hidden activation stays on chip.
+    x [M, C] bf16 rows, w1 [hidden, C] / w2 [C, hidden] bf16 contiguous, biases fp32."""
+    _require_cuda(x, w1, b1, w2, b2, residual, row_scale)
+    M, C = x.shape
+    Hd = w1.shape[0]
+    if x.dtype != torch.bfloat16 or w1.dtype != torch.bfloat16 or w2.dtype != torch.bfloat16:
+        raise TypeError("mlp_fwd: bf16 activations and weights only")
+    if tuple(w1.shape) != (Hd, C) or tuple(w2.shape) != (C, Hd) or not w1.is_contiguous() or not w2.is_contiguous():
+        raise ValueError("mlp_fwd: w1 must be [hidden, C] and w2 [C, hidden], both contiguous")
+    _rows(x, "x")
+    _f32(b1, "b1")
+    _f32(b2, "b2")
+    _f32(row_scale, "row_scale")
+    if residual is not None:
+        _rows(residual, "residual")
+        if residual.dtype != x.dtype or tuple(residual.shape) != (M, C):
+            raise ValueError("mlp_fwd: residual must match x")
+    y = torch.empty((M, C), device=x.device, dtype=x.dtype)
+    if PROFILER.enabled:
+        PROFILER.cur_bytes = 2 * (M * C * (2 + (residual is not None)) + 2 * Hd * C)
+        PROFILER.cur_flops = 4 * M * C * Hd
+        PROFILER.cur_kernel = f"mlp_fwd_kernel<{C}>"
+    _call("ogv_mlp_fwd", ctypes.c_void_p(x.data_ptr()), x.stride(0), ctypes.c_void_p(w1.data_ptr()), ctypes.c_void_p(b1.data_ptr()),
+          ctypes.c_void_p(w2.data_ptr()), ctypes.c_void_p(b2.data_ptr()),
+          ctypes.c_void_p(residual.data_ptr()) if residual is not None else None,
+          residual.stride(0) if residual is not None else 0,
+          ctypes.c_void_p(row_scale.data_ptr()) if row_scale is not None else None, int(rows_per_scale),
+          ctypes.c_void_p(y.data_ptr()), y.stride(0), M, C, Hd, ACT[act], _stream())
+    return y
+
+
 # ----------------------------------------------------------------------- flat-arena train-step tail
 def sumsq(g: Tensor, out: Tensor) -> None:
     """out[0] += sum g^2 (g: flat fp32 arena)."""

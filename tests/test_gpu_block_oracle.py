@@ -67,7 +67,9 @@ def test_outgrid_block_train_matches_oracle(C, H, heads, oheads, g, B, dtype):
     torch.cuda.synchronize()
     rtol = RTOL[dtype]
     assert_close(y.float(), yo, rtol, "forward")
-    assert_close_rms(y.float(), yo, rtol, "forward (elementwise rtol, atol = rtol * rms)")
+    bf = dtype == torch.bfloat16
+    assert_close_rms(y.float(), yo, rtol, "forward (elementwise rtol, atol = rtol * rms)",
+                     outlier_frac=1e-4 if bf else 0.0, outlier_band=1.5 if bf else 1.0)
     assert_close(xg.grad.float(), dxo, rtol, "dx", atol=1e-6)
     for k, p in blk.named_parameters():
         assert p.grad is not None, f"no gradient for {k}"
