@@ -246,6 +246,13 @@ int ogv_mlp_fused_supported(int C, int hidden);
 int ogv_mlp_fwd(const void* x, long long ldx, const void* w1, const float* b1, const void* w2, const float* b2,
                 const void* residual, long long ldr, const float* row_scale, int rows_per_scale, void* y, long long ldy,
                 long long M, int C, int hidden, int act, void* stream);
+/* Backward of the same (autograd of the reference lines above) with the hidden activation RECOMPUTED on chip:
+ *   z = xn W1^T + b1 ;  dz = (dy W2) * act'(z) * s ;  hs = act(z) * s ;  dxn = dz W1      (s = row_scale[m / rows_per_scale] or 1)
+ * dz, hs: [M, hidden] bf16 outputs for the weight-gradient GEMMs (dW1 = dz^T xn, db1 = colsum dz, dW2 = dy^T hs);
+ * w2t = W2^T [hidden, C] and w1t = W1^T [C, hidden] are the pre-transposed bf16 copies the dgrad GEMMs use. */
+int ogv_mlp_bwd(const void* xn, long long ldx, const void* dy, long long ldg, const void* w1, const void* w2t,
+                const void* w1t, const float* b1, const float* row_scale, int rows_per_scale, void* dz, void* hs,
+                void* dxn, long long lddx, long long M, int C, int hidden, int act, void* stream);
 
 #ifdef __cplusplus
 }

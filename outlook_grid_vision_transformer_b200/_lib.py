@@ -80,6 +80,7 @@ SIGNATURES = {
     "ogv_train_metrics": [_P, _L, _P, _I, _I, _P, _P, _P],
     "ogv_mlp_fused_supported": [_I, _I],
     "ogv_mlp_fwd": [_P, _L, _P, _P, _P, _P, _P, _L, _P, _I, _P, _L, _L, _I, _I, _I, _P],
+    "ogv_mlp_bwd": [_P, _L, _P, _L, _P, _P, _P, _P, _P, _I, _P, _P, _P, _L, _L, _I, _I, _I, _P],
 }
 _RESTYPES = {"ogv_last_error": c_char_p}
 

@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(COLREDUCE_THREADS) rowscale_colsum_kernel(cons
       v[i] *= s;
       acc[0][i] += v[i];
     }
-    st8(y + (row * nv + cv) * 8, v);
+    if (y) st8(y + (row * nv + cv) * 8, v);
   }
   float* outs[1] = {out};
   colreduce_finish<1>(acc, outs, nv);
@@ -372,7 +372,7 @@ extern "C" int ogv_rowscale(const void* x, const float* scale, void* y, long lon
 extern "C" int ogv_rowscale_colsum(const void* x, const float* scale, void* y, float* out, long long rows, int cols,
                                    int rows_per_scale, int dtype, void* stream) {
   if (rows == 0 || cols == 0) return OGV_OK;
-  OGV_REQUIRE(x && y && scale && out && cols % 8 == 0 && rows_per_scale > 0, "rowscale_colsum: bad args (cols %% 8 == 0)");
+  OGV_REQUIRE(x && scale && out && cols % 8 == 0 && rows_per_scale > 0, "rowscale_colsum: bad args (cols %% 8 == 0)");  // y may be null: reduction only
   OGV_REQUIRE(rows < 0x7fffffffLL, "rowscale_colsum: too many rows");
   OGV_DISPATCH_DTYPE(dtype, T, {
     ColReduceCfg cfg;

@@ -323,6 +323,322 @@ mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   }
 }
 
+// =================================================================================================
+// Backward, same idea: per 128-row tile and 64-wide hidden chunk j
+//     Z_j  = XN W1_j^T            (recompute of the fc1 pre-activation; the forward saved nothing wide)
+//     DH_j = DY W2[:, j]          (= DY (W2^T)_j^T)
+//     epilogue:  (h, h') = act, act'(Z_j + b1);  dz = DH_j * h' * s;  hs = h * s        (s = DropPath row scale)
+//     DXN += dz W1_j              (dz tile in swizzled smem as the A operand)
+// and dz / hs leave through TMA stores from the very tiles the epilogue wrote (they feed the two weight-gradient
+// GEMMs:  dW1 = dz^T XN,  dW2 = DY^T hs,  db1 = colsum(dz)).  One wide write each instead of: h + act' written by the
+// forward, act' and dz through the fc2 dgrad epilogue, dz read again by the fc1 dgrad.
+// =================================================================================================
+constexpr int B_BH = 64;
+
+template <int C>
+struct MlpBwdCfg {
+  static constexpr int KC = C / 64;
+  static constexpr int XB = C == 64 ? 2 : 1;               // x/dy tile buffers (the C=128 budget has room for one)
+  static constexpr int NW = C == 64 ? 6 : 3;               // weight-chunk ring depth (3 chunks of weights per hidden chunk)
+  static constexpr int XA_BYTES = F_BM * C * 2;            // one activation tile
+  static constexpr int T_BYTES = F_BM * B_BH * 2;          // one dz / hs tile (16 KB)
+  static constexpr int W_BYTES = B_BH * C * 2;
+  static constexpr int OUT_WARPS = 4 * (C / 32);
+  static constexpr int STAGE_BYTES = OUT_WARPS * F_SLOT;
+  static constexpr int NBAR = 2 * XB + 2 * NW + 4 + 4 + 4;
+  static constexpr int SMEM = XB * 2 * XA_BYTES + 4 * T_BYTES + NW * W_BYTES + STAGE_BYTES + NBAR * 8 + 16 + 1024;
+  static constexpr int TMEM_COLS = 512;                    // Z[2] + DH[2] (4 x 64) + DXN[2] (2 x C)
+  static_assert(4 * B_BH + 2 * C <= 512, "TMEM budget");
+  static_assert(SMEM <= 227 * 1024, "shared memory budget");
+};
+
+struct MlpBwdParams {
+  long long M;
+  int Hd, NJ, m_tiles;
+  int act;
+  const float* b1;
+  const float* row_scale;
+  int rows_per_scale;
+};
+
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+template <int C>
+__global__ void __launch_bounds__(F_THREADS, 1)
+mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmG,
+               const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2T,
+               const __grid_constant__ CUtensorMap tmW1T, const __grid_constant__ CUtensorMap tmDZ,
+               const __grid_constant__ CUtensorMap tmHS, const __grid_constant__ CUtensorMap tmDX, const MlpBwdParams p) {
+  using Cfg = MlpBwdCfg<C>;
+  constexpr int BH = B_BH;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* xn = smem;                                        // [XB][XA_BYTES]
+  uint8_t* gy = xn + Cfg::XB * Cfg::XA_BYTES;                // [XB][XA_BYTES]
+  uint8_t* dzt = gy + Cfg::XB * Cfg::XA_BYTES;               // [2][T_BYTES]
+  uint8_t* hst = dzt + 2 * Cfg::T_BYTES;                     // [2][T_BYTES]
+  uint8_t* wring = hst + 2 * Cfg::T_BYTES;                   // [NW][W_BYTES]
+  uint8_t* staging = wring + Cfg::NW * Cfg::W_BYTES;         // [OUT_WARPS][F_SLOT]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + Cfg::STAGE_BYTES);
+  uint64_t* x_full = bars;
+  uint64_t* x_empty = x_full + Cfg::XB;
+  uint64_t* w_full = x_empty + Cfg::XB;
+  uint64_t* w_empty = w_full + Cfg::NW;
+  uint64_t* zd_full = w_empty + Cfg::NW;
+  uint64_t* zd_empty = zd_full + 2;
+  uint64_t* dz_full = zd_empty + 2;
+  uint64_t* dz_empty = dz_full + 2;
+  uint64_t* dx_full = dz_empty + 2;
+  uint64_t* dx_empty = dx_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dx_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == F_PRODUCER && lane == 0) {
+    ptx::tma_prefetch_desc(&tmX);
+    ptx::tma_prefetch_desc(&tmG);
+    ptx::tma_prefetch_desc(&tmW1);
+    ptx::tma_prefetch_desc(&tmW2T);
+    ptx::tma_prefetch_desc(&tmW1T);
+    for (int s = 0; s < Cfg::XB; ++s) {
+      ptx::mbar_init(&x_full[s], 1);
+      ptx::mbar_init(&x_empty[s], 1);
+    }
+    for (int s = 0; s < Cfg::NW; ++s) {
+      ptx::mbar_init(&w_full[s], 1);
+      ptx::mbar_init(&w_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(&zd_full[s], 1);
+      ptx::mbar_init(&zd_empty[s], F_EPI_WARPS);
+      ptx::mbar_init(&dz_full[s], F_EPI_WARPS);
+      ptx::mbar_init(&dz_empty[s], 1);
+      ptx::mbar_init(&dx_full[s], 1);
+      ptx::mbar_init(&dx_empty[s], Cfg::OUT_WARPS);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == F_MMA) {
+    ptx::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_z = tmem_base;                 // Z[b]  at column b * 64
+  const uint32_t tmem_dh = tmem_base + 2 * BH;       // DH[b] at column 128 + b * 64
+  const uint32_t tmem_dx = tmem_base + 4 * BH;       // DXN[b] at column 256 + b * C
+  const int NJ = p.NJ;
+
+  if (warp == F_PRODUCER) {
+    if (lane == 0) {
+      uint32_t wc = 0;
+      int it = 0;
+      auto load_w = [&](const CUtensorMap* tm, int c0, int c1, bool k_is_hidden) {
+        const int ws = wc % Cfg::NW;
+        ptx::mbar_wait(&w_empty[ws], ((wc / Cfg::NW) & 1) ^ 1u);
+        ptx::mbar_arrive_expect_tx(&w_full[ws], Cfg::W_BYTES);
+        uint8_t* dst = wring + ws * Cfg::W_BYTES;
+        if (!k_is_hidden) {  // [64 hidden rows x C]: one box {64 k, 64 rows} per 64-column slice of C
+#pragma unroll
+          for (int ks = 0; ks < Cfg::KC; ++ks) ptx::tma_load_2d(dst + ks * (BH * 128), tm, &w_full[ws], ks * 64, c1);
+        } else {             // [C rows x 64 hidden]: one box {64 k, C rows}
+          ptx::tma_load_2d(dst, tm, &w_full[ws], c0, 0);
+        }
+        ++wc;
+      };
+      for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, ++it) {
+        const int xb = it % Cfg::XB;
+        ptx::mbar_wait(&x_empty[xb], ((it / Cfg::XB) & 1) ^ 1u);
+        ptx::mbar_arrive_expect_tx(&x_full[xb], 2 * Cfg::XA_BYTES);
+#pragma unroll
+        for (int ks = 0; ks < Cfg::KC; ++ks) {
+          ptx::tma_load_2d(xn + xb * Cfg::XA_BYTES + ks * (F_BM * 128), &tmX, &x_full[xb], ks * 64, tile * F_BM);
+          ptx::tma_load_2d(gy + xb * Cfg::XA_BYTES + ks * (F_BM * 128), &tmG, &x_full[xb], ks * 64, tile * F_BM);
+        }
+        for (int step = 0; step <= NJ; ++step) {
+          if (step < NJ) {
+            load_w(&tmW1, 0, step * BH, false);    // W1 rows of chunk `step`
+            load_w(&tmW2T, 0, step * BH, false);   // (W2^T) rows of chunk `step`
+          }
+          if (step >= 1) load_w(&tmW1T, (step - 1) * BH, 0, true);  // (W1^T)[:, chunk step-1]
+        }
+      }
+    }
+  } else if (warp == F_MMA) {
+    if (lane == 0) {
+      const uint32_t idesc_h = ptx::umma_idesc_bf16(F_BM, BH, 0, 0);
+      const uint32_t idesc_x = ptx::umma_idesc_bf16(F_BM, C, 0, 0);
+      uint32_t wc = 0, zc = 0, hc = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, ++it) {
+        const int xb = it % Cfg::XB, ob = it & 1;
+        ptx::mbar_wait(&dx_empty[ob], ((it >> 1) & 1) ^ 1u);
+        ptx::mbar_wait(&x_full[xb], (it / Cfg::XB) & 1);
+        ptx::tc_fence_after();
+        const uint32_t xn_addr = ptx::smem_u32(xn + xb * Cfg::XA_BYTES);
+        const uint32_t gy_addr = ptx::smem_u32(gy + xb * Cfg::XA_BYTES);
+        for (int step = 0; step <= NJ; ++step) {
+          if (step < NJ) {
+            const int zb = zc & 1;
+            ptx::mbar_wait(&zd_empty[zb], ((zc >> 1) & 1) ^ 1u);
+#pragma unroll
+            for (int which = 0; which < 2; ++which) {  // 0: Z = XN W1_j^T   1: DH = DY (W2^T)_j^T
+              const int ws = wc % Cfg::NW;
+              ptx::mbar_wait(&w_full[ws], (wc / Cfg::NW) & 1);
+              ptx::tc_fence_after();
+              const uint32_t wb = ptx::smem_u32(wring + ws * Cfg::W_BYTES);
+              const uint32_t a0 = which ? gy_addr : xn_addr;
+              const uint32_t d = (which ? tmem_dh : tmem_z) + zb * BH;
+#pragma unroll
+              for (int ks = 0; ks < Cfg::KC; ++ks)
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                  const uint64_t ad = ptx::umma_smem_desc(a0 + ks * (F_BM * 128) + kk * 32, 16u, 1024u);
+                  const uint64_t bd = ptx::umma_smem_desc(wb + ks * (BH * 128) + kk * 32, 16u, 1024u);
+                  ptx::umma_f16(d, ad, bd, idesc_h, (ks > 0 || kk > 0) ? 1u : 0u);
+                }
+              ptx::umma_commit(&w_empty[ws]);
+              ++wc;
+            }
+            ptx::umma_commit(&zd_full[zb]);
+            ++zc;
+            if (step == NJ - 1) ptx::umma_commit(&x_empty[xb]);
+          }
+          if (step >= 1) {  // DXN += dz_{step-1} W1_{step-1}
+            const int hb = hc & 1;
+            ptx::mbar_wait(&dz_full[hb], (hc >> 1) & 1);
+            const int ws = wc % Cfg::NW;
+            ptx::mbar_wait(&w_full[ws], (wc / Cfg::NW) & 1);
+            ptx::tc_fence_after();
+            const uint32_t da = ptx::smem_u32(dzt + hb * Cfg::T_BYTES);
+            const uint32_t wb = ptx::smem_u32(wring + ws * Cfg::W_BYTES);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              const uint64_t ad = ptx::umma_smem_desc(da + kk * 32, 16u, 1024u);
+              const uint64_t bd = ptx::umma_smem_desc(wb + kk * 32, 16u, 1024u);
+              ptx::umma_f16(tmem_dx + ob * C, ad, bd, idesc_x, (step > 1 || kk > 0) ? 1u : 0u);
+            }
+            ptx::umma_commit(&w_empty[ws]);
+            ++wc;
+            ptx::umma_commit(&dz_empty[hb]);
+            ++hc;
+            if (step == NJ) ptx::umma_commit(&dx_full[ob]);
+          }
+        }
+      }
+    }
+  } else {
+    // ------------------------------- epilogue warps -------------------------------
+    constexpr int ZW = BH / 4;  // 16 hidden columns per warp and chunk
+    const int q = warp & 3;
+    const int cg = warp >> 2;
+    const bool out_warp = cg < C / 32;
+    const bool store_warp = cg == 0;  // issues the quarter's dz / hs tile stores
+    uint8_t* slot = staging + (q * (C / 32) + (out_warp ? cg : 0)) * F_SLOT;
+    uint32_t zc = 0, hc = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, ++it) {
+      const int ob = it & 1;
+      const int mrow0 = tile * F_BM + q * 32;
+      const long long m = (long long)mrow0 + lane;
+      const float rsf = p.row_scale ? (m < p.M ? p.row_scale[m / p.rows_per_scale] : 0.f) : 1.f;
+      const f32x2 rs = splat2(rsf);
+      for (int j = 0; j < NJ; ++j) {
+        const int zb = zc & 1;
+        ptx::mbar_wait(&zd_full[zb], (zc >> 1) & 1);
+        ptx::tc_fence_after();
+        const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+        float zf[ZW], df[ZW];
+        ptx::tmem_ld16(tmem_z + lane_off + zb * BH + cg * ZW, zf);
+        ptx::tmem_ld16(tmem_dh + lane_off + zb * BH + cg * ZW, df);
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&zd_empty[zb]);
+        ++zc;
+        f32x2 z2[ZW / 2], d2[ZW / 2], g2[ZW / 2];
+        pack_n<ZW / 2>(zf, z2);
+        pack_n<ZW / 2>(df, d2);
+        const float* b1 = p.b1 + j * BH + cg * ZW;
+#pragma unroll
+        for (int i = 0; i < ZW / 4; ++i) {
+          const ulonglong2 b4 = __ldg(reinterpret_cast<const ulonglong2*>(b1) + i);
+          z2[2 * i] = add2(z2[2 * i], b4.x);
+          z2[2 * i + 1] = add2(z2[2 * i + 1], b4.y);
+        }
+        act_both_p<ZW / 2, true>(p.act, z2, g2);  // z2 <- act(z), g2 <- act'(z)
+#pragma unroll
+        for (int i = 0; i < ZW / 2; ++i) {
+          d2[i] = mul2(mul2(d2[i], g2[i]), rs);    // dz
+          z2[i] = mul2(z2[i], rs);                 // hs
+        }
+        const int hb = hc & 1;
+        // buffer hb is free once (a) the MMA that read dz two chunks ago has retired and (b) the TMA stores issued
+        // from it two chunks ago have finished reading shared memory (the storing thread waits, the quarter syncs)
+        ptx::mbar_wait(&dz_empty[hb], ((hc >> 1) & 1) ^ 1u);
+        if (store_warp && lane == 0) ptx::bulk_wait_read<1>();
+        named_bar_sync(1 + q, 128);
+        const int row = q * 32 + lane;
+        const int c16_0 = (cg * ZW) / 8;
+        uint8_t* dzb = dzt + hb * Cfg::T_BYTES;
+        uint8_t* hsb = hst + hb * Cfg::T_BYTES;
+#pragma unroll
+        for (int c = 0; c < ZW / 8; ++c) {
+          const f32x2 pd[4] = {d2[4 * c], d2[4 * c + 1], d2[4 * c + 2], d2[4 * c + 3]};
+          const f32x2 ph[4] = {z2[4 * c], z2[4 * c + 1], z2[4 * c + 2], z2[4 * c + 3]};
+          *reinterpret_cast<uint4*>(dzb + sw128(row, c16_0 + c)) = pack8_bf16(pd);
+          *reinterpret_cast<uint4*>(hsb + sw128(row, c16_0 + c)) = pack8_bf16(ph);
+        }
+        ptx::fence_proxy_async();
+        named_bar_sync(1 + q, 128);  // the quarter's 32 x 64 slab of both tiles is complete
+        if (store_warp && lane == 0) {
+          ptx::tma_store_2d(&tmDZ, dzb + q * 4096, j * BH, mrow0);   // box {64 hidden, 32 rows}
+          ptx::tma_store_2d(&tmHS, hsb + q * 4096, j * BH, mrow0);
+          ptx::bulk_commit();
+        }
+        if (lane == 0) ptx::mbar_arrive(&dz_full[hb]);
+        ++hc;
+      }
+      if (out_warp) {
+        ptx::mbar_wait(&dx_full[ob], (it >> 1) & 1);
+        ptx::tc_fence_after();
+        float v[32];
+        ptx::tmem_ld32(tmem_dx + (static_cast<uint32_t>(q * 32) << 16) + ob * C + cg * 32, v);
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&dx_empty[ob]);
+        // the slot's previous store must have finished reading.  A store warp also has dz/hs groups in flight: its
+        // slot store is always the OLDEST-but-(2 chunk groups) group, so waiting for "all but the newest two" covers it
+        if (lane == 0) {
+          if (store_warp) ptx::bulk_wait_read<2>();
+          else ptx::bulk_wait_read<0>();
+        }
+        __syncwarp();
+        stage_write_row(slot, lane, v);
+        ptx::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          ptx::tma_store_2d(&tmDX, slot, cg * 32, mrow0);
+          ptx::bulk_commit();
+        }
+      }
+    }
+    if (lane == 0) ptx::bulk_wait<0>();
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == F_MMA) {
+    __syncwarp();
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
 int tmap2d(CUtensorMap* tm, const void* ptr, long long inner, long long outer, long long ld, int box_inner, int box_outer,
            int swizzle) {
   const unsigned long long dims[2] = {(unsigned long long)inner, (unsigned long long)outer};
@@ -363,10 +679,43 @@ int launch_mlp_fwd(const void* x, long long ldx, const void* w1, const float* b1
   return ogv_check_launch("mlp_fwd");
 }
 
+
+template <int C>
+int launch_mlp_bwd(const void* xn, long long ldx, const void* dy, long long ldg, const void* w1, const void* w2t,
+                   const void* w1t, const float* b1, const float* row_scale, int rows_per_scale, void* dz, void* hs,
+                   void* dxn, long long lddx, long long M, int Hd, int act, cudaStream_t stream) {
+  using Cfg = MlpBwdCfg<C>;
+  CUtensorMap tmX, tmG, tmW1, tmW2T, tmW1T, tmDZ, tmHS, tmDX;
+  int rc;
+  if ((rc = tmap2d(&tmX, xn, C, M, ldx, 64, F_BM, 3))) return rc;
+  if ((rc = tmap2d(&tmG, dy, C, M, ldg, 64, F_BM, 3))) return rc;
+  if ((rc = tmap2d(&tmW1, w1, C, Hd, C, 64, B_BH, 3))) return rc;
+  if ((rc = tmap2d(&tmW2T, w2t, C, Hd, C, 64, B_BH, 3))) return rc;
+  if ((rc = tmap2d(&tmW1T, w1t, Hd, C, Hd, 64, C, 3))) return rc;
+  if ((rc = tmap2d(&tmDZ, dz, Hd, M, Hd, 64, 32, 3))) return rc;
+  if ((rc = tmap2d(&tmHS, hs, Hd, M, Hd, 64, 32, 3))) return rc;
+  if ((rc = tmap2d(&tmDX, dxn, C, M, lddx, 32, 32, 2))) return rc;
+  MlpBwdParams p;
+  p.M = M; p.Hd = Hd; p.NJ = Hd / B_BH; p.m_tiles = ogv_ceil_div(M, F_BM); p.act = act; p.b1 = b1;
+  p.row_scale = row_scale; p.rows_per_scale = rows_per_scale > 0 ? rows_per_scale : 1;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t err = cudaFuncSetAttribute(mlp_bwd_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    if (err != cudaSuccess) {
+      ogv_set_error("mlp_bwd: cudaFuncSetAttribute failed: %s", cudaGetErrorString(err));
+      return OGV_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  const int grid = p.m_tiles < ogv_num_sms() ? p.m_tiles : ogv_num_sms();
+  mlp_bwd_kernel<C><<<grid, F_THREADS, Cfg::SMEM, stream>>>(tmX, tmG, tmW1, tmW2T, tmW1T, tmDZ, tmHS, tmDX, p);
+  return ogv_check_launch("mlp_bwd");
+}
+
 // hidden-chunk width of the forward kernel for a given channel count (0: shape not served by the fused kernel)
 int fwd_chunk(int C, int Hd) {
   const int bh = C == 64 ? 128 : (C == 128 ? 64 : 0);
-  return (bh && Hd % bh == 0 && Hd >= bh) ? bh : 0;
+  return (bh && Hd % bh == 0 && Hd >= bh && Hd % B_BH == 0) ? bh : 0;
 }
 
 }  // namespace
@@ -391,4 +740,24 @@ extern "C" int ogv_mlp_fwd(const void* x, long long ldx, const void* w1, const f
   if (C == 64)
     return launch_mlp_fwd<64, 128>(x, ldx, w1, b1, w2, b2, residual, ldr, row_scale, rows_per_scale, y, ldy, M, Hd, act, st);
   return launch_mlp_fwd<128, 64>(x, ldx, w1, b1, w2, b2, residual, ldr, row_scale, rows_per_scale, y, ldy, M, Hd, act, st);
+}
+
+extern "C" int ogv_mlp_bwd(const void* xn, long long ldx, const void* dy, long long ldg, const void* w1, const void* w2t,
+                           const void* w1t, const float* b1, const float* row_scale, int rows_per_scale, void* dz, void* hs,
+                           void* dxn, long long lddx, long long M, int C, int Hd, int act, void* stream) {
+  if (M == 0) return OGV_OK;
+  OGV_REQUIRE(xn && dy && w1 && w2t && w1t && b1 && dz && hs && dxn, "mlp_bwd: null argument");
+  OGV_REQUIRE(act >= OGV_ACT_NONE && act <= OGV_ACT_RELU, "mlp_bwd: bad activation code %d", act);
+  if (!fwd_chunk(C, Hd)) {
+    ogv_set_error("mlp_bwd: unsupported shape C=%d hidden=%d", C, Hd);
+    return OGV_ERR_UNSUPPORTED;
+  }
+  OGV_REQUIRE(aligned16(xn) && aligned16(dy) && aligned16(w1) && aligned16(w2t) && aligned16(w1t) && aligned16(b1) &&
+                  aligned16(dz) && aligned16(hs) && aligned16(dxn) && ldx % 8 == 0 && ldg % 8 == 0 && lddx % 8 == 0,
+              "mlp_bwd: tensors must be 16-byte aligned with row strides that are multiples of 8 elements");
+  OGV_REQUIRE(M <= 0x7fffffffll - F_BM, "mlp_bwd: too many rows");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (C == 64)
+    return launch_mlp_bwd<64>(xn, ldx, dy, ldg, w1, w2t, w1t, b1, row_scale, rows_per_scale, dz, hs, dxn, lddx, M, Hd, act, st);
+  return launch_mlp_bwd<128>(xn, ldx, dy, ldg, w1, w2t, w1t, b1, row_scale, rows_per_scale, dz, hs, dxn, lddx, M, Hd, act, st);
 }

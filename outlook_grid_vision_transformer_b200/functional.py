@@ -47,6 +47,12 @@ class PreparedLinear:
         self.wt = wt
 
 
+# fc1 -> act -> fc2 in one kernel with the hidden tile on chip (ogv_mlp_fwd / ogv_mlp_bwd) for the shapes it serves;
+# OGV_MLP_FUSED=0 keeps the two-GEMM route (A/B measurements).
+import os as _os
+
+MLP_FUSED = _os.environ.get("OGV_MLP_FUSED", "1") != "0"
+
 # When a list, every cast issued by prepare_* below is also recorded as (src, dst, dst_t): modules._Prep keeps the
 # records so that modules.refresh_prepared() can re-run all of a model's casts in ONE launch per step.
 _CAST_LOG: Optional[list] = None
@@ -132,13 +138,22 @@ class MlpBranchFn(torch.autograd.Function):
             xn, mean, rstd = ops.layernorm_fwd(x, ln_w, ln_b, meta["eps"])
         else:
             xn, mean, rstd = x, None, None
-        # the forward epilogue saves act'(z) (it has the transcendental in hand), so the backward epilogue is a
-        # plain multiply instead of a second erf/exp evaluation per element
-        z = _empty((M, Hd), x)
-        h = _empty((M, Hd), x)
-        ops.gemm(xn, p1.w, h, bias=b1, pre_out=z, act=act, pre_out_grad=True)
-        y = _empty((M, C), x)
-        ops.gemm(h, p2.w, y, bias=b2, row_scale=scale, rows_per_scale=P, residual=x if with_res else None)
+        fused = MLP_FUSED and ops.mlp_fused_supported(C, Hd, x.dtype) and b1 is not None and b2 is not None
+        if fused:
+            # fc1 -> act -> fc2 -> DropPath scale -> residual in ONE kernel; the [M, hidden] activation never leaves the
+            # SM, and nothing wide is saved: the backward kernel recomputes it from the (narrow) LayerNorm output
+            y = ops.mlp_fwd(xn, p1.w, b1, p2.w, b2, act=act, residual=x if with_res else None, row_scale=scale,
+                            rows_per_scale=P)
+            z = h = None
+        else:
+            # the forward epilogue saves act'(z) (it has the transcendental in hand), so the backward epilogue is a
+            # plain multiply instead of a second erf/exp evaluation per element
+            z = _empty((M, Hd), x)
+            h = _empty((M, Hd), x)
+            ops.gemm(xn, p1.w, h, bias=b1, pre_out=z, act=act, pre_out_grad=True)
+            y = _empty((M, C), x)
+            ops.gemm(h, p2.w, y, bias=b2, row_scale=scale, rows_per_scale=P, residual=x if with_res else None)
+        ctx.fused = fused
         ctx.meta = meta
         ctx.params = (ln_w, ln_b, w1, b1, w2, b2)
         ctx.save_for_backward(x, xn, mean, rstd, z, h, ln_w, scale)
@@ -170,21 +185,37 @@ class MlpBranchFn(torch.autograd.Function):
             db2 = arena[o:o + C]; o += C
             dg = arena[o:o + C]; o += C
             dbt = arena[o:o + C]; o += C
-        gy = _scaled_grad(dy, scale, P, db2)
-        # fc2 backward (+ activation derivative and the fc1 bias gradient fused into the dgrad epilogue)
-        dz = _empty((M, Hd), x)
-        # bias gradient as a separate full-rate pass: the column sum fused into this wide-N epilogue costs about
-        # twice what the streaming reduction does (measured 165 us vs 81 us at stage 0)
-        ops.gemm(gy, p2.wt, dz, dact_src=z, dact="mul")
-        ops.colsum(dz, db1)
-        ops.wgrad(gy, h, dW2)
-        # fc1 backward
-        dxn = _empty((M, C), x)
-        if with_ln:
-            ops.gemm(dz, p1.wt, dxn)
+        if ctx.fused and (with_ln or not with_res):
+            # one kernel: recompute z, h on chip; dz = (dy W2) * act'(z) * s, hs = act(z) * s, dxn = dz W1.  The DropPath
+            # scale s rides in dz / hs, so dy itself is the operand of the fc2 weight gradient (no scaled copy of dy)
+            if scale is None:
+                ops.colsum(dy, db2)
+            else:
+                ops.rowscale_colsum(dy, scale, P, db2, store=False)
+            dxn, dz, hs = ops.mlp_bwd(xn, dy, p1.w, p2.wt, p1.wt, b1, act=act, row_scale=scale, rows_per_scale=P)
+            ops.colsum(dz, db1)
+            ops.wgrad(dy, hs, dW2)
+            ops.wgrad(dz, xn, dW1)
         else:
-            ops.gemm(dz, p1.wt, dxn, residual=dy if with_res else None)
-        ops.wgrad(dz, xn, dW1)
+            if ctx.fused:  # shapes the fused backward does not serve: recompute the saved pair the unfused way
+                z = _empty((M, Hd), x)
+                h = _empty((M, Hd), x)
+                ops.gemm(xn, p1.w, h, bias=b1, pre_out=z, act=act, pre_out_grad=True)
+            gy = _scaled_grad(dy, scale, P, db2)
+            # fc2 backward (+ activation derivative and the fc1 bias gradient fused into the dgrad epilogue)
+            dz = _empty((M, Hd), x)
+            # bias gradient as a separate full-rate pass: the column sum fused into this wide-N epilogue costs about
+            # twice what the streaming reduction does (measured 165 us vs 81 us at stage 0)
+            ops.gemm(gy, p2.wt, dz, dact_src=z, dact="mul")
+            ops.colsum(dz, db1)
+            ops.wgrad(gy, h, dW2)
+            # fc1 backward
+            dxn = _empty((M, C), x)
+            if with_ln:
+                ops.gemm(dz, p1.wt, dxn)
+            else:
+                ops.gemm(dz, p1.wt, dxn, residual=dy if with_res else None)
+            ops.wgrad(dz, xn, dW1)
         dx = ops.layernorm_bwd(dxn, x, ln_w, mean, rstd, dy if with_res else None, dg, dbt) if with_ln else dxn
         if direct:
             _notify(ctx.params)

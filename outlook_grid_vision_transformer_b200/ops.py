@@ -318,12 +318,12 @@ def rowscale(x: Tensor, scale: Tensor, rows_per_scale: int) -> Tensor:
     return y
 
 
-def rowscale_colsum(x: Tensor, scale: Tensor, rows_per_scale: int, out: Tensor) -> Tensor:
-    """-> y = x * scale[row // rows_per_scale];  out[n] += sum_m y[m,n]  (one pass)."""
+def rowscale_colsum(x: Tensor, scale: Tensor, rows_per_scale: int, out: Tensor, store: bool = True) -> Optional[Tensor]:
+    """-> y = x * scale[row // rows_per_scale];  out[n] += sum_m y[m,n]  (one pass).  store=False: reduction only."""
     _require_cuda(x, scale, out)
     _f32(scale, "scale")
     _f32(out, "out")
-    y = torch.empty_like(x)
+    y = torch.empty_like(x) if store else None
     _call("ogv_rowscale_colsum", _p(x), _p(scale), _p(y), _p(out), x.shape[0], x.shape[1], rows_per_scale,
           dtype_code(x), _stream())
     return y
@@ -536,6 +536,39 @@ def mlp_fwd(x: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor, *, act: s
           ctypes.c_void_p(row_scale.data_ptr()) if row_scale is not None else None, int(rows_per_scale),
           ctypes.c_void_p(y.data_ptr()), y.stride(0), M, C, Hd, ACT[act], _stream())
     return y
+
+
+def mlp_bwd(xn: Tensor, dy: Tensor, w1: Tensor, w2t: Tensor, w1t: Tensor, b1: Tensor, *, act: str,
+            row_scale: Optional[Tensor] = None, rows_per_scale: int = 1):
+    """Backward of the fused MLP with the hidden activation RECOMPUTED on chip:
+        z = xn w1^T + b1;  dz = (dy w2) * act'(z) * s;  hs = act(z) * s;  dxn = dz w1      (s = row_scale or 1)
+    -> (dxn [M, C], dz [M, hidden], hs [M, hidden]); dz / hs feed the weight-gradient GEMMs dW1 = dz^T xn, dW2 = dy^T hs.
+    w2t = w2^T [hidden, C], w1t = w1^T [C, hidden] (the pre-transposed copies the dgrad GEMMs use)."""
+    _require_cuda(xn, dy, w1, w2t, w1t, b1, row_scale)
+    M, C = xn.shape
+    Hd = w1.shape[0]
+    for name, t in (("xn", xn), ("dy", dy), ("w1", w1), ("w2t", w2t), ("w1t", w1t)):
+        if t.dtype != torch.bfloat16:
+            raise TypeError(f"mlp_bwd: {name} must be bf16")
+    if tuple(w1.shape) != (Hd, C) or tuple(w2t.shape) != (Hd, C) or tuple(w1t.shape) != (C, Hd) or tuple(dy.shape) != (M, C):
+        raise ValueError("mlp_bwd: shape mismatch")
+    if not (w1.is_contiguous() and w2t.is_contiguous() and w1t.is_contiguous()):
+        raise ValueError("mlp_bwd: weights must be contiguous")
+    _rows(xn, "xn")
+    _rows(dy, "dy")
+    _f32(b1, "b1")
+    _f32(row_scale, "row_scale")
+    dz = torch.empty((M, Hd), device=xn.device, dtype=xn.dtype)
+    hs = torch.empty((M, Hd), device=xn.device, dtype=xn.dtype)
+    dxn = torch.empty((M, C), device=xn.device, dtype=xn.dtype)
+    if PROFILER.enabled:
+        PROFILER.cur_bytes = 2 * (3 * M * C + 2 * M * Hd + 3 * Hd * C)
+        PROFILER.cur_flops = 6 * M * C * Hd
+        PROFILER.cur_kernel = f"mlp_bwd_kernel<{C}>"
+    vp = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None  # noqa: E731
+    _call("ogv_mlp_bwd", vp(xn), xn.stride(0), vp(dy), dy.stride(0), vp(w1), vp(w2t), vp(w1t), vp(b1), vp(row_scale),
+          int(rows_per_scale), vp(dz), vp(hs), vp(dxn), dxn.stride(0), M, C, Hd, ACT[act], _stream())
+    return dxn, dz, hs
 
 
 # ----------------------------------------------------------------------- flat-arena train-step tail
