@@ -192,7 +192,8 @@ class MlpBranchFn(torch.autograd.Function):
                 ops.colsum(dy, db2)
             else:
                 ops.rowscale_colsum(dy, scale, P, db2, store=False)
-            dxn, dz, hs = ops.mlp_bwd(xn, dy, p1.w, p2.wt, p1.wt, b1, act=act, row_scale=scale, rows_per_scale=P)
+            dxn, dz, hs = ops.mlp_bwd(xn, dy, p1.w, p2.wt, p1.wt, ctx.params[3].detach(), act=act, row_scale=scale,
+                                      rows_per_scale=P)
             ops.colsum(dz, db1)
             ops.wgrad(dy, hs, dW2)
             ops.wgrad(dz, xn, dW1)
@@ -200,7 +201,7 @@ class MlpBranchFn(torch.autograd.Function):
             if ctx.fused:  # shapes the fused backward does not serve: recompute the saved pair the unfused way
                 z = _empty((M, Hd), x)
                 h = _empty((M, Hd), x)
-                ops.gemm(xn, p1.w, h, bias=b1, pre_out=z, act=act, pre_out_grad=True)
+                ops.gemm(xn, p1.w, h, bias=ctx.params[3].detach(), pre_out=z, act=act, pre_out_grad=True)
             gy = _scaled_grad(dy, scale, P, db2)
             # fc2 backward (+ activation derivative and the fc1 bias gradient fused into the dgrad epilogue)
             dz = _empty((M, Hd), x)

@@ -161,6 +161,17 @@ def main():
         run("gemm qkv", s, lambda: ops.gemm(x, wq, q3, bias=torch.zeros(3 * C, **f32)), nbytes(x, q3), 2 * M * 3 * C * C)
         wp = (torch.randn(C, C, device=dev) * 0.05).to(dt)
         run("gemm proj+res", s, lambda: ops.gemm(x, wp, out_c, bias=bC, residual=dy), nbytes(x, dy, out_c), 2 * M * C * C)
+        # ---- fused MLP (hidden tile on chip): fc1 -> act -> fc2 -> +res in one kernel; backward recomputes it
+        for tag, Hd in (("mlp 4C", 4 * C), ("mlp2d 2C", 2 * C)):
+            if not ops.mlp_fused_supported(C, Hd, dt):
+                continue
+            wa = (torch.randn(Hd, C, device=dev) * 0.05).to(dt)
+            wb = (torch.randn(C, Hd, device=dev) * 0.05).to(dt)
+            wat, wbt = wa.t().contiguous(), wb.t().contiguous()
+            ba = torch.zeros(Hd, **f32)
+            run(f"fused {tag} fwd", s, lambda: ops.mlp_fwd(x, wa, ba, wb, bC, act="gelu", residual=dy), nbytes(x, dy, out_c), 4 * M * Hd * C)
+            run(f"fused {tag} bwd", s, lambda: ops.mlp_bwd(x, dy, wa, wbt, wat, ba, act="gelu"),
+                nbytes(x, dy, out_c) + 2 * M * Hd * 2, 6 * M * Hd * C)
         del x, dy, wide, z, h, out_c, q3
         torch.cuda.empty_cache()
     Path(a.out).parent.mkdir(exist_ok=True)
