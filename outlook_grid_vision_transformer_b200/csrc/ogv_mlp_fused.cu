@@ -22,7 +22,6 @@ constexpr int F_EPI_WARPS = 16;
 constexpr int F_THREADS = (F_EPI_WARPS + 2) * 32;
 constexpr int F_PRODUCER = F_EPI_WARPS;
 constexpr int F_MMA = F_EPI_WARPS + 1;
-constexpr int F_NW = 4;                 // weight-chunk ring depth
 constexpr int F_SLOT = 32 * 32 * 2;     // one warp's 32 x 32 bf16 staging tile (SWIZZLE_64B)
 
 template <int C, int BH>
@@ -30,15 +29,17 @@ struct MlpFwdCfg {
   static_assert(C % 64 == 0 && BH % 64 == 0, "tiles are cut in 64-column (128-byte) sub-tiles");
   static constexpr int KC = C / 64;
   static constexpr int KH = BH / 64;
+  static constexpr int NW = C == 64 ? 4 : 3;               // weight-chunk ring depth
+  static constexpr int NZ = 3;                             // fc1 accumulator buffers in TMEM
   static constexpr int XA_BYTES = F_BM * C * 2;
   static constexpr int H_BYTES = F_BM * BH * 2;
   static constexpr int W_BYTES = BH * C * 2;
-  static constexpr int OUT_WARPS = 4 * (C / 32);          // (lane quarter, 32-column chunk) pairs of the output tile
-  static constexpr int STAGE_BYTES = OUT_WARPS * F_SLOT;
-  static constexpr int NBAR = 2 + 2 + 2 * F_NW + 2 + 2 + 2 + 2 + 2 + 2 + F_EPI_WARPS;
-  static constexpr int SMEM = 2 * XA_BYTES + 2 * H_BYTES + F_NW * W_BYTES + STAGE_BYTES + NBAR * 8 + 16 + 1024;
-  static constexpr int TMEM_COLS = 512;                   // 2*BH (Z) + 2*C (Y) = 384 -> next power of two
-  static_assert(2 * BH + 2 * C <= 512, "TMEM budget");
+  static constexpr int NOC = (C / 32) / 2;                 // 32-column output chunks per warp of a group (1 or 2)
+  static constexpr int STAGE_BYTES = F_EPI_WARPS * NOC * F_SLOT;
+  static constexpr int NBAR = 2 + 2 + 2 * NW + 2 * NZ + 2 + 2 + 2 + 2 + F_EPI_WARPS * NOC;
+  static constexpr int SMEM = 2 * XA_BYTES + 2 * H_BYTES + NW * W_BYTES + STAGE_BYTES + NBAR * 8 + 16 + 1024;
+  static constexpr int TMEM_COLS = 512;                    // NZ*BH (Z) + 2*C (Y) <= 512
+  static_assert(NZ * BH + 2 * C <= 512, "TMEM budget");
   static_assert(SMEM <= 227 * 1024, "shared memory budget");
 };
 
@@ -53,31 +54,37 @@ struct MlpFwdParams {
   int rows_per_scale;
 };
 
+// The kernel sees the work of one CTA as a FLAT STREAM of hidden chunks f = 0, 1, ... (tile it = f / NJ, chunk
+// j = f % NJ).  TMEM reads are the scarce resource of the epilogue (64 B/clk/SM: a 128 x 128 fp32 chunk costs 1024
+// clocks to read, about as much as its GELU costs to compute), so the 16 epilogue warps form TWO groups that work on
+// alternate chunks and drift into anti-phase -- one group reads TMEM while the other one computes.  The MMA issuer runs
+// fc1 two chunks ahead of fc2 (three Z buffers), so a group that finishes chunk f finds Z of chunk f + 2 waiting.
 template <int C, int BH>
 __global__ void __launch_bounds__(F_THREADS, 1)
 mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
                const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmY,
                const __grid_constant__ CUtensorMap tmR, const MlpFwdParams p) {
   using Cfg = MlpFwdCfg<C, BH>;
+  constexpr int NW = Cfg::NW, NZ = Cfg::NZ;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* xa = smem;                                   // [2][XA_BYTES]
   uint8_t* hbuf = xa + 2 * Cfg::XA_BYTES;               // [2][H_BYTES]
-  uint8_t* wring = hbuf + 2 * Cfg::H_BYTES;             // [F_NW][W_BYTES]
-  uint8_t* staging = wring + F_NW * Cfg::W_BYTES;       // [OUT_WARPS][F_SLOT]
+  uint8_t* wring = hbuf + 2 * Cfg::H_BYTES;             // [NW][W_BYTES]
+  uint8_t* staging = wring + NW * Cfg::W_BYTES;         // [F_EPI_WARPS][NOC][F_SLOT]
   uint64_t* bars = reinterpret_cast<uint64_t*>(staging + Cfg::STAGE_BYTES);
   uint64_t* xa_full = bars;
   uint64_t* xa_empty = xa_full + 2;
   uint64_t* w_full = xa_empty + 2;
-  uint64_t* w_empty = w_full + F_NW;
-  uint64_t* z_full = w_empty + F_NW;
-  uint64_t* z_empty = z_full + 2;
-  uint64_t* h_full = z_empty + 2;
+  uint64_t* w_empty = w_full + NW;
+  uint64_t* z_full = w_empty + NW;
+  uint64_t* z_empty = z_full + NZ;
+  uint64_t* h_full = z_empty + NZ;
   uint64_t* h_empty = h_full + 2;
   uint64_t* y_full = h_empty + 2;
   uint64_t* y_empty = y_full + 2;
-  uint64_t* ld_bar = y_empty + 2;                       // [F_EPI_WARPS]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ld_bar + F_EPI_WARPS);
+  uint64_t* ld_bar = y_empty + 2;                       // [F_EPI_WARPS][NOC]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ld_bar + F_EPI_WARPS * Cfg::NOC);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -89,18 +96,20 @@ mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(&xa_full[s], 1);
       ptx::mbar_init(&xa_empty[s], 1);
-      ptx::mbar_init(&z_full[s], 1);
-      ptx::mbar_init(&z_empty[s], F_EPI_WARPS);
-      ptx::mbar_init(&h_full[s], F_EPI_WARPS);
+      ptx::mbar_init(&h_full[s], F_EPI_WARPS / 2);
       ptx::mbar_init(&h_empty[s], 1);
       ptx::mbar_init(&y_full[s], 1);
-      ptx::mbar_init(&y_empty[s], Cfg::OUT_WARPS);
+      ptx::mbar_init(&y_empty[s], F_EPI_WARPS / 2);
     }
-    for (int s = 0; s < F_NW; ++s) {
+    for (int s = 0; s < NZ; ++s) {
+      ptx::mbar_init(&z_full[s], 1);
+      ptx::mbar_init(&z_empty[s], F_EPI_WARPS / 2);
+    }
+    for (int s = 0; s < NW; ++s) {
       ptx::mbar_init(&w_full[s], 1);
       ptx::mbar_init(&w_empty[s], 1);
     }
-    for (int s = 0; s < F_EPI_WARPS; ++s) ptx::mbar_init(&ld_bar[s], 1);
+    for (int s = 0; s < F_EPI_WARPS * Cfg::NOC; ++s) ptx::mbar_init(&ld_bar[s], 1);
     ptx::fence_barrier_init();
   }
   if (warp == F_MMA) {
@@ -111,41 +120,46 @@ mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_z = tmem_base;             // Z[zb] at column zb * BH
-  const uint32_t tmem_y = tmem_base + 2 * BH;    // Y[yb] at column 2*BH + yb * C
+  const uint32_t tmem_z = tmem_base;               // Z[b] at column b * BH
+  const uint32_t tmem_y = tmem_base + NZ * BH;     // Y[b] at column NZ*BH + b * C
   const int NJ = p.NJ;
+  const int my_tiles = (p.m_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // tiles of this CTA
+  const int T = my_tiles * NJ;                     // chunks of this CTA
 
   if (warp == F_PRODUCER) {
     // ------------------------------- TMA producer -------------------------------
     if (lane == 0) {
       uint32_t wc = 0;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, ++it) {
-        const int xb = it & 1;
-        ptx::mbar_wait(&xa_empty[xb], ((it >> 1) & 1) ^ 1u);
-        ptx::mbar_arrive_expect_tx(&xa_full[xb], Cfg::XA_BYTES);
+      auto slot_for = [&]() {
+        const int ws = wc % NW;
+        ptx::mbar_wait(&w_empty[ws], ((wc / NW) & 1) ^ 1u);
+        ptx::mbar_arrive_expect_tx(&w_full[ws], Cfg::W_BYTES);
+        ++wc;
+        return ws;
+      };
+      for (int f = 0; f < T + NZ; ++f) {  // same order as the MMA issuer consumes: [x tile], W1(f), W2(f - NZ)
+        if (f < T) {
+          const int it = f / NJ, j = f - it * NJ;
+          if (j == 0) {
+            const int xb = it & 1;
+            const int tile = blockIdx.x + it * gridDim.x;
+            ptx::mbar_wait(&xa_empty[xb], ((it >> 1) & 1) ^ 1u);
+            ptx::mbar_arrive_expect_tx(&xa_full[xb], Cfg::XA_BYTES);
 #pragma unroll
-        for (int ks = 0; ks < Cfg::KC; ++ks)  // box {64 k, 128 rows}
-          ptx::tma_load_2d(xa + xb * Cfg::XA_BYTES + ks * (F_BM * 128), &tmX, &xa_full[xb], ks * 64, tile * F_BM);
-        for (int step = 0; step <= NJ; ++step) {
-          if (step < NJ) {  // W1 rows [step*BH, +BH): box {64 k, BH rows} per 64-column slice of C
-            const int ws = wc % F_NW;
-            ptx::mbar_wait(&w_empty[ws], ((wc / F_NW) & 1) ^ 1u);
-            ptx::mbar_arrive_expect_tx(&w_full[ws], Cfg::W_BYTES);
-#pragma unroll
-            for (int ks = 0; ks < Cfg::KC; ++ks)
-              ptx::tma_load_2d(wring + ws * Cfg::W_BYTES + ks * (BH * 128), &tmW1, &w_full[ws], ks * 64, step * BH);
-            ++wc;
+            for (int ks = 0; ks < Cfg::KC; ++ks)  // box {64 k, 128 rows}
+              ptx::tma_load_2d(xa + xb * Cfg::XA_BYTES + ks * (F_BM * 128), &tmX, &xa_full[xb], ks * 64, tile * F_BM);
           }
-          if (step >= 1) {  // W2[:, (step-1)*BH ..): box {64 hidden, C rows} per 64-column slice of the chunk
-            const int ws = wc % F_NW;
-            ptx::mbar_wait(&w_empty[ws], ((wc / F_NW) & 1) ^ 1u);
-            ptx::mbar_arrive_expect_tx(&w_full[ws], Cfg::W_BYTES);
+          const int ws = slot_for();  // W1 rows [j*BH, +BH): box {64 k, BH rows} per 64-column slice of C
 #pragma unroll
-            for (int hs = 0; hs < Cfg::KH; ++hs)
-              ptx::tma_load_2d(wring + ws * Cfg::W_BYTES + hs * (C * 128), &tmW2, &w_full[ws], (step - 1) * BH + hs * 64, 0);
-            ++wc;
-          }
+          for (int ks = 0; ks < Cfg::KC; ++ks)
+            ptx::tma_load_2d(wring + ws * Cfg::W_BYTES + ks * (BH * 128), &tmW1, &w_full[ws], ks * 64, j * BH);
+        }
+        if (f >= NZ) {
+          const int j2 = (f - NZ) % NJ;
+          const int ws = slot_for();  // W2[:, j2*BH ..): box {64 hidden, C rows} per 64-column slice of the chunk
+#pragma unroll
+          for (int hs = 0; hs < Cfg::KH; ++hs)
+            ptx::tma_load_2d(wring + ws * Cfg::W_BYTES + hs * (C * 128), &tmW2, &w_full[ws], j2 * BH + hs * 64, 0);
         }
       }
     }
@@ -154,164 +168,186 @@ mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     if (lane == 0) {
       const uint32_t idesc1 = ptx::umma_idesc_bf16(F_BM, BH, 0, 0);
       const uint32_t idesc2 = ptx::umma_idesc_bf16(F_BM, C, 0, 0);
-      uint32_t wc = 0, zc = 0, hc = 0;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, ++it) {
-        const int xb = it & 1, yb = it & 1;
-        ptx::mbar_wait(&y_empty[yb], ((it >> 1) & 1) ^ 1u);
-        ptx::mbar_wait(&xa_full[xb], (it >> 1) & 1);
-        ptx::tc_fence_after();
-        const uint32_t xa_addr = ptx::smem_u32(xa + xb * Cfg::XA_BYTES);
-        for (int step = 0; step <= NJ; ++step) {
-          if (step < NJ) {  // fc1 of chunk `step`
-            const int zb = zc & 1;
-            ptx::mbar_wait(&z_empty[zb], ((zc >> 1) & 1) ^ 1u);
-            const int ws = wc % F_NW;
-            ptx::mbar_wait(&w_full[ws], (wc / F_NW) & 1);
-            ptx::tc_fence_after();
-            const uint32_t wb = ptx::smem_u32(wring + ws * Cfg::W_BYTES);
+      uint32_t wc = 0;
+      // fc1 runs NZ chunks ahead of fc2: Z(f) is issued the moment the epilogue has READ chunk f - NZ out of TMEM, long
+      // before that chunk's activation tile is complete, so no epilogue group ever waits for the tensor pipe
+      for (int f = 0; f < T + NZ; ++f) {
+        if (f < T) {  // fc1 of chunk f
+          const int it = f / NJ, j = f - it * NJ;
+          const int xb = it & 1;
+          if (j == 0) ptx::mbar_wait(&xa_full[xb], (it >> 1) & 1);
+          const int zb = f % NZ;
+          ptx::mbar_wait(&z_empty[zb], ((f / NZ) & 1) ^ 1u);
+          const int ws = wc % NW;
+          ptx::mbar_wait(&w_full[ws], (wc / NW) & 1);
+          ptx::tc_fence_after();
+          const uint32_t xa_addr = ptx::smem_u32(xa + xb * Cfg::XA_BYTES);
+          const uint32_t wb = ptx::smem_u32(wring + ws * Cfg::W_BYTES);
 #pragma unroll
-            for (int ks = 0; ks < Cfg::KC; ++ks)
+          for (int ks = 0; ks < Cfg::KC; ++ks)
 #pragma unroll
-              for (int kk = 0; kk < 4; ++kk) {
-                const uint64_t ad = ptx::umma_smem_desc(xa_addr + ks * (F_BM * 128) + kk * 32, 16u, 1024u);
-                const uint64_t bd = ptx::umma_smem_desc(wb + ks * (BH * 128) + kk * 32, 16u, 1024u);
-                ptx::umma_f16(tmem_z + zb * BH, ad, bd, idesc1, (ks > 0 || kk > 0) ? 1u : 0u);
-              }
-            ptx::umma_commit(&w_empty[ws]);
-            ++wc;
-            ptx::umma_commit(&z_full[zb]);
-            ++zc;
-            if (step == NJ - 1) ptx::umma_commit(&xa_empty[xb]);
-          }
-          if (step >= 1) {  // fc2 of chunk `step - 1`
-            const int hb = hc & 1;
-            ptx::mbar_wait(&h_full[hb], (hc >> 1) & 1);
-            const int ws = wc % F_NW;
-            ptx::mbar_wait(&w_full[ws], (wc / F_NW) & 1);
-            ptx::tc_fence_after();
-            const uint32_t ha = ptx::smem_u32(hbuf + hb * Cfg::H_BYTES);
-            const uint32_t wb = ptx::smem_u32(wring + ws * Cfg::W_BYTES);
+            for (int kk = 0; kk < 4; ++kk) {
+              const uint64_t ad = ptx::umma_smem_desc(xa_addr + ks * (F_BM * 128) + kk * 32, 16u, 1024u);
+              const uint64_t bd = ptx::umma_smem_desc(wb + ks * (BH * 128) + kk * 32, 16u, 1024u);
+              ptx::umma_f16(tmem_z + zb * BH, ad, bd, idesc1, (ks > 0 || kk > 0) ? 1u : 0u);
+            }
+          ptx::umma_commit(&w_empty[ws]);
+          ++wc;
+          ptx::umma_commit(&z_full[zb]);
+          if (j == NJ - 1) ptx::umma_commit(&xa_empty[xb]);
+        }
+        if (f >= NZ) {  // fc2 of chunk f - NZ
+          const int f2 = f - NZ;
+          const int it = f2 / NJ, j = f2 - it * NJ;
+          const int yb = it & 1, hb = f2 & 1;
+          if (j == 0) ptx::mbar_wait(&y_empty[yb], ((it >> 1) & 1) ^ 1u);
+          ptx::mbar_wait(&h_full[hb], (f2 >> 1) & 1);
+          const int ws = wc % NW;
+          ptx::mbar_wait(&w_full[ws], (wc / NW) & 1);
+          ptx::tc_fence_after();
+          const uint32_t ha = ptx::smem_u32(hbuf + hb * Cfg::H_BYTES);
+          const uint32_t wb = ptx::smem_u32(wring + ws * Cfg::W_BYTES);
 #pragma unroll
-            for (int hs = 0; hs < Cfg::KH; ++hs)
+          for (int hs = 0; hs < Cfg::KH; ++hs)
 #pragma unroll
-              for (int kk = 0; kk < 4; ++kk) {
-                const uint64_t ad = ptx::umma_smem_desc(ha + hs * (F_BM * 128) + kk * 32, 16u, 1024u);
-                const uint64_t bd = ptx::umma_smem_desc(wb + hs * (C * 128) + kk * 32, 16u, 1024u);
-                ptx::umma_f16(tmem_y + yb * C, ad, bd, idesc2, (step > 1 || hs > 0 || kk > 0) ? 1u : 0u);
-              }
-            ptx::umma_commit(&w_empty[ws]);
-            ++wc;
-            ptx::umma_commit(&h_empty[hb]);
-            ++hc;
-            if (step == NJ) ptx::umma_commit(&y_full[yb]);
-          }
+            for (int kk = 0; kk < 4; ++kk) {
+              const uint64_t ad = ptx::umma_smem_desc(ha + hs * (F_BM * 128) + kk * 32, 16u, 1024u);
+              const uint64_t bd = ptx::umma_smem_desc(wb + hs * (C * 128) + kk * 32, 16u, 1024u);
+              ptx::umma_f16(tmem_y + yb * C, ad, bd, idesc2, (j > 0 || hs > 0 || kk > 0) ? 1u : 0u);
+            }
+          ptx::umma_commit(&w_empty[ws]);
+          ++wc;
+          ptx::umma_commit(&h_empty[hb]);
+          if (j == NJ - 1) ptx::umma_commit(&y_full[yb]);
         }
       }
     }
   } else {
-    // ------------------------------- epilogue warps -------------------------------
-    constexpr int ZW = BH / 4;  // hidden columns of a chunk this warp converts (32 or 16)
-    const int q = warp & 3;
-    const int cg = warp >> 2;
-    const bool out_warp = cg < C / 32;
-    uint8_t* slot = staging + (q * (C / 32) + (out_warp ? cg : 0)) * F_SLOT;
-    uint64_t* my_ld = &ld_bar[warp];
-    uint32_t zc = 0, hc = 0, ldc = 0;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, ++it) {
+    // ------------------------------- epilogue warps: two groups on alternate chunks -------------------------------
+    constexpr int HW = BH / 2;          // hidden columns of a chunk per warp (64 or 32)
+    constexpr int NP = HW / 32;         // ... in 32-column pieces
+    constexpr int NOC = Cfg::NOC;
+    const int g = warp >> 3;            // group: chunks with f % 2 == g, hidden tile buffer H[g]
+    const int q = warp & 3;             // TMEM lane quarter
+    const int half = (warp >> 2) & 1;   // column half within the group
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    uint8_t* slots = staging + warp * NOC * F_SLOT;
+    uint64_t* my_ld = &ld_bar[warp * NOC];
+    const int row = q * 32 + lane;
+    uint32_t ldc = 0;
+    // writes tile `it` out: y = (Y + b2) * row_scale + residual.  Called one own-chunk AFTER the tile's last chunk was
+    // converted, so the fc2 accumulator and the residual tile have long arrived.
+    auto write_tile = [&](int it) {
+      const int tile = blockIdx.x + it * gridDim.x;
       const int yb = it & 1;
       const int mrow0 = tile * F_BM + q * 32;
       const long long m = (long long)mrow0 + lane;
-      if (out_warp && p.has_res) {  // the residual tile arrives while the chunks are being processed
-        if (lane == 0) {
-          ptx::bulk_wait_read<0>();  // the previous tile's store has finished reading the slot
-          ptx::mbar_arrive_expect_tx(my_ld, F_SLOT);
-          ptx::tma_load_2d(slot, &tmR, my_ld, cg * 32, mrow0);
-        }
-      }
-      for (int j = 0; j < NJ; ++j) {
-        const int zb = zc & 1;
-        ptx::mbar_wait(&z_full[zb], (zc >> 1) & 1);
-        ptx::tc_fence_after();
-        const uint32_t taddr = tmem_z + (static_cast<uint32_t>(q * 32) << 16) + zb * BH + cg * ZW;
-        float v[ZW];
-        if constexpr (ZW == 32) ptx::tmem_ld32(taddr, v);
-        else ptx::tmem_ld16(taddr, v);
-        ptx::tc_fence_before();
+      ptx::mbar_wait(&y_full[yb], (it >> 1) & 1);
+      ptx::tc_fence_after();
+      const float rsf = (p.row_scale && m < p.M) ? p.row_scale[m / p.rows_per_scale] : 1.f;
+      const f32x2 rs = splat2(rsf);
+      if (!p.has_res) {
+        if (lane == 0) ptx::bulk_wait_read<0>();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&z_empty[zb]);
-        ++zc;
-        f32x2 v2[ZW / 2];
-        pack_n<ZW / 2>(v, v2);
-        const float* b1 = p.b1 + j * BH + cg * ZW;
-#pragma unroll
-        for (int i = 0; i < ZW / 4; ++i) {
-          const ulonglong2 b4 = __ldg(reinterpret_cast<const ulonglong2*>(b1) + i);
-          v2[2 * i] = add2(v2[2 * i], b4.x);
-          v2[2 * i + 1] = add2(v2[2 * i + 1], b4.y);
-        }
-        act_apply_p<ZW / 2, true>(p.act, v2);
-        const int hb = hc & 1;
-        ptx::mbar_wait(&h_empty[hb], ((hc >> 1) & 1) ^ 1u);
-        // row `q*32 + lane` of the chunk, columns [cg*ZW, +ZW): 16-byte pieces of a 128B-swizzled K-major tile
-        uint8_t* ht = hbuf + hb * Cfg::H_BYTES + ((cg * ZW) / 64) * (F_BM * 128);
-        const int c16_0 = ((cg * ZW) % 64) / 8;
-        const int row = q * 32 + lane;
-#pragma unroll
-        for (int c = 0; c < ZW / 8; ++c) {
-          const f32x2 piece[4] = {v2[4 * c], v2[4 * c + 1], v2[4 * c + 2], v2[4 * c + 3]};
-          *reinterpret_cast<uint4*>(ht + sw128(row, c16_0 + c)) = pack8_bf16(piece);
-        }
-        ptx::fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&h_full[hb]);
-        ++hc;
       }
-      if (out_warp) {
-        ptx::mbar_wait(&y_full[yb], (it >> 1) & 1);
-        ptx::tc_fence_after();
+#pragma unroll
+      for (int oc = 0; oc < NOC; ++oc) {
+        const int ccol = (half * NOC + oc) * 32;
+        uint8_t* slot = slots + oc * F_SLOT;
         float v[32];
-        ptx::tmem_ld32(tmem_y + (static_cast<uint32_t>(q * 32) << 16) + yb * C + cg * 32, v);
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&y_empty[yb]);
+        ptx::tmem_ld32(tmem_y + lane_off + yb * C + ccol, v);
+        if (oc == NOC - 1) {
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&y_empty[yb]);
+        }
         f32x2 v2[16];
         pack_n<16>(v, v2);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const ulonglong2 b4 = __ldg(reinterpret_cast<const ulonglong2*>(p.b2 + cg * 32) + i);
+          const ulonglong2 b4 = __ldg(reinterpret_cast<const ulonglong2*>(p.b2 + ccol) + i);
           v2[2 * i] = add2(v2[2 * i], b4.x);
           v2[2 * i + 1] = add2(v2[2 * i + 1], b4.y);
         }
-        const float rsf = (p.row_scale && m < p.M) ? p.row_scale[m / p.rows_per_scale] : 1.f;
-        const f32x2 rs = splat2(rsf);
         if (p.has_res) {
-          ptx::mbar_wait(my_ld, ldc & 1u);
-          ++ldc;
+          ptx::mbar_wait(&my_ld[oc], ldc & 1u);
           f32x2 r2[16];
           stage_read_row(slot, lane, r2);
 #pragma unroll
           for (int i = 0; i < 16; ++i) v2[i] = fma2(v2[i], rs, r2[i]);
           __syncwarp();  // every lane has read its residual row before anyone overwrites the slot
-        } else {
-          if (p.row_scale) {
+        } else if (p.row_scale) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v2[i] = mul2(v2[i], rs);
-          }
-          if (lane == 0) ptx::bulk_wait_read<0>();
-          __syncwarp();
+          for (int i = 0; i < 16; ++i) v2[i] = mul2(v2[i], rs);
         }
         stage_write_row(slot, lane, v2);
         ptx::fence_proxy_async();
         __syncwarp();
-        if (lane == 0) {
-          ptx::tma_store_2d(&tmY, slot, cg * 32, mrow0);
-          ptx::bulk_commit();
+        if (lane == 0) ptx::tma_store_2d(&tmY, slot, ccol, mrow0);
+      }
+      if (lane == 0) ptx::bulk_commit();
+      ++ldc;
+    };
+    int pending = -1;  // tile whose last chunk this group converted and which it still has to write out
+    for (int f = g; f < T; f += 2) {
+      const int it = f / NJ, j = f - it * NJ;
+      const int zb = f % NZ;
+      ptx::mbar_wait(&z_full[zb], (f / NZ) & 1);
+      ptx::tc_fence_after();
+      uint8_t* hb = hbuf + g * Cfg::H_BYTES;
+#pragma unroll
+      for (int pc = 0; pc < NP; ++pc) {
+        const int col0 = half * HW + pc * 32;  // within the chunk
+        float v[32];
+        ptx::tmem_ld32(tmem_z + lane_off + zb * BH + col0, v);
+        if (pc == NP - 1) {
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&z_empty[zb]);
+        }
+        f32x2 v2[16];
+        pack_n<16>(v, v2);
+        const float* b1 = p.b1 + j * BH + col0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const ulonglong2 b4 = __ldg(reinterpret_cast<const ulonglong2*>(b1) + i);
+          v2[2 * i] = add2(v2[2 * i], b4.x);
+          v2[2 * i + 1] = add2(v2[2 * i + 1], b4.y);
+        }
+        act_apply_p<16, true>(p.act, v2);
+        // H[g] is rewritten only after the fc2 MMA of this group's previous chunk has read it
+        if (pc == 0) ptx::mbar_wait(&h_empty[g], ((f >> 1) & 1) ^ 1u);
+        // row `row` of the chunk, columns [col0, +32): four 16-byte pieces of a 128B-swizzled K-major tile
+        uint8_t* ht = hb + (col0 / 64) * (F_BM * 128);
+        const int c16_0 = (col0 % 64) / 8;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const f32x2 piece[4] = {v2[4 * c], v2[4 * c + 1], v2[4 * c + 2], v2[4 * c + 3]};
+          *reinterpret_cast<uint4*>(ht + sw128(row, c16_0 + c)) = pack8_bf16(piece);
+        }
+      }
+      ptx::fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&h_full[g]);
+      if (pending >= 0) {
+        write_tile(pending);
+        pending = -1;
+      }
+      if (j == NJ - 1) {  // this group writes tile `it` out -- after its next chunk; fetch the residual tile meanwhile
+        pending = it;
+        if (p.has_res && lane == 0) {
+          const int mrow0 = (blockIdx.x + it * gridDim.x) * F_BM + q * 32;
+          ptx::bulk_wait_read<0>();  // this warp's previous stores have finished reading the slots
+#pragma unroll
+          for (int oc = 0; oc < NOC; ++oc) {
+            ptx::mbar_arrive_expect_tx(&my_ld[oc], F_SLOT);
+            ptx::tma_load_2d(slots + oc * F_SLOT, &tmR, &my_ld[oc], (half * NOC + oc) * 32, mrow0);
+          }
         }
       }
     }
-    if (out_warp && lane == 0) ptx::bulk_wait<0>();
+    if (pending >= 0) write_tile(pending);
+    if (lane == 0) ptx::bulk_wait<0>();
   }
 
   ptx::tc_fence_before();
@@ -339,16 +375,18 @@ template <int C>
 struct MlpBwdCfg {
   static constexpr int KC = C / 64;
   static constexpr int XB = C == 64 ? 2 : 1;               // x/dy tile buffers (the C=128 budget has room for one)
-  static constexpr int NW = C == 64 ? 6 : 3;               // weight-chunk ring depth (3 chunks of weights per hidden chunk)
+  static constexpr int NW = C == 64 ? 6 : 3;               // weight-chunk ring depth (3 weight chunks per hidden chunk)
+  static constexpr int NZ = 3;                             // Z / DH accumulator buffers
+  static constexpr int NDX = C == 64 ? 2 : 1;              // DXN accumulator buffers
   static constexpr int XA_BYTES = F_BM * C * 2;            // one activation tile
   static constexpr int T_BYTES = F_BM * B_BH * 2;          // one dz / hs tile (16 KB)
   static constexpr int W_BYTES = B_BH * C * 2;
-  static constexpr int OUT_WARPS = 4 * (C / 32);
-  static constexpr int STAGE_BYTES = OUT_WARPS * F_SLOT;
-  static constexpr int NBAR = 2 * XB + 2 * NW + 4 + 4 + 4;
+  static constexpr int NOC = (C / 32) / 2;                 // 32-column dxn chunks per warp of the output group
+  static constexpr int STAGE_BYTES = F_EPI_WARPS * F_SLOT;
+  static constexpr int NBAR = 2 * XB + 2 * NW + 2 * NZ + 4 + 2 * NDX;
   static constexpr int SMEM = XB * 2 * XA_BYTES + 4 * T_BYTES + NW * W_BYTES + STAGE_BYTES + NBAR * 8 + 16 + 1024;
-  static constexpr int TMEM_COLS = 512;                    // Z[2] + DH[2] (4 x 64) + DXN[2] (2 x C)
-  static_assert(4 * B_BH + 2 * C <= 512, "TMEM budget");
+  static constexpr int TMEM_COLS = 512;                    // Z[3] + DH[3] (6 x 64) + DXN[NDX] (NDX x C)
+  static_assert(2 * NZ * B_BH + NDX * C <= 512, "TMEM budget");
   static_assert(SMEM <= 227 * 1024, "shared memory budget");
 };
 
@@ -365,6 +403,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
+// Same flat chunk stream / two epilogue groups / two-chunk MMA lookahead as the forward kernel.
 template <int C>
 __global__ void __launch_bounds__(F_THREADS, 1)
 mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmG,
@@ -372,27 +411,27 @@ mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
                const __grid_constant__ CUtensorMap tmW1T, const __grid_constant__ CUtensorMap tmDZ,
                const __grid_constant__ CUtensorMap tmHS, const __grid_constant__ CUtensorMap tmDX, const MlpBwdParams p) {
   using Cfg = MlpBwdCfg<C>;
-  constexpr int BH = B_BH;
+  constexpr int BH = B_BH, NW = Cfg::NW, NZ = Cfg::NZ, XB = Cfg::XB, NDX = Cfg::NDX;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* xn = smem;                                        // [XB][XA_BYTES]
-  uint8_t* gy = xn + Cfg::XB * Cfg::XA_BYTES;                // [XB][XA_BYTES]
-  uint8_t* dzt = gy + Cfg::XB * Cfg::XA_BYTES;               // [2][T_BYTES]
+  uint8_t* gy = xn + XB * Cfg::XA_BYTES;                     // [XB][XA_BYTES]
+  uint8_t* dzt = gy + XB * Cfg::XA_BYTES;                    // [2][T_BYTES]
   uint8_t* hst = dzt + 2 * Cfg::T_BYTES;                     // [2][T_BYTES]
   uint8_t* wring = hst + 2 * Cfg::T_BYTES;                   // [NW][W_BYTES]
-  uint8_t* staging = wring + Cfg::NW * Cfg::W_BYTES;         // [OUT_WARPS][F_SLOT]
+  uint8_t* staging = wring + NW * Cfg::W_BYTES;              // [F_EPI_WARPS][F_SLOT]
   uint64_t* bars = reinterpret_cast<uint64_t*>(staging + Cfg::STAGE_BYTES);
   uint64_t* x_full = bars;
-  uint64_t* x_empty = x_full + Cfg::XB;
-  uint64_t* w_full = x_empty + Cfg::XB;
-  uint64_t* w_empty = w_full + Cfg::NW;
-  uint64_t* zd_full = w_empty + Cfg::NW;
-  uint64_t* zd_empty = zd_full + 2;
-  uint64_t* dz_full = zd_empty + 2;
+  uint64_t* x_empty = x_full + XB;
+  uint64_t* w_full = x_empty + XB;
+  uint64_t* w_empty = w_full + NW;
+  uint64_t* zd_full = w_empty + NW;
+  uint64_t* zd_empty = zd_full + NZ;
+  uint64_t* dz_full = zd_empty + NZ;
   uint64_t* dz_empty = dz_full + 2;
   uint64_t* dx_full = dz_empty + 2;
-  uint64_t* dx_empty = dx_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dx_empty + 2);
+  uint64_t* dx_empty = dx_full + NDX;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dx_empty + NDX);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -403,21 +442,25 @@ mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     ptx::tma_prefetch_desc(&tmW1);
     ptx::tma_prefetch_desc(&tmW2T);
     ptx::tma_prefetch_desc(&tmW1T);
-    for (int s = 0; s < Cfg::XB; ++s) {
+    for (int s = 0; s < XB; ++s) {
       ptx::mbar_init(&x_full[s], 1);
       ptx::mbar_init(&x_empty[s], 1);
     }
-    for (int s = 0; s < Cfg::NW; ++s) {
+    for (int s = 0; s < NW; ++s) {
       ptx::mbar_init(&w_full[s], 1);
       ptx::mbar_init(&w_empty[s], 1);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < NZ; ++s) {
       ptx::mbar_init(&zd_full[s], 1);
-      ptx::mbar_init(&zd_empty[s], F_EPI_WARPS);
-      ptx::mbar_init(&dz_full[s], F_EPI_WARPS);
+      ptx::mbar_init(&zd_empty[s], F_EPI_WARPS / 2);
+    }
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(&dz_full[s], F_EPI_WARPS / 2);
       ptx::mbar_init(&dz_empty[s], 1);
+    }
+    for (int s = 0; s < NDX; ++s) {
       ptx::mbar_init(&dx_full[s], 1);
-      ptx::mbar_init(&dx_empty[s], Cfg::OUT_WARPS);
+      ptx::mbar_init(&dx_empty[s], F_EPI_WARPS / 2);
     }
     ptx::fence_barrier_init();
   }
@@ -429,43 +472,50 @@ mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_z = tmem_base;                 // Z[b]  at column b * 64
-  const uint32_t tmem_dh = tmem_base + 2 * BH;       // DH[b] at column 128 + b * 64
-  const uint32_t tmem_dx = tmem_base + 4 * BH;       // DXN[b] at column 256 + b * C
+  const uint32_t tmem_z = tmem_base;                     // Z[b]   at column b * 64
+  const uint32_t tmem_dh = tmem_base + NZ * BH;          // DH[b]  at column 192 + b * 64
+  const uint32_t tmem_dx = tmem_base + 2 * NZ * BH;      // DXN[b] at column 384 + b * C
   const int NJ = p.NJ;
+  const int my_tiles = (p.m_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int T = my_tiles * NJ;
 
   if (warp == F_PRODUCER) {
     if (lane == 0) {
       uint32_t wc = 0;
-      int it = 0;
-      auto load_w = [&](const CUtensorMap* tm, int c0, int c1, bool k_is_hidden) {
-        const int ws = wc % Cfg::NW;
-        ptx::mbar_wait(&w_empty[ws], ((wc / Cfg::NW) & 1) ^ 1u);
+      auto slot_for = [&]() {
+        const int ws = wc % NW;
+        ptx::mbar_wait(&w_empty[ws], ((wc / NW) & 1) ^ 1u);
         ptx::mbar_arrive_expect_tx(&w_full[ws], Cfg::W_BYTES);
-        uint8_t* dst = wring + ws * Cfg::W_BYTES;
-        if (!k_is_hidden) {  // [64 hidden rows x C]: one box {64 k, 64 rows} per 64-column slice of C
-#pragma unroll
-          for (int ks = 0; ks < Cfg::KC; ++ks) ptx::tma_load_2d(dst + ks * (BH * 128), tm, &w_full[ws], ks * 64, c1);
-        } else {             // [C rows x 64 hidden]: one box {64 k, C rows}
-          ptx::tma_load_2d(dst, tm, &w_full[ws], c0, 0);
-        }
         ++wc;
+        return ws;
       };
-      for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, ++it) {
-        const int xb = it % Cfg::XB;
-        ptx::mbar_wait(&x_empty[xb], ((it / Cfg::XB) & 1) ^ 1u);
-        ptx::mbar_arrive_expect_tx(&x_full[xb], 2 * Cfg::XA_BYTES);
+      for (int f = 0; f < T + NZ; ++f) {  // order of consumption: [x, dy tiles], W1(f), W2T(f), W1T(f - NZ)
+        if (f < T) {
+          const int it = f / NJ, j = f - it * NJ;
+          if (j == 0) {
+            const int xb = it % XB;
+            const int tile = blockIdx.x + it * gridDim.x;
+            ptx::mbar_wait(&x_empty[xb], ((it / XB) & 1) ^ 1u);
+            ptx::mbar_arrive_expect_tx(&x_full[xb], 2 * Cfg::XA_BYTES);
 #pragma unroll
-        for (int ks = 0; ks < Cfg::KC; ++ks) {
-          ptx::tma_load_2d(xn + xb * Cfg::XA_BYTES + ks * (F_BM * 128), &tmX, &x_full[xb], ks * 64, tile * F_BM);
-          ptx::tma_load_2d(gy + xb * Cfg::XA_BYTES + ks * (F_BM * 128), &tmG, &x_full[xb], ks * 64, tile * F_BM);
-        }
-        for (int step = 0; step <= NJ; ++step) {
-          if (step < NJ) {
-            load_w(&tmW1, 0, step * BH, false);    // W1 rows of chunk `step`
-            load_w(&tmW2T, 0, step * BH, false);   // (W2^T) rows of chunk `step`
+            for (int ks = 0; ks < Cfg::KC; ++ks) {
+              ptx::tma_load_2d(xn + xb * Cfg::XA_BYTES + ks * (F_BM * 128), &tmX, &x_full[xb], ks * 64, tile * F_BM);
+              ptx::tma_load_2d(gy + xb * Cfg::XA_BYTES + ks * (F_BM * 128), &tmG, &x_full[xb], ks * 64, tile * F_BM);
+            }
           }
-          if (step >= 1) load_w(&tmW1T, (step - 1) * BH, 0, true);  // (W1^T)[:, chunk step-1]
+          int ws = slot_for();  // W1 rows of chunk j: one box {64 k, 64 rows} per 64-column slice of C
+#pragma unroll
+          for (int ks = 0; ks < Cfg::KC; ++ks)
+            ptx::tma_load_2d(wring + ws * Cfg::W_BYTES + ks * (BH * 128), &tmW1, &w_full[ws], ks * 64, j * BH);
+          ws = slot_for();      // (W2^T) rows of chunk j
+#pragma unroll
+          for (int ks = 0; ks < Cfg::KC; ++ks)
+            ptx::tma_load_2d(wring + ws * Cfg::W_BYTES + ks * (BH * 128), &tmW2T, &w_full[ws], ks * 64, j * BH);
+        }
+        if (f >= NZ) {          // (W1^T)[:, chunk]: one box {64 hidden, C rows}
+          const int j2 = (f - NZ) % NJ;
+          const int ws = slot_for();
+          ptx::tma_load_2d(wring + ws * Cfg::W_BYTES, &tmW1T, &w_full[ws], j2 * BH, 0);
         }
       }
     }
@@ -473,97 +523,127 @@ mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     if (lane == 0) {
       const uint32_t idesc_h = ptx::umma_idesc_bf16(F_BM, BH, 0, 0);
       const uint32_t idesc_x = ptx::umma_idesc_bf16(F_BM, C, 0, 0);
-      uint32_t wc = 0, zc = 0, hc = 0;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, ++it) {
-        const int xb = it % Cfg::XB, ob = it & 1;
-        ptx::mbar_wait(&dx_empty[ob], ((it >> 1) & 1) ^ 1u);
-        ptx::mbar_wait(&x_full[xb], (it / Cfg::XB) & 1);
-        ptx::tc_fence_after();
-        const uint32_t xn_addr = ptx::smem_u32(xn + xb * Cfg::XA_BYTES);
-        const uint32_t gy_addr = ptx::smem_u32(gy + xb * Cfg::XA_BYTES);
-        for (int step = 0; step <= NJ; ++step) {
-          if (step < NJ) {
-            const int zb = zc & 1;
-            ptx::mbar_wait(&zd_empty[zb], ((zc >> 1) & 1) ^ 1u);
+      uint32_t wc = 0;
+      for (int f = 0; f < T + NZ; ++f) {  // Z / DH run NZ chunks ahead of the DXN accumulation (see the forward kernel)
+        if (f < T) {
+          const int it = f / NJ, j = f - it * NJ;
+          const int xb = it % XB;
+          if (j == 0) ptx::mbar_wait(&x_full[xb], (it / XB) & 1);
+          const int zb = f % NZ;
+          ptx::mbar_wait(&zd_empty[zb], ((f / NZ) & 1) ^ 1u);
+          const uint32_t xn_addr = ptx::smem_u32(xn + xb * Cfg::XA_BYTES);
+          const uint32_t gy_addr = ptx::smem_u32(gy + xb * Cfg::XA_BYTES);
 #pragma unroll
-            for (int which = 0; which < 2; ++which) {  // 0: Z = XN W1_j^T   1: DH = DY (W2^T)_j^T
-              const int ws = wc % Cfg::NW;
-              ptx::mbar_wait(&w_full[ws], (wc / Cfg::NW) & 1);
-              ptx::tc_fence_after();
-              const uint32_t wb = ptx::smem_u32(wring + ws * Cfg::W_BYTES);
-              const uint32_t a0 = which ? gy_addr : xn_addr;
-              const uint32_t d = (which ? tmem_dh : tmem_z) + zb * BH;
-#pragma unroll
-              for (int ks = 0; ks < Cfg::KC; ++ks)
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk) {
-                  const uint64_t ad = ptx::umma_smem_desc(a0 + ks * (F_BM * 128) + kk * 32, 16u, 1024u);
-                  const uint64_t bd = ptx::umma_smem_desc(wb + ks * (BH * 128) + kk * 32, 16u, 1024u);
-                  ptx::umma_f16(d, ad, bd, idesc_h, (ks > 0 || kk > 0) ? 1u : 0u);
-                }
-              ptx::umma_commit(&w_empty[ws]);
-              ++wc;
-            }
-            ptx::umma_commit(&zd_full[zb]);
-            ++zc;
-            if (step == NJ - 1) ptx::umma_commit(&x_empty[xb]);
-          }
-          if (step >= 1) {  // DXN += dz_{step-1} W1_{step-1}
-            const int hb = hc & 1;
-            ptx::mbar_wait(&dz_full[hb], (hc >> 1) & 1);
-            const int ws = wc % Cfg::NW;
-            ptx::mbar_wait(&w_full[ws], (wc / Cfg::NW) & 1);
+          for (int which = 0; which < 2; ++which) {  // 0: Z = XN W1_j^T   1: DH = DY (W2^T)_j^T
+            const int ws = wc % NW;
+            ptx::mbar_wait(&w_full[ws], (wc / NW) & 1);
             ptx::tc_fence_after();
-            const uint32_t da = ptx::smem_u32(dzt + hb * Cfg::T_BYTES);
             const uint32_t wb = ptx::smem_u32(wring + ws * Cfg::W_BYTES);
+            const uint32_t a0 = which ? gy_addr : xn_addr;
+            const uint32_t d = (which ? tmem_dh : tmem_z) + zb * BH;
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-              const uint64_t ad = ptx::umma_smem_desc(da + kk * 32, 16u, 1024u);
-              const uint64_t bd = ptx::umma_smem_desc(wb + kk * 32, 16u, 1024u);
-              ptx::umma_f16(tmem_dx + ob * C, ad, bd, idesc_x, (step > 1 || kk > 0) ? 1u : 0u);
-            }
+            for (int ks = 0; ks < Cfg::KC; ++ks)
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) {
+                const uint64_t ad = ptx::umma_smem_desc(a0 + ks * (F_BM * 128) + kk * 32, 16u, 1024u);
+                const uint64_t bd = ptx::umma_smem_desc(wb + ks * (BH * 128) + kk * 32, 16u, 1024u);
+                ptx::umma_f16(d, ad, bd, idesc_h, (ks > 0 || kk > 0) ? 1u : 0u);
+              }
             ptx::umma_commit(&w_empty[ws]);
             ++wc;
-            ptx::umma_commit(&dz_empty[hb]);
-            ++hc;
-            if (step == NJ) ptx::umma_commit(&dx_full[ob]);
           }
+          ptx::umma_commit(&zd_full[zb]);
+          if (j == NJ - 1) ptx::umma_commit(&x_empty[xb]);
+        }
+        if (f >= NZ) {  // DXN += dz W1 for chunk f - NZ
+          const int f2 = f - NZ;
+          const int it = f2 / NJ, j = f2 - it * NJ;
+          const int ob = it % NDX, hb = f2 & 1;
+          if (j == 0) ptx::mbar_wait(&dx_empty[ob], ((it / NDX) & 1) ^ 1u);
+          ptx::mbar_wait(&dz_full[hb], (f2 >> 1) & 1);
+          const int ws = wc % NW;
+          ptx::mbar_wait(&w_full[ws], (wc / NW) & 1);
+          ptx::tc_fence_after();
+          const uint32_t da = ptx::smem_u32(dzt + hb * Cfg::T_BYTES);
+          const uint32_t wb = ptx::smem_u32(wring + ws * Cfg::W_BYTES);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const uint64_t ad = ptx::umma_smem_desc(da + kk * 32, 16u, 1024u);
+            const uint64_t bd = ptx::umma_smem_desc(wb + kk * 32, 16u, 1024u);
+            ptx::umma_f16(tmem_dx + ob * C, ad, bd, idesc_x, (j > 0 || kk > 0) ? 1u : 0u);
+          }
+          ptx::umma_commit(&w_empty[ws]);
+          ++wc;
+          ptx::umma_commit(&dz_empty[hb]);
+          if (j == NJ - 1) ptx::umma_commit(&dx_full[ob]);
         }
       }
     }
   } else {
-    // ------------------------------- epilogue warps -------------------------------
-    constexpr int ZW = BH / 4;  // 16 hidden columns per warp and chunk
+    // ------------------------------- epilogue warps: two groups on alternate chunks -------------------------------
+    constexpr int ZW = 16;              // columns converted at a time (register budget)
+    constexpr int NOC = Cfg::NOC;
+    const int g = warp >> 3;
     const int q = warp & 3;
-    const int cg = warp >> 2;
-    const bool out_warp = cg < C / 32;
-    const bool store_warp = cg == 0;  // issues the quarter's dz / hs tile stores
-    uint8_t* slot = staging + (q * (C / 32) + (out_warp ? cg : 0)) * F_SLOT;
-    uint32_t zc = 0, hc = 0;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, ++it) {
-      const int ob = it & 1;
-      const int mrow0 = tile * F_BM + q * 32;
+    const int half = (warp >> 2) & 1;   // 32 of the chunk's 64 hidden columns
+    const bool store_thread = half == 0 && lane == 0;  // issues the (group, quarter) slab stores of dz / hs
+    const int bar_id = 1 + g * 4 + q;   // the two warps (half 0 / 1) that share a 32-row slab
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    uint8_t* slot = staging + warp * F_SLOT;
+    const int row = q * 32 + lane;
+    auto write_tile = [&](int it) {  // dxn tile of `it`, one own-chunk after its last chunk (the accumulator has arrived)
+      const int ob = it % NDX;
+      const int mrow0 = (blockIdx.x + it * gridDim.x) * F_BM + q * 32;
+      ptx::mbar_wait(&dx_full[ob], (it / NDX) & 1);
+      ptx::tc_fence_after();
+#pragma unroll
+      for (int oc = 0; oc < NOC; ++oc) {
+        const int ccol = (half * NOC + oc) * 32;
+        float v[32];
+        ptx::tmem_ld32(tmem_dx + lane_off + ob * C + ccol, v);
+        if (oc == NOC - 1) {
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&dx_empty[ob]);
+        }
+        if (lane == 0) ptx::bulk_wait_read<0>();  // earlier stores of this thread have finished reading the slot
+        __syncwarp();
+        stage_write_row(slot, lane, v);
+        ptx::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          ptx::tma_store_2d(&tmDX, slot, ccol, mrow0);
+          ptx::bulk_commit();
+        }
+      }
+    };
+    int pending = -1;
+    for (int f = g; f < T; f += 2) {
+      const int it = f / NJ, j = f - it * NJ;
+      const int mrow0 = (blockIdx.x + it * gridDim.x) * F_BM + q * 32;
       const long long m = (long long)mrow0 + lane;
       const float rsf = p.row_scale ? (m < p.M ? p.row_scale[m / p.rows_per_scale] : 0.f) : 1.f;
       const f32x2 rs = splat2(rsf);
-      for (int j = 0; j < NJ; ++j) {
-        const int zb = zc & 1;
-        ptx::mbar_wait(&zd_full[zb], (zc >> 1) & 1);
-        ptx::tc_fence_after();
-        const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+      const int zb = f % NZ;
+      ptx::mbar_wait(&zd_full[zb], (f / NZ) & 1);
+      ptx::tc_fence_after();
+      uint8_t* dzb = dzt + g * Cfg::T_BYTES;
+      uint8_t* hsb = hst + g * Cfg::T_BYTES;
+#pragma unroll
+      for (int pc = 0; pc < 2; ++pc) {
+        const int col0 = half * 32 + pc * ZW;
         float zf[ZW], df[ZW];
-        ptx::tmem_ld16(tmem_z + lane_off + zb * BH + cg * ZW, zf);
-        ptx::tmem_ld16(tmem_dh + lane_off + zb * BH + cg * ZW, df);
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&zd_empty[zb]);
-        ++zc;
+        ptx::tmem_ld16(tmem_z + lane_off + zb * BH + col0, zf);
+        ptx::tmem_ld16(tmem_dh + lane_off + zb * BH + col0, df);
+        if (pc == 1) {
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&zd_empty[zb]);
+        }
         f32x2 z2[ZW / 2], d2[ZW / 2], g2[ZW / 2];
         pack_n<ZW / 2>(zf, z2);
         pack_n<ZW / 2>(df, d2);
-        const float* b1 = p.b1 + j * BH + cg * ZW;
+        const float* b1 = p.b1 + j * BH + col0;
 #pragma unroll
         for (int i = 0; i < ZW / 4; ++i) {
           const ulonglong2 b4 = __ldg(reinterpret_cast<const ulonglong2*>(b1) + i);
@@ -576,16 +656,14 @@ mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
           d2[i] = mul2(mul2(d2[i], g2[i]), rs);    // dz
           z2[i] = mul2(z2[i], rs);                 // hs
         }
-        const int hb = hc & 1;
-        // buffer hb is free once (a) the MMA that read dz two chunks ago has retired and (b) the TMA stores issued
-        // from it two chunks ago have finished reading shared memory (the storing thread waits, the quarter syncs)
-        ptx::mbar_wait(&dz_empty[hb], ((hc >> 1) & 1) ^ 1u);
-        if (store_warp && lane == 0) ptx::bulk_wait_read<1>();
-        named_bar_sync(1 + q, 128);
-        const int row = q * 32 + lane;
-        const int c16_0 = (cg * ZW) / 8;
-        uint8_t* dzb = dzt + hb * Cfg::T_BYTES;
-        uint8_t* hsb = hst + hb * Cfg::T_BYTES;
+        if (pc == 0) {
+          // DZ[g] / HS[g] are free once the MMA that read this group's previous dz tile has retired and the slab stores
+          // issued from them have finished reading shared memory (the storing thread waits, the slab's two warps sync)
+          ptx::mbar_wait(&dz_empty[g], ((f >> 1) & 1) ^ 1u);
+          if (store_thread) ptx::bulk_wait_read<0>();
+          named_bar_sync(bar_id, 64);
+        }
+        const int c16_0 = col0 / 8;
 #pragma unroll
         for (int c = 0; c < ZW / 8; ++c) {
           const f32x2 pd[4] = {d2[4 * c], d2[4 * c + 1], d2[4 * c + 2], d2[4 * c + 3]};
@@ -593,40 +671,22 @@ mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
           *reinterpret_cast<uint4*>(dzb + sw128(row, c16_0 + c)) = pack8_bf16(pd);
           *reinterpret_cast<uint4*>(hsb + sw128(row, c16_0 + c)) = pack8_bf16(ph);
         }
-        ptx::fence_proxy_async();
-        named_bar_sync(1 + q, 128);  // the quarter's 32 x 64 slab of both tiles is complete
-        if (store_warp && lane == 0) {
-          ptx::tma_store_2d(&tmDZ, dzb + q * 4096, j * BH, mrow0);   // box {64 hidden, 32 rows}
-          ptx::tma_store_2d(&tmHS, hsb + q * 4096, j * BH, mrow0);
-          ptx::bulk_commit();
-        }
-        if (lane == 0) ptx::mbar_arrive(&dz_full[hb]);
-        ++hc;
       }
-      if (out_warp) {
-        ptx::mbar_wait(&dx_full[ob], (it >> 1) & 1);
-        ptx::tc_fence_after();
-        float v[32];
-        ptx::tmem_ld32(tmem_dx + (static_cast<uint32_t>(q * 32) << 16) + ob * C + cg * 32, v);
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&dx_empty[ob]);
-        // the slot's previous store must have finished reading.  A store warp also has dz/hs groups in flight: its
-        // slot store is always the OLDEST-but-(2 chunk groups) group, so waiting for "all but the newest two" covers it
-        if (lane == 0) {
-          if (store_warp) ptx::bulk_wait_read<2>();
-          else ptx::bulk_wait_read<0>();
-        }
-        __syncwarp();
-        stage_write_row(slot, lane, v);
-        ptx::fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) {
-          ptx::tma_store_2d(&tmDX, slot, cg * 32, mrow0);
-          ptx::bulk_commit();
-        }
+      ptx::fence_proxy_async();
+      named_bar_sync(bar_id, 64);  // the 32 x 64 slab of both tiles is complete
+      if (store_thread) {
+        ptx::tma_store_2d(&tmDZ, dzb + q * 4096, j * BH, mrow0);   // box {64 hidden, 32 rows}
+        ptx::tma_store_2d(&tmHS, hsb + q * 4096, j * BH, mrow0);
+        ptx::bulk_commit();
       }
+      if (lane == 0) ptx::mbar_arrive(&dz_full[g]);
+      if (pending >= 0) {
+        write_tile(pending);
+        pending = -1;
+      }
+      if (j == NJ - 1) pending = it;
     }
+    if (pending >= 0) write_tile(pending);
     if (lane == 0) ptx::bulk_wait<0>();
   }
 

@@ -43,13 +43,16 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-// Bounded wait: a protocol bug must trap (the launch then fails loudly) instead of hanging the GPU.
+// Bounded wait: a protocol bug must trap (the launch then fails loudly) instead of hanging the GPU.  The clock is
+// read once per 1024 polls only (try_wait itself suspends the thread for a hardware-defined interval).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  uint64_t t0 = globaltimer_ns();
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 0x3ffu) == 0 && globaltimer_ns() - t0 > 4000000000ull) __trap();
+  const uint64_t t0 = globaltimer_ns();
+  for (;;) {
+#pragma unroll 1
+    for (int i = 0; i < 1024; ++i)
+      if (mbar_try_wait(bar, parity)) return;
+    if (globaltimer_ns() - t0 > 4000000000ull) __trap();
   }
 }
 
