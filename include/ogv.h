@@ -86,6 +86,9 @@ typedef struct ogv_gemm_args {
   float* col_sumsq; /* optional [N]: += sum_m of stored value^2 */
   int pre_out_grad; /* 1: pre_out receives act'(v) instead of v, so that the backward pass multiplies by it
                        (dact = OGV_ACT_MUL) without re-evaluating a transcendental */
+  float* row_sum;   /* optional [M], accumulate mode only: += sum_k A(m,k).  With the wgrad operands (A(m,k) = dY[k,m])
+                       this is the BIAS gradient colsum(dY), produced by one extra N=16 MMA per K step against a tile
+                       of ones instead of a separate pass over dY */
 } ogv_gemm_args;
 
 int ogv_gemm(const ogv_gemm_args* args, int engine, void* stream);

@@ -33,6 +33,7 @@ class GemmArgs(Structure):
         ("accumulate", c_int), ("split_k", c_int),
         ("col_sum", c_void_p), ("col_sumsq", c_void_p),
         ("pre_out_grad", c_int),
+        ("row_sum", c_void_p),
     ]
 
 

@@ -652,6 +652,162 @@ dwconv_fwd_sweep_kernel(const T* __restrict__ e_pre, const float* __restrict__ s
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// forward, register-window sweep fed by a per-warp cp.async ring.  The sweep above issues the loads of window column
+// x + 1 and needs them at once: one column (4 rows x 256 B per warp) in flight per warp, 16 KB per SM -- half of what
+// the HBM latency-bandwidth product asks for, and `long_scoreboard` is its top stall.  Here every warp streams its
+// columns through a private shared-memory ring KD columns deep (cp.async, 8/16 bytes per lane, no barrier: a lane
+// only ever reads back the bytes it copied itself), so KD columns per warp are in flight, across band boundaries too
+// (the prefetch cursor runs ahead into the warp's next band).  Registers, math and stores are those of the sweep.
+// ------------------------------------------------------------------------------------------------
+template <typename T, int ACT, int RR, int KD>
+__global__ void __launch_bounds__(256, 2)
+dwconv_fwd_sweep_pf_kernel(const T* __restrict__ e_pre, const float* __restrict__ scale1, const float* __restrict__ shift1,
+                           const float* __restrict__ wgt, T* __restrict__ d_pre, float* __restrict__ sum2,
+                           float* __restrict__ sumsq2, int B, int H, int W, int Cm, int bands_per_img, int nbands) {
+  constexpr int NR = RR + 2;
+  constexpr int VB = 4 * (int)sizeof(T);  // bytes per lane and (row, column): 4 channels
+  extern __shared__ __align__(16) uint8_t dw_ring[];  // [8 warps][KD][NR][32 lanes][VB]
+  __shared__ float s_red[2][8][128];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = (blockIdx.y * 32 + lane) * 4;
+  const bool cvalid = c < Cm;
+  uint8_t* const ring = dw_ring + (size_t)warp * KD * NR * 32 * VB + lane * VB;
+  float w[9][4], sc[4], sh[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    sc[k] = cvalid ? scale1[c + k] : 0.f;
+    sh[k] = cvalid ? shift1[c + k] : 0.f;
+#pragma unroll
+    for (int t9 = 0; t9 < 9; ++t9) w[t9][k] = cvalid ? wgt[(c + k) * 9 + t9] : 0.f;
+  }
+  float st_s[4] = {0.f, 0.f, 0.f, 0.f}, st_q[4] = {0.f, 0.f, 0.f, 0.f};
+  const long long rowpitch = (long long)W * Cm;
+  const int item0 = blockIdx.x * 8 + warp, istride = gridDim.x * 8;
+
+  // ---- prefetch cursor: (band, column) of the next column to request ----
+  int pf_item = cvalid ? item0 : nbands, pf_n = 0;
+  const T* pf_in0 = e_pre;
+  unsigned pf_rv = 0;
+  auto pf_setup = [&]() {
+    if (pf_item < nbands) {
+      const int b = pf_item / bands_per_img;
+      const int r0 = (pf_item - b * bands_per_img) * RR;
+      pf_in0 = e_pre + ((long long)b * H + (r0 - 1)) * rowpitch + c;
+      pf_rv = 0;
+#pragma unroll
+      for (int i = 0; i < NR; ++i) pf_rv |= ((r0 - 1 + i >= 0) && (r0 - 1 + i < H)) ? (1u << i) : 0u;
+    }
+  };
+  auto prefetch = [&](int slot) {
+    if (pf_item < nbands) {
+      if (pf_n < W) {
+#pragma unroll
+        for (int i = 0; i < NR; ++i)
+          if ((pf_rv >> i) & 1u)
+            ptx::cp_async<VB>(ring + (size_t)(slot * NR + i) * 32 * VB, pf_in0 + (long long)i * rowpitch + (long long)pf_n * Cm);
+      }
+      if (++pf_n > W) {  // W + 1 columns per band: 0 .. W-1 and the all-zero column beyond the right edge
+        pf_n = 0;
+        pf_item += istride;
+        pf_setup();
+      }
+    }
+    ptx::cp_async_commit();  // one group per column, empty or not: the consumer counts groups
+  };
+  pf_setup();
+#pragma unroll
+  for (int k = 0; k < KD; ++k) prefetch(k);
+  int cs = 0;  // ring slot of the next column to consume
+
+  for (int item = item0; item < nbands && cvalid; item += istride) {
+    const int b = item / bands_per_img;
+    const int r0 = (item - b * bands_per_img) * RR;
+    T* out0 = d_pre + ((long long)b * H + r0) * rowpitch + c;
+    bool rv[NR];
+#pragma unroll
+    for (int i = 0; i < NR; ++i) rv[i] = (r0 - 1 + i >= 0) && (r0 - 1 + i < H);
+    float win[3][NR][4];
+    // take one column of the window out of the ring + activate it (zeros outside the image), refill the slot
+    auto load_col = [&](float (&col)[NR][4], int x) {
+      ptx::cp_async_wait<KD - 1>();
+      const bool xv = x < W;
+#pragma unroll
+      for (int i = 0; i < NR; ++i) {
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        const bool ok = xv && rv[i];
+        if (ok) ldv<4>(reinterpret_cast<const T*>(ring + (size_t)(cs * NR + i) * 32 * VB), v);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) col[i][k] = ok ? act_apply_t<ACT, FastAct<T>::value>(fmaf(v[k], sc[k], sh[k])) : 0.f;
+      }
+      prefetch(cs);
+      cs = cs + 1 == KD ? 0 : cs + 1;
+    };
+    auto step = [&](const float (&L)[NR][4], const float (&M)[NR][4], const float (&Rc)[NR][4], int x) {
+      float acc[RR][4];
+#pragma unroll
+      for (int r = 0; r < RR; ++r)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float a = 0.f;
+#pragma unroll
+          for (int ki = 0; ki < 3; ++ki) {
+            a = fmaf(w[ki * 3 + 0][k], L[r + ki][k], a);
+            a = fmaf(w[ki * 3 + 1][k], M[r + ki][k], a);
+            a = fmaf(w[ki * 3 + 2][k], Rc[r + ki][k], a);
+          }
+          acc[r][k] = a;
+        }
+#pragma unroll
+      for (int r = 0; r < RR; ++r) {
+        if (r0 + r < H) {
+          stv<4>(out0 + (long long)r * rowpitch + (long long)x * Cm, acc[r]);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float sv = round_to<T>(acc[r][k]);  // statistics of the values AS STORED (see the sweep above)
+            st_s[k] += sv;
+            st_q[k] = fmaf(sv, sv, st_q[k]);
+          }
+        }
+      }
+    };
+#pragma unroll
+    for (int i = 0; i < NR; ++i)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) win[0][i][k] = 0.f;
+    load_col(win[1], 0);
+    for (int x = 0; x < W; x += 3) {
+      load_col(win[2], x + 1);
+      step(win[0], win[1], win[2], x);
+      if (x + 1 < W) {
+        load_col(win[0], x + 2);
+        step(win[1], win[2], win[0], x + 1);
+      }
+      if (x + 2 < W) {
+        load_col(win[1], x + 3);
+        step(win[2], win[0], win[1], x + 2);
+      }
+    }
+  }
+  ptx::cp_async_wait<0>();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    s_red[0][warp][lane * 4 + k] = st_s[k];
+    s_red[1][warp][lane * 4 + k] = st_q[k];
+  }
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int ch = blockIdx.y * 128 + threadIdx.x;
+    if (ch < Cm) {
+      float a = 0.f, q = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { a += s_red[0][j][threadIdx.x]; q += s_red[1][j][threadIdx.x]; }
+      if (sum2) atomicAdd(sum2 + ch, a);
+      if (sumsq2) atomicAdd(sumsq2 + ch, q);
+    }
+  }
+}
+
 // opt in to the dynamic shared memory and report how many CTAs of this kernel are resident per SM:
 // the persistent grid is sized to exactly one wave (a second, partly filled wave would idle SMs).
 template <typename K>
@@ -686,10 +842,38 @@ extern "C" int ogv_dwconv_fwd(const void* e_pre, const float* scale1, const floa
   OGV_REQUIRE(Cm > 0 && Cm % 8 == 0 && H > 0 && W > 0, "dwconv_fwd: channels must be a multiple of 8");
   OGV_REQUIRE((reinterpret_cast<uintptr_t>(e_pre) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_pre) & 15) == 0,
               "dwconv_fwd: tensors must be 16-byte aligned");
-  static int variant = -1;  // OGV_DW_FWD=tile selects the TMA-tiled kernel (A/B measurements)
+  static int variant = -1;  // OGV_DW_FWD=tile | sweep select the older kernels (A/B measurements); default: prefetched sweep
   if (variant < 0) {
     const char* e = getenv("OGV_DW_FWD");
-    variant = (e && e[0] == 't') ? 1 : 0;
+    // measured (stage shapes of cfg 2): the ring does NOT help -- 549 vs 519 us at stage 0: the sweep is bound by its
+    // ~30 issued instructions per output (halo rows make it activate every input twice), not by load latency.  The
+    // plain sweep stays the default; OGV_DW_FWD=pf / tile select the other two for A/B runs.
+    variant = (e && e[0] == 't') ? 1 : ((e && e[0] == 'p') ? 2 : 0);
+  }
+  if (variant == 2) {
+    constexpr int RR = 2, KD = 6;
+    const int bands = (H + RR - 1) / RR;
+    const long long nb = (long long)B * bands;
+    OGV_REQUIRE(nb < 0x7fffffffLL, "dwconv_fwd: too many row bands");
+    const int ychunks = ogv_ceil_div(Cm, 128);
+    long long gx = (nb + 7) / 8;
+    // persistent: exactly the resident CTAs (2 per SM), every warp walks its bands with the ring running ahead
+    const long long cap = ((long long)ogv_num_sms() * 2 + ychunks - 1) / ychunks;
+    if (gx > cap) gx = cap;
+    OGV_DISPATCH_DTYPE(dtype, T, {
+      constexpr int smem = 8 * KD * (RR + 2) * 32 * 4 * (int)sizeof(T);
+      OGV_DISPATCH_ACT(act, ACT, {
+        static bool attr = false;
+        if (!attr) {
+          cudaFuncSetAttribute(dwconv_fwd_sweep_pf_kernel<T, ACT, RR, KD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+          attr = true;
+        }
+        dwconv_fwd_sweep_pf_kernel<T, ACT, RR, KD><<<dim3((unsigned)gx, ychunks), 256, smem, (cudaStream_t)stream>>>(
+            reinterpret_cast<const T*>(e_pre), scale1, shift1, w, reinterpret_cast<T*>(d_pre), sum2, sumsq2, B, H, W,
+            Cm, bands, (int)nb);
+      });
+      return ogv_check_launch("dwconv_fwd");
+    });
   }
   if (variant == 0) {
     constexpr int RR = 2;

@@ -36,6 +36,7 @@ constexpr int SLOT_BYTES = 32 * CH * 2;    // one warp's 32 x 32 bf16 staging ti
 constexpr int MAX_STAGES = 8;
 constexpr int SMEM_LIMIT = 227 * 1024;
 constexpr int BAR_BYTES = (2 * MAX_STAGES + 4 + 2 * EPI_WARPS) * 8 + 16;
+constexpr int ONES_BYTES = 2048;  // B operand of the row-sum MMA: 16 rows x 64 k of bf16 ones (K-major)
 
 struct TcParams {
   int M, N, K;
@@ -48,6 +49,8 @@ struct TcParams {
   int col_stats;    // staged epilogue also accumulates per-column sum (and sum of squares) of the stored values
   int plain;        // staged epilogue with no bias / activation / operand / scale / statistics: convert and store
   int n_pad;        // n_tiles * BN: extent of the per-CTA column accumulators in shared memory
+  float* row_sum;   // optional [M]: += sum_k A(m, k) -- the bias gradient riding with a weight-gradient GEMM
+  int rs_col;       // TMEM column of the 16-column row-sum accumulator
   GemmEpi epi;
 };
 
@@ -115,9 +118,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   constexpr int B_BYTES = BN * TC_BK * 2;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr int TMEM_COLS = 2 * BN;
+  // the row-sum path exists only in the fp32-output instantiations (weight gradients): the bf16 epilogues, whose
+  // register budget is exact, do not carry it
+  constexpr bool kRowSum = sizeof(TO) == 4;
   extern __shared__ uint8_t smem_raw[];
   // 128B-swizzled TMA/UMMA tiles need 1024-byte alignment.
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_al = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* ones_tile = smem_al;  // only present (and skipped over) when p.row_sum
+  uint8_t* smem = smem_al + ((kRowSum && p.row_sum) ? ONES_BYTES : 0);
   uint8_t* staging = smem + p.stages * STAGE_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + EPI_WARPS * p.slots * SLOT_BYTES);
   uint64_t* empty_bar = full_bar + MAX_STAGES;
@@ -144,9 +152,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int s = 0; s < 2 * EPI_WARPS; ++s) ptx::mbar_init(&ld_bar[s], 1);
     ptx::fence_barrier_init();
   }
+  const uint32_t tmem_cols = (kRowSum && p.row_sum) ? 512u : (uint32_t)TMEM_COLS;  // room for the row-sum accumulator
   if (warp == MMA_WARP) {
-    ptx::tmem_alloc(tmem_slot, TMEM_COLS);
+    ptx::tmem_alloc(tmem_slot, tmem_cols);
     ptx::tmem_relinquish();
+  }
+  if (kRowSum && p.row_sum) {
+    for (int i = threadIdx.x; i < ONES_BYTES / 4; i += TC_THREADS) reinterpret_cast<uint32_t*>(ones_tile)[i] = 0x3f803f80u;
+    ptx::fence_proxy_async();
   }
   if (p.col_stats)
     for (int i = threadIdx.x; i < 2 * p.n_pad; i += TC_THREADS) colacc[i] = 0.f;
@@ -202,6 +215,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       //            +2048 B (16 k-rows) per UMMA_K step.
       const uint32_t a_lbo = p.a_mn ? 8192u : 16u, b_lbo = p.b_mn ? 8192u : 16u;
       const uint32_t a_step = p.a_mn ? 2048u : 32u, b_step = p.b_mn ? 2048u : 32u;
+      // row sums of A as one more (N = 16) MMA per K step against a tile of ones: every column of its accumulator
+      // holds sum_k A(m, k).  Only the CTAs of the first N tile do it.
+      const uint32_t idesc_rs = ptx::umma_idesc_bf16(TC_BM, 16, p.a_mn, 0);
+      const uint32_t ones_addr = ptx::smem_u32(ones_tile);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -210,6 +227,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int kc0 = sp * p.chunks_per_split;
         const int kc1 = min(p.k_chunks, kc0 + p.chunks_per_split);
         const int as = it & 1;
+        const bool do_rs = kRowSum && p.row_sum != nullptr && (w % p.n_tiles) == 0;
         ptx::mbar_wait(&tempty_bar[as], ((it >> 1) & 1) ^ 1u);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
@@ -223,6 +241,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint64_t adesc = ptx::umma_smem_desc(sa + k * a_step, a_lbo, 1024u);
             const uint64_t bdesc = ptx::umma_smem_desc(sb + k * b_step, b_lbo, 1024u);
             ptx::umma_f16(d_tmem, adesc, bdesc, idesc, (kc > kc0 || k > 0) ? 1u : 0u);
+            if (do_rs)
+              ptx::umma_f16(tmem_base + p.rs_col, adesc, ptx::umma_smem_desc(ones_addr + k * 32u, 16u, 1024u), idesc_rs,
+                            (kc > kc0 || k > 0) ? 1u : 0u);
           }
           ptx::umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
@@ -385,6 +406,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       if (!waited) {  // warps without a chunk in this tile still pace themselves on the accumulator
         ptx::mbar_wait(&tfull_bar[as], (it >> 1) & 1);
+        ptx::tc_fence_after();
+      }
+      if (kRowSum && p.row_sum && nt == 0 && cg == 0) {  // one warp per lane quarter: column 0 of the row-sum accumulator
+        float rs16[16];
+        ptx::tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + p.rs_col, rs16);
+        if (m < p.M) atomicAdd(p.row_sum + m, rs16[0]);
       }
       ptx::tc_fence_before();
       __syncwarp();
@@ -404,7 +431,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == MMA_WARP) {
     __syncwarp();
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+    ptx::tmem_dealloc(tmem_base, tmem_cols);
   }
 }
 
@@ -462,7 +489,7 @@ template <int BN, typename TO>
 int launch_tc(const CUtensorMap* tms, TcParams& p, cudaStream_t stream) {
   constexpr int STAGE_BYTES = TC_BM * TC_BK * 2 + BN * TC_BK * 2;
   const int staging = EPI_WARPS * p.slots * SLOT_BYTES;
-  const int colbytes = p.col_stats ? 2 * p.n_pad * 4 : 0;
+  const int colbytes = (p.col_stats ? 2 * p.n_pad * 4 : 0) + (p.row_sum ? ONES_BYTES : 0);
   int stages = (SMEM_LIMIT - 1024 - BAR_BYTES - staging - colbytes) / STAGE_BYTES;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages < 2) {
@@ -483,6 +510,13 @@ int launch_tc(const CUtensorMap* tms, TcParams& p, cudaStream_t stream) {
   }
   int total = p.m_tiles * p.n_tiles * p.splits;
   int grid = total < ogv_num_sms() ? total : ogv_num_sms();
+  // the row-sum accumulator sits behind the two output accumulators; with BN = 256 they fill the TMEM, and it takes
+  // the place of the second one -- which is idle exactly when no CTA gets a second work item
+  p.rs_col = 2 * BN < 512 ? 2 * BN : BN;
+  if (p.row_sum && 2 * BN >= 512 && total > grid) {
+    ogv_set_error("gemm_tc: row_sum with a 256-wide tile needs at most one work item per CTA (%d items, %d CTAs)", total, grid);
+    return OGV_ERR_UNSUPPORTED;
+  }
   gemm_tc_kernel<BN, TO><<<grid, TC_THREADS, smem_bytes, stream>>>(tms[0], tms[1], tms[2], tms[3], tms[4], p);
   return ogv_check_launch("gemm_tc");
 }
@@ -512,6 +546,12 @@ bool ogv_gemm_tc_supported(const ogv_gemm_args& a, const char** why) {
     if (a.N > 4096) return fail("column statistics: N too large");
   }
   if (a.split_k > 1 && !a.accumulate) return fail("split_k>1 needs accumulate");
+  if (a.row_sum) {
+    if (!a.accumulate) return fail("row_sum rides with accumulate (weight-gradient) GEMMs only");
+    const int bn = a.N <= 64 ? 64 : (a.N <= 128 ? 128 : 256);
+    const long long items = (long long)ogv_ceil_div(a.M, 128) * ogv_ceil_div(a.N, bn) * (a.split_k > 0 ? a.split_k : 1);
+    if (bn == 256 && items > ogv_num_sms()) return fail("row_sum with a 256-wide tile needs one work item per CTA");
+  }
   if (a.accumulate && a.out_dtype != OGV_F32) return fail("accumulate needs fp32 output");
   return true;
 }
@@ -540,6 +580,8 @@ int ogv_gemm_tc(const ogv_gemm_args& a, cudaStream_t stream) {
   p.splits = ogv_ceil_div(p.k_chunks, p.chunks_per_split);
   p.epi = make_epi(a);
   p.stages = 0;
+  p.row_sum = a.row_sum;
+  p.rs_col = 0;
 
   // staged (TMA) epilogue: bf16 tensors, 16-byte aligned rows, at most one epilogue input operand
   const bool obf = a.out_dtype == OGV_BF16;

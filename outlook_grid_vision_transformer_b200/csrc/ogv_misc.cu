@@ -67,7 +67,16 @@ extern "C" int ogv_gemm(const ogv_gemm_args* args, int engine, void* stream) {
     engine = (!force_simt && ogv_gemm_tc_supported(a, nullptr)) ? OGV_ENGINE_TC : OGV_ENGINE_SIMT;
   }
   if (engine == OGV_ENGINE_TC) return ogv_gemm_tc(a, st);
-  if (engine == OGV_ENGINE_SIMT) return ogv_gemm_simt(a, st);
+  if (engine == OGV_ENGINE_SIMT) {
+    if (a.row_sum) {  // the FFMA engine has no row-sum path: one column-sum pass over the operand instead
+      OGV_REQUIRE(a.a_rs == 1, "ogv_gemm: row_sum on the FFMA engine needs the weight-gradient operand layout (a_rs == 1)");
+      if (int rc = ogv_colsum(a.A, a.a_cs, a.row_sum, a.K, a.M, a.in_dtype, stream)) return rc;
+      ogv_gemm_args b = a;
+      b.row_sum = nullptr;
+      return ogv_gemm_simt(b, st);
+    }
+    return ogv_gemm_simt(a, st);
+  }
   ogv_set_error("ogv_gemm: unknown engine %d", engine);
   return OGV_ERR_ARG;
 }

@@ -194,9 +194,8 @@ class MlpBranchFn(torch.autograd.Function):
                 ops.rowscale_colsum(dy, scale, P, db2, store=False)
             dxn, dz, hs = ops.mlp_bwd(xn, dy, p1.w, p2.wt, p1.wt, ctx.params[3].detach(), act=act, row_scale=scale,
                                       rows_per_scale=P)
-            ops.colsum(dz, db1)
             ops.wgrad(dy, hs, dW2)
-            ops.wgrad(dz, xn, dW1)
+            ops.wgrad(dz, xn, dW1, bias_grad=db1)  # db1 = colsum(dz) rides with the weight gradient
         else:
             if ctx.fused:  # shapes the fused backward does not serve: recompute the saved pair the unfused way
                 z = _empty((M, Hd), x)
@@ -208,7 +207,6 @@ class MlpBranchFn(torch.autograd.Function):
             # bias gradient as a separate full-rate pass: the column sum fused into this wide-N epilogue costs about
             # twice what the streaming reduction does (measured 165 us vs 81 us at stage 0)
             ops.gemm(gy, p2.wt, dz, dact_src=z, dact="mul")
-            ops.colsum(dz, db1)
             ops.wgrad(gy, h, dW2)
             # fc1 backward
             dxn = _empty((M, C), x)
@@ -216,7 +214,7 @@ class MlpBranchFn(torch.autograd.Function):
                 ops.gemm(dz, p1.wt, dxn)
             else:
                 ops.gemm(dz, p1.wt, dxn, residual=dy if with_res else None)
-            ops.wgrad(dz, xn, dW1)
+            ops.wgrad(dz, xn, dW1, bias_grad=db1)
         dx = ops.layernorm_bwd(dxn, x, ln_w, mean, rstd, dy if with_res else None, dg, dbt) if with_ln else dxn
         if direct:
             _notify(ctx.params)
@@ -306,8 +304,7 @@ class OutlookBranchFn(torch.autograd.Function):
             ops.gemm(dva, pva.wt, dxn)
         else:
             ops.gemm(dva, pva.wt, dxn, residual=dy if with_res else None)
-        ops.wgrad(dva, xn, dWva)
-        ops.colsum(dva, dbva)
+        ops.wgrad(dva, xn, dWva, bias_grad=dbva)
         if direct:
             dx = ops.layernorm_bwd(dxn, x, ln_w, mean, rstd, dy if with_res else None, dg, dbt) if with_ln else dxn
             _notify(ctx.params)
@@ -418,8 +415,7 @@ class GridBranchFn(torch.autograd.Function):
             ops.gemm(dqkv, pq.wt, dxn)
         else:
             ops.gemm(dqkv, pq.wt, dxn, residual=dy if with_res else None)
-        ops.wgrad(dqkv, xn, dWq)
-        ops.colsum(dqkv, dbq)
+        ops.wgrad(dqkv, xn, dWq, bias_grad=dbq)
         if direct:
             dx = ops.layernorm_bwd(dxn, x, ln_w, mean, rstd, dy if with_res else None, dg, dbt) if with_ln else dxn
             _notify(ctx.params)

@@ -148,9 +148,10 @@ def gemm(A: Tensor, B: Tensor, D: Tensor, *, bias: Optional[Tensor] = None, pre_
          act: Optional[str] = None, dact_src: Optional[Tensor] = None, dact: Optional[str] = None,
          row_scale: Optional[Tensor] = None, rows_per_scale: int = 1, residual: Optional[Tensor] = None,
          accumulate: bool = False, split_k: int = 1, engine: int = ENGINE_AUTO, col_sum: Optional[Tensor] = None,
-         col_sumsq: Optional[Tensor] = None, pre_out_grad: bool = False) -> Tensor:
+         col_sumsq: Optional[Tensor] = None, pre_out_grad: bool = False, row_sum: Optional[Tensor] = None) -> Tensor:
     """D[m,n] = epi(sum_k A[m,k] * B[n,k]); A:[M,K], B:[N,K] (any strides), D:[M,N] row-major.
-    col_sum / col_sumsq (fp32 [N]) are accumulated (+=) with the per-column sum / sum of squares of D."""
+    col_sum / col_sumsq (fp32 [N]) are accumulated (+=) with the per-column sum / sum of squares of D.
+    row_sum (fp32 [M], accumulate mode): += sum_k A[m,k] -- the bias gradient when A is the transposed output gradient."""
     _require_cuda(A, B, D, bias, pre_out, dact_src, row_scale, residual)
     if A.dim() != 2 or B.dim() != 2 or D.dim() != 2:
         raise ValueError("gemm operands must be 2-D")
@@ -170,10 +171,16 @@ def gemm(A: Tensor, B: Tensor, D: Tensor, *, bias: Optional[Tensor] = None, pre_
     _f32(row_scale, "row_scale")
     _f32(col_sum, "col_sum")
     _f32(col_sumsq, "col_sumsq")
+    _f32(row_sum, "row_sum")
+    if row_sum is not None and (not accumulate or row_sum.numel() != M):
+        raise ValueError("gemm: row_sum needs accumulate=True and M elements")
     if (FP32_ON_TENSOR_CORES and engine == ENGINE_AUTO and A.dtype == torch.float32 and D.dtype == torch.float32
             and K >= 8 and M >= 64 and not (accumulate and col_sum is not None)):
         A3, B3 = _split3(A, 0), _split3(B, 1)
         if A3 is not None and B3 is not None:
+            if row_sum is not None:  # the three-plane operand would sum its planes: reduce the fp32 operand itself
+                colsum(A.t(), row_sum)
+                row_sum = None
             gemm(A3, B3, D, bias=bias, pre_out=pre_out, act=act, dact_src=dact_src, dact=dact,
                  row_scale=row_scale, rows_per_scale=rows_per_scale, residual=residual, accumulate=accumulate,
                  split_k=split_k, engine=ENGINE_AUTO, pre_out_grad=pre_out_grad)
@@ -201,6 +208,7 @@ def gemm(A: Tensor, B: Tensor, D: Tensor, *, bias: Optional[Tensor] = None, pre_
     a.col_sum = col_sum.data_ptr() if col_sum is not None else None
     a.col_sumsq = col_sumsq.data_ptr() if col_sumsq is not None else None
     a.pre_out_grad = int(bool(pre_out_grad))
+    a.row_sum = row_sum.data_ptr() if row_sum is not None else None
     if PROFILER.enabled:
         extra = sum(1 for t in (pre_out, dact_src, residual) if t is not None)
         PROFILER.cur_bytes = A.element_size() * (M * K + N * K) + D.element_size() * M * N * (1 + extra)
@@ -217,8 +225,9 @@ def gemm(A: Tensor, B: Tensor, D: Tensor, *, bias: Optional[Tensor] = None, pre_
     return D
 
 
-def wgrad(dY: Tensor, X: Tensor, out: Tensor, engine: int = ENGINE_AUTO) -> Tensor:
-    """out[n,k] += sum_m dY[m,n] * X[m,k]   (out fp32, pre-zeroed by the caller)."""
+def wgrad(dY: Tensor, X: Tensor, out: Tensor, engine: int = ENGINE_AUTO, bias_grad: Optional[Tensor] = None) -> Tensor:
+    """out[n,k] += sum_m dY[m,n] * X[m,k]   (out fp32, pre-zeroed by the caller).
+    bias_grad (fp32 [n]): += sum_m dY[m,n] in the same launch (one extra N=16 MMA per K step against a tile of ones)."""
     M, N = dY.shape
     K = X.shape[1]
     # output tiles as the tcgen05 kernel cuts them (128 x 64|128|256); one split-K work item per CTA at most: every
@@ -226,7 +235,7 @@ def wgrad(dY: Tensor, X: Tensor, out: Tensor, engine: int = ENGINE_AUTO) -> Tens
     bn = 64 if K <= 64 else (128 if K <= 128 else 256)
     tiles = max(1, math.ceil(N / 128) * math.ceil(K / bn))
     split = max(1, min(math.ceil(M / 256), sm_count() // tiles))
-    return gemm(dY.t(), X.t(), out, accumulate=True, split_k=split, engine=engine)
+    return gemm(dY.t(), X.t(), out, accumulate=True, split_k=split, engine=engine, row_sum=bias_grad)
 
 
 _SM = None

@@ -187,3 +187,24 @@ def test_fp32_gemm_on_tensor_cores_bf16x3(M, N, K):
     s = torch.zeros(N, device=DEV)
     ops.gemm(A, W, D, col_sum=s)
     _check(s, _ref(A, W).sum(0), 1e-4, "fp32 col_sum after bf16x3 product")
+
+
+@pytest.mark.parametrize("M,N,K", [(1000, 256, 64), (4096 + 24, 88, 64), (2048, 192, 64), (8192, 512, 128), (3000, 384, 128),
+                                   (2048, 1024, 256), (1024, 768, 256), (520, 1536, 384), (64 * 1024, 256, 64)])
+def test_wgrad_bias_gradient_rides_with_the_weight_gradient(M, N, K):
+    """ops.wgrad(dY, X, dW, bias_grad=db): dW += dY^T X and db += colsum(dY) in ONE launch (an extra N=16 MMA per K
+    step against a tile of ones) == the separate column-sum pass, in bf16 (tcgen05) and fp32 (three-plane / FFMA)."""
+    from outlook_grid_vision_transformer_b200 import ops
+    g = torch.Generator().manual_seed(M + N + K)
+    for dt in (torch.bfloat16, torch.float32):
+        dY = torch.randn(M, N, generator=g).to(DEV, dt)
+        X = torch.randn(M, K, generator=g).to(DEV, dt)
+        dW = torch.zeros(N, K, device=DEV)
+        db = torch.full((N,), 0.5, device=DEV)  # accumulates on top of what is there
+        ops.wgrad(dY, X, dW, bias_grad=db)
+        torch.cuda.synchronize()
+        want_w = dY.float().t() @ X.float()
+        want_b = dY.float().sum(0) + 0.5
+        tol = 2e-2 if dt == torch.bfloat16 else 1e-3
+        torch.testing.assert_close(dW, want_w, rtol=tol, atol=tol * float(want_w.abs().max()))
+        torch.testing.assert_close(db, want_b, rtol=1e-3, atol=1e-3 * float(want_b.abs().max()) + 1e-3)
