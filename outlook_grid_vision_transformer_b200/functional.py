@@ -591,6 +591,81 @@ def mbconv(x, we, g1, b1, wdw, g2, b2, sw1, sb1, sw2, sb2, wp, g3, b3, *, pe, pp
 
 
 # =================================================================================================
+# stand-alone SqueezeExcite (mbc_conv.py:9-27) and the outlook core as their own autograd nodes
+# =================================================================================================
+class SqueezeExciteFn(torch.autograd.Function):
+    """y = x * sigmoid(W2 act(W1 mean_hw(x) + b1) + b2) on rows [B*HW, C]; backward as autograd derives it:
+    dx = dy*gate + dpool/HW, dgate = sum_hw dy*x (the same kernels MBConv's fused backward uses, with the BatchNorm of
+    the depthwise stage replaced by the identity)."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, B, HW, act):
+        x = x.contiguous()
+        M, C = x.shape
+        Cs = w1.shape[0]
+        dev = x.device
+        one, zero = torch.ones(C, device=dev), torch.zeros(C, device=dev)
+        pool = ops.se_pool(x, one, zero, B, HW, "none")
+        w1m, w2m = w1.detach().reshape(Cs, C), w2.detach().reshape(C, Cs)
+        s1_pre = torch.empty((B, Cs), device=dev)
+        s1a = torch.empty((B, Cs), device=dev)
+        ops.gemm(pool, w1m, s1a, bias=b1.detach(), pre_out=s1_pre, act=act, engine=ENGINE_SIMT)
+        gate_pre = torch.empty((B, C), device=dev)
+        gate = torch.empty((B, C), device=dev)
+        ops.gemm(s1a, w2m, gate, bias=b2.detach(), pre_out=gate_pre, act="sigmoid", engine=ENGINE_SIMT)
+        y = ops.bn_act_gate(x, one, zero, gate, B, HW, "none")
+        ctx.geom = (B, HW, act)
+        ctx.shapes = (tuple(w1.shape), tuple(w2.shape))
+        ctx.save_for_backward(x, pool, s1_pre, s1a, gate_pre, gate, w1m, w2m, one, zero)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, pool, s1_pre, s1a, gate_pre, gate, w1m, w2m, one, zero = ctx.saved_tensors
+        B, HW, act = ctx.geom
+        dy = dy.contiguous()
+        C, Cs = w2m.shape
+        dgate = ops.se_bwd_reduce(dy, x, one, zero, B, HW, "none")
+        dgate_pre = ops.mul_dact(dgate, gate_pre, "sigmoid")
+        ds1_pre = torch.empty((B, Cs), device=x.device)
+        ops.gemm(dgate_pre, w2m.t(), ds1_pre, dact_src=s1_pre, dact=act, engine=ENGINE_SIMT)
+        dW2 = torch.zeros((C, Cs), device=x.device)
+        ops.wgrad(dgate_pre, s1a, dW2, engine=ENGINE_SIMT)
+        db2 = torch.zeros(C, device=x.device)
+        ops.colsum(dgate_pre, db2)
+        dpool = torch.empty((B, C), device=x.device)
+        ops.gemm(ds1_pre, w1m.t(), dpool, engine=ENGINE_SIMT)
+        dW1 = torch.zeros((Cs, C), device=x.device)
+        ops.wgrad(ds1_pre, pool, dW1, engine=ENGINE_SIMT)
+        db1 = torch.zeros(Cs, device=x.device)
+        ops.colsum(ds1_pre, db1)
+        # dx = (dy * gate + dpool / HW) through an identity BatchNorm (gamma = rstd = 1, no batch coupling)
+        dx = ops.dw_bn2_bwd_apply(dy, x, gate, dpool, one, zero, zero, one, one, zero, zero, B, HW, "none")
+        return dx, dW1.view(ctx.shapes[0]), db1, dW2.view(ctx.shapes[1]), db2, None, None, None
+
+
+def squeeze_excite(x: Tensor, w1, b1, w2, b2, B: int, HW: int, act: str) -> Tensor:
+    return SqueezeExciteFn.apply(x, w1, b1, w2, b2, B, HW, act)
+
+
+class OutlookCoreFn(torch.autograd.Function):
+    """softmax over the 9 taps + weighted 3x3 gather on va = [v | logits | pad] rows (outlook_attention.py:104-120)."""
+
+    @staticmethod
+    def forward(ctx, va, B, H, W, C, heads):
+        va = va.contiguous()
+        ctx.geom = (B, H, W, C, heads)
+        ctx.save_for_backward(va)
+        return ops.outlook_core_fwd(va, B, H, W, C, heads)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (va,) = ctx.saved_tensors
+        B, H, W, C, heads = ctx.geom
+        return ops.outlook_core_bwd(va, dy.contiguous(), B, H, W, C, heads), None, None, None, None, None
+
+
+# =================================================================================================
 # stand-alone LayerNorm on rows (LayerNorm2d) and layout conversion
 # =================================================================================================
 class LayerNormRowsFn(torch.autograd.Function):

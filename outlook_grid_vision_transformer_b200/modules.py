@@ -251,8 +251,36 @@ class OutlookAttention2d(nn.Module):
         pp = _prep_attr(self, "proj").get(self.training, [self.proj.weight], dtype, lambda: OF.prepare_linear(self.proj.weight, dtype))
         return pva, bva, pp
 
+    def _hooked(self) -> bool:
+        """A forward (pre-)hook sits on one of the 1x1 convs -- e.g. the logits capture of the attention-map tools
+        (src/experiments/heat_map_att_outlooker.py:25-42), which hooks `self.attn`."""
+        return any(m._forward_hooks or m._forward_pre_hooks for m in (self.attn, self.v, self.proj))
+
+    def _composed_rows_forward(self, rows, geom, ln, scale, with_res):
+        """The same math with the three 1x1 convs CALLED as modules, so hooks on them fire with the tensors the
+        reference would hand them (NCHW input, NCHW output); LayerNorm and the softmax / gather core stay on the
+        library kernels.  Analysis path: correctness over speed."""
+        C, nl = self.dim, self.attn.weight.shape[0]
+        xn = OF.layernorm_rows(rows, ln.weight, ln.bias, ln.eps) if ln is not None else rows
+        xn4 = OF.from_rows(xn, geom)
+        with torch.autocast("cuda", enabled=False):
+            w_dt = xn4.dtype
+            conv = lambda m, t: m(t) if w_dt == torch.float32 else m(t.float()).to(w_dt)  # noqa: E731
+            logits = conv(self.attn, xn4)                      # hook on self.attn sees [B, heads*9, H, W]
+            v = conv(self.v, xn4)
+            va = torch.zeros((rows.shape[0], OF.outlook_npad(C, self.num_heads)), device=rows.device, dtype=rows.dtype)
+            va[:, :C] = v.permute(0, 2, 3, 1).reshape(-1, C)
+            va[:, C:C + nl] = logits.permute(0, 2, 3, 1).reshape(-1, nl)
+            yc = OF.OutlookCoreFn.apply(va, geom.B, geom.H, geom.W, C, self.num_heads)
+            y = conv(self.proj, OF.from_rows(yc, geom)).permute(0, 2, 3, 1).reshape(-1, C)
+        if scale is not None:
+            y = y * scale.repeat_interleave(geom.P).to(y.dtype)[:, None]
+        return rows + y if with_res else y
+
     def rows_forward(self, rows: Tensor, geom: Geom, ln: Optional[nn.LayerNorm], scale: Optional[Tensor],
                      with_res: bool) -> Tensor:
+        if self.kernel_size == 3 and self.stride == 1 and self._hooked():
+            return self._composed_rows_forward(rows, geom, ln, scale, with_res)
         if self.kernel_size != 3 or self.stride != 1:
             raise NotImplementedError("the sm_100a outlook kernel implements kernel_size=3, stride=1 "
                                       "(the only configuration OutGridBlock constructs, Out_Grid_Block.py:44-49)")
@@ -351,23 +379,14 @@ class SqueezeExcite(nn.Module):
         self.gate = nn.Sigmoid()
 
     def forward(self, x: Tensor) -> Tensor:
-        # Stand-alone use is inference-only; inside MBConv the SE is part of the fused autograd function.
-        if torch.is_grad_enabled() and (x.requires_grad or self.fc1.weight.requires_grad):
-            raise NotImplementedError("stand-alone SqueezeExcite is forward-only; use MBConv for training")
+        """Stand-alone use (inside MBConv the SE is part of the fused autograd function).  fp32 or bf16 rows; the two
+        tiny 1x1 convs on the pooled [B, C] vector run in fp32."""
         rows, geom = OF.to_rows(x)
-        Cm = rows.shape[1]
-        one = torch.ones(Cm, device=x.device)
-        zero = torch.zeros(Cm, device=x.device)
-        rows = rows.contiguous()
-        pool = ops.se_pool(rows, one, zero, geom.B, geom.P, "none")
-        Cs = self.fc1.weight.shape[0]
-        s1 = torch.empty((geom.B, Cs), device=x.device)
-        ops.gemm(pool, self.fc1.weight.detach().reshape(Cs, Cm), s1, bias=self.fc1.bias.detach(),
-                 act=_act_name(self.act), engine=ops.ENGINE_SIMT)
-        gate = torch.empty((geom.B, Cm), device=x.device)
-        ops.gemm(s1, self.fc2.weight.detach().reshape(Cm, Cs), gate, bias=self.fc2.bias.detach(), act="sigmoid",
-                 engine=ops.ENGINE_SIMT)
-        return OF.from_rows(ops.bn_act_gate(rows, one, zero, gate, geom.B, geom.P, "none"), geom)
+        dt = _compute_dtype(x)
+        rows = rows.to(dt) if rows.dtype != dt else rows
+        y = OF.squeeze_excite(rows, self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias, geom.B, geom.P,
+                              _act_name(self.act))
+        return OF.from_rows(y, geom)
 
 
 ActType = Literal["silu", "gelu", "relu"]

@@ -1,0 +1,97 @@
+"""-m gpu, needs >= 2 GPUs (run with `gpurun --gpus 2`): the data-parallel exchange on the REAL path -- the CUDA blocks,
+the flat gradient arena, bucketed NCCL all-reduce launched from backward, all inside the captured CUDA graph.
+After a replayed step on rank r's shard, arena / world == mean over ranks of the gradients a single replica computes on
+each shard (per-replica BatchNorm statistics, like N independent reference runs)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+CFG = {"type": "model_a", "num_classes": 10, "stem_dim": 16, "dpr_max": 0.0,
+       "stages": [dict(dim=16, depth=1, num_heads=2, grid_size=2, outlook_heads=2),
+                  dict(dim=32, depth=2, num_heads=2, grid_size=2, outlook_heads=2)]}
+
+
+def _shard(rank):
+    g = torch.Generator().manual_seed(50 + rank)
+    return torch.randn(8, 3, 8, 8, generator=g), torch.randint(0, 10, (8,), generator=g)
+
+
+def _worker(rank, world, port, use_graph, q):
+    import torch.distributed as dist
+    import torch.nn.functional as F
+
+    import outlook_grid_vision_transformer_b200 as og
+    from outlook_grid_vision_transformer_b200.ddp import ArenaGradAllReduce, broadcast_parameters
+    from outlook_grid_vision_transformer_b200.engine import FlatState, TrainStep
+
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        torch.manual_seed(100 + rank)  # different init per rank: broadcast must make them equal
+        model = og.build_model(CFG).to(dev).train()
+        broadcast_parameters(model)
+        state = {k: v.detach().clone() for k, v in model.state_dict().items()}
+        # single-replica gradients on EVERY shard (no exchange), bf16 autocast like the step
+        ref = og.build_model(CFG).to(dev).train()
+        want = None
+        for r in range(world):
+            ref.load_state_dict(state)
+            ref.zero_grad(set_to_none=True)
+            x, y = (t.to(dev) for t in _shard(r))
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                lg = ref(x)
+            F.cross_entropy(lg.float(), y).backward()
+            g = {k: p.grad.detach().float().clone() for k, p in ref.named_parameters()}
+            want = g if want is None else {k: want[k] + g[k] for k in g}
+        want = {k: v / world for k, v in want.items()}
+        flat = FlatState(model)
+        sync = ArenaGradAllReduce(flat, bucket_bytes=32 << 10, tail_bytes=4 << 10)  # several buckets on this tiny net
+        x, y = (t.to(dev) for t in _shard(rank))
+        step = TrainStep(model, lambda lg, yy: F.cross_entropy(lg, yy), x, y, lr=0.0, weight_decay=0.0, autocast_bf16=True,
+                         grad_sync=sync, use_graph=use_graph, warmup=2, world=world, flat=flat)
+        for _ in range(2):  # twice: bucket counters re-arm, the arena is re-zeroed by the step's memset
+            step()
+        torch.cuda.synchronize()
+        worst, worst_k = 0.0, ""
+        for k, p in model.named_parameters():
+            got = p.grad.detach().float() / world
+            err = float((got - want[k]).norm() / (want[k].norm() + 1e-6 * want[k].numel() ** 0.5))
+            if err > worst:
+                worst, worst_k = err, k
+        q.put((rank, worst, worst_k, len(sync.buckets)))
+        sync.remove()
+        step.graph = None
+        del step
+        torch.cuda.synchronize()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("use_graph", [False, True], ids=["eager", "graph"])
+def test_nccl_allreduced_arena_equals_mean_of_shard_gradients(use_graph):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    world = 2
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, use_graph, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    for rank, worst, k, nb in res:
+        assert nb > 2
+        # bf16 step vs bf16 single-replica gradients: only summation order differs
+        assert worst < 2e-2, f"rank {rank}: all-reduced gradient of {k} off by {worst:.3e} (normwise)"

@@ -138,3 +138,57 @@ def test_cast_batch_matches_per_weight_casts():
     for big, a, big_t, b in want:
         assert torch.equal(big, a) and torch.equal(big_t, b)
     assert torch.equal(cat[:72], bias[0]) and float(cat[72:].abs().sum()) == 0.0
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+def test_standalone_squeeze_excite_forward_and_backward(dt):
+    """SqueezeExcite used on its own (mbc_conv.py:9-27): forward AND every gradient against a PyTorch restatement."""
+    import outlook_grid_vision_transformer_b200 as og
+    torch.manual_seed(3)
+    B, C, H = 3, 32, 8
+    se = og.SqueezeExcite(C, se_ratio=0.25, act="silu").to(DEV)
+    x = torch.randn(B, C, H, H, device=DEV).to(dt).requires_grad_(True)
+    R = torch.randn(B, C, H, H, device=DEV)
+    y = se(x)
+    (y.float() * R).sum().backward()
+    xr = x.detach().float().requires_grad_(True)
+    w1 = se.fc1.weight.detach().clone().requires_grad_(True)
+    b1 = se.fc1.bias.detach().clone().requires_grad_(True)
+    w2 = se.fc2.weight.detach().clone().requires_grad_(True)
+    b2 = se.fc2.bias.detach().clone().requires_grad_(True)
+    s = torch.nn.functional.silu(torch.nn.functional.conv2d(xr.mean(dim=(2, 3), keepdim=True), w1, b1))
+    yr = xr * torch.sigmoid(torch.nn.functional.conv2d(s, w2, b2))
+    (yr * R).sum().backward()
+    tol = 1e-3 if dt == torch.float32 else 2e-2
+    close = lambda a, b, what: torch.testing.assert_close(a.float(), b, rtol=tol, atol=tol * float(b.abs().max()), msg=lambda m: f"{what}: {m}")  # noqa: E731
+    close(y, yr.detach(), "forward")
+    close(x.grad, xr.grad, "dx")
+    close(se.fc1.weight.grad, w1.grad, "dW1")
+    close(se.fc1.bias.grad, b1.grad, "db1")
+    close(se.fc2.weight.grad, w2.grad, "dW2")
+    close(se.fc2.bias.grad, b2.grad, "db2")
+
+
+def test_forward_hook_on_outlook_logits_conv_fires_and_matches():
+    """The attention-map tools hook `OutlookAttention2d.attn` (heat_map_att_outlooker.py:25-42): the hook must fire with
+    the logits [B, heads*9, H, W] the reference conv would produce, and the block output must not change."""
+    blk = _block(C=32, oheads=2).eval()
+    x = torch.randn(2, 32, 8, 8, device=DEV)
+    with torch.no_grad():
+        want = blk(x)
+    seen = {}
+    h = blk.outlook.attn.attn.register_forward_hook(lambda m, inp, out: seen.update(inp=inp[0].detach(), out=out.detach()))
+    try:
+        with torch.no_grad():
+            got = blk(x)
+    finally:
+        h.remove()
+    assert "out" in seen and tuple(seen["out"].shape) == (2, 2 * 9, 8, 8)
+    ref_logits = torch.nn.functional.conv2d(seen["inp"], blk.outlook.attn.attn.weight, blk.outlook.attn.attn.bias)
+    torch.testing.assert_close(seen["out"], ref_logits, rtol=1e-4, atol=1e-5)
+    xn = torch.nn.functional.layer_norm(x.permute(0, 2, 3, 1), (32,), blk.outlook.norm1.ln.weight, blk.outlook.norm1.ln.bias, 1e-6)
+    torch.testing.assert_close(seen["inp"], xn.permute(0, 3, 1, 2), rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(got, want, rtol=1e-3, atol=1e-4)
+    with torch.no_grad():
+        again = blk(x)  # hook removed: back on the fused path
+    torch.testing.assert_close(again, want, rtol=0, atol=0)
