@@ -150,6 +150,7 @@ class ArenaGradAllReduce:
         if cur:
             self.buckets.append(dict(lo=0, hi=cur_hi, params=cur, pending=len(cur), work=None))
         self._owner = {p: b for b in self.buckets for p in b["params"]}
+        self._seen = set()  # parameters already reported this step (both notification routes may fire for one)
         self._comm_stream = None
         self._hooks = []
         self._OF = _OF
@@ -163,9 +164,13 @@ class ArenaGradAllReduce:
             self._on_grad_ready(p)
 
     def _on_grad_ready(self, p) -> None:
+        # A parameter can be reported twice in one backward: autograd runs the post-accumulate hook of a leaf even when
+        # the fused branch returned None for it (it accumulated into the arena itself and reported through GRAD_READY).
+        # Count every parameter once, or a bucket is launched while half of its gradients are still to be written.
         b = self._owner.get(p)
-        if b is None:
+        if b is None or id(p) in self._seen:
             return
+        self._seen.add(id(p))
         b["pending"] -= 1
         if b["pending"] == 0:
             self._launch(b)
@@ -200,6 +205,7 @@ class ArenaGradAllReduce:
         for b in self.buckets:
             b["pending"] = len(b["params"])
             b["work"] = None
+        self._seen.clear()
 
     def remove(self) -> None:
         for h in self._hooks:
