@@ -419,7 +419,14 @@ def profile_step(w, peaks, nprof=2):
         tw = sum(r["ms_per_step"] for r in rows)
         fwd_flops = model_forward_flops(w.mcfg, w.img) * w.batch
         step_flops = 3 * fwd_flops if w.training else fwd_flops
-        roof = {"bound": top["bound"], "achieved": ach, "peak": pk, "unit": unit, "frac": ach / pk, "traffic": None,
+        # DRAM bytes of ONE instance of the dominant branch (all its launches), from the committed ncu pass (profiles/)
+        br_traffic = None
+        try:
+            tj = json.loads((ROOT / "profiles" / "traffic.json").read_text())
+            br_traffic = tj.get(f"{top['branch']} {top['dir']} M={top['M']} C={top['C']}", {}).get("dram_bytes_per_instance")
+        except Exception:
+            br_traffic = None
+        roof = {"bound": top["bound"], "achieved": ach, "peak": pk, "unit": unit, "frac": ach / pk, "traffic": br_traffic,
                 "kernel": f"{top['branch']} {top['dir']} (fused branch: {top['launches_per_step'] // n} launches) M={top['M']} C={top['C']}",
                 "avg_us": per_s * 1e6, "accounting": "SURVEY 8(d): alg_bytes = elt*2*M*C fwd / elt*3*M*C bwd per fused branch; "
                 "frac = max(alg_bytes/HBM, alg_flops/TC) / measured time of ALL the branch's launches",

@@ -10,6 +10,8 @@
 // Warp roles as in the GEMM engine: warps 0..15 epilogue (lane = row, warp % 4 = TMEM lane quarter, warp / 4 = column
 // group), warp 16 TMA producer (x tile, weight-chunk ring), warp 17 single-thread MMA issuer.  The MMA issuer runs
 // fc1 of chunk j+1 BEFORE fc2 of chunk j, so the tensor pipe works while the epilogue warps compute the activation.
+#include <stdlib.h>
+
 #include "ogv_gemm.cuh"
 #include "ogv_ptx.cuh"
 #include "ogv_stage.cuh"
@@ -30,14 +32,15 @@ struct MlpFwdCfg {
   static constexpr int KC = C / 64;
   static constexpr int KH = BH / 64;
   static constexpr int NW = C == 64 ? 4 : 3;               // weight-chunk ring depth
-  static constexpr int NZ = 3;                             // fc1 accumulator buffers in TMEM
+  static constexpr int NZ = (512 - 2 * C) / BH > 6 ? 6 : (512 - 2 * C) / BH;  // fc1 accumulator buffers in TMEM
+  static constexpr int NHB = (BH == 64 && C == 64) ? 2 : 1;  // hidden-tile buffers per epilogue group
   static constexpr int XA_BYTES = F_BM * C * 2;
   static constexpr int H_BYTES = F_BM * BH * 2;
   static constexpr int W_BYTES = BH * C * 2;
   static constexpr int NOC = (C / 32) / 2;                 // 32-column output chunks per warp of a group (1 or 2)
   static constexpr int STAGE_BYTES = F_EPI_WARPS * NOC * F_SLOT;
-  static constexpr int NBAR = 2 + 2 + 2 * NW + 2 * NZ + 2 + 2 + 2 + 2 + F_EPI_WARPS * NOC;
-  static constexpr int SMEM = 2 * XA_BYTES + 2 * H_BYTES + NW * W_BYTES + STAGE_BYTES + NBAR * 8 + 16 + 1024;
+  static constexpr int NBAR = 2 + 2 + 2 * NW + 2 * NZ + 4 * NHB + 2 + 2 + F_EPI_WARPS * NOC;
+  static constexpr int SMEM = 2 * XA_BYTES + 2 * NHB * H_BYTES + NW * W_BYTES + STAGE_BYTES + NBAR * 8 + 16 + 1024;
   static constexpr int TMEM_COLS = 512;                    // NZ*BH (Z) + 2*C (Y) <= 512
   static_assert(NZ * BH + 2 * C <= 512, "TMEM budget");
   static_assert(SMEM <= 227 * 1024, "shared memory budget");
@@ -65,12 +68,12 @@ mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
                const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmY,
                const __grid_constant__ CUtensorMap tmR, const MlpFwdParams p) {
   using Cfg = MlpFwdCfg<C, BH>;
-  constexpr int NW = Cfg::NW, NZ = Cfg::NZ;
+  constexpr int NW = Cfg::NW, NZ = Cfg::NZ, NHB = Cfg::NHB;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* xa = smem;                                   // [2][XA_BYTES]
-  uint8_t* hbuf = xa + 2 * Cfg::XA_BYTES;               // [2][H_BYTES]
-  uint8_t* wring = hbuf + 2 * Cfg::H_BYTES;             // [NW][W_BYTES]
+  uint8_t* hbuf = xa + 2 * Cfg::XA_BYTES;               // [2 groups][NHB][H_BYTES]
+  uint8_t* wring = hbuf + 2 * NHB * Cfg::H_BYTES;       // [NW][W_BYTES]
   uint8_t* staging = wring + NW * Cfg::W_BYTES;         // [F_EPI_WARPS][NOC][F_SLOT]
   uint64_t* bars = reinterpret_cast<uint64_t*>(staging + Cfg::STAGE_BYTES);
   uint64_t* xa_full = bars;
@@ -80,8 +83,8 @@ mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   uint64_t* z_full = w_empty + NW;
   uint64_t* z_empty = z_full + NZ;
   uint64_t* h_full = z_empty + NZ;
-  uint64_t* h_empty = h_full + 2;
-  uint64_t* y_full = h_empty + 2;
+  uint64_t* h_empty = h_full + 2 * NHB;
+  uint64_t* y_full = h_empty + 2 * NHB;
   uint64_t* y_empty = y_full + 2;
   uint64_t* ld_bar = y_empty + 2;                       // [F_EPI_WARPS][NOC]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ld_bar + F_EPI_WARPS * Cfg::NOC);
@@ -96,10 +99,12 @@ mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(&xa_full[s], 1);
       ptx::mbar_init(&xa_empty[s], 1);
-      ptx::mbar_init(&h_full[s], F_EPI_WARPS / 2);
-      ptx::mbar_init(&h_empty[s], 1);
       ptx::mbar_init(&y_full[s], 1);
       ptx::mbar_init(&y_empty[s], F_EPI_WARPS / 2);
+    }
+    for (int s = 0; s < 2 * NHB; ++s) {
+      ptx::mbar_init(&h_full[s], F_EPI_WARPS / 2);
+      ptx::mbar_init(&h_empty[s], 1);
     }
     for (int s = 0; s < NZ; ++s) {
       ptx::mbar_init(&z_full[s], 1);
@@ -199,9 +204,10 @@ mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         if (f >= NZ) {  // fc2 of chunk f - NZ
           const int f2 = f - NZ;
           const int it = f2 / NJ, j = f2 - it * NJ;
-          const int yb = it & 1, hb = f2 & 1;
+          const int yb = it & 1;
+          const int hb = (f2 & 1) * NHB + ((f2 >> 1) % NHB);  // buffer of group f2 % 2, its (f2 / 2)-th chunk
           if (j == 0) ptx::mbar_wait(&y_empty[yb], ((it >> 1) & 1) ^ 1u);
-          ptx::mbar_wait(&h_full[hb], (f2 >> 1) & 1);
+          ptx::mbar_wait(&h_full[hb], ((f2 >> 1) / NHB) & 1);
           const int ws = wc % NW;
           ptx::mbar_wait(&w_full[ws], (wc / NW) & 1);
           ptx::tc_fence_after();
@@ -294,7 +300,8 @@ mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       const int zb = f % NZ;
       ptx::mbar_wait(&z_full[zb], (f / NZ) & 1);
       ptx::tc_fence_after();
-      uint8_t* hb = hbuf + g * Cfg::H_BYTES;
+      const int hbi = g * NHB + ((f >> 1) % NHB);
+      uint8_t* hb = hbuf + hbi * Cfg::H_BYTES;
 #pragma unroll
       for (int pc = 0; pc < NP; ++pc) {
         const int col0 = half * HW + pc * 32;  // within the chunk
@@ -316,7 +323,7 @@ mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         }
         act_apply_p<16, true>(p.act, v2);
         // H[g] is rewritten only after the fc2 MMA of this group's previous chunk has read it
-        if (pc == 0) ptx::mbar_wait(&h_empty[g], ((f >> 1) & 1) ^ 1u);
+        if (pc == 0) ptx::mbar_wait(&h_empty[hbi], (((f >> 1) / NHB) & 1) ^ 1u);
         // row `row` of the chunk, columns [col0, +32): four 16-byte pieces of a 128B-swizzled K-major tile
         uint8_t* ht = hb + (col0 / 64) * (F_BM * 128);
         const int c16_0 = (col0 % 64) / 8;
@@ -328,7 +335,7 @@ mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       }
       ptx::fence_proxy_async();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&h_full[g]);
+      if (lane == 0) ptx::mbar_arrive(&h_full[hbi]);
       if (pending >= 0) {
         write_tile(pending);
         pending = -1;
@@ -774,7 +781,9 @@ int launch_mlp_bwd(const void* xn, long long ldx, const void* dy, long long ldg,
 
 // hidden-chunk width of the forward kernel for a given channel count (0: shape not served by the fused kernel)
 int fwd_chunk(int C, int Hd) {
-  const int bh = C == 64 ? 128 : (C == 128 ? 64 : 0);
+  static int bh64 = -1;  // OGV_MLP_BH64=1: 64-wide hidden chunks at C = 64 too (two hidden tiles per group, 6 Z buffers)
+  if (bh64 < 0) { const char* e = getenv("OGV_MLP_BH64"); bh64 = (e && e[0] == '1') ? 1 : 0; }
+  const int bh = C == 64 ? (bh64 ? 64 : 128) : (C == 128 ? 64 : 0);
   return (bh && Hd % bh == 0 && Hd >= bh && Hd % B_BH == 0) ? bh : 0;
 }
 
@@ -797,6 +806,8 @@ extern "C" int ogv_mlp_fwd(const void* x, long long ldx, const void* w1, const f
               "mlp_fwd: tensors must be 16-byte aligned with row strides that are multiples of 8 elements");
   OGV_REQUIRE(M <= 0x7fffffffll - F_BM, "mlp_fwd: too many rows");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (C == 64 && fwd_chunk(C, Hd) == 64)
+    return launch_mlp_fwd<64, 64>(x, ldx, w1, b1, w2, b2, residual, ldr, row_scale, rows_per_scale, y, ldy, M, Hd, act, st);
   if (C == 64)
     return launch_mlp_fwd<64, 128>(x, ldx, w1, b1, w2, b2, residual, ldr, row_scale, rows_per_scale, y, ldy, M, Hd, act, st);
   return launch_mlp_fwd<128, 64>(x, ldx, w1, b1, w2, b2, residual, ldr, row_scale, rows_per_scale, y, ldy, M, Hd, act, st);

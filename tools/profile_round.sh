@@ -8,7 +8,7 @@
 tag=${1:-r01}; top=${2:-gemm_tc_kernel}; nfull=${3:-6}
 export PYTHONDONTWRITEBYTECODE=1
 mkdir -p gpurun_out
-BENCH="python bench.py --steps 1 --warmup 3 --no-graph --no-profile --no-cpu-baseline"
+BENCH="python bench.py --steps 1 --warmup 3 --no-graph --no-profile --no-cpu-baseline --no-eager-gpu --no-extra"
 $BENCH > gpurun_out/${tag}_plain.log 2>&1 || { echo "plain bench run failed"; tail -5 gpurun_out/${tag}_plain.log; exit 1; }
 tail -n 1 gpurun_out/${tag}_plain.log | cut -c1-160
 if [ -z "$SKIP_LIST" ]; then
