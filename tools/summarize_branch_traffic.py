@@ -32,11 +32,16 @@ def main():
         per[i]["name"] = short(r["Kernel Name"])
         per[i][r["Metric Name"]] = float(r["Metric Value"].replace(",", ""))
     rows = [per[i] for i in order]
-    n_iter = len(rows) // 3
-    last = rows[len(rows) - n_iter:]
-    # forward / backward split: the backward starts at the first kernel after the forward's last bn_apply
-    names = [r["name"] for r in last]
-    split = max(i for i, nm in enumerate(names) if nm.startswith("bn_apply_kernel")) + 1 if len(sys.argv) <= 6 else int(sys.argv[6])
+    # the third iteration: forward = from after the previous iteration's last weight-gradient GEMM up to the last
+    # bn_apply; backward = from there to the end, minus the three torch kernels of the script's final print
+    names = [r["name"] for r in rows]
+    while names and not (names[-1].startswith("gemm_tc_kernel") or names[-1].startswith("bn_") or names[-1].startswith("dw")):
+        rows.pop()
+        names.pop()
+    fwd_end = max(i for i, nm in enumerate(names) if nm.startswith("bn_apply_kernel")) + 1
+    fwd_start = max(i for i, nm in enumerate(names[:fwd_end]) if nm.startswith("gemm_tc_kernel<64, float>")) + 1
+    last = rows[fwd_start:]
+    split = fwd_end - fwd_start
     elt = 2
     out = [f"# {tag}: DRAM traffic of branch {branch} (MBConv) at M={M}, C={C}, bf16 -- every launch of one forward and one backward\n",
            f"source: `{path.name}` (ncu metrics pass over `tools/run_mbconv.py`, third iteration; cold-cache serialised launches)\n"]
