@@ -318,14 +318,17 @@ __device__ __forceinline__ void silu_both_fast(float x, float* a, float* da) {
   *da = fmaf(v, 1.f - s, s);
 }
 constexpr float kGeluC1 = 1.12777659f, kGeluC3 = 0.1047942f, kGeluC5 = -0.0020293f;
+// The fit holds for |x| <= 7; beyond, its negative z^4 coefficient would turn the argument around (|x| > 10.5 gave
+// gelu(x) = x/2 or gelu(-x) = -x).  z^2 is clamped at its |x| = 7 value, where tanh is saturated (|arg| > 12) for good.
+constexpr float kGeluZ2Max = 24.5f;
 __device__ __forceinline__ float gelu_fast(float x) {
-  const float z2 = 0.5f * x * x;
+  const float z2 = fminf(0.5f * x * x, kGeluZ2Max);
   const float p = x * 0.70710678118654752440f * fmaf(z2, fmaf(z2, kGeluC5, kGeluC3), kGeluC1);
   const float h = 0.5f * x;
   return fmaf(h, tanh_approx(p), h);
 }
 __device__ __forceinline__ void gelu_both_fast(float x, float* a, float* da) {
-  const float z2 = 0.5f * x * x;
+  const float z2 = fminf(0.5f * x * x, kGeluZ2Max);
   const float p = x * 0.70710678118654752440f * fmaf(z2, fmaf(z2, kGeluC5, kGeluC3), kGeluC1);
   const float dp = 0.70710678118654752440f * fmaf(z2, fmaf(z2, 5.f * kGeluC5, 3.f * kGeluC3), kGeluC1);
   const float t = tanh_approx(p);
@@ -471,9 +474,14 @@ __device__ __forceinline__ f32x2 tanh_approx2(f32x2 p) {
   unpk2(p, a, b);
   return pk2(tanh_approx(a), tanh_approx(b));
 }
+__device__ __forceinline__ f32x2 min2(f32x2 a, float c) {
+  float lo, hi;
+  unpk2(a, lo, hi);
+  return pk2(fminf(lo, c), fminf(hi, c));
+}
 __device__ __forceinline__ f32x2 gelu_fast2(f32x2 x) {
   const f32x2 half = splat2(0.5f);
-  const f32x2 z2 = mul2(mul2(half, x), x);
+  const f32x2 z2 = min2(mul2(mul2(half, x), x), kGeluZ2Max);
   const f32x2 q = fma2(z2, fma2(z2, splat2(kGeluC5), splat2(kGeluC3)), splat2(kGeluC1));
   const f32x2 t = tanh_approx2(mul2(mul2(x, splat2(0.70710678118654752440f)), q));
   const f32x2 h = mul2(half, x);
@@ -482,7 +490,7 @@ __device__ __forceinline__ f32x2 gelu_fast2(f32x2 x) {
 __device__ __forceinline__ void gelu_both_fast2(f32x2 x, f32x2* a, f32x2* da) {
   const f32x2 half = splat2(0.5f), rs2 = splat2(0.70710678118654752440f);
   const f32x2 h = mul2(half, x);
-  const f32x2 z2 = mul2(h, x);
+  const f32x2 z2 = min2(mul2(h, x), kGeluZ2Max);
   const f32x2 q = fma2(z2, fma2(z2, splat2(kGeluC5), splat2(kGeluC3)), splat2(kGeluC1));
   const f32x2 dp = mul2(rs2, fma2(z2, fma2(z2, splat2(5.f * kGeluC5), splat2(3.f * kGeluC3)), splat2(kGeluC1)));
   const f32x2 t = tanh_approx2(mul2(mul2(x, rs2), q));

@@ -13,6 +13,8 @@
 //   * operands may be K-major (forward / dgrad) or MN-major (wgrad: reduction over the row index
 //     of both global tensors) -- only the TMA box and the UMMA descriptors differ;
 //   * split-K work items (wgrad) accumulate with fp32 atomics into D (direct, non-TMA epilogue).
+#include <stdlib.h>
+
 #include "ogv_gemm.cuh"
 #include "ogv_ptx.cuh"
 #include "ogv_stage.cuh"
@@ -109,15 +111,20 @@ __device__ __forceinline__ void epi_row16(const GemmEpi& e, int m, int n0, const
   }
 }
 
-template <int BN, typename TO>
+// MT = M sub-tiles (of 128 rows) per work item.  MT = 2 (narrow outputs, BN <= 128): a 128 x 64 output tile keeps only half
+// of the epilogue warps busy and pays the per-tile hand-off latency (MMA commit -> epilogue -> TMA store -> accumulator
+// free) for very little data; 256 rows per item put all 16 warps to work and halve the number of hand-offs.
+template <int BN, typename TO, int MT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmP,
                const __grid_constant__ CUtensorMap tmL, const TcParams p) {
-  constexpr int A_BYTES = TC_BM * TC_BK * 2;
+  constexpr int A_BYTES = MT * TC_BM * TC_BK * 2;
   constexpr int B_BYTES = BN * TC_BK * 2;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  constexpr int TMEM_COLS = 2 * BN;
+  constexpr int ACC_COLS = MT * BN;        // TMEM columns of one accumulator buffer
+  constexpr int TMEM_COLS = 2 * ACC_COLS;
+  static_assert(TMEM_COLS <= 512, "TMEM budget");
   // the row-sum path exists only in the fp32-output instantiations (weight gradients): the bf16 epilogues, whose
   // register budget is exact, do not carry it
   constexpr bool kRowSum = sizeof(TO) == 4;
@@ -179,7 +186,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int nt = w % p.n_tiles;
         const int mt = (w / p.n_tiles) % p.m_tiles;
         const int sp = w / (p.n_tiles * p.m_tiles);
-        const int m0 = mt * TC_BM, n0 = nt * BN;
+        const int m0 = mt * (MT * TC_BM), n0 = nt * BN;
         const int kc0 = sp * p.chunks_per_split;
         const int kc1 = min(p.k_chunks, kc0 + p.chunks_per_split);
         for (int kc = kc0; kc < kc1; ++kc) {
@@ -189,7 +196,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           uint8_t* sb = sa + A_BYTES;
           const int k0 = kc * TC_BK;
           if (!p.a_mn) {
-            ptx::tma_load_2d(sa, &tmA, &full_bar[stage], k0, m0);  // box {64 k, 128 rows}
+#pragma unroll
+            for (int i = 0; i < MT; ++i)  // box {64 k, 128 rows} per M sub-tile
+              ptx::tma_load_2d(sa + i * (TC_BM * TC_BK * 2), &tmA, &full_bar[stage], k0, m0 + i * TC_BM);
           } else {
 #pragma unroll
             for (int j = 0; j < TC_BM / 64; ++j)  // box {64 mn, 64 k-rows}
@@ -230,7 +239,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const bool do_rs = kRowSum && p.row_sum != nullptr && (w % p.n_tiles) == 0;
         ptx::mbar_wait(&tempty_bar[as], ((it >> 1) & 1) ^ 1u);
         ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * BN;
+        const uint32_t d_tmem = tmem_base + as * ACC_COLS;
         for (int kc = kc0; kc < kc1; ++kc) {
           ptx::mbar_wait(&full_bar[stage], phase);
           ptx::tc_fence_after();
@@ -241,6 +250,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint64_t adesc = ptx::umma_smem_desc(sa + k * a_step, a_lbo, 1024u);
             const uint64_t bdesc = ptx::umma_smem_desc(sb + k * b_step, b_lbo, 1024u);
             ptx::umma_f16(d_tmem, adesc, bdesc, idesc, (kc > kc0 || k > 0) ? 1u : 0u);
+            if constexpr (MT == 2)  // second 128-row sub-tile: same B, next accumulator (K-major A only)
+              ptx::umma_f16(d_tmem + BN, ptx::umma_smem_desc(sa + TC_BM * TC_BK * 2 + k * a_step, a_lbo, 1024u), bdesc,
+                            idesc, (kc > kc0 || k > 0) ? 1u : 0u);
             if (do_rs)
               ptx::umma_f16(tmem_base + p.rs_col, adesc, ptx::umma_smem_desc(ones_addr + k * 32u, 16u, 1024u), idesc_rs,
                             (kc > kc0 || k > 0) ? 1u : 0u);
@@ -264,16 +276,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
       const int nt = w % p.n_tiles;
       const int mt = (w / p.n_tiles) % p.m_tiles;
-      const int m0 = mt * TC_BM, n0 = nt * BN;
+      const int m0 = mt * (MT * TC_BM), n0 = nt * BN;
       const int as = it & 1;
-      const int mrow0 = m0 + q * 32;
-      const int m = mrow0 + lane;
-      const uint32_t t0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
       bool waited = false;
 #pragma unroll 1
-      for (int c = cg; c < BN / CH; c += EPI_WARPS / 4) {
+      for (int cc = cg; cc < MT * (BN / CH); cc += EPI_WARPS / 4) {
+        const int sub = MT == 1 ? 0 : cc / (BN / CH);   // M sub-tile
+        const int c = MT == 1 ? cc : cc - sub * (BN / CH);  // 32-column chunk within the tile
+        const int mrow0 = m0 + sub * TC_BM + q * 32;
+        const int m = mrow0 + lane;
+        const uint32_t t0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * ACC_COLS + sub * BN;
         const int n0c = n0 + c * CH;
-        if (n0c >= p.N) break;
+        if (n0c >= p.N) {
+          if (MT == 1) break;
+          continue;
+        }
         uint8_t* s0 = nullptr;
         uint8_t* s1 = nullptr;
         int pr = 0;
@@ -411,6 +428,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (kRowSum && p.row_sum && nt == 0 && cg == 0) {  // one warp per lane quarter: column 0 of the row-sum accumulator
         float rs16[16];
         ptx::tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + p.rs_col, rs16);
+        const int m = m0 + q * 32 + lane;  // (row sums ride with MT = 1 work items only)
         if (m < p.M) atomicAdd(p.row_sum + m, rs16[0]);
       }
       ptx::tc_fence_before();
@@ -485,9 +503,9 @@ bool tma_ok(const void* ptr, long long ld) {
   return ptr != nullptr && (reinterpret_cast<uintptr_t>(ptr) % 16 == 0) && (ld % 8 == 0);
 }
 
-template <int BN, typename TO>
+template <int BN, typename TO, int MT>
 int launch_tc(const CUtensorMap* tms, TcParams& p, cudaStream_t stream) {
-  constexpr int STAGE_BYTES = TC_BM * TC_BK * 2 + BN * TC_BK * 2;
+  constexpr int STAGE_BYTES = MT * TC_BM * TC_BK * 2 + BN * TC_BK * 2;
   const int staging = EPI_WARPS * p.slots * SLOT_BYTES;
   const int colbytes = (p.col_stats ? 2 * p.n_pad * 4 : 0) + (p.row_sum ? ONES_BYTES : 0);
   int stages = (SMEM_LIMIT - 1024 - BAR_BYTES - staging - colbytes) / STAGE_BYTES;
@@ -500,7 +518,7 @@ int launch_tc(const CUtensorMap* tms, TcParams& p, cudaStream_t stream) {
   const int smem_bytes = stages * STAGE_BYTES + staging + BAR_BYTES + colbytes + 1024;
   static int attr_bytes = 0;
   if (attr_bytes < smem_bytes) {
-    cudaError_t err = cudaFuncSetAttribute(gemm_tc_kernel<BN, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t err = cudaFuncSetAttribute(gemm_tc_kernel<BN, TO, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            SMEM_LIMIT);
     if (err != cudaSuccess) {
       ogv_set_error("gemm_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(err));
@@ -517,7 +535,7 @@ int launch_tc(const CUtensorMap* tms, TcParams& p, cudaStream_t stream) {
     ogv_set_error("gemm_tc: row_sum with a 256-wide tile needs at most one work item per CTA (%d items, %d CTAs)", total, grid);
     return OGV_ERR_UNSUPPORTED;
   }
-  gemm_tc_kernel<BN, TO><<<grid, TC_THREADS, smem_bytes, stream>>>(tms[0], tms[1], tms[2], tms[3], tms[4], p);
+  gemm_tc_kernel<BN, TO, MT><<<grid, TC_THREADS, smem_bytes, stream>>>(tms[0], tms[1], tms[2], tms[3], tms[4], p);
   return ogv_check_launch("gemm_tc");
 }
 
@@ -571,6 +589,9 @@ int ogv_gemm_tc(const ogv_gemm_args& a, cudaStream_t stream) {
   p.a_mn = operand_major(a.a_rs, a.a_cs);
   p.b_mn = operand_major(a.b_rs, a.b_cs);
   const int BN = a.N <= 64 ? 64 : (a.N <= 128 ? 128 : 256);
+  // two 128-row sub-tiles per work item for narrow bf16 outputs with enough rows to keep every SM busy
+  static int mt_mode = -1;  // OGV_GEMM_MT=1 forces single sub-tiles (A/B measurements)
+  if (mt_mode < 0) { const char* e = getenv("OGV_GEMM_MT"); mt_mode = e ? atoi(e) : 2; }
   p.m_tiles = ogv_ceil_div(a.M, TC_BM);
   p.n_tiles = ogv_ceil_div(a.N, BN);
   p.k_chunks = ogv_ceil_div(a.K, TC_BK);
@@ -588,6 +609,8 @@ int ogv_gemm_tc(const ogv_gemm_args& a, cudaStream_t stream) {
   const bool staged = obf && !a.accumulate && tma_ok(a.D, a.ldd) && (!a.pre_out || tma_ok(a.pre_out, a.ld_pre)) &&
                       (!a.residual || tma_ok(a.residual, a.ld_res)) && (!a.dact_src || tma_ok(a.dact_src, a.ld_dact)) &&
                       !(a.residual && a.dact_src);
+  const int MT = (mt_mode >= 2 && BN <= 64 && staged && p.a_mn == 0 && !a.row_sum && a.M >= 2 * 256 * ogv_num_sms()) ? 2 : 1;
+  p.m_tiles = ogv_ceil_div(a.M, TC_BM * MT);
   p.slots = staged ? (a.pre_out ? 4 : 2) : 0;
   p.col_stats = (a.col_sum != nullptr) ? 1 : 0;
   p.n_pad = p.n_tiles * BN;
@@ -623,8 +646,10 @@ int ogv_gemm_tc(const ogv_gemm_args& a, cudaStream_t stream) {
   }
 
   switch (BN) {
-    case 64: return obf ? launch_tc<64, bf16>(tms, p, stream) : launch_tc<64, float>(tms, p, stream);
-    case 128: return obf ? launch_tc<128, bf16>(tms, p, stream) : launch_tc<128, float>(tms, p, stream);
-    default: return obf ? launch_tc<256, bf16>(tms, p, stream) : launch_tc<256, float>(tms, p, stream);
+    case 64:
+      if (MT == 2) return launch_tc<64, bf16, 2>(tms, p, stream);
+      return obf ? launch_tc<64, bf16, 1>(tms, p, stream) : launch_tc<64, float, 1>(tms, p, stream);
+    case 128: return obf ? launch_tc<128, bf16, 1>(tms, p, stream) : launch_tc<128, float, 1>(tms, p, stream);
+    default: return obf ? launch_tc<256, bf16, 1>(tms, p, stream) : launch_tc<256, float, 1>(tms, p, stream);
   }
 }

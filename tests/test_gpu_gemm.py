@@ -208,3 +208,57 @@ def test_wgrad_bias_gradient_rides_with_the_weight_gradient(M, N, K):
         tol = 2e-2 if dt == torch.bfloat16 else 1e-3
         torch.testing.assert_close(dW, want_w, rtol=tol, atol=tol * float(want_w.abs().max()))
         torch.testing.assert_close(db, want_b, rtol=1e-3, atol=1e-3 * float(want_b.abs().max()) + 1e-3)
+
+
+@pytest.mark.parametrize("M,N,K", [(148 * 512, 64, 64), (148 * 512 + 300 * 128 + 37, 64, 256), (148 * 512 + 77, 40, 88),
+                                   (1048576, 64, 64)])
+def test_tc_gemm_two_subtile_work_items(M, N, K):
+    """Narrow outputs with many rows run 256-row work items (two 128-row sub-tiles, all 16 epilogue warps busy): plain,
+    bias + GELU + saved derivative, DropPath scale + residual, dgrad x saved derivative -- ragged M, N below the tile."""
+    from outlook_grid_vision_transformer_b200 import ops
+    g = torch.Generator().manual_seed(M % 1000 + N + K)
+    A = torch.randn(M, K, generator=g).to(DEV, torch.bfloat16)
+    B = (torch.randn(N, K, generator=g) * 0.2).to(DEV, torch.bfloat16)
+    bias = torch.randn(N, generator=g).to(DEV)
+    res = torch.randn(M, N, generator=g).to(DEV, torch.bfloat16)
+    P = 64
+    scale = ((torch.arange((M + P - 1) // P, device=DEV) % 3 != 0).float() / 0.75).contiguous()
+    acc = A.float() @ B.float().t()
+    # plain
+    D = torch.full((M, N), float("nan"), device=DEV, dtype=torch.bfloat16)
+    ops.gemm(A, B, D, engine=ops.ENGINE_TC)
+    torch.testing.assert_close(D.float(), acc, rtol=1e-2, atol=1e-2 * float(acc.abs().max()))
+    # bias + act + saved derivative
+    pre = torch.empty_like(D)
+    ops.gemm(A, B, D, bias=bias, act="gelu", pre_out=pre, pre_out_grad=True, engine=ops.ENGINE_TC)
+    z = (acc + bias).requires_grad_(True)
+    h = torch.nn.functional.gelu(z)
+    (dh,) = torch.autograd.grad(h, z, torch.ones_like(h))
+    torch.testing.assert_close(D.float(), h.detach(), rtol=2e-2, atol=2e-2)
+    torch.testing.assert_close(pre.float(), dh, rtol=2e-2, atol=2e-2)
+    # bias + DropPath scale + residual
+    ops.gemm(A, B, D, bias=bias, row_scale=scale, rows_per_scale=P, residual=res, engine=ops.ENGINE_TC)
+    want = (acc + bias) * scale.repeat_interleave(P)[:M, None] + res.float()
+    torch.testing.assert_close(D.float(), want, rtol=2e-2, atol=2e-2 * float(want.abs().max()))
+    # dgrad x saved derivative
+    ops.gemm(A, B, D, dact_src=res, dact="mul", engine=ops.ENGINE_TC)
+    want = acc * res.float()
+    torch.testing.assert_close(D.float(), want, rtol=2e-2, atol=2e-2 * float(want.abs().max()))
+    torch.cuda.synchronize()
+
+
+def test_fast_gelu_is_right_far_from_zero():
+    """The bf16-mode GELU (tanh of an odd polynomial) must saturate correctly for large |x|: gelu(x) -> x, gelu(-x) -> 0,
+    gelu' -> 1 / 0 (its polynomial fit is only valid for |x| <= 7 and is clamped there)."""
+    from outlook_grid_vision_transformer_b200 import ops
+    M = 4096
+    x = torch.linspace(-60.0, 60.0, M * 64, device=DEV).reshape(M, 64).bfloat16()
+    eye = torch.eye(64, device=DEV).bfloat16()
+    D = torch.empty((M, 64), device=DEV, dtype=torch.bfloat16)
+    pre = torch.empty_like(D)
+    ops.gemm(x, eye, D, act="gelu", pre_out=pre, pre_out_grad=True, engine=ops.ENGINE_TC)
+    z = x.float().requires_grad_(True)
+    h = torch.nn.functional.gelu(z)
+    (dh,) = torch.autograd.grad(h, z, torch.ones_like(h))
+    torch.testing.assert_close(D.float(), h.detach(), rtol=1e-2, atol=2e-3)
+    torch.testing.assert_close(pre.float(), dh, rtol=1e-2, atol=4e-3)
