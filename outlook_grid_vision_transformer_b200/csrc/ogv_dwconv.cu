@@ -59,7 +59,10 @@ int dw_make_geom(int B, int H, int W, int Cm, int CC, int ctas_per_sm, DwGeom* g
   if (nt > 0x7fffffff) return -1;
   g->ntiles = (int)nt;
   g->nchunks = (Cm + CC - 1) / CC;
-  long long want = ((long long)ogv_num_sms() * ctas_per_sm + g->nchunks - 1) / g->nchunks;
+  // workers per channel chunk: nchunks * nworkers CTAs must FIT the resident slots (one wave).  Rounding up put 304 CTAs
+  // on 296 slots at Cm = 512 (16 chunks x 19 workers): eight CTAs ran alone in a second wave and the kernel took twice
+  // its time (stage 1: 626 us for half the elements of stage 0's 754 us).
+  long long want = ((long long)ogv_num_sms() * ctas_per_sm) / g->nchunks;
   if (want > nt) want = nt;
   if (want < 1) want = 1;
   g->nworkers = (int)want;
@@ -322,10 +325,13 @@ dwconv_bwd_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constan
   constexpr int NAV = CC / AV;
   constexpr int BUF_ELEMS = DW_BUF_POS * CC;
   extern __shared__ __align__(128) uint8_t dsm[];
+  // raw gradient halo slot | fp32 gradient tile | TWO pre-activation centre slots (the load of tile i+1 is issued at the
+  // top of tile i, so its DRAM latency hides behind the whole tile instead of being waited for after the stencil)
+  constexpr int E_ELEMS = 256 * CC;  // centre tile: TH * TW * NI <= 8 * 32 positions
   T* const graw = reinterpret_cast<T*>(dsm);
-  T* const eraw = reinterpret_cast<T*>(dsm + BUF_ELEMS * sizeof(T));
-  float* const gt = reinterpret_cast<float*>(dsm + 2 * BUF_ELEMS * sizeof(T));
-  uint64_t* const bar = reinterpret_cast<uint64_t*>(dsm + BUF_ELEMS * (2 * sizeof(T) + sizeof(float)));
+  float* const gt = reinterpret_cast<float*>(dsm + BUF_ELEMS * sizeof(T));
+  T* const eraw0 = reinterpret_cast<T*>(dsm + BUF_ELEMS * (sizeof(T) + sizeof(float)));
+  uint64_t* const bar = reinterpret_cast<uint64_t*>(dsm + BUF_ELEMS * (sizeof(T) + sizeof(float)) + 2 * E_ELEMS * sizeof(T));
   __shared__ float s_dw[CC * 9], s_db[CC], s_dg[CC];
   __shared__ __align__(16) float s_par[4][CC];  // scale1, shift1, mean1, rstd1 of the chunk
   __shared__ __align__(16) float s_w[9][CC];
@@ -358,6 +364,7 @@ dwconv_bwd_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constan
     ptx::tma_prefetch_desc(&tm_e);
     ptx::mbar_init(&bar[0], 1);
     ptx::mbar_init(&bar[1], 1);
+    ptx::mbar_init(&bar[2], 1);
     ptx::fence_barrier_init();
   }
   // channel pairs (k, k+1) ride in one 64-bit register: the 18 FMAs per element issue as 9 FFMA2
@@ -386,7 +393,7 @@ dwconv_bwd_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constan
     ptx::mbar_arrive_expect_tx(&bar[0], g_bytes);
     ptx::tma_load_4d(graw, &tm_g, &bar[0], c0, w0 - 1, h0 - 1, b0);
     ptx::mbar_arrive_expect_tx(&bar[1], e_bytes);
-    ptx::tma_load_4d(eraw, &tm_e, &bar[1], c0, w0, h0, b0);
+    ptx::tma_load_4d(eraw0, &tm_e, &bar[1], c0, w0, h0, b0);
   }
   for (int it = 0; t < g.ntiles; t += g.nworkers, ++it) {
     int b0, h0, w0;
@@ -394,6 +401,13 @@ dwconv_bwd_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constan
     const int tn = t + g.nworkers;
     int nb0 = 0, nh0 = 0, nw0 = 0;
     if (tn < g.ntiles) dw_decode_tile(g, tn, nb0, nh0, nw0);
+    const int eb = it & 1;
+    const T* const eraw = eraw0 + eb * E_ELEMS;
+    // the other centre slot was last read by tile it-1's stencil, which every thread left before the closing barrier
+    if (tid == 0 && tn < g.ntiles) {
+      ptx::mbar_arrive_expect_tx(&bar[1 + (eb ^ 1)], e_bytes);
+      ptx::tma_load_4d(eraw0 + (eb ^ 1) * E_ELEMS, &tm_e, &bar[1 + (eb ^ 1)], c0, nw0, nh0, nb0);
+    }
 
     // ---- gradient halo tile: raw (T) -> fp32 (TMA zero fill already handled the borders) ----
     ptx::mbar_wait(&bar[0], it & 1);
@@ -413,7 +427,7 @@ dwconv_bwd_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constan
       ptx::mbar_arrive_expect_tx(&bar[0], g_bytes);
       ptx::tma_load_4d(graw, &tm_g, &bar[0], c0, nw0 - 1, nh0 - 1, nb0);
     }
-    ptx::mbar_wait(&bar[1], it & 1);
+    ptx::mbar_wait(&bar[1 + eb], (it >> 1) & 1);
 
     if (cvalid) {
       f32x2 w[9][2];
@@ -506,10 +520,6 @@ dwconv_bwd_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constan
     }
     ptx::fence_proxy_async();
     __syncthreads();
-    if (tid == 0 && tn < g.ntiles) {
-      ptx::mbar_arrive_expect_tx(&bar[1], e_bytes);
-      ptx::tma_load_4d(eraw, &tm_e, &bar[1], c0, nw0, nh0, nb0);
-    }
   }
   if (cvalid) {
 #pragma unroll
@@ -923,7 +933,7 @@ extern "C" int ogv_dwconv_bwd(const void* dd_pre, const void* e_pre, const float
               "dwconv_bwd: tensors must be 16-byte aligned");
   OGV_DISPATCH_DTYPE(dtype, T, {
     constexpr int CC = dw_cc<T>();
-    const int smem = DW_BUF_POS * CC * (int)(2 * sizeof(T) + sizeof(float)) + 64;
+    const int smem = DW_BUF_POS * CC * (int)(sizeof(T) + sizeof(float)) + 2 * 256 * CC * (int)sizeof(T) + 64;
     OGV_DISPATCH_ACT(act, ACT, {
       int occ = 1;
       if (int rc = dw_smem_optin(dwconv_bwd_kernel<T, CC, ACT>, smem, &occ)) return rc;

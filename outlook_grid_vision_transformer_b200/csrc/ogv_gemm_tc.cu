@@ -609,7 +609,7 @@ int ogv_gemm_tc(const ogv_gemm_args& a, cudaStream_t stream) {
   const bool staged = obf && !a.accumulate && tma_ok(a.D, a.ldd) && (!a.pre_out || tma_ok(a.pre_out, a.ld_pre)) &&
                       (!a.residual || tma_ok(a.residual, a.ld_res)) && (!a.dact_src || tma_ok(a.dact_src, a.ld_dact)) &&
                       !(a.residual && a.dact_src);
-  const int MT = (mt_mode >= 2 && BN <= 64 && staged && p.a_mn == 0 && !a.row_sum && a.M >= 2 * 256 * ogv_num_sms()) ? 2 : 1;
+  const int MT = (mt_mode >= 2 && BN <= (mt_mode >= 3 ? 128 : 64) && staged && p.a_mn == 0 && !a.row_sum && a.M >= 2 * 256 * ogv_num_sms()) ? 2 : 1;
   p.m_tiles = ogv_ceil_div(a.M, TC_BM * MT);
   p.slots = staged ? (a.pre_out ? 4 : 2) : 0;
   p.col_stats = (a.col_sum != nullptr) ? 1 : 0;
@@ -649,7 +649,9 @@ int ogv_gemm_tc(const ogv_gemm_args& a, cudaStream_t stream) {
     case 64:
       if (MT == 2) return launch_tc<64, bf16, 2>(tms, p, stream);
       return obf ? launch_tc<64, bf16, 1>(tms, p, stream) : launch_tc<64, float, 1>(tms, p, stream);
-    case 128: return obf ? launch_tc<128, bf16, 1>(tms, p, stream) : launch_tc<128, float, 1>(tms, p, stream);
+    case 128:
+      if (MT == 2) return launch_tc<128, bf16, 2>(tms, p, stream);
+      return obf ? launch_tc<128, bf16, 1>(tms, p, stream) : launch_tc<128, float, 1>(tms, p, stream);
     default: return obf ? launch_tc<256, bf16, 1>(tms, p, stream) : launch_tc<256, float, 1>(tms, p, stream);
   }
 }

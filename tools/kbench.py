@@ -161,6 +161,26 @@ def main():
         run("gemm qkv", s, lambda: ops.gemm(x, wq, q3, bias=torch.zeros(3 * C, **f32)), nbytes(x, q3), 2 * M * 3 * C * C)
         wp = (torch.randn(C, C, device=dev) * 0.05).to(dt)
         run("gemm proj+res", s, lambda: ops.gemm(x, wp, out_c, bias=bC, residual=dy), nbytes(x, dy, out_c), 2 * M * C * C)
+        # ---- the squeeze-excite GEMMs on [B, Cm] rows: tcgen05 engine (bf16 operands) vs FFMA engine (fp32 operands)
+        Cs = C
+        pool32 = torch.randn(B, Cm, **f32)
+        pool16 = pool32.to(dt)
+        ws1_32 = torch.randn(Cs, Cm, **f32) * 0.05
+        ws2_32 = torch.randn(Cm, Cs, **f32) * 0.05
+        ws1_16, ws2_16 = ws1_32.to(dt), ws2_32.to(dt)
+        s1_16, s1p_16 = torch.empty(B, Cs, device=dev, dtype=dt), torch.empty(B, Cs, device=dev, dtype=dt)
+        s1_32, s1p_32 = torch.empty(B, Cs, **f32), torch.empty(B, Cs, **f32)
+        g32, gp32 = torch.empty(B, Cm, **f32), torch.empty(B, Cm, **f32)
+        bs1, bs2 = torch.zeros(Cs, **f32), torch.zeros(Cm, **f32)
+        run("se fc1 tc", s, lambda: ops.gemm(pool16, ws1_16, s1_16, bias=bs1, pre_out=s1p_16, act="silu"), nbytes(pool16, ws1_16), 2 * B * Cm * Cs)
+        run("se fc1 simt", s, lambda: ops.gemm(pool32, ws1_32, s1_32, bias=bs1, pre_out=s1p_32, act="silu", engine=ops.ENGINE_SIMT), nbytes(pool32, ws1_32), 2 * B * Cm * Cs)
+        run("se fc2 tc", s, lambda: ops.gemm(s1_16, ws2_16, g32, bias=bs2, pre_out=gp32, act="sigmoid"), nbytes(g32, ws2_16), 2 * B * Cm * Cs)
+        run("se fc2 simt", s, lambda: ops.gemm(s1_32, ws2_32, g32, bias=bs2, pre_out=gp32, act="sigmoid", engine=ops.ENGINE_SIMT), nbytes(g32, ws2_32), 2 * B * Cm * Cs)
+        dWs = torch.zeros(Cm, Cs, **f32)
+        g16 = g32.to(dt)
+        run("se wgrad tc", s, lambda: ops.wgrad(g16, s1_16, dWs), nbytes(g16, s1_16), 2 * B * Cm * Cs)
+        run("se wgrad simt", s, lambda: ops.wgrad(g32, s1_32, dWs, engine=ops.ENGINE_SIMT), nbytes(g32, s1_32), 2 * B * Cm * Cs)
+        run("se cast", s, lambda: ops.cast(pool32, dt), nbytes(pool32, pool16))
         # ---- fused MLP (hidden tile on chip): fc1 -> act -> fc2 -> +res in one kernel; backward recomputes it
         for tag, Hd in (("mlp 4C", 4 * C), ("mlp2d 2C", 2 * C)):
             if not ops.mlp_fused_supported(C, Hd, dt):
