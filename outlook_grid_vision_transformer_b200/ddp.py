@@ -180,10 +180,14 @@ class ArenaGradAllReduce:
         if buf.is_cuda:
             if self._comm_stream is None:
                 self._comm_stream = torch.cuda.Stream(device=buf.device)
+            from . import ops as _ops
+
             ready = torch.cuda.Event()
             ready.record(torch.cuda.current_stream(buf.device))
             with torch.cuda.stream(self._comm_stream):
                 self._comm_stream.wait_event(ready)
+                if _ops.SIDE is not None:  # weight gradients of this bucket may still be running on the side stream
+                    self._comm_stream.wait_stream(_ops.SIDE.stream)
                 b["work"] = dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
         else:
             b["work"] = dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group, async_op=True)

@@ -13,6 +13,7 @@ gradient all-reduce (ddp.ArenaGradAllReduce) runs in place on arena slices.  Lea
 from __future__ import annotations
 
 import math
+import os
 from typing import Callable, Dict, List, Optional
 
 import torch
@@ -211,7 +212,7 @@ class TrainStep:
                  autocast_bf16: bool = True, grad_sync=None, use_graph: bool = True, warmup: int = 3,
                  grad_clip_norm: Optional[float] = None, scheduler: Optional[WarmupCosineLR] = None,
                  no_decay: Callable[[str], bool] = default_no_decay, fused_droppath: bool = True, world: int = 1,
-                 flat: Optional[FlatState] = None):
+                 flat: Optional[FlatState] = None, side_wgrad: Optional[bool] = None):
         self.model, self.loss_fn = model, loss_fn
         self.flat = flat if flat is not None else FlatState(model, no_decay)
         self.autocast_bf16 = autocast_bf16
@@ -222,6 +223,10 @@ class TrainStep:
         self._lr_override: Optional[float] = None
         self.step_num = 0
         dev = self.flat.P.device
+        if side_wgrad is None:
+            side_wgrad = os.environ.get("OGV_SIDE_WGRAD", "1") != "0"
+        # weight-gradient GEMMs on a second stream (joined before the gradient exchange / the optimizer)
+        self._side = ops.SideStream(dev) if (side_wgrad and dev.type == "cuda") else None
         self.x = example_x.clone()
         self.y = example_y.clone()
         self.hyper = torch.zeros(5, device=dev, dtype=torch.float32)
@@ -282,8 +287,12 @@ class TrainStep:
                 logits = self.model(self.x)
             logits = logits.float()
             loss = self.loss_fn(logits, self.y)
+            ops.SIDE = self._side
             loss.backward()
         finally:
+            ops.SIDE = None
+            if self._side is not None:
+                self._side.join()
             _modules._BULK_FRESH = False
             _modules.DROP_TABLE = None
             _OF.SCRATCH = None

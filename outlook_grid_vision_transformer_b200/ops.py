@@ -225,7 +225,37 @@ def gemm(A: Tensor, B: Tensor, D: Tensor, *, bias: Optional[Tensor] = None, pre_
     return D
 
 
+class SideStream:
+    """Where the train-step executor sends work that only produces PARAMETER gradients (weight-gradient GEMMs): nothing in
+    the rest of backward depends on it, so it runs on a second stream next to the dgrad chain and fills the SMs the
+    latency-bound small-stage kernels leave idle.  `keep` holds the operands until the executor joins the stream (the
+    caching allocator must not hand their blocks to later main-stream allocations while the side stream still reads them)."""
+
+    def __init__(self, device):
+        self.stream = torch.cuda.Stream(device=device)
+        self.keep = []
+
+    def join(self) -> None:
+        torch.cuda.current_stream().wait_stream(self.stream)
+        self.keep.clear()
+
+
+SIDE: Optional[SideStream] = None  # set by engine.TrainStep around backward
+
+
 def wgrad(dY: Tensor, X: Tensor, out: Tensor, engine: int = ENGINE_AUTO, bias_grad: Optional[Tensor] = None) -> Tensor:
+    side = SIDE
+    if side is not None and dY.is_cuda and not PROFILER.enabled:
+        ready = torch.cuda.Event()
+        ready.record()
+        side.keep.append((dY, X, out, bias_grad))
+        with torch.cuda.stream(side.stream):
+            side.stream.wait_event(ready)
+            return _wgrad(dY, X, out, engine, bias_grad)
+    return _wgrad(dY, X, out, engine, bias_grad)
+
+
+def _wgrad(dY: Tensor, X: Tensor, out: Tensor, engine: int = ENGINE_AUTO, bias_grad: Optional[Tensor] = None) -> Tensor:
     """out[n,k] += sum_m dY[m,n] * X[m,k]   (out fp32, pre-zeroed by the caller).
     bias_grad (fp32 [n]): += sum_m dY[m,n] in the same launch (one extra N=16 MMA per K step against a tile of ones)."""
     M, N = dY.shape
