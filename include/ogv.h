@@ -166,6 +166,18 @@ int ogv_bn_bwd_apply(const void* dy, const void* x, const float* mean, const flo
                      const float* dgamma, const float* dbeta, void* dx, long long M, int C, int dtype,
                      void* stream);
 
+/* conv -> BatchNorm -> act units around the blocks (stem_head.py:23-32, downsampling.py:28-65), the BN + act part:
+ * out = act(scale*x + shift); backward with g = dy * act'(scale*x + shift) recomputed in both passes:
+ * dbeta += sum g, dgamma += sum g*xhat; dx = gamma*rstd*(g - dbeta/n - xhat*dgamma/n). */
+int ogv_bn_act_apply(const void* x, const float* scale, const float* shift, void* out, long long M, int C, int act,
+                     int dtype, void* stream);
+int ogv_bn_act_bwd_reduce(const void* dy, const void* x, const float* scale, const float* shift, const float* mean,
+                          const float* rstd, float* dgamma, float* dbeta, long long M, int C, int act, int dtype,
+                          void* stream);
+int ogv_bn_act_bwd_apply(const void* dy, const void* x, const float* scale, const float* shift, const float* mean,
+                         const float* rstd, const float* gamma, const float* dgamma, const float* dbeta, void* dx,
+                         long long M, int C, int act, int dtype, void* stream);
+
 /* Depthwise 3x3 (mbc_conv.py:73-78) with BN1-affine + SiLU applied to the input on load and the
  * batch statistics of the output accumulated on store.  w is [Cm, 9] fp32. */
 int ogv_dwconv_fwd(const void* e_pre, const float* scale1, const float* shift1, const float* w, void* d_pre,

@@ -64,6 +64,9 @@ SIGNATURES = {
     "ogv_bn_apply": [_P, _P, _P, _P, _P, _L, _I, _I, _P],
     "ogv_bn_bwd_reduce": [_P, _P, _P, _P, _P, _P, _L, _I, _I, _P],
     "ogv_bn_bwd_apply": [_P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _P],
+    "ogv_bn_act_apply": [_P, _P, _P, _P, _L, _I, _I, _I, _P],
+    "ogv_bn_act_bwd_reduce": [_P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _P],
+    "ogv_bn_act_bwd_apply": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _P],
     "ogv_dwconv_fwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "ogv_se_pool": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "ogv_bn_act_gate": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],

@@ -357,6 +357,132 @@ bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const flo
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// BatchNorm + activation of the conv → BN → act units around the blocks (stem_head.py:23-32, downsampling.py:28-65):
+// out = act(scale*x + shift), and its backward with g = dy * act'(scale*x + shift) recomputed on the fly in both
+// passes (nothing but the pre-BN tensor is saved).  Same thread layout as bn_apply / bn_bwd_reduce / bn_bwd_apply.
+// ------------------------------------------------------------------------------------------------
+template <typename T, int ACT, int U>
+__global__ void __launch_bounds__(COLREDUCE_THREADS)
+bn_act_apply_kernel(const T* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
+                    T* __restrict__ out, long long M, int nv) {
+  constexpr bool FAST = FastAct<T>::value;
+  const int cv = threadIdx.x % nv;
+  const int kk = blockDim.x / nv;
+  float sc[8], sh[8];
+  ld8(scale + cv * 8, sc);
+  ld8(shift + cv * 8, sh);
+  const long long stride = (long long)gridDim.x * kk;
+  for (long long row0 = (long long)blockIdx.x * kk + threadIdx.x / nv; row0 < M; row0 += stride * U) {
+    Raw8<T> rx[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long row = row0 + u * stride;
+      if (row < M) ld_raw8(x + (row * nv + cv) * 8, rx[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long row = row0 + u * stride;
+      if (row < M) {
+        float v[8];
+        cvt_raw8(rx[u], v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = act_apply_t<ACT, FAST>(fmaf(v[k], sc[k], sh[k]));
+        st8(out + (row * nv + cv) * 8, v);
+      }
+    }
+  }
+}
+
+template <typename T, int ACT>
+__global__ void __launch_bounds__(COLREDUCE_THREADS)
+bn_act_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ scale,
+                         const float* __restrict__ shift, const float* __restrict__ mean,
+                         const float* __restrict__ rstd, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                         long long M, int nv) {
+  constexpr bool FAST = FastAct<T>::value;
+  float acc[2][8];
+  colreduce_init(acc);
+  float mu[8], rs[8], sc[8], sh[8];
+  {
+    const int cv0 = threadIdx.x % nv;
+    ld8(mean + cv0 * 8, mu);
+    ld8(rstd + cv0 * 8, rs);
+    ld8(scale + cv0 * 8, sc);
+    ld8(shift + cv0 * 8, sh);
+  }
+  COLREDUCE_LOOP(M, nv, row, cv) {
+    float d[8], xv[8];
+    ld8(dy + (row * nv + cv) * 8, d);
+    ld8(x + (row * nv + cv) * 8, xv);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float g = d[i] * act_grad_t<ACT, FAST>(fmaf(xv[i], sc[i], sh[i]));
+      acc[0][i] += g;
+      acc[1][i] += g * (xv[i] - mu[i]) * rs[i];
+    }
+  }
+  float* outs[2] = {dbeta, dgamma};
+  colreduce_finish<2>(acc, outs, nv);
+}
+
+template <typename T, int ACT, int U>
+__global__ void __launch_bounds__(COLREDUCE_THREADS)
+bn_act_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ scale,
+                        const float* __restrict__ shift, const float* __restrict__ mean,
+                        const float* __restrict__ rstd, const float* __restrict__ gamma,
+                        const float* __restrict__ dgamma, const float* __restrict__ dbeta, T* __restrict__ dx,
+                        long long M, int nv, float inv_n) {
+  constexpr bool FAST = FastAct<T>::value;
+  const int cv = threadIdx.x % nv;
+  const int kk = blockDim.x / nv;
+  float A[8], Bc[8], Cx[8], sc[8], sh[8];
+  {
+    float mu[8], rs[8], g[8], dg[8], db[8];
+    ld8(mean + cv * 8, mu);
+    ld8(rstd + cv * 8, rs);
+    ld8(gamma + cv * 8, g);
+    ld8(dgamma + cv * 8, dg);
+    ld8(dbeta + cv * 8, db);
+    ld8(scale + cv * 8, sc);
+    ld8(shift + cv * 8, sh);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      A[k] = g[k] * rs[k];
+      Cx[k] = A[k] * rs[k] * dg[k] * inv_n;
+      Bc[k] = A[k] * db[k] * inv_n - Cx[k] * mu[k];
+    }
+  }
+  const long long stride = (long long)gridDim.x * kk;
+  for (long long row0 = (long long)blockIdx.x * kk + threadIdx.x / nv; row0 < M; row0 += stride * U) {
+    Raw8<T> rd[U], rx[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long row = row0 + u * stride;
+      if (row < M) {
+        ld_raw8(dy + (row * nv + cv) * 8, rd[u]);
+        ld_raw8(x + (row * nv + cv) * 8, rx[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long row = row0 + u * stride;
+      if (row < M) {
+        float d[8], xv[8], o[8];
+        cvt_raw8(rd[u], d);
+        cvt_raw8(rx[u], xv);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float g = d[k] * act_grad_t<ACT, FAST>(fmaf(xv[k], sc[k], sh[k]));
+          o[k] = fmaf(A[k], g, -fmaf(Cx[k], xv[k], Bc[k]));
+        }
+        st8(dx + (row * nv + cv) * 8, o);
+      }
+    }
+  }
+}
+
 inline int flat_grid(long long n, int threads) {
   long long b = (n + threads - 1) / threads;
   long long cap = (long long)ogv_num_sms() * 16;
@@ -464,5 +590,67 @@ extern "C" int ogv_bn_bwd_apply(const void* dy, const void* x, const float* mean
         reinterpret_cast<const T*>(dy), reinterpret_cast<const T*>(x), mean, rstd, gamma, dgamma, dbeta,
         reinterpret_cast<T*>(dx), M, nv, 1.f / (float)M);
     return ogv_check_launch("bn_bwd_apply");
+  });
+}
+
+extern "C" int ogv_bn_act_apply(const void* x, const float* scale, const float* shift, void* out, long long M, int C,
+                                int act, int dtype, void* stream) {
+  if (M == 0) return OGV_OK;
+  OGV_REQUIRE(x && scale && shift && out && C > 0 && C % 8 == 0, "bn_act_apply: bad args (C %% 8 == 0)");
+  const int nv = C / 8;
+  if (nv > 256) { ogv_set_error("bn_act_apply: C=%d too wide", C); return OGV_ERR_UNSUPPORTED; }
+  const int kk = COLREDUCE_THREADS / nv;
+  const long long blocks = (M + kk - 1) / kk;
+  const long long cap = (long long)ogv_num_sms() * 2;
+  const int grid = (int)(blocks < cap ? blocks : cap);
+  OGV_DISPATCH_DTYPE(dtype, T, {
+    OGV_DISPATCH_ACT(act, ACT, {
+      bn_act_apply_kernel<T, ACT, 4><<<grid, nv * kk, 0, (cudaStream_t)stream>>>(
+          reinterpret_cast<const T*>(x), scale, shift, reinterpret_cast<T*>(out), M, nv);
+    });
+    return ogv_check_launch("bn_act_apply");
+  });
+}
+
+extern "C" int ogv_bn_act_bwd_reduce(const void* dy, const void* x, const float* scale, const float* shift,
+                                     const float* mean, const float* rstd, float* dgamma, float* dbeta, long long M,
+                                     int C, int act, int dtype, void* stream) {
+  if (M == 0) return OGV_OK;
+  OGV_REQUIRE(dy && x && scale && shift && mean && rstd && dgamma && dbeta && C % 8 == 0, "bn_act_bwd_reduce: bad args");
+  OGV_DISPATCH_DTYPE(dtype, T, {
+    OGV_DISPATCH_ACT(act, ACT, {
+      ColReduceCfg cfg;
+      if (!colreduce_config(M, C / 8, &cfg, bn_act_bwd_reduce_kernel<T, ACT>)) {
+        ogv_set_error("bn_act_bwd_reduce: C=%d too wide", C);
+        return OGV_ERR_UNSUPPORTED;
+      }
+      bn_act_bwd_reduce_kernel<T, ACT><<<cfg.grid, cfg.block, 0, (cudaStream_t)stream>>>(
+          reinterpret_cast<const T*>(dy), reinterpret_cast<const T*>(x), scale, shift, mean, rstd, dgamma, dbeta, M,
+          C / 8);
+    });
+    return ogv_check_launch("bn_act_bwd_reduce");
+  });
+}
+
+extern "C" int ogv_bn_act_bwd_apply(const void* dy, const void* x, const float* scale, const float* shift,
+                                    const float* mean, const float* rstd, const float* gamma, const float* dgamma,
+                                    const float* dbeta, void* dx, long long M, int C, int act, int dtype,
+                                    void* stream) {
+  if (M == 0) return OGV_OK;
+  OGV_REQUIRE(dy && x && scale && shift && mean && rstd && gamma && dgamma && dbeta && dx && C % 8 == 0,
+              "bn_act_bwd_apply: bad args");
+  const int nv = C / 8;
+  if (nv > 256) { ogv_set_error("bn_act_bwd_apply: C=%d too wide", C); return OGV_ERR_UNSUPPORTED; }
+  const int kk = COLREDUCE_THREADS / nv;
+  const long long blocks = (M + kk - 1) / kk;
+  const long long cap = (long long)ogv_num_sms() * 2;
+  const int grid = (int)(blocks < cap ? blocks : cap);
+  OGV_DISPATCH_DTYPE(dtype, T, {
+    OGV_DISPATCH_ACT(act, ACT, {
+      bn_act_bwd_apply_kernel<T, ACT, 4><<<grid, nv * kk, 0, (cudaStream_t)stream>>>(
+          reinterpret_cast<const T*>(dy), reinterpret_cast<const T*>(x), scale, shift, mean, rstd, gamma, dgamma, dbeta,
+          reinterpret_cast<T*>(dx), M, nv, 1.f / (float)M);
+    });
+    return ogv_check_launch("bn_act_bwd_apply");
   });
 }

@@ -668,6 +668,78 @@ class OutlookCoreFn(torch.autograd.Function):
 # =================================================================================================
 # stand-alone LayerNorm on rows (LayerNorm2d) and layout conversion
 # =================================================================================================
+# =================================================================================================
+# conv -> BatchNorm -> act units around the blocks: ConvStem (stem_head.py:23-32) and Downsample (downsampling.py:28-65)
+# =================================================================================================
+class ConvBnActFn(torch.autograd.Function):
+    """The k x k convolution itself is the library's (cuDNN implicit GEMM through aten, like cuBLAS for a plain GEMM);
+    everything after it -- batch statistics, running-statistics update, normalise + activation, and the whole BatchNorm +
+    activation backward -- runs on this package's streaming kernels over the channels_last rows, saving only the
+    pre-BN conv output (the activation derivative is recomputed in both backward passes)."""
+
+    @staticmethod
+    def forward(ctx, x, w, gamma, beta, meta):
+        dt, act, training = meta["dtype"], meta["act"], meta["training"]
+        stride, padding = meta["stride"], meta["padding"]
+        rm, rv = meta["running"]
+        xc = x.to(dt).contiguous(memory_format=torch.channels_last)
+        wc = w.detach().to(dt).contiguous(memory_format=torch.channels_last)
+        y_pre = torch.ops.aten.convolution(xc, wc, None, stride, padding, [1, 1], False, [0, 0], 1)
+        y_pre = y_pre.contiguous(memory_format=torch.channels_last)
+        B, Co, H, W = y_pre.shape
+        M = B * H * W
+        rows = y_pre.permute(0, 2, 3, 1).reshape(M, Co)
+        ops.PROFILER.tag = ("F2", "fwd", M, Co)
+        st = _scratch_zeros(6 * Co, rows)
+        ssum, ssq, scale, shift, mean, rstd = (st[i * Co:(i + 1) * Co] for i in range(6))
+        if training:
+            ops.colstats(rows, ssum, ssq)
+        ops.bn_finalize(ssum, ssq, gamma, beta, rm, rv, scale, shift, mean, rstd, M, meta["eps"], meta["momentum"],
+                        training)
+        out = ops.bn_act_apply(rows, scale, shift, act)
+        ops.PROFILER.tag = None
+        ctx.meta = meta
+        ctx.geom = (B, Co, H, W)
+        ctx.x_needs_grad = x.requires_grad
+        ctx.x_dtype = x.dtype
+        ctx.st = st  # a view of the per-step scratch arena (shared version counter): kept as an attribute
+        ctx.save_for_backward(xc, wc, y_pre, gamma)
+        return out.view(B, H, W, Co).permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, dy):
+        xc, wc, y_pre, gamma = ctx.saved_tensors
+        meta = ctx.meta
+        if not meta["training"]:
+            raise RuntimeError("ConvBnActFn.backward: eval-mode BatchNorm backward is not implemented")
+        B, Co, H, W = ctx.geom
+        M = B * H * W
+        st = ctx.st
+        scale, shift, mean, rstd = (st[i * Co:(i + 1) * Co] for i in range(2, 6))
+        rows = y_pre.permute(0, 2, 3, 1).reshape(M, Co)
+        dyr = dy.to(rows.dtype).contiguous(memory_format=torch.channels_last).permute(0, 2, 3, 1).reshape(M, Co)
+        ops.PROFILER.tag = ("F2", "bwd", M, Co)
+        red = _scratch_zeros(2 * Co, rows)
+        dgamma, dbeta = red[:Co], red[Co:]
+        ops.bn_act_bwd_reduce(dyr, rows, scale, shift, mean, rstd, dgamma, dbeta, meta["act"])
+        dpre = ops.bn_act_bwd_apply(dyr, rows, scale, shift, mean, rstd, gamma.detach(), dgamma, dbeta, meta["act"])
+        ops.PROFILER.tag = None
+        dpre4 = dpre.view(B, H, W, Co).permute(0, 3, 1, 2)
+        dx, dw, _ = torch.ops.aten.convolution_backward(dpre4, xc, wc, None, meta["stride"], meta["padding"], [1, 1],
+                                                        False, [0, 0], 1, [ctx.x_needs_grad, True, False])
+        if dx is not None and dx.dtype != ctx.x_dtype:
+            dx = dx.to(ctx.x_dtype)
+        return dx, dw.float(), dgamma.clone(), dbeta.clone(), None
+
+
+def conv_bn_act(x: Tensor, w: Tensor, gamma: Tensor, beta: Tensor, *, running, stride: int, padding: int, act: str,
+                eps: float, momentum: float, training: bool, dtype: torch.dtype) -> Tensor:
+    meta = dict(running=running, stride=[stride, stride], padding=[padding, padding], act=act, eps=eps,
+                momentum=momentum, training=training, dtype=dtype)
+    return ConvBnActFn.apply(x, w, gamma, beta, meta)
+
+
+
 class LayerNormRowsFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, b, eps):

@@ -3,8 +3,10 @@ Model B (OutlookerFrontGridNet, src/Model_B_OutGridNet.py:11-100), re-stated so 
 self-contained on a box without the reference checkout.  Constructor signatures, attribute names
 and state_dict keys match the reference, so its checkpoints load with strict=True.
 
-Out of the hot-path scope: the 3x3 stem, the 3x3 stride-2 Downsample
-convs, the head BatchNorm + global average pool + classifier stay on cuDNN/cuBLAS through PyTorch.
+SURVEY section 8 row (f2): in the conv -> BatchNorm -> act units of the stem and the Downsample layers only the k x k
+convolution itself is the library's (cuDNN through aten); batch statistics, normalise + activation and their backward
+run on this package's streaming kernels (functional.ConvBnActFn).  The head (BatchNorm on [B, C, 4, 4], global average
+pool, classifier) stays on PyTorch: 16K rows, latency only.
 """
 from __future__ import annotations
 
@@ -14,10 +16,38 @@ from typing import List, Literal
 import torch
 import torch.nn as nn
 
+from . import functional as OF
 from .config import StageCfg, build_stages
-from .modules import GridOnlyBlock, OutGridBlock, OutlookerBlock2d, make_activation
+from .modules import GridOnlyBlock, OutGridBlock, OutlookerBlock2d, _act_name, _compute_dtype, make_activation
 
 DownsampleType = Literal["conv", "pool"]
+
+
+def _conv_bn_act(seq: nn.Sequential, x: torch.Tensor) -> torch.Tensor:
+    """Run a (Conv2d, BatchNorm2d, act) Sequential: fused BatchNorm + activation kernels on CUDA; the plain module chain
+    when a hook sits on one of the three (it must see the tensors the reference would hand it), when the layout is not
+    the fused one (no BatchNorm, conv bias, channel count not a multiple of 8), or off the GPU (construction-time shape
+    checks on CPU; the blocks themselves refuse CPU tensors)."""
+    conv, bn, act = seq[-3], seq[-2], seq[-1]
+    fused = (x.is_cuda and isinstance(conv, nn.Conv2d) and isinstance(bn, nn.BatchNorm2d) and conv.bias is None
+             and conv.groups == 1 and conv.dilation == (1, 1) and conv.padding_mode == "zeros"
+             and conv.stride[0] == conv.stride[1] and conv.padding[0] == conv.padding[1]
+             and conv.out_channels % 8 == 0 and bn.affine and bn.track_running_stats
+             and not any(m._forward_hooks or m._forward_pre_hooks or m._backward_hooks for m in (conv, bn, act)))
+    if not fused:
+        return seq(x)
+    for m in seq[:-3]:  # the AvgPool2d of the "pool" kind
+        x = m(x)
+    training = bn.training
+    if training and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)
+    if training and bn.momentum is None:  # cumulative moving average (nn.BatchNorm2d semantics)
+        momentum = 1.0 / float(bn.num_batches_tracked)
+    else:
+        momentum = bn.momentum if bn.momentum is not None else 0.0
+    return OF.conv_bn_act(x, conv.weight, bn.weight, bn.bias, running=(bn.running_mean, bn.running_var),
+                          stride=conv.stride[0], padding=conv.padding[0], act=_act_name(act), eps=bn.eps,
+                          momentum=momentum, training=training, dtype=_compute_dtype(x))
 
 
 def make_dpr(total_blocks: int, dpr_max: float) -> List[float]:
@@ -37,7 +67,7 @@ class ConvStem(nn.Module):
                                   make_activation(act))
 
     def forward(self, x):
-        return self.stem(x)
+        return _conv_bn_act(self.stem, x)
 
 
 @dataclass(frozen=True)
@@ -68,7 +98,7 @@ class Downsample(nn.Module):
             raise ValueError("cfg.kind must be 'conv' or 'pool'")
 
     def forward(self, x):
-        return self.op(x)
+        return _conv_bn_act(self.op, x)
 
 
 def _with_drop_path(scfg: StageCfg, p: float) -> StageCfg:

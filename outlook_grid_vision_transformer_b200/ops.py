@@ -459,6 +459,27 @@ def bn_bwd_apply(dy, x, mean, rstd, gamma, dgamma, dbeta) -> Tensor:
     return dx
 
 
+def bn_act_apply(x: Tensor, scale: Tensor, shift: Tensor, act: str) -> Tensor:
+    """out = act(scale*x + shift) on rows [M, C]  (the BN + act of stem_head.py:23-32 / downsampling.py:28-65)"""
+    _rows(x, "x")
+    out = torch.empty_like(x)
+    _call("ogv_bn_act_apply", _p(x), _p(scale), _p(shift), _p(out), x.shape[0], x.shape[1], ACT[act], dtype_code(x),
+          _stream())
+    return out
+
+
+def bn_act_bwd_reduce(dy, x, scale, shift, mean, rstd, dgamma, dbeta, act: str) -> None:
+    _call("ogv_bn_act_bwd_reduce", _p(dy), _p(x), _p(scale), _p(shift), _p(mean), _p(rstd), _p(dgamma), _p(dbeta),
+          x.shape[0], x.shape[1], ACT[act], dtype_code(x), _stream())
+
+
+def bn_act_bwd_apply(dy, x, scale, shift, mean, rstd, gamma, dgamma, dbeta, act: str) -> Tensor:
+    dx = torch.empty_like(x)
+    _call("ogv_bn_act_bwd_apply", _p(dy), _p(x), _p(scale), _p(shift), _p(mean), _p(rstd), _p(gamma), _p(dgamma),
+          _p(dbeta), _p(dx), x.shape[0], x.shape[1], ACT[act], dtype_code(x), _stream())
+    return dx
+
+
 # ---------------------------------------------------------------------------------------- MBConv
 def dwconv_fwd(e_pre, scale1, shift1, w, ssum2, ssq2, B, H, W, act: str) -> Tensor:
     d_pre = torch.empty_like(e_pre)

@@ -1,0 +1,115 @@
+"""-m gpu: SURVEY section 8 row f2 -- the conv -> BatchNorm -> act units around the blocks (ConvStem, stem_head.py:23-32;
+Downsample, downsampling.py:28-65) with their BatchNorm + activation forward / backward on this package's kernels,
+against the same nn.Sequential run by PyTorch (the reference's code path for these units): outputs, input / weight /
+BatchNorm gradients, running statistics and the batch counter.  fp32 rtol 1e-3, bf16 (under autocast) rtol 2e-2."""
+import copy
+
+import pytest
+import torch
+import torch.nn as nn
+
+from oracle_cases import assert_close
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _units():
+    from outlook_grid_vision_transformer_b200.model import ConvStem, Downsample, DownsampleConfig
+    return {
+        "stem_3_64": (lambda: ConvStem(3, 64), (5, 3, 32, 32)),
+        "stem_3_24_relu": (lambda: ConvStem(3, 24, act="relu"), (3, 3, 9, 7)),
+        "down_conv_64_128": (lambda: Downsample(64, 128), (4, 64, 16, 16)),
+        "down_conv_odd": (lambda: Downsample(16, 40, DownsampleConfig(kind="conv", act="gelu")), (3, 16, 7, 5)),
+        "down_pool_32_64": (lambda: Downsample(32, 64, DownsampleConfig(kind="pool")), (4, 32, 8, 8)),
+    }
+
+
+def _seq(unit):
+    return unit.stem if hasattr(unit, "stem") else unit.op
+
+
+@pytest.mark.parametrize("name", list(_units()))
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_conv_bn_act_matches_torch_sequential(name, mode):
+    make, shape = _units()[name]
+    torch.manual_seed(3)
+    unit = make().to(DEV).train()
+    with torch.no_grad():
+        bn = _seq(unit)[-2]
+        bn.weight.uniform_(0.5, 1.5)
+        bn.bias.uniform_(-0.5, 0.5)
+        bn.running_mean.uniform_(-0.2, 0.2)
+        bn.running_var.uniform_(0.5, 1.5)
+    ref = copy.deepcopy(_seq(unit))          # plain PyTorch modules, same parameters and buffers
+    rtol = 1e-3 if mode == "fp32" else 2e-2
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(shape, generator=g).to(DEV).contiguous(memory_format=torch.channels_last)
+    x1, x2 = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=mode == "bf16"):
+        y = unit(x1)
+        yr = ref(x2)
+    assert y.shape == yr.shape and y.dtype == yr.dtype
+    dy = torch.randn(y.shape, generator=g).to(DEV).to(y.dtype)
+    y.backward(dy)
+    yr.backward(dy)
+    torch.cuda.synchronize()
+    assert_close(y.float(), yr.float(), rtol, "output")
+    assert_close(x1.grad, x2.grad, rtol, "dx")
+    for (k, p), (_, q) in zip(_seq(unit).named_parameters(), ref.named_parameters()):
+        assert_close(p.grad, q.grad, rtol, f"grad[{k}]", atol=1e-6)
+    for (k, b), (_, q) in zip(_seq(unit).named_buffers(), ref.named_buffers()):
+        if b.is_floating_point():
+            assert_close(b, q, 1e-3 if mode == "fp32" else 5e-3, f"buffer[{k}]")
+        else:
+            assert int(b) == int(q) == 1, k
+
+
+def test_eval_mode_uses_running_statistics():
+    from outlook_grid_vision_transformer_b200.model import Downsample
+    torch.manual_seed(5)
+    unit = Downsample(32, 64).to(DEV)
+    with torch.no_grad():
+        unit.op[1].running_mean.uniform_(-0.3, 0.3)
+        unit.op[1].running_var.uniform_(0.5, 2.0)
+    unit.eval()
+    ref = copy.deepcopy(unit.op)
+    x = torch.randn(3, 32, 8, 8, device=DEV).contiguous(memory_format=torch.channels_last)
+    with torch.no_grad():
+        y, yr = unit(x), ref(x)
+    assert_close(y, yr, 1e-3, "eval output")
+    assert int(unit.op[1].num_batches_tracked) == 0
+    assert torch.equal(unit.op[1].running_mean, ref[1].running_mean)
+
+
+def test_hooks_fall_back_to_the_module_chain():
+    """A forward hook on the conv or the BatchNorm must fire with the tensors the reference would hand it."""
+    from outlook_grid_vision_transformer_b200.model import ConvStem
+    torch.manual_seed(6)
+    unit = ConvStem(3, 32).to(DEV).train()
+    seen = {}
+    def hook(m, i, o):
+        seen["bn_in"] = i[0].shape  # returns None: the output is left alone
+
+    h = unit.stem[1].register_forward_hook(hook)
+    x = torch.randn(2, 3, 8, 8, device=DEV)
+    y = unit(x)
+    h.remove()
+    assert seen["bn_in"] == (2, 32, 8, 8) and y.shape == (2, 32, 8, 8)
+    y2 = unit(x)  # fused again
+    assert_close(y2, y, 1e-3, "fused vs module chain")
+
+
+def test_momentum_none_is_a_cumulative_average():
+    from outlook_grid_vision_transformer_b200.model import ConvStem
+    torch.manual_seed(7)
+    unit = ConvStem(3, 16).to(DEV).train()
+    unit.stem[1].momentum = None
+    ref = copy.deepcopy(unit.stem)
+    for i in range(3):
+        x = torch.randn(4, 3, 8, 8, device=DEV) + i
+        unit(x)
+        ref(x)
+    assert_close(unit.stem[1].running_mean, ref[1].running_mean, 1e-3, "running_mean")
+    assert_close(unit.stem[1].running_var, ref[1].running_var, 1e-3, "running_var")
+    assert int(unit.stem[1].num_batches_tracked) == 3
