@@ -166,6 +166,11 @@ int ogv_bn_bwd_apply(const void* dy, const void* x, const float* mean, const flo
                      const float* dgamma, const float* dbeta, void* dx, long long M, int C, int dtype,
                      void* stream);
 
+/* 3x3 stride-1 pad-1 patches of a channels_last image x[B,H,W,Cin] as GEMM rows cols[B*H*W, Kpad], column
+ * (ky*3+kx)*Cin + ci, zeros outside the image and in columns >= 9*Cin: the stem convolution (stem_head.py:23-32) becomes
+ * ogv_gemm forward and weight gradient. */
+int ogv_im2col3x3(const void* x, void* cols, int B, int H, int W, int Cin, int Kpad, int dtype, void* stream);
+
 /* conv -> BatchNorm -> act units around the blocks (stem_head.py:23-32, downsampling.py:28-65), the BN + act part:
  * out = act(scale*x + shift); backward with g = dy * act'(scale*x + shift) recomputed in both passes:
  * dbeta += sum g, dgamma += sum g*xhat; dx = gamma*rstd*(g - dbeta/n - xhat*dgamma/n). */

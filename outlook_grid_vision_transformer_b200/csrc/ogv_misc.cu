@@ -316,7 +316,67 @@ __global__ void __launch_bounds__(COLREDUCE_THREADS) colstats_kernel(const T* __
   colreduce_finish<2>(acc, outs, nv);
 }
 
+// ------------------------------------------------------------------------------------------------
+// 3x3 stride-1 pad-1 patches of a few-channel channels_last image as GEMM rows: cols[p, (ky*3+kx)*Cin + ci] =
+// x[b, h+ky-1, w+kx-1, ci] (zero outside the image and in the pad columns up to Kpad).  The stem convolution
+// (stem_head.py:23-32, Cin = 3) then runs -- forward and weight gradient -- on the tcgen05 GEMM with K = 32: the image is
+// 6 MB at batch 1024, the patches 67 MB, against 134 MB of output.  Thread = (pixel, 8 patch columns).
+// ------------------------------------------------------------------------------------------------
+template <typename T, int CIN>
+__global__ void im2col3x3_kernel(const T* __restrict__ x, T* __restrict__ cols, int H, int W, unsigned npix) {
+  constexpr int KP = (9 * CIN + 7) / 8 * 8;
+  for (unsigned p = blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += gridDim.x * blockDim.x) {
+    const unsigned w = p % (unsigned)W, t = p / (unsigned)W;
+    const unsigned h = t % (unsigned)H;
+    const T* centre = x + (size_t)p * CIN;
+    float v[KP];
+#pragma unroll
+    for (int k = 9 * CIN; k < KP; ++k) v[k] = 0.f;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+      const bool in = (unsigned)((int)h + dy) < (unsigned)H && (unsigned)((int)w + dx) < (unsigned)W;
+      const T* src = centre + (dy * W + dx) * CIN;
+#pragma unroll
+      for (int ci = 0; ci < CIN; ++ci) v[tap * CIN + ci] = in ? ld1(src + ci) : 0.f;
+    }
+    T* dst = cols + (size_t)p * KP;
+#pragma unroll
+    for (int g = 0; g < KP / 8; ++g) {
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = v[g * 8 + j];
+      st8(dst + g * 8, o);
+    }
+  }
+}
+
 }  // namespace
+
+extern "C" int ogv_im2col3x3(const void* x, void* cols, int B, int H, int W, int Cin, int Kpad, int dtype, void* stream) {
+  OGV_REQUIRE(x && cols && B > 0 && H > 0 && W > 0, "im2col3x3: bad args");
+  OGV_REQUIRE(Cin >= 1 && Cin <= 7, "im2col3x3: Cin=%d (1..7: the patch row must fit one 64-wide K tile)", Cin);
+  OGV_REQUIRE(Kpad == (9 * Cin + 7) / 8 * 8, "im2col3x3: Kpad=%d must be 9*Cin=%d rounded up to 8", Kpad, 9 * Cin);
+  const long long npix = (long long)B * H * W;
+  OGV_REQUIRE(npix < 0x7fffffffLL, "im2col3x3: too many pixels");
+  long long blocks = (npix + 255) / 256;
+  const long long cap = (long long)ogv_num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+#define OGV_IM2COL_CASE(N)                                                                                         \
+  case N:                                                                                                          \
+    im2col3x3_kernel<T, N><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const T*>(x),      \
+                                                                               reinterpret_cast<T*>(cols), H, W,   \
+                                                                               (unsigned)npix);                    \
+    break;
+  OGV_DISPATCH_DTYPE(dtype, T, {
+    switch (Cin) {
+      OGV_IM2COL_CASE(1) OGV_IM2COL_CASE(2) OGV_IM2COL_CASE(3) OGV_IM2COL_CASE(4)
+      OGV_IM2COL_CASE(5) OGV_IM2COL_CASE(6) OGV_IM2COL_CASE(7)
+    }
+    return ogv_check_launch("im2col3x3");
+  });
+#undef OGV_IM2COL_CASE
+}
 
 extern "C" int ogv_nchw_to_nhwc(const void* src, void* dst, int B, int C, int HW, int dtype, void* stream) {
   OGV_REQUIRE(src && dst && B >= 0 && C > 0 && HW > 0, "nchw_to_nhwc: bad args");

@@ -672,10 +672,12 @@ class OutlookCoreFn(torch.autograd.Function):
 # conv -> BatchNorm -> act units around the blocks: ConvStem (stem_head.py:23-32) and Downsample (downsampling.py:28-65)
 # =================================================================================================
 class ConvBnActFn(torch.autograd.Function):
-    """The k x k convolution itself is the library's (cuDNN implicit GEMM through aten, like cuBLAS for a plain GEMM);
-    everything after it -- batch statistics, running-statistics update, normalise + activation, and the whole BatchNorm +
-    activation backward -- runs on this package's streaming kernels over the channels_last rows, saving only the
-    pre-BN conv output (the activation derivative is recomputed in both backward passes)."""
+    """conv -> BatchNorm -> act.  The stem convolution (3x3, stride 1, a few input channels) is patches (ogv_im2col3x3)
+    x tcgen05 GEMM, forward and weight gradient; the Downsample convolutions (3x3 stride 2, C -> 2C) are the library's
+    (cuDNN implicit GEMM through aten, like cuBLAS for a plain GEMM).  Everything after the convolution -- batch
+    statistics, running-statistics update, normalise + activation, and the whole BatchNorm + activation backward -- runs
+    on this package's streaming kernels over the channels_last rows, saving only the pre-BN conv output (the
+    activation derivative is recomputed in both backward passes)."""
 
     @staticmethod
     def forward(ctx, x, w, gamma, beta, meta):
@@ -683,13 +685,30 @@ class ConvBnActFn(torch.autograd.Function):
         stride, padding = meta["stride"], meta["padding"]
         rm, rv = meta["running"]
         xc = x.to(dt).contiguous(memory_format=torch.channels_last)
-        wc = w.detach().to(dt).contiguous(memory_format=torch.channels_last)
-        y_pre = torch.ops.aten.convolution(xc, wc, None, stride, padding, [1, 1], False, [0, 0], 1)
-        y_pre = y_pre.contiguous(memory_format=torch.channels_last)
-        B, Co, H, W = y_pre.shape
-        M = B * H * W
-        rows = y_pre.permute(0, 2, 3, 1).reshape(M, Co)
-        ops.PROFILER.tag = ("F2", "fwd", M, Co)
+        Co, Cin, kh, kw = w.shape
+        B = xc.shape[0]
+        # patches x GEMM when the patch row fits one K tile and nobody needs the input gradient (the network input)
+        as_gemm = (kh == 3 and kw == 3 and stride == [1, 1] and padding == [1, 1] and 9 * Cin <= 64
+                   and not x.requires_grad)
+        ops.PROFILER.tag = ("F2", "fwd", B * xc.shape[2] * xc.shape[3] // (stride[0] * stride[1]), Co)
+        if as_gemm:
+            H, W = xc.shape[2], xc.shape[3]
+            M = B * H * W
+            kpad = (9 * Cin + 7) // 8 * 8
+            cols = ops.im2col3x3(xc, kpad)
+            w2 = torch.zeros((Co, kpad), device=w.device, dtype=dt)
+            w2[:, :9 * Cin] = w.detach().permute(0, 2, 3, 1).reshape(Co, 9 * Cin)
+            rows = _empty((M, Co), cols)
+            ops.gemm(cols, w2, rows)
+            saved = (cols, w2)
+        else:
+            wc = w.detach().to(dt).contiguous(memory_format=torch.channels_last)
+            y_pre = torch.ops.aten.convolution(xc, wc, None, stride, padding, [1, 1], False, [0, 0], 1)
+            y_pre = y_pre.contiguous(memory_format=torch.channels_last)
+            _, _, H, W = y_pre.shape
+            M = B * H * W
+            rows = y_pre.permute(0, 2, 3, 1).reshape(M, Co)
+            saved = (xc, wc)
         st = _scratch_zeros(6 * Co, rows)
         ssum, ssq, scale, shift, mean, rstd = (st[i * Co:(i + 1) * Co] for i in range(6))
         if training:
@@ -700,15 +719,17 @@ class ConvBnActFn(torch.autograd.Function):
         ops.PROFILER.tag = None
         ctx.meta = meta
         ctx.geom = (B, Co, H, W)
+        ctx.as_gemm = as_gemm
+        ctx.w_shape = (Co, Cin, kh, kw)
         ctx.x_needs_grad = x.requires_grad
         ctx.x_dtype = x.dtype
         ctx.st = st  # a view of the per-step scratch arena (shared version counter): kept as an attribute
-        ctx.save_for_backward(xc, wc, y_pre, gamma)
+        ctx.save_for_backward(saved[0], saved[1], rows, gamma)
         return out.view(B, H, W, Co).permute(0, 3, 1, 2)
 
     @staticmethod
     def backward(ctx, dy):
-        xc, wc, y_pre, gamma = ctx.saved_tensors
+        a, wc, rows, gamma = ctx.saved_tensors
         meta = ctx.meta
         if not meta["training"]:
             raise RuntimeError("ConvBnActFn.backward: eval-mode BatchNorm backward is not implemented")
@@ -716,20 +737,27 @@ class ConvBnActFn(torch.autograd.Function):
         M = B * H * W
         st = ctx.st
         scale, shift, mean, rstd = (st[i * Co:(i + 1) * Co] for i in range(2, 6))
-        rows = y_pre.permute(0, 2, 3, 1).reshape(M, Co)
         dyr = dy.to(rows.dtype).contiguous(memory_format=torch.channels_last).permute(0, 2, 3, 1).reshape(M, Co)
         ops.PROFILER.tag = ("F2", "bwd", M, Co)
         red = _scratch_zeros(2 * Co, rows)
         dgamma, dbeta = red[:Co], red[Co:]
         ops.bn_act_bwd_reduce(dyr, rows, scale, shift, mean, rstd, dgamma, dbeta, meta["act"])
         dpre = ops.bn_act_bwd_apply(dyr, rows, scale, shift, mean, rstd, gamma.detach(), dgamma, dbeta, meta["act"])
+        if ctx.as_gemm:
+            _, Cin, kh, kw = ctx.w_shape
+            dw2 = _zeros((Co, a.shape[1]), gamma)
+            ops._wgrad(dpre, a, dw2)  # on the main stream: autograd accumulates the returned view right away
+            dw = dw2[:, :kh * kw * Cin].view(Co, kh, kw, Cin).permute(0, 3, 1, 2)
+            dx = None
+        else:
+            dpre4 = dpre.view(B, H, W, Co).permute(0, 3, 1, 2)
+            dx, dw, _ = torch.ops.aten.convolution_backward(dpre4, a, wc, None, meta["stride"], meta["padding"], [1, 1],
+                                                            False, [0, 0], 1, [ctx.x_needs_grad, True, False])
+            dw = dw.float()
+            if dx is not None and dx.dtype != ctx.x_dtype:
+                dx = dx.to(ctx.x_dtype)
         ops.PROFILER.tag = None
-        dpre4 = dpre.view(B, H, W, Co).permute(0, 3, 1, 2)
-        dx, dw, _ = torch.ops.aten.convolution_backward(dpre4, xc, wc, None, meta["stride"], meta["padding"], [1, 1],
-                                                        False, [0, 0], 1, [ctx.x_needs_grad, True, False])
-        if dx is not None and dx.dtype != ctx.x_dtype:
-            dx = dx.to(ctx.x_dtype)
-        return dx, dw.float(), dgamma.clone(), dbeta.clone(), None
+        return dx, dw, dgamma.clone(), dbeta.clone(), None
 
 
 def conv_bn_act(x: Tensor, w: Tensor, gamma: Tensor, beta: Tensor, *, running, stride: int, padding: int, act: str,

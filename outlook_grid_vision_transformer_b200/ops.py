@@ -459,6 +459,17 @@ def bn_bwd_apply(dy, x, mean, rstd, gamma, dgamma, dbeta) -> Tensor:
     return dx
 
 
+def im2col3x3(x: Tensor, kpad: int) -> Tensor:
+    """channels_last [B, Cin, H, W] -> 3x3 / stride 1 / pad 1 patches as rows [B*H*W, kpad] (column (ky*3+kx)*Cin + ci)."""
+    _require_cuda(x)
+    B, Cin, H, W = x.shape
+    if not x.permute(0, 2, 3, 1).is_contiguous():
+        raise ValueError("im2col3x3 needs a channels_last tensor")
+    cols = torch.empty((B * H * W, kpad), device=x.device, dtype=x.dtype)
+    _call("ogv_im2col3x3", _p(x), _p(cols), B, H, W, Cin, kpad, dtype_code(x), _stream())
+    return cols
+
+
 def bn_act_apply(x: Tensor, scale: Tensor, shift: Tensor, act: str) -> Tensor:
     """out = act(scale*x + shift) on rows [M, C]  (the BN + act of stem_head.py:23-32 / downsampling.py:28-65)"""
     _rows(x, "x")

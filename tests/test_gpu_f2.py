@@ -113,3 +113,50 @@ def test_momentum_none_is_a_cumulative_average():
     assert_close(unit.stem[1].running_mean, ref[1].running_mean, 1e-3, "running_mean")
     assert_close(unit.stem[1].running_var, ref[1].running_var, 1e-3, "running_var")
     assert int(unit.stem[1].num_batches_tracked) == 3
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+@pytest.mark.parametrize("shape", [(2, 3, 5, 7), (3, 1, 4, 4), (2, 4, 9, 3), (1, 7, 6, 6)])
+def test_im2col3x3_is_unfold_bit_exact(shape, dtype):
+    """ogv_im2col3x3 against F.unfold on integer-valued inputs: bit-exact, pad columns zero."""
+    from outlook_grid_vision_transformer_b200 import ops
+    B, C, H, W = shape
+    g = torch.Generator().manual_seed(8)
+    x = torch.randint(-8, 9, shape, generator=g).to(dtype).to(DEV).contiguous(memory_format=torch.channels_last)
+    kpad = (9 * C + 7) // 8 * 8
+    cols = ops.im2col3x3(x, kpad)
+    want = torch.nn.functional.unfold(x.float(), 3, padding=1)            # [B, C*9, H*W], row c*9 + tap
+    want = want.view(B, C, 9, H * W).permute(0, 3, 2, 1).reshape(B * H * W, 9 * C)  # column tap*C + c
+    assert torch.equal(cols[:, :9 * C].float(), want)
+    assert not cols[:, 9 * C:].any()
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_stem_as_patches_gemm(mode):
+    """The network input needs no gradient: the stem convolution runs as patches x tcgen05 GEMM (forward and weight
+    gradient); same outputs / gradients / buffers as the PyTorch module chain."""
+    from outlook_grid_vision_transformer_b200 import functional as OF
+    from outlook_grid_vision_transformer_b200.model import ConvStem
+    torch.manual_seed(9)
+    unit = ConvStem(3, 64).to(DEV).train()
+    ref = copy.deepcopy(unit.stem)
+    rtol = 1e-3 if mode == "fp32" else 2e-2
+    x = torch.randn(6, 3, 32, 32, device=DEV).contiguous(memory_format=torch.channels_last)
+    seen = []
+    orig = OF.ops.im2col3x3
+    OF.ops.im2col3x3 = lambda *a: (seen.append(1), orig(*a))[1]
+    try:
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=mode == "bf16"):
+            y, yr = unit(x), ref(x)
+    finally:
+        OF.ops.im2col3x3 = orig
+    assert seen, "the stem did not take the patches x GEMM path"
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    yr.backward(dy)
+    assert_close(y.float(), yr.float(), rtol, "output")
+    for (k, p), (_, q) in zip(unit.stem.named_parameters(), ref.named_parameters()):
+        assert_close(p.grad, q.grad, rtol, f"grad[{k}]", atol=1e-6)
+    for (k, b), (_, q) in zip(unit.stem.named_buffers(), ref.named_buffers()):
+        if b.is_floating_point():
+            assert_close(b, q, 1e-3 if mode == "fp32" else 5e-3, f"buffer[{k}]")
