@@ -95,28 +95,41 @@ __global__ void __launch_bounds__(IMG_THREADS) mbconv_bwd_stats_kernel(
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const int cv = blockIdx.y * 32 + cx;
   const int b = blockIdx.x;
+  // The loop accumulates the xh-weighted sums against x itself (A2 = sum g*a'*x, A4 = sum a'*x); the last step turns
+  // them into S2 = rstd*(A2 - mean*S1), S4 = rstd*(A4 - mean*S3).  That keeps mean / rstd out of the loop's registers,
+  // which pays for a second set of row registers: the loads of batch i+1 are in flight while batch i is being reduced
+  // (with 4 warps per scheduler and ~300 issue slots of math per batch, load -> math -> load left the SM idle for
+  // most of every DRAM round trip: 48 % of HBM before, measured).
   float acc[5][8];
 #pragma unroll
   for (int q = 0; q < 5; ++q)
 #pragma unroll
     for (int k = 0; k < 8; ++k) acc[q][k] = 0.f;
   if (cv < nv) {
-    float sc[8], sh[8], mu[8], rs[8];
+    float sc[8], sh[8];
     ld8(scale + cv * 8, sc);
     ld8(shift + cv * 8, sh);
-    ld8(mean + cv * 8, mu);
-    ld8(rstd + cv * 8, rs);
     const T* xp = d_pre + ((long long)b * HW) * Cm + cv * 8;
     const T* gp = dd_act + ((long long)b * HW) * Cm + cv * 8;
-    constexpr int U = MBS_U;  // rows in flight per thread
-    for (int p0 = ry; p0 < HW; p0 += IMG_ROWLANES * U) {
-      Raw8<T> rx[U], rg[U];
+    constexpr int U = MBS_U;  // rows per batch
+    constexpr int STEP = IMG_ROWLANES * U;
+    Raw8<T> rx[U], rg[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int p = ry + u * IMG_ROWLANES;
+      if (p < HW) {
+        ld_raw8(xp + (long long)p * Cm, rx[u]);
+        ld_raw8(gp + (long long)p * Cm, rg[u]);
+      }
+    }
+    for (int p0 = ry; p0 < HW; p0 += STEP) {
+      Raw8<T> nx[U], ng[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const int p = p0 + u * IMG_ROWLANES;
+        const int p = p0 + STEP + u * IMG_ROWLANES;
         if (p < HW) {
-          ld_raw8(xp + (long long)p * Cm, rx[u]);
-          ld_raw8(gp + (long long)p * Cm, rg[u]);
+          ld_raw8(xp + (long long)p * Cm, nx[u]);
+          ld_raw8(gp + (long long)p * Cm, ng[u]);
         }
       }
 #pragma unroll
@@ -130,34 +143,55 @@ __global__ void __launch_bounds__(IMG_THREADS) mbconv_bwd_stats_kernel(
             const float uu = OGV_BN_U(k);
             float a, da;
             act_both_t<ACT, FastAct<T>::value>(uu, &a, &da);
-            const float xh = (x[k] - mu[k]) * rs[k];
             const float gda = g[k] * da;
             acc[0][k] = fmaf(g[k], a, acc[0][k]);
             acc[1][k] += gda;
-            acc[2][k] = fmaf(gda, xh, acc[2][k]);
+            acc[2][k] = fmaf(gda, x[k], acc[2][k]);
             acc[3][k] += da;
-            acc[4][k] = fmaf(da, xh, acc[4][k]);
+            acc[4][k] = fmaf(da, x[k], acc[4][k]);
           }
         }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        rx[u] = nx[u];
+        rg[u] = ng[u];
       }
     }
   }
   const long long plane = (long long)B * Cm;
+  float tot[5][8];
 #pragma unroll
   for (int q = 0; q < 5; ++q) {
 #pragma unroll
     for (int k = 0; k < 8; ++k) red[ry][cx][k] = acc[q][k];
     __syncthreads();
-    if (ry == 0 && cv < nv) {
+    if (ry == 0) {
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        float s = 0.f;
+        float sum = 0.f;
 #pragma unroll
-        for (int j = 0; j < IMG_ROWLANES; ++j) s += red[j][cx][k];
-        stats[q * plane + (long long)b * Cm + cv * 8 + k] = s;
+        for (int j = 0; j < IMG_ROWLANES; ++j) sum += red[j][cx][k];
+        tot[q][k] = sum;
       }
     }
     __syncthreads();
+  }
+  if (ry == 0 && cv < nv) {
+    float mu[8], rs[8];
+    ld8(mean + cv * 8, mu);
+    ld8(rstd + cv * 8, rs);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      tot[2][k] = rs[k] * fmaf(-mu[k], tot[1][k], tot[2][k]);
+      tot[4][k] = rs[k] * fmaf(-mu[k], tot[3][k], tot[4][k]);
+    }
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+      float* dst = stats + q * plane + (long long)b * Cm + cv * 8;
+      *reinterpret_cast<float4*>(dst) = make_float4(tot[q][0], tot[q][1], tot[q][2], tot[q][3]);
+      *reinterpret_cast<float4*>(dst + 4) = make_float4(tot[q][4], tot[q][5], tot[q][6], tot[q][7]);
+    }
   }
 }
 

@@ -731,8 +731,6 @@ class ConvBnActFn(torch.autograd.Function):
     def backward(ctx, dy):
         a, wc, rows, gamma = ctx.saved_tensors
         meta = ctx.meta
-        if not meta["training"]:
-            raise RuntimeError("ConvBnActFn.backward: eval-mode BatchNorm backward is not implemented")
         B, Co, H, W = ctx.geom
         M = B * H * W
         st = ctx.st
@@ -742,7 +740,12 @@ class ConvBnActFn(torch.autograd.Function):
         red = _scratch_zeros(2 * Co, rows)
         dgamma, dbeta = red[:Co], red[Co:]
         ops.bn_act_bwd_reduce(dyr, rows, scale, shift, mean, rstd, dgamma, dbeta, meta["act"])
-        dpre = ops.bn_act_bwd_apply(dyr, rows, scale, shift, mean, rstd, gamma.detach(), dgamma, dbeta, meta["act"])
+        if meta["training"]:
+            dpre = ops.bn_act_bwd_apply(dyr, rows, scale, shift, mean, rstd, gamma.detach(), dgamma, dbeta, meta["act"])
+        else:
+            # running statistics: BatchNorm is a fixed affine map, dpre = gamma*rstd * g (no batch-mean terms)
+            zero = _zeros(Co, gamma)
+            dpre = ops.bn_act_bwd_apply(dyr, rows, scale, shift, mean, rstd, gamma.detach(), zero, zero, meta["act"])
         if ctx.as_gemm:
             _, Cin, kh, kw = ctx.w_shape
             dw2 = _zeros((Co, a.shape[1]), gamma)

@@ -75,9 +75,15 @@ def test_eval_mode_uses_running_statistics():
     unit.eval()
     ref = copy.deepcopy(unit.op)
     x = torch.randn(3, 32, 8, 8, device=DEV).contiguous(memory_format=torch.channels_last)
-    with torch.no_grad():
-        y, yr = unit(x), ref(x)
+    x1, x2 = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    y, yr = unit(x1), ref(x2)
     assert_close(y, yr, 1e-3, "eval output")
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    yr.backward(dy)
+    assert_close(x1.grad, x2.grad, 1e-3, "eval dx")
+    for (k, p), (_, q) in zip(unit.op.named_parameters(), ref.named_parameters()):
+        assert_close(p.grad, q.grad, 1e-3, f"eval grad[{k}]", atol=1e-6)
     assert int(unit.op[1].num_batches_tracked) == 0
     assert torch.equal(unit.op[1].running_mean, ref[1].running_mean)
 
