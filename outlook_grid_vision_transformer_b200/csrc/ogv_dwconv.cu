@@ -313,13 +313,18 @@ dwconv_fwd_kernel(const __grid_constant__ CUtensorMap tm_in, const float* __rest
 // smem: raw G slot (T) | fp32 G tile | raw E slot (T) | barriers.  Per tile:
 //   wait G -> convert G to fp32 -> sync -> TMA(next G) -> wait E -> stencil -> sync -> TMA(next E)
 // ------------------------------------------------------------------------------------------------
-template <typename T, int CC, int ACT>
+template <typename T, int CC, int ACT, int TWc, int THc, int NIc>
 __global__ void __launch_bounds__(DW_THREADS, 2)
 dwconv_bwd_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ CUtensorMap tm_e,
                   const float* __restrict__ scale1, const float* __restrict__ shift1, const float* __restrict__ mean1,
                   const float* __restrict__ rstd1, const float* __restrict__ wgt, T* __restrict__ du1,
                   float* __restrict__ dwgt, float* __restrict__ dgamma1, float* __restrict__ dbeta1, const DwGeom g) {
   constexpr int R = 2;
+  // TWc > 0: the tile geometry (columns, rows, images per tile) is a compile-time constant and every tile is full
+  // (W % TW == 0, H % TH == 0, TH % R == 0): shared-memory offsets fold into immediates, the strip decode into shifts,
+  // the row / column validity tests disappear.  ncu on the generic kernel: 60 issued instructions per element for 9
+  // FFMA2, a third of them IMAD / IADD3 / SHF / ISETP / BRA from exactly that bookkeeping.
+  constexpr bool SPEC = TWc > 0;
   constexpr int NTV = CC / 4;
   constexpr int AV = 16 / sizeof(T);
   constexpr int NAV = CC / AV;
@@ -375,14 +380,15 @@ dwconv_bwd_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constan
   float a_db[4] = {0.f, 0.f, 0.f, 0.f}, a_dg[4] = {0.f, 0.f, 0.f, 0.f};
   __syncthreads();
 
-  const int TW2 = g.TW2, TH2 = g.TH2;
-  const int npos = g.NI * TH2 * TW2;
+  const int TW = SPEC ? TWc : g.TW, TH = SPEC ? THc : g.TH, NI = SPEC ? NIc : g.NI;
+  const int TW2 = TW + 2, TH2 = TH + 2;
+  const int npos = NI * TH2 * TW2;
   const uint32_t g_bytes = (uint32_t)npos * CC * sizeof(T);
-  const uint32_t e_bytes = (uint32_t)(g.NI * g.TH * g.TW) * CC * sizeof(T);
-  const int nstrips = (g.TH + R - 1) / R;
-  const DwItems im = dw_items<NTV>(g.TW);
-  const int nrowitems = g.NI * nstrips;
-  const int nitems = nrowitems * g.TW * NTV;
+  const uint32_t e_bytes = (uint32_t)(NI * TH * TW) * CC * sizeof(T);
+  const int nstrips = (TH + R - 1) / R;
+  const DwItems im = dw_items<NTV>(TW);
+  const int nrowitems = NI * nstrips;
+  const int nitems = nrowitems * TW * NTV;
   const int x_fixed = (tid % im.lanes_per_row) / NTV;
   const int sub = tid / im.lanes_per_row;
 
@@ -438,6 +444,7 @@ dwconv_bwd_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constan
       }
       const int step = im.regular ? im.rows_par : DW_THREADS;
       const int last = im.regular ? nrowitems : nitems;
+#pragma unroll 1
       for (int s = im.regular ? sub : tid; s < last; s += step) {
         int x, rowitem;
         if (im.regular) {
@@ -446,29 +453,29 @@ dwconv_bwd_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constan
         } else {
           const int rest = s / NTV;
           rowitem = fdiv(rest, g.d_tw);
-          x = rest - rowitem * g.TW;
+          x = rest - rowitem * TW;
         }
-        const int img = fdiv(rowitem, g.d_ns2);
+        const int img = SPEC ? rowitem / nstrips : fdiv(rowitem, g.d_ns2);
         const int r0 = (rowitem - img * nstrips) * R;
         const int b = b0 + img;
-        if (b >= g.B || w0 + x >= g.W) continue;
+        if (b >= g.B || (!SPEC && w0 + x >= g.W)) continue;
         f32x2 de[R][2], ea[R][2];
         float da[R][4];
         bool rvalid[R];
-        const T* ep = eraw + ((img * g.TH + r0) * g.TW + x) * CC + tv * 4;
+        const T* ep = eraw + ((img * TH + r0) * TW + x) * CC + tv * 4;
         {
           const float4 sc = *reinterpret_cast<const float4*>(&s_par[0][tv * 4]);
           const float4 sh = *reinterpret_cast<const float4*>(&s_par[1][tv * 4]);
           const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
 #pragma unroll
           for (int r = 0; r < R; ++r) {
-            rvalid[r] = (r0 + r < g.TH) && (h0 + r0 + r < g.H);
+            rvalid[r] = SPEC || ((r0 + r < TH) && (h0 + r0 + r < g.H));
             de[r][0] = de[r][1] = ea[r][0] = ea[r][1] = 0ull;
 #pragma unroll
             for (int k = 0; k < 4; ++k) da[r][k] = 0.f;
             if (rvalid[r]) {
               float ev[4], av4[4];
-              ldv<4>(ep + r * g.TW * CC, ev);
+              ldv<4>(ep + r * TW * CC, ev);
 #pragma unroll
               for (int k = 0; k < 4; ++k) act_both_t<ACT, FastAct<T>::value>(fmaf(ev[k], scv[k], shv[k]), &av4[k], &da[r][k]);
               ea[r][0] = pk2(av4[0], av4[1]);
@@ -479,7 +486,7 @@ dwconv_bwd_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constan
         const float* base = gt + ((img * TH2 + r0) * TW2 + x) * CC + tv * 4;
 #pragma unroll
         for (int ry = 0; ry < R + 2; ++ry) {  // gradient row (halo coords) r0 + ry  <->  image row h0 + r0 + ry - 1
-          if (r0 + ry >= TH2) break;
+          if (!SPEC && r0 + ry >= TH2) break;
           ulonglong2 gr[3];
 #pragma unroll
           for (int dx = 0; dx < 3; ++dx) gr[dx] = *reinterpret_cast<const ulonglong2*>(base + (ry * TW2 + dx) * CC);
@@ -504,7 +511,7 @@ dwconv_bwd_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constan
         for (int r = 0; r < R; ++r) {
           if (rvalid[r]) {
             float o[4], ev[4], dv[4];
-            ldv<4>(ep + r * g.TW * CC, ev);  // re-read (smem) instead of carrying it through the stencil
+            ldv<4>(ep + r * TW * CC, ev);  // re-read (smem) instead of carrying it through the stencil
             unpk2(de[r][0], dv[0], dv[1]);
             unpk2(de[r][1], dv[2], dv[3]);
 #pragma unroll
@@ -822,20 +829,23 @@ dwconv_fwd_sweep_pf_kernel(const T* __restrict__ e_pre, const float* __restrict_
 // the persistent grid is sized to exactly one wave (a second, partly filled wave would idle SMs).
 template <typename K>
 int dw_smem_optin(K kernel, int bytes, int* ctas_per_sm) {
-  static int cached_bytes = -1, cached_occ = 0;  // one instance per kernel instantiation
-  if (cached_bytes != bytes) {
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    if (e != cudaSuccess) {
-      ogv_set_error("dwconv: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
-      return OGV_ERR_CUDA;
-    }
-    int occ = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, DW_THREADS, bytes);
-    if (e != cudaSuccess || occ < 1) occ = 1;
-    cached_occ = occ;
-    cached_bytes = bytes;
+  // keyed by the kernel ADDRESS: instantiations that share a signature share this function (and its statics)
+  struct Entry { const void* fn; int bytes, occ; };
+  static Entry cache[32] = {};
+  static int used = 0;
+  const void* fn = reinterpret_cast<const void*>(kernel);
+  for (int i = 0; i < used; ++i)
+    if (cache[i].fn == fn && cache[i].bytes == bytes) { *ctas_per_sm = cache[i].occ; return OGV_OK; }
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) {
+    ogv_set_error("dwconv: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+    return OGV_ERR_CUDA;
   }
-  *ctas_per_sm = cached_occ;
+  int occ = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, DW_THREADS, bytes);
+  if (e != cudaSuccess || occ < 1) occ = 1;
+  if (used < 32) cache[used++] = Entry{fn, bytes, occ};
+  *ctas_per_sm = occ;
   return OGV_OK;
 }
 
@@ -920,6 +930,18 @@ extern "C" int ogv_dwconv_fwd(const void* e_pre, const float* scale1, const floa
   });
 }
 
+#define OGV_DW_BWD_SPEC(TWc, THc, NIc)                                                                              \
+  if (full && g.TW == TWc && g.TH == THc && g.NI == NIc) {                                                          \
+auto kern = dwconv_bwd_kernel<T, CC, ACT, TWc, THc, NIc>;                                                       \
+int occ2 = 1;                                                                                                   \
+if (int rc = dw_smem_optin(kern, smem, &occ2)) return rc;                                                       \
+if (occ2 >= occ) {                                                                                              \
+  kern<<<g.nchunks * g.nworkers, DW_THREADS, smem, (cudaStream_t)stream>>>(                                     \
+      tmg, tme, scale1, shift1, mean1, rstd1, w, reinterpret_cast<T*>(du1), dw, dgamma1, dbeta1, g);            \
+  return ogv_check_launch("dwconv_bwd");                                                                        \
+}                                                                                                               \
+  }
+
 extern "C" int ogv_dwconv_bwd(const void* dd_pre, const void* e_pre, const float* scale1, const float* shift1,
                               const float* mean1, const float* rstd1, const float* w, void* du1, float* dw,
                               float* dgamma1, float* dbeta1, int B, int H, int W, int Cm, int act, int dtype,
@@ -936,13 +958,23 @@ extern "C" int ogv_dwconv_bwd(const void* dd_pre, const void* e_pre, const float
     const int smem = DW_BUF_POS * CC * (int)(sizeof(T) + sizeof(float)) + 2 * 256 * CC * (int)sizeof(T) + 64;
     OGV_DISPATCH_ACT(act, ACT, {
       int occ = 1;
-      if (int rc = dw_smem_optin(dwconv_bwd_kernel<T, CC, ACT>, smem, &occ)) return rc;
+      if (int rc = dw_smem_optin(dwconv_bwd_kernel<T, CC, ACT, 0, 0, 0>, smem, &occ)) return rc;
       DwGeom g;
       if (dw_make_geom(B, H, W, Cm, CC, occ, &g)) { ogv_set_error("dwconv_bwd: cannot tile %dx%d", H, W); return OGV_ERR_UNSUPPORTED; }
       CUtensorMap tmg, tme;
       if (int rc = dw_tmap<T>(&tmg, dd_pre, dtype, g, CC, 1)) return rc;
       if (int rc = dw_tmap<T>(&tme, e_pre, dtype, g, CC, 0)) return rc;
-      dwconv_bwd_kernel<T, CC, ACT><<<g.nchunks * g.nworkers, DW_THREADS, smem, (cudaStream_t)stream>>>(
+      // the 32- and 16-pixel square-image geometries (stages 0-1 of the 32 px configs, 1-2 of the 64 px ones) are compiled
+      // with constant tile shapes; anything else (ragged edges, other sizes) runs the generic instantiation.
+      // OGV_DW_BWD_GENERIC=1: A/B
+      static int generic = -1;
+      if (generic < 0) { const char* e = getenv("OGV_DW_BWD_GENERIC"); generic = (e && e[0] == '1') ? 1 : 0; }
+      const bool full = !generic && W % g.TW == 0 && H % g.TH == 0 && g.TH % 2 == 0;
+      OGV_DW_BWD_SPEC(32, 8, 1)   // 745 -> 610 us at stage 0 of cfg 2
+      OGV_DW_BWD_SPEC(16, 16, 1)  // 394 -> 387 us at stage 1
+      // (8, 8, 3) and (4, 4, 9) measured 2 % / 10 % SLOWER than the generic kernel (the folded offsets let ptxas hoist all
+      // twelve tile loads of an item, 100 bytes of spills at the 128-register cap): not instantiated
+      dwconv_bwd_kernel<T, CC, ACT, 0, 0, 0><<<g.nchunks * g.nworkers, DW_THREADS, smem, (cudaStream_t)stream>>>(
           tmg, tme, scale1, shift1, mean1, rstd1, w, reinterpret_cast<T*>(du1), dw, dgamma1, dbeta1, g);
     });
     return ogv_check_launch("dwconv_bwd");
