@@ -90,7 +90,12 @@ def _outlook_core_ref(va, B, H, W, C, heads):
 
 
 @pytest.mark.parametrize("dt", DT, ids=IDS)
-@pytest.mark.parametrize("B,H,W,C,heads", [(2, 8, 8, 16, 4), (1, 6, 5, 48, 2), (2, 32, 32, 64, 2), (3, 4, 4, 384, 6)])
+@pytest.mark.parametrize("B,H,W,C,heads", [
+    (2, 8, 8, 16, 4), (1, 6, 5, 48, 2), (2, 32, 32, 64, 2), (3, 4, 4, 384, 6),
+    # the tiled bf16 kernels (W in {4, 8, 16, 32}, C % 64 == 0): every stage shape, ragged image groups (B not a multiple
+    # of the images per tile), heights that are not a multiple of the tile rows, 16- / 32- / 64- / 128-wide heads
+    (3, 16, 16, 128, 4), (5, 8, 8, 256, 8), (2, 12, 16, 64, 4), (9, 5, 8, 64, 1), (2, 20, 32, 128, 2), (11, 4, 4, 128, 1),
+    (1, 3, 4, 64, 2), (2, 16, 16, 64, 2)])
 def test_outlook_core_fwd_bwd(B, H, W, C, heads, dt):
     from outlook_grid_vision_transformer_b200 import ops
     from outlook_grid_vision_transformer_b200.functional import outlook_npad
@@ -112,20 +117,23 @@ def test_outlook_core_fwd_bwd(B, H, W, C, heads, dt):
     assert float(dva[:, C + 9 * heads:].abs().sum()) == 0.0, "padding columns must be zero"
 
 
-def test_outlook_core_integer_indexing_bit_exact():
+@pytest.mark.parametrize("B,H,W,C,heads,dt", [(1, 5, 6, 8, 1, torch.float32), (3, 9, 8, 64, 2, torch.bfloat16),
+                                              (2, 32, 32, 64, 2, torch.bfloat16), (9, 4, 4, 128, 2, torch.bfloat16)],
+                         ids=["generic_fp32", "tiled_w8", "tiled_w32", "tiled_w4"])
+def test_outlook_core_integer_indexing_bit_exact(B, H, W, C, heads, dt):
     """One-hot attention (huge logit on one tap) with integer v: the gather must pick exactly v[p + d_t]."""
     from outlook_grid_vision_transformer_b200 import ops
     from outlook_grid_vision_transformer_b200.functional import outlook_npad
-    B, H, W, C, heads = 1, 5, 6, 8, 1
     npad = outlook_npad(C, heads)
     M = B * H * W
     v = torch.arange(1, M * C + 1, dtype=torch.float32).reshape(M, C).remainder(97) + 1
     for t in range(9):
         va = torch.zeros(M, npad)
         va[:, :C] = v
-        va[:, C:C + 9] = -1e4
-        va[:, C + t] = 1e4
-        y = ops.outlook_core_fwd(dev(va), B, H, W, C, heads).cpu()
+        va[:, C:C + 9 * heads] = -1e4
+        for hh in range(heads):
+            va[:, C + 9 * hh + t] = 1e4
+        y = ops.outlook_core_fwd(dev(va.to(dt)), B, H, W, C, heads).float().cpu()
         ki, kj = divmod(t, 3)
         want = O.shift2d(v.reshape(B, H, W, C), ki - 1, kj - 1).reshape(M, C)
         assert torch.equal(y, want), f"tap {t}"
