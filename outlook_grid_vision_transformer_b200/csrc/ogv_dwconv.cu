@@ -852,6 +852,220 @@ int dw_smem_optin(K kernel, int bytes, int* ctas_per_sm) {
 template <typename T>
 constexpr int dw_cc() { return 64 / (int)sizeof(T); }  // 64-byte channel chunk per position
 
+// ------------------------------------------------------------------------------------------------
+// forward, TMA tile + register-window walkers (bf16, W in {4, 8, 16, 32}, Cm % 64 == 0: every stage of the model
+// configs).  A persistent CTA owns a 64-channel chunk and walks (image group, row band) tiles; the halo tile of step
+// i+1 is in flight (cp.async.bulk.tensor.4d, zero-filled borders) while step i is computed, so no thread ever waits
+// for DRAM -- the sweep kernel above is latency-bound at 16 warps per SM.  Every thread is a walker: two adjacent
+// columns x four channels, moving down the band with the 3 x 4 window of ACTIVATED inputs in registers: one new row
+// (4 LDS.64, 16 BN-affine + activation) per 8 outputs, tap weights in registers, 36 FFMA2 per step.
+// ------------------------------------------------------------------------------------------------
+constexpr int DWW_CC = 64;
+template <int W_> struct DwwShape;
+template <> struct DwwShape<32> { static constexpr int NI = 1, NSB = 1, TRS = 8; };
+template <> struct DwwShape<16> { static constexpr int NI = 1, NSB = 2, TRS = 8; };
+template <> struct DwwShape<8> { static constexpr int NI = 4, NSB = 1, TRS = 8; };
+template <> struct DwwShape<4> { static constexpr int NI = 8, NSB = 1, TRS = 4; };
+
+struct DwwGeom {
+  int B, H, Cm, bands, ntiles, nchunks, nworkers;
+};
+
+template <int ACT, int W_>
+__global__ void __launch_bounds__(DW_THREADS, 2)
+dwconv_fwd_walk_kernel(const __grid_constant__ CUtensorMap tm_in, const float* __restrict__ scale1,
+                       const float* __restrict__ shift1, const float* __restrict__ wgt, bf16* __restrict__ d_pre,
+                       float* __restrict__ sum2, float* __restrict__ sumsq2, const DwwGeom g) {
+  using S = DwwShape<W_>;
+  constexpr int NI = S::NI, NSB = S::NSB, TRS = S::TRS, TRT = TRS * NSB;
+  constexpr int W2 = W_ + 2, TR2 = TRT + 2;
+  constexpr int TILE_ELEMS = NI * TR2 * W2 * DWW_CC;
+  constexpr int ROW = W2 * DWW_CC;
+  extern __shared__ __align__(128) uint8_t dsm[];
+  bf16* const slot0 = reinterpret_cast<bf16*>(dsm);
+  __shared__ uint64_t bar[2];
+  __shared__ float s_sum[DWW_CC], s_sq[DWW_CC];
+
+  const int tid = threadIdx.x;
+  const int chunk = blockIdx.x % g.nchunks;
+  const int worker = blockIdx.x / g.nchunks;
+  const int c0 = chunk * DWW_CC;
+  const int cg = tid % 16;
+  const int xp = (tid / 16) % (W_ / 2);
+  const int grp = tid / (8 * W_);
+  const int img = grp / NSB, rs = (grp % NSB) * TRS;
+  const int x0 = xp * 2;
+  const int c = c0 + cg * 4;
+
+  if (tid < DWW_CC) { s_sum[tid] = 0.f; s_sq[tid] = 0.f; }
+  if (tid == 0) {
+    ptx::tma_prefetch_desc(&tm_in);
+    ptx::mbar_init(&bar[0], 1);
+    ptx::mbar_init(&bar[1], 1);
+    ptx::fence_barrier_init();
+  }
+  // tap weights and BN1 affine of the thread's four channels, as channel pairs
+  f32x2 w2[9][2], sc2[2], sh2[2];
+  {
+    float wv[4][9];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int t = 0; t < 9; ++t) wv[k][t] = wgt[(long long)(c + k) * 9 + t];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      w2[t][0] = pk2(wv[0][t], wv[1][t]);
+      w2[t][1] = pk2(wv[2][t], wv[3][t]);
+    }
+    const float4 sc = *reinterpret_cast<const float4*>(scale1 + c);
+    const float4 sh = *reinterpret_cast<const float4*>(shift1 + c);
+    sc2[0] = pk2(sc.x, sc.y); sc2[1] = pk2(sc.z, sc.w);
+    sh2[0] = pk2(sh.x, sh.y); sh2[1] = pk2(sh.z, sh.w);
+  }
+  float st_s[4] = {0.f, 0.f, 0.f, 0.f}, st_q[4] = {0.f, 0.f, 0.f, 0.f};
+  const bool col_ok[4] = {x0 >= 1, true, true, x0 + 2 < W_};
+  __syncthreads();
+
+  auto tile_coords = [&](int t, int& b0, int& r0) {
+    const int bgrp = t / g.bands;
+    b0 = bgrp * NI;
+    r0 = (t - bgrp * g.bands) * TRT;
+  };
+  int t = worker;
+  if (tid == 0 && t < g.ntiles) {
+    int b0, r0;
+    tile_coords(t, b0, r0);
+    ptx::mbar_arrive_expect_tx(&bar[0], (uint32_t)(TILE_ELEMS * sizeof(bf16)));
+    ptx::tma_load_4d(slot0, &tm_in, &bar[0], c0, -1, r0 - 1, b0);
+  }
+  for (int it = 0; t < g.ntiles; t += g.nworkers, ++it) {
+    int b0, r0;
+    tile_coords(t, b0, r0);
+    const int sl = it & 1;
+    const int tn = t + g.nworkers;
+    // the other slot was last read in iteration it-1, which every thread left through the closing barrier
+    if (tid == 0 && tn < g.ntiles) {
+      int nb0, nr0;
+      tile_coords(tn, nb0, nr0);
+      ptx::mbar_arrive_expect_tx(&bar[sl ^ 1], (uint32_t)(TILE_ELEMS * sizeof(bf16)));
+      ptx::tma_load_4d(slot0 + (sl ^ 1) * TILE_ELEMS, &tm_in, &bar[sl ^ 1], c0, -1, nr0 - 1, nb0);
+    }
+    ptx::mbar_wait(&bar[sl], (it >> 1) & 1);
+    const int b = b0 + img;
+    if (b < g.B) {
+      const bf16* tcol = slot0 + sl * TILE_ELEMS + ((img * TR2 + rs) * W2 + x0) * DWW_CC + cg * 4;
+      const int h0 = r0 + rs;  // image row of the walker's first output; tile row j <-> image row h0 - 1 + j
+      bf16* out = d_pre + (((long long)b * g.H + h0) * W_ + x0) * g.Cm + c;
+      const long long row_stride = (long long)W_ * g.Cm;
+      f32x2 win[3][4][2];
+      auto load_row = [&](int j, f32x2 (&row)[4][2]) {
+        const int h = h0 - 1 + j;
+        const bool rok = h >= 0 && h < g.H;
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          const uint2 u = *reinterpret_cast<const uint2*>(tcol + j * ROW + cc * DWW_CC);
+          const f32x2 x01 = pk2(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u));
+          const f32x2 x23 = pk2(__uint_as_float(u.y << 16), __uint_as_float(u.y & 0xffff0000u));
+          float a0, a1, a2, a3;
+          unpk2(fma2(x01, sc2[0], sh2[0]), a0, a1);
+          unpk2(fma2(x23, sc2[1], sh2[1]), a2, a3);
+          const bool ok = rok && col_ok[cc];  // outside the image the conv input is ZERO, not act(shift)
+          a0 = ok ? act_apply_t<ACT, true>(a0) : 0.f;
+          a1 = ok ? act_apply_t<ACT, true>(a1) : 0.f;
+          a2 = ok ? act_apply_t<ACT, true>(a2) : 0.f;
+          a3 = ok ? act_apply_t<ACT, true>(a3) : 0.f;
+          row[cc][0] = pk2(a0, a1);
+          row[cc][1] = pk2(a2, a3);
+        }
+      };
+      load_row(0, win[0]);
+      load_row(1, win[1]);
+#pragma unroll
+      for (int j = 0; j < TRS; ++j) {
+        load_row(j + 2, win[(j + 2) % 3]);
+        f32x2 acc[2][2] = {{0ull, 0ull}, {0ull, 0ull}};
+#pragma unroll
+        for (int t9 = 0; t9 < 9; ++t9) {
+          const int r = (j + t9 / 3) % 3;
+#pragma unroll
+          for (int p = 0; p < 2; ++p) {
+            acc[p][0] = fma2(w2[t9][0], win[r][t9 % 3 + p][0], acc[p][0]);
+            acc[p][1] = fma2(w2[t9][1], win[r][t9 % 3 + p][1], acc[p][1]);
+          }
+        }
+        if (h0 + j < g.H) {
+#pragma unroll
+          for (int p = 0; p < 2; ++p) {
+            float f[4];
+            unpk2(acc[p][0], f[0], f[1]);
+            unpk2(acc[p][1], f[2], f[3]);
+            const __nv_bfloat162 h01 = __floats2bfloat162_rn(f[0], f[1]), h23 = __floats2bfloat162_rn(f[2], f[3]);
+            *reinterpret_cast<uint2*>(out + j * row_stride + p * g.Cm) =
+                make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+            // statistics of the values as stored
+            const float2 s01 = __bfloat1622float2(h01), s23 = __bfloat1622float2(h23);
+            st_s[0] += s01.x; st_q[0] = fmaf(s01.x, s01.x, st_q[0]);
+            st_s[1] += s01.y; st_q[1] = fmaf(s01.y, s01.y, st_q[1]);
+            st_s[2] += s23.x; st_q[2] = fmaf(s23.x, s23.x, st_q[2]);
+            st_s[3] += s23.y; st_q[3] = fmaf(s23.y, s23.y, st_q[3]);
+          }
+        }
+      }
+    }
+    __syncthreads();  // every walker is done with slot `sl` before the next iteration's TMA overwrites it
+  }
+  if (sum2) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      // fold the 16 / W_ * ... walkers that share a channel inside the warp first (lanes cg, cg + 16)
+      float a = st_s[k] + __shfl_xor_sync(0xffffffffu, st_s[k], 16);
+      float q = st_q[k] + __shfl_xor_sync(0xffffffffu, st_q[k], 16);
+      if ((tid & 16) == 0) {
+        atomicAdd(&s_sum[cg * 4 + k], a);
+        atomicAdd(&s_sq[cg * 4 + k], q);
+      }
+    }
+    __syncthreads();
+    if (tid < DWW_CC) {
+      atomicAdd(sum2 + c0 + tid, s_sum[tid]);
+      if (sumsq2) atomicAdd(sumsq2 + c0 + tid, s_sq[tid]);
+    }
+  }
+}
+
+template <int ACT, int W_>
+int dww_launch(const void* e_pre, const float* scale1, const float* shift1, const float* w, void* d_pre, float* sum2,
+               float* sumsq2, int B, int H, int Cm, cudaStream_t st) {
+  using S = DwwShape<W_>;
+  constexpr int TRT = S::TRS * S::NSB;
+  constexpr int TILE_BYTES = S::NI * (TRT + 2) * (W_ + 2) * DWW_CC * 2;
+  const int smem = 2 * TILE_BYTES;
+  auto kern = dwconv_fwd_walk_kernel<ACT, W_>;
+  int occ = 1;
+  if (int rc = dw_smem_optin(kern, smem, &occ)) return rc;
+  DwwGeom g;
+  g.B = B; g.H = H; g.Cm = Cm;
+  g.bands = (H + TRT - 1) / TRT;
+  const long long nt = (long long)((B + S::NI - 1) / S::NI) * g.bands;
+  if (nt > 0x7fffffffLL) { ogv_set_error("dwconv_fwd: too many tiles"); return OGV_ERR_UNSUPPORTED; }
+  g.ntiles = (int)nt;
+  g.nchunks = Cm / DWW_CC;
+  long long want = ((long long)ogv_num_sms() * occ) / g.nchunks;
+  if (want > nt) want = nt;
+  if (want < 1) want = 1;
+  g.nworkers = (int)want;
+  CUtensorMap tm;
+  {
+    unsigned long long dims[4] = {(unsigned long long)Cm, (unsigned long long)W_, (unsigned long long)H, (unsigned long long)B};
+    unsigned long long str[3] = {(unsigned long long)Cm * 2, (unsigned long long)W_ * Cm * 2, (unsigned long long)H * W_ * Cm * 2};
+    unsigned box[4] = {(unsigned)DWW_CC, (unsigned)(W_ + 2), (unsigned)(TRT + 2), (unsigned)S::NI};
+    if (int rc = ogv_make_tmap(&tm, e_pre, OGV_BF16, 4, dims, str, box, 0)) return rc;
+  }
+  kern<<<g.nchunks * g.nworkers, DW_THREADS, smem, st>>>(tm, scale1, shift1, w, reinterpret_cast<bf16*>(d_pre), sum2,
+                                                         sumsq2, g);
+  return ogv_check_launch("dwconv_fwd");
+}
+
 }  // namespace
 
 extern "C" int ogv_dwconv_fwd(const void* e_pre, const float* scale1, const float* shift1, const float* w,
@@ -868,7 +1082,19 @@ extern "C" int ogv_dwconv_fwd(const void* e_pre, const float* scale1, const floa
     // measured (stage shapes of cfg 2): the ring does NOT help -- 549 vs 519 us at stage 0: the sweep is bound by its
     // ~30 issued instructions per output (halo rows make it activate every input twice), not by load latency.  The
     // plain sweep stays the default; OGV_DW_FWD=pf / tile select the other two for A/B runs.
-    variant = (e && e[0] == 't') ? 1 : ((e && e[0] == 'p') ? 2 : 0);
+    variant = (e && e[0] == 't') ? 1 : ((e && e[0] == 'p') ? 2 : ((e && e[0] == 's') ? 0 : 3));
+  }
+  if (variant == 3 && dtype == OGV_BF16 && (W == 4 || W == 8 || W == 16 || W == 32) && Cm % DWW_CC == 0 &&
+      (reinterpret_cast<uintptr_t>(scale1) & 15) == 0 && (reinterpret_cast<uintptr_t>(shift1) & 15) == 0) {
+    cudaStream_t st = (cudaStream_t)stream;
+    OGV_DISPATCH_ACT(act, ACT, {
+      switch (W) {
+        case 32: return dww_launch<ACT, 32>(e_pre, scale1, shift1, w, d_pre, sum2, sumsq2, B, H, Cm, st);
+        case 16: return dww_launch<ACT, 16>(e_pre, scale1, shift1, w, d_pre, sum2, sumsq2, B, H, Cm, st);
+        case 8: return dww_launch<ACT, 8>(e_pre, scale1, shift1, w, d_pre, sum2, sumsq2, B, H, Cm, st);
+        default: return dww_launch<ACT, 4>(e_pre, scale1, shift1, w, d_pre, sum2, sumsq2, B, H, Cm, st);
+      }
+    });
   }
   if (variant == 2) {
     constexpr int RR = 2, KD = 6;
@@ -895,7 +1121,7 @@ extern "C" int ogv_dwconv_fwd(const void* e_pre, const float* scale1, const floa
       return ogv_check_launch("dwconv_fwd");
     });
   }
-  if (variant == 0) {
+  if (variant == 0 || variant == 3) {
     constexpr int RR = 2;
     const int bands = (H + RR - 1) / RR;
     const long long nb = (long long)B * bands;

@@ -184,7 +184,11 @@ def _dw_ref(e_pre, sc, sh, w, B, H, W):
 
 @pytest.mark.parametrize("dt", DT, ids=IDS)
 @pytest.mark.parametrize("B,H,W,Cm", [(3, 8, 8, 32), (2, 32, 32, 64), (5, 4, 4, 96), (2, 16, 16, 40), (1, 5, 7, 96),
-                                      (2, 64, 64, 32), (300, 32, 32, 32)])
+                                      (2, 64, 64, 32), (300, 32, 32, 32),
+                                      # the TMA-tile walker forward (bf16, W in {4, 8, 16, 32}, Cm % 64 == 0): stage shapes,
+                                      # ragged image groups, heights that are not a multiple of the tile rows, many tiles per CTA
+                                      (3, 32, 32, 256), (2, 16, 16, 512), (5, 8, 8, 128), (11, 4, 4, 192), (2, 12, 16, 64),
+                                      (9, 5, 8, 64), (1, 3, 4, 64), (700, 8, 8, 64)])
 def test_dwconv_fwd_bwd(B, H, W, Cm, dt):
     from outlook_grid_vision_transformer_b200 import ops
     torch.manual_seed(B + H + Cm)
