@@ -1066,6 +1066,199 @@ int dww_launch(const void* e_pre, const float* scale1, const float* shift1, cons
   return ogv_check_launch("dwconv_fwd");
 }
 
+// ------------------------------------------------------------------------------------------------
+// backward, TMA tiles + register-window walkers (bf16, W in {4, 8, 16, 32}, Cm % 32 == 0).  Same structure as the
+// forward walker; a thread owns two adjacent columns x TWO channels (one fp32 pair) so that the 9 tap weights, the 9
+// filter-gradient accumulators and the 3 x 4 gradient window fit in registers together (four channels need 136).
+// Per step: window element (i, k) = G[q + (i-1, k-1)] carries weight w[8 - (3i+k)] into de[q] and a[q] into
+// dw[8 - (3i+k)]; du1 = de * act'(u1), dbeta1 += du1, dgamma1 += du1 * xhat (x-form, folded with mean / rstd at the end).
+// The gradient tile needs no masks at all (TMA zero fill); rows / images outside the tensor are skipped per warp.
+// ------------------------------------------------------------------------------------------------
+constexpr int DWB_CC = 32;
+
+template <int ACT, int W_>
+__global__ void __launch_bounds__(DW_THREADS, 2)
+dwconv_bwd_walk_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ CUtensorMap tm_e,
+                       const float* __restrict__ scale1, const float* __restrict__ shift1,
+                       const float* __restrict__ mean1, const float* __restrict__ rstd1, const float* __restrict__ wgt,
+                       bf16* __restrict__ du1, float* __restrict__ dwgt, float* __restrict__ dgamma1,
+                       float* __restrict__ dbeta1, const DwwGeom g) {
+  using S = DwwShape<W_>;
+  constexpr int NI = S::NI, NSB = S::NSB, TRS = S::TRS, TRT = TRS * NSB;
+  constexpr int W2 = W_ + 2, TR2 = TRT + 2;
+  constexpr int G_ELEMS = NI * TR2 * W2 * DWB_CC, E_ELEMS = NI * TRT * W_ * DWB_CC;
+  constexpr int SLOT = G_ELEMS + E_ELEMS;
+  constexpr int GROW = W2 * DWB_CC, EROW = W_ * DWB_CC;
+  extern __shared__ __align__(128) uint8_t dsm[];
+  bf16* const slot0 = reinterpret_cast<bf16*>(dsm);
+  __shared__ uint64_t bar[2];
+  __shared__ float s_dw[DWB_CC * 9], s_db[DWB_CC], s_dg[DWB_CC];
+
+  const int tid = threadIdx.x;
+  const int chunk = blockIdx.x % g.nchunks;
+  const int worker = blockIdx.x / g.nchunks;
+  const int c0 = chunk * DWB_CC;
+  const int cg = tid % 16;
+  const int xp = (tid / 16) % (W_ / 2);
+  const int grp = tid / (8 * W_);
+  const int img = grp / NSB, rs = (grp % NSB) * TRS;
+  const int x0 = xp * 2;
+  const int c = c0 + cg * 2;
+
+  for (int i = tid; i < DWB_CC * 9; i += DW_THREADS) s_dw[i] = 0.f;
+  if (tid < DWB_CC) { s_db[tid] = 0.f; s_dg[tid] = 0.f; }
+  if (tid == 0) {
+    ptx::tma_prefetch_desc(&tm_g);
+    ptx::tma_prefetch_desc(&tm_e);
+    ptx::mbar_init(&bar[0], 1);
+    ptx::mbar_init(&bar[1], 1);
+    ptx::fence_barrier_init();
+  }
+  f32x2 wf[9];  // wf[s] = w[8 - s]: the weight window element s = 3i + k carries
+#pragma unroll
+  for (int s9 = 0; s9 < 9; ++s9) wf[s9] = pk2(wgt[(long long)c * 9 + 8 - s9], wgt[(long long)(c + 1) * 9 + 8 - s9]);
+  const f32x2 sc2 = pk2(scale1[c], scale1[c + 1]), sh2 = pk2(shift1[c], shift1[c + 1]);
+  f32x2 dwa[9];  // dwa[s] accumulates dw[8 - s]
+#pragma unroll
+  for (int s9 = 0; s9 < 9; ++s9) dwa[s9] = 0ull;
+  f32x2 a_db = 0ull, a_dg = 0ull;
+  __syncthreads();
+
+  auto tile_coords = [&](int t, int& b0, int& r0) {
+    const int bgrp = t / g.bands;
+    b0 = bgrp * NI;
+    r0 = (t - bgrp * g.bands) * TRT;
+  };
+  auto issue = [&](int t, int sl) {
+    int b0, r0;
+    tile_coords(t, b0, r0);
+    bf16* dst = slot0 + sl * SLOT;
+    ptx::mbar_arrive_expect_tx(&bar[sl], (uint32_t)(SLOT * sizeof(bf16)));
+    ptx::tma_load_4d(dst, &tm_g, &bar[sl], c0, -1, r0 - 1, b0);
+    ptx::tma_load_4d(dst + G_ELEMS, &tm_e, &bar[sl], c0, 0, r0, b0);
+  };
+  int t = worker;
+  if (tid == 0 && t < g.ntiles) issue(t, 0);
+  for (int it = 0; t < g.ntiles; t += g.nworkers, ++it) {
+    int b0, r0;
+    tile_coords(t, b0, r0);
+    const int sl = it & 1;
+    if (tid == 0 && t + g.nworkers < g.ntiles) issue(t + g.nworkers, sl ^ 1);
+    ptx::mbar_wait(&bar[sl], (it >> 1) & 1);
+    const int b = b0 + img;
+    if (b < g.B) {
+      const bf16* gcol = slot0 + sl * SLOT + ((img * TR2 + rs) * W2 + x0) * DWB_CC + cg * 2;
+      const bf16* ecol = slot0 + sl * SLOT + G_ELEMS + ((img * TRT + rs) * W_ + x0) * DWB_CC + cg * 2;
+      const int h0 = r0 + rs;
+      bf16* out = du1 + (((long long)b * g.H + h0) * W_ + x0) * g.Cm + c;
+      const long long row_stride = (long long)W_ * g.Cm;
+      f32x2 win[3][4];
+      auto load_row = [&](int j, f32x2 (&row)[4]) {
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          const uint32_t u = *reinterpret_cast<const uint32_t*>(gcol + j * GROW + cc * DWB_CC);
+          row[cc] = pk2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+        }
+      };
+      load_row(0, win[0]);
+      load_row(1, win[1]);
+#pragma unroll
+      for (int j = 0; j < TRS; ++j) {
+        load_row(j + 2, win[(j + 2) % 3]);
+        if (h0 + j < g.H) {  // warp-uniform: the lanes of a warp share (image, row)
+#pragma unroll
+          for (int p = 0; p < 2; ++p) {
+            const uint32_t eu = *reinterpret_cast<const uint32_t*>(ecol + j * EROW + p * DWB_CC);
+            const f32x2 ev = pk2(__uint_as_float(eu << 16), __uint_as_float(eu & 0xffff0000u));
+            float u0, u1, a0, a1, d0, d1;
+            unpk2(fma2(ev, sc2, sh2), u0, u1);
+            act_both_t<ACT, true>(u0, &a0, &d0);
+            act_both_t<ACT, true>(u1, &a1, &d1);
+            const f32x2 ea = pk2(a0, a1);
+            f32x2 de = 0ull;
+#pragma unroll
+            for (int s9 = 0; s9 < 9; ++s9) {
+              const f32x2 gv = win[(j + s9 / 3) % 3][s9 % 3 + p];
+              de = fma2(wf[s9], gv, de);
+              dwa[s9] = fma2(ea, gv, dwa[s9]);
+            }
+            const f32x2 o = mul2(de, pk2(d0, d1));
+            float o0, o1;
+            unpk2(o, o0, o1);
+            const __nv_bfloat162 ob = __floats2bfloat162_rn(o0, o1);
+            *reinterpret_cast<uint32_t*>(out + j * row_stride + p * g.Cm) = *reinterpret_cast<const uint32_t*>(&ob);
+            a_db = add2(a_db, o);
+            a_dg = fma2(o, ev, a_dg);  // sum o*e; xhat = (e - mean)*rstd is folded in at the end
+          }
+        }
+      }
+    }
+    __syncthreads();  // slot `sl` is free for the TMA issued at the top of the next iteration
+  }
+  // fold: lanes (cg, cg + 16) of a warp share the channel pair; then shared-memory atomics, one global flush per CTA
+  {
+    float v[22];
+#pragma unroll
+    for (int s9 = 0; s9 < 9; ++s9) unpk2(dwa[s9], v[2 * s9], v[2 * s9 + 1]);
+    unpk2(a_db, v[18], v[19]);
+    unpk2(a_dg, v[20], v[21]);
+#pragma unroll
+    for (int i = 0; i < 22; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], 16);
+    if ((tid & 16) == 0) {
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int ch = cg * 2 + k;
+#pragma unroll
+        for (int s9 = 0; s9 < 9; ++s9) atomicAdd(&s_dw[ch * 9 + 8 - s9], v[2 * s9 + k]);
+        atomicAdd(&s_db[ch], v[18 + k]);
+        atomicAdd(&s_dg[ch], rstd1[c0 + ch] * (v[20 + k] - mean1[c0 + ch] * v[18 + k]));
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < DWB_CC * 9; i += DW_THREADS) atomicAdd(dwgt + (long long)c0 * 9 + i, s_dw[i]);
+  if (tid < DWB_CC) {
+    atomicAdd(dbeta1 + c0 + tid, s_db[tid]);
+    atomicAdd(dgamma1 + c0 + tid, s_dg[tid]);
+  }
+}
+
+template <int ACT, int W_>
+int dwb_walk_launch(const void* dd_pre, const void* e_pre, const float* scale1, const float* shift1, const float* mean1,
+                    const float* rstd1, const float* w, void* du1, float* dw, float* dgamma1, float* dbeta1, int B, int H,
+                    int Cm, cudaStream_t st) {
+  using S = DwwShape<W_>;
+  constexpr int TRT = S::TRS * S::NSB;
+  constexpr int SLOT_BYTES = (S::NI * (TRT + 2) * (W_ + 2) + S::NI * TRT * W_) * DWB_CC * 2;
+  const int smem = 2 * SLOT_BYTES;
+  auto kern = dwconv_bwd_walk_kernel<ACT, W_>;
+  int occ = 1;
+  if (int rc = dw_smem_optin(kern, smem, &occ)) return rc;
+  DwwGeom g;
+  g.B = B; g.H = H; g.Cm = Cm;
+  g.bands = (H + TRT - 1) / TRT;
+  const long long nt = (long long)((B + S::NI - 1) / S::NI) * g.bands;
+  if (nt > 0x7fffffffLL) { ogv_set_error("dwconv_bwd: too many tiles"); return OGV_ERR_UNSUPPORTED; }
+  g.ntiles = (int)nt;
+  g.nchunks = Cm / DWB_CC;
+  long long want = ((long long)ogv_num_sms() * occ) / g.nchunks;
+  if (want > nt) want = nt;
+  if (want < 1) want = 1;
+  g.nworkers = (int)want;
+  CUtensorMap tmg, tme;
+  {
+    unsigned long long dims[4] = {(unsigned long long)Cm, (unsigned long long)W_, (unsigned long long)H, (unsigned long long)B};
+    unsigned long long str[3] = {(unsigned long long)Cm * 2, (unsigned long long)W_ * Cm * 2, (unsigned long long)H * W_ * Cm * 2};
+    unsigned boxg[4] = {(unsigned)DWB_CC, (unsigned)(W_ + 2), (unsigned)(TRT + 2), (unsigned)S::NI};
+    unsigned boxe[4] = {(unsigned)DWB_CC, (unsigned)W_, (unsigned)TRT, (unsigned)S::NI};
+    if (int rc = ogv_make_tmap(&tmg, dd_pre, OGV_BF16, 4, dims, str, boxg, 0)) return rc;
+    if (int rc = ogv_make_tmap(&tme, e_pre, OGV_BF16, 4, dims, str, boxe, 0)) return rc;
+  }
+  kern<<<g.nchunks * g.nworkers, DW_THREADS, smem, st>>>(tmg, tme, scale1, shift1, mean1, rstd1, w,
+                                                         reinterpret_cast<bf16*>(du1), dw, dgamma1, dbeta1, g);
+  return ogv_check_launch("dwconv_bwd");
+}
+
 }  // namespace
 
 extern "C" int ogv_dwconv_fwd(const void* e_pre, const float* scale1, const float* shift1, const float* w,
@@ -1179,6 +1372,19 @@ extern "C" int ogv_dwconv_bwd(const void* dd_pre, const void* e_pre, const float
   OGV_REQUIRE((reinterpret_cast<uintptr_t>(dd_pre) & 15) == 0 && (reinterpret_cast<uintptr_t>(e_pre) & 15) == 0 &&
                   (reinterpret_cast<uintptr_t>(du1) & 15) == 0,
               "dwconv_bwd: tensors must be 16-byte aligned");
+  static int walk = -1;  // OGV_DW_BWD=tile selects the older TMA-tiled strip kernel (A/B measurements)
+  if (walk < 0) { const char* e = getenv("OGV_DW_BWD"); walk = (e && e[0] == 't') ? 0 : 1; }
+  if (walk && dtype == OGV_BF16 && (W == 4 || W == 8 || W == 16 || W == 32) && Cm % DWB_CC == 0) {
+    cudaStream_t st = (cudaStream_t)stream;
+    OGV_DISPATCH_ACT(act, ACT, {
+      switch (W) {
+        case 32: return dwb_walk_launch<ACT, 32>(dd_pre, e_pre, scale1, shift1, mean1, rstd1, w, du1, dw, dgamma1, dbeta1, B, H, Cm, st);
+        case 16: return dwb_walk_launch<ACT, 16>(dd_pre, e_pre, scale1, shift1, mean1, rstd1, w, du1, dw, dgamma1, dbeta1, B, H, Cm, st);
+        case 8: return dwb_walk_launch<ACT, 8>(dd_pre, e_pre, scale1, shift1, mean1, rstd1, w, du1, dw, dgamma1, dbeta1, B, H, Cm, st);
+        default: return dwb_walk_launch<ACT, 4>(dd_pre, e_pre, scale1, shift1, mean1, rstd1, w, du1, dw, dgamma1, dbeta1, B, H, Cm, st);
+      }
+    });
+  }
   OGV_DISPATCH_DTYPE(dtype, T, {
     constexpr int CC = dw_cc<T>();
     const int smem = DW_BUF_POS * CC * (int)(sizeof(T) + sizeof(float)) + 2 * 256 * CC * (int)sizeof(T) + 64;
