@@ -404,6 +404,8 @@ def profile_step(w, peaks, nprof=2):
         n_blocks = sum(s["depth"] for s in w.mcfg["stages"] if s["dim"] == r["C"])
         if str(w.mcfg.get("type", "model_a")).lower() in ("b", "model_b", "outlooker_front", "front") and r["branch"] in ("K1", "K4a"):
             n_blocks = int(w.mcfg.get("outlooker_front_depth", 2))
+        if r["branch"] == "F2":  # one conv-BN-act unit (stem or Downsample) per output shape
+            n_blocks = 1
         r["instances"] = max(n_blocks, 1)
         r["frac"] = r["floor_ms_one"] * r["instances"] / max(r["ms_per_step"], 1e-9)
         r["bound"] = "hbm" if r["alg_bytes"] / (peaks["hbm"] * 1e9) >= r["alg_flops"] / (peaks["tc"] * 1e12) else "tensor"

@@ -39,7 +39,7 @@ def main():
         rows.pop()
         names.pop()
     fwd_end = max(i for i, nm in enumerate(names) if nm.startswith("bn_apply_kernel")) + 1
-    fwd_start = max(i for i, nm in enumerate(names[:fwd_end]) if nm.startswith("gemm_tc_kernel<64, float>")) + 1
+    fwd_start = max(i for i, nm in enumerate(names[:fwd_end]) if nm.startswith("gemm_tc_kernel<64, float")) + 1
     last = rows[fwd_start:]
     split = fwd_end - fwd_start
     elt = 2
