@@ -59,10 +59,17 @@ def _worker(rank, world, port, use_graph, q):
         for _ in range(2):  # twice: bucket counters re-arm, the arena is re-zeroed by the step's memset
             step()
         torch.cuda.synchronize()
+        # Normwise error per parameter, with the model-wide gradient RMS as the floor of the denominator: several
+        # parameters have an EXACTLY zero gradient in exact arithmetic (a bias in front of a BatchNorm -- the last block's
+        # mlp.fc2.bias feeds the head BatchNorm -- or the key bias of the attention), so what both sides hold there is
+        # bf16 summation noise, and two runs of the same code differ by O(1) relative to it whenever an atomic lands in
+        # a different order.  Judged against the scale of the gradients that matter, that noise is ~1e-3.
+        n_all = sum(v.numel() for v in want.values())
+        rms_all = (sum(float(v.pow(2).sum()) for v in want.values()) / n_all) ** 0.5
         worst, worst_k = 0.0, ""
         for k, p in model.named_parameters():
             got = p.grad.detach().float() / world
-            err = float((got - want[k]).norm() / (want[k].norm() + 1e-6 * want[k].numel() ** 0.5))
+            err = float((got - want[k]).norm() / (want[k].norm() + rms_all * want[k].numel() ** 0.5))
             if err > worst:
                 worst, worst_k = err, k
         q.put((rank, worst, worst_k, len(sync.buckets)))
