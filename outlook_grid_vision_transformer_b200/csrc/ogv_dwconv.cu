@@ -1075,9 +1075,12 @@ int dww_launch(const void* e_pre, const float* scale1, const float* shift1, cons
 // The gradient tile needs no masks at all (TMA zero fill); rows / images outside the tensor are skipped per warp.
 // ------------------------------------------------------------------------------------------------
 constexpr int DWB_CC = 32;
+#ifndef DWB_MINB
+#define DWB_MINB 2
+#endif
 
 template <int ACT, int W_>
-__global__ void __launch_bounds__(DW_THREADS, 2)
+__global__ void __launch_bounds__(DW_THREADS, DWB_MINB)
 dwconv_bwd_walk_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ CUtensorMap tm_e,
                        const float* __restrict__ scale1, const float* __restrict__ shift1,
                        const float* __restrict__ mean1, const float* __restrict__ rstd1, const float* __restrict__ wgt,
