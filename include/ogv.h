@@ -166,6 +166,18 @@ int ogv_bn_bwd_apply(const void* dy, const void* x, const float* mean, const flo
                      const float* dgamma, const float* dbeta, void* dx, long long M, int C, int dtype,
                      void* stream);
 
+/* Squeeze-excite MLP (mbc_conv.py:17-19,24-26) on [B, Cm] rows, both 1x1 convs in one kernel per direction (bf16
+ * compute mode; ogv_se_mlp_supported tells which shapes).  w1t = W1^T [Cm, Cs], w2t = W2^T [Cs, Cm] (forward),
+ * w2 = W2 [Cm, Cs], w1 = W1 [Cs, Cm] (backward): the K-major bf16 copies.  pool_c / s1_pre / s1a / dgate_c / ds1_pre are
+ * bf16 (operands of the weight-gradient GEMMs), gate_pre / gate / dpool fp32.
+ *   forward : s1_pre = pool W1^T + b1, s1a = act(s1_pre), gate_pre = s1a W2^T + b2, gate = sigmoid(gate_pre)
+ *   backward: dgate_c = dgate * sigmoid'(gate_pre), ds1_pre = (dgate_c W2) * act'(s1_pre), dpool = ds1_pre W1 */
+int ogv_se_mlp_supported(int Cm, int Cs, int dtype);
+int ogv_se_mlp_fwd(const float* pool, const void* w1t, const float* b1, const void* w2t, const float* b2, void* pool_c,
+                   void* s1_pre, void* s1a, float* gate_pre, float* gate, int B, int Cm, int Cs, int act, void* stream);
+int ogv_se_mlp_bwd(const float* dgate, const float* gate_pre, const void* s1_pre, const void* w2, const void* w1,
+                   void* dgate_c, void* ds1_pre, float* dpool, int B, int Cm, int Cs, int act, void* stream);
+
 /* 3x3 stride-1 pad-1 patches of a channels_last image x[B,H,W,Cin] as GEMM rows cols[B*H*W, Kpad], column
  * (ky*3+kx)*Cin + ci, zeros outside the image and in columns >= 9*Cin: the stem convolution (stem_head.py:23-32) becomes
  * ogv_gemm forward and weight gradient. */

@@ -325,6 +325,161 @@ __global__ void __launch_bounds__(IMG_THREADS) dw_bn2_bwd_apply_kernel(
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Squeeze-excite MLP on [B, Cm] rows as ONE kernel per direction (bf16 compute mode, stages whose two weight matrices
+// are small: Cs a power of two <= 256, Cm a multiple of 256).  The two 1x1 convs (mbc_conv.py:17-19,24-26) are a few
+// MFLOP per block: as tcgen05 GEMM launches they cost 10-25 us EACH (8-CTA grids, pure latency), plus the casts, the
+// sigma' pass and the bias-gradient sums around them -- 13 launches per block and step.  Here a CTA owns RB = 8 images,
+// keeps their rows in shared memory ([k][image], so one broadcast LDS.128 pair feeds 8 FMAs) and runs both layers with
+// the K-major weight copy streamed from L2 once per CTA; operands are rounded to bf16 exactly where the GEMM route
+// rounds them (inputs, the hidden activation), accumulation in fp32.
+//   forward : s1_pre = pool W1^T + b1, s1a = act(s1_pre), gate_pre = s1a W2^T + b2, gate = sigmoid(gate_pre)
+//   backward: dgp = dgate * sigmoid'(gate_pre), ds1_pre = (dgp W2) * act'(s1_pre), dpool = ds1_pre W1
+// ------------------------------------------------------------------------------------------------
+constexpr int SE_RB = 8;
+constexpr int SE_THREADS = 1024;  // 32 warps: the loops below are chains of L2 loads, latency is hidden by warps
+constexpr int SE_TN = 256;        // output columns per round; SE_THREADS / SE_TN k-groups share a column
+
+// out[r][n] = sum_k in_s[k][r] * Wt[k][n] for n in [0, N), all RB images; epi(n, acc) is called by ONE thread per n.
+template <typename Epi>
+__device__ __forceinline__ void se_layer(const float* __restrict__ in_s, const bf16* __restrict__ Wt, int K, int N,
+                                         float* __restrict__ red_s, Epi&& epi) {
+  const int tid = threadIdx.x;
+  const int TN = N < SE_TN ? N : SE_TN;             // N is a power of two <= 256 or a multiple of 256
+  const int G = SE_THREADS / TN;                    // k-groups sharing an output column (>= 4)
+  const int tn = tid % TN, kg = tid / TN;
+  const int kper = K / G;
+  for (int n0 = 0; n0 < N; n0 += TN) {
+    const int n = n0 + tn;
+    float acc[SE_RB];
+#pragma unroll
+    for (int r = 0; r < SE_RB; ++r) acc[r] = 0.f;
+    const bf16* wp = Wt + (long long)(kg * kper) * N + n;
+    const float* ip = in_s + (kg * kper) * SE_RB;
+#pragma unroll 8
+    for (int k = 0; k < kper; ++k) {
+      const float w = __bfloat162float(wp[(long long)k * N]);
+      const float4 a0 = *reinterpret_cast<const float4*>(ip + k * SE_RB);
+      const float4 a1 = *reinterpret_cast<const float4*>(ip + k * SE_RB + 4);
+      acc[0] = fmaf(w, a0.x, acc[0]); acc[1] = fmaf(w, a0.y, acc[1]);
+      acc[2] = fmaf(w, a0.z, acc[2]); acc[3] = fmaf(w, a0.w, acc[3]);
+      acc[4] = fmaf(w, a1.x, acc[4]); acc[5] = fmaf(w, a1.y, acc[5]);
+      acc[6] = fmaf(w, a1.z, acc[6]); acc[7] = fmaf(w, a1.w, acc[7]);
+    }
+    if (G > 1) {
+      __syncthreads();  // red_s may still be read by the previous round
+#pragma unroll
+      for (int r = 0; r < SE_RB; ++r) red_s[(kg * TN + tn) * SE_RB + r] = acc[r];
+      __syncthreads();
+      if (kg == 0) {
+        for (int gdx = 1; gdx < G; ++gdx)
+#pragma unroll
+          for (int r = 0; r < SE_RB; ++r) acc[r] += red_s[(gdx * TN + tn) * SE_RB + r];
+      }
+    }
+    if (kg == 0) epi(n, acc);
+  }
+}
+
+template <int ACT>
+__global__ void __launch_bounds__(SE_THREADS)
+se_mlp_fwd_kernel(const float* __restrict__ pool, const bf16* __restrict__ w1t, const float* __restrict__ b1,
+                  const bf16* __restrict__ w2t, const float* __restrict__ b2, bf16* __restrict__ pool_c,
+                  bf16* __restrict__ s1_pre, bf16* __restrict__ s1a, float* __restrict__ gate_pre,
+                  float* __restrict__ gate, int B, int Cm, int Cs) {
+  extern __shared__ __align__(16) float se_sm[];
+  float* const in_s = se_sm;                       // [Cm][RB]
+  float* const h_s = se_sm + Cm * SE_RB;           // [Cs][RB]
+  float* const red_s = h_s + Cs * SE_RB;           // [SE_THREADS][RB]
+  const int b0 = blockIdx.x * SE_RB;
+  for (int i = threadIdx.x; i < Cm * SE_RB; i += SE_THREADS) {
+    const int r = i / Cm, k = i - r * Cm;          // coalesced over k
+    float v = 0.f;
+    if (b0 + r < B) {
+      v = round_to<bf16>(pool[(long long)(b0 + r) * Cm + k]);
+      pool_c[(long long)(b0 + r) * Cm + k] = __float2bfloat16_rn(v);
+    }
+    in_s[k * SE_RB + r] = v;
+  }
+  __syncthreads();
+  se_layer(in_s, w1t, Cm, Cs, red_s, [&](int n, const float (&acc)[SE_RB]) {
+    const float bias = b1[n];
+#pragma unroll
+    for (int r = 0; r < SE_RB; ++r) {
+      const float pre = round_to<bf16>(acc[r] + bias);
+      const float a = round_to<bf16>(act_apply_t<ACT, true>(acc[r] + bias));
+      h_s[n * SE_RB + r] = a;
+      if (b0 + r < B) {
+        s1_pre[(long long)(b0 + r) * Cs + n] = __float2bfloat16_rn(pre);
+        s1a[(long long)(b0 + r) * Cs + n] = __float2bfloat16_rn(a);
+      }
+    }
+  });
+  __syncthreads();
+  se_layer(h_s, w2t, Cs, Cm, red_s, [&](int n, const float (&acc)[SE_RB]) {
+    const float bias = b2[n];
+#pragma unroll
+    for (int r = 0; r < SE_RB; ++r) {
+      if (b0 + r < B) {
+        const float pre = acc[r] + bias;
+        gate_pre[(long long)(b0 + r) * Cm + n] = pre;
+        gate[(long long)(b0 + r) * Cm + n] = sigmoid_f(pre);
+      }
+    }
+  });
+}
+
+template <int ACT>
+__global__ void __launch_bounds__(SE_THREADS)
+se_mlp_bwd_kernel(const float* __restrict__ dgate, const float* __restrict__ gate_pre, const bf16* __restrict__ s1_pre,
+                  const bf16* __restrict__ w2, const bf16* __restrict__ w1, bf16* __restrict__ dgate_c,
+                  bf16* __restrict__ ds1_pre, float* __restrict__ dpool, int B, int Cm, int Cs) {
+  extern __shared__ __align__(16) float se_sm[];
+  float* const in_s = se_sm;                       // [Cm][RB]
+  float* const h_s = se_sm + Cm * SE_RB;           // [Cs][RB]
+  float* const red_s = h_s + Cs * SE_RB;
+  const int b0 = blockIdx.x * SE_RB;
+  for (int i = threadIdx.x; i < Cm * SE_RB; i += SE_THREADS) {
+    const int r = i / Cm, k = i - r * Cm;
+    float v = 0.f;
+    if (b0 + r < B) {
+      const long long o = (long long)(b0 + r) * Cm + k;
+      const float sg = sigmoid_f(gate_pre[o]);
+      v = round_to<bf16>(dgate[o] * sg * (1.f - sg));
+      dgate_c[o] = __float2bfloat16_rn(v);
+    }
+    in_s[k * SE_RB + r] = v;
+  }
+  __syncthreads();
+  se_layer(in_s, w2, Cm, Cs, red_s, [&](int n, const float (&acc)[SE_RB]) {
+#pragma unroll
+    for (int r = 0; r < SE_RB; ++r) {
+      float d = 0.f;
+      if (b0 + r < B) {
+        const long long o = (long long)(b0 + r) * Cs + n;
+        d = round_to<bf16>(acc[r] * act_grad_t<ACT, false>(__bfloat162float(s1_pre[o])));
+        ds1_pre[o] = __float2bfloat16_rn(d);
+      }
+      h_s[n * SE_RB + r] = d;
+    }
+  });
+  __syncthreads();
+  se_layer(h_s, w1, Cs, Cm, red_s, [&](int n, const float (&acc)[SE_RB]) {
+#pragma unroll
+    for (int r = 0; r < SE_RB; ++r)
+      if (b0 + r < B) dpool[(long long)(b0 + r) * Cm + n] = acc[r];
+  });
+}
+
+inline bool se_mlp_shape_ok(int Cm, int Cs) {
+  // k-groups must divide both reduction lengths: K / G with G = SE_THREADS / min(N, SE_TN)
+  const bool cs_ok = Cs >= 16 && Cs <= 256 && (Cs & (Cs - 1)) == 0;
+  if (!(cs_ok && Cm >= 256 && Cm % 256 == 0 && Cm <= 2048)) return false;
+  const int g1 = SE_THREADS / (Cs < SE_TN ? Cs : SE_TN), g2 = SE_THREADS / SE_TN;
+  return Cm % g1 == 0 && Cs % g2 == 0;
+}
+inline size_t se_mlp_smem(int Cm, int Cs) { return (size_t)(Cm + Cs + SE_THREADS) * SE_RB * sizeof(float); }
+
 // row splits so that small batches still fill the machine
 inline int img_row_splits(int B, int nvb, int HW) {
   long long ctas = (long long)B * nvb;
@@ -426,4 +581,50 @@ extern "C" int ogv_dw_bn2_bwd_apply(const void* dd_act, const void* d_pre, const
     });
     return ogv_check_launch("dw_bn2_bwd_apply");
   });
+}
+
+extern "C" int ogv_se_mlp_supported(int Cm, int Cs, int dtype) {
+  return dtype == OGV_BF16 && se_mlp_shape_ok(Cm, Cs) ? 1 : 0;
+}
+
+extern "C" int ogv_se_mlp_fwd(const float* pool, const void* w1t, const float* b1, const void* w2t, const float* b2,
+                              void* pool_c, void* s1_pre, void* s1a, float* gate_pre, float* gate, int B, int Cm, int Cs,
+                              int act, void* stream) {
+  if (B == 0) return OGV_OK;
+  OGV_REQUIRE(pool && w1t && b1 && w2t && b2 && pool_c && s1_pre && s1a && gate_pre && gate, "se_mlp_fwd: null pointer");
+  OGV_REQUIRE(se_mlp_shape_ok(Cm, Cs), "se_mlp_fwd: unsupported shape Cm=%d Cs=%d", Cm, Cs);
+  const size_t smem = se_mlp_smem(Cm, Cs);
+  OGV_DISPATCH_ACT(act, ACT, {
+    static bool attr = false;
+    if (!attr) {
+      cudaFuncSetAttribute(se_mlp_fwd_kernel<ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+      attr = true;
+    }
+    se_mlp_fwd_kernel<ACT><<<ogv_ceil_div(B, SE_RB), SE_THREADS, smem, (cudaStream_t)stream>>>(
+        pool, reinterpret_cast<const bf16*>(w1t), b1, reinterpret_cast<const bf16*>(w2t), b2,
+        reinterpret_cast<bf16*>(pool_c), reinterpret_cast<bf16*>(s1_pre), reinterpret_cast<bf16*>(s1a), gate_pre, gate, B,
+        Cm, Cs);
+  });
+  return ogv_check_launch("se_mlp_fwd");
+}
+
+extern "C" int ogv_se_mlp_bwd(const float* dgate, const float* gate_pre, const void* s1_pre, const void* w2,
+                              const void* w1, void* dgate_c, void* ds1_pre, float* dpool, int B, int Cm, int Cs, int act,
+                              void* stream) {
+  if (B == 0) return OGV_OK;
+  OGV_REQUIRE(dgate && gate_pre && s1_pre && w2 && w1 && dgate_c && ds1_pre && dpool, "se_mlp_bwd: null pointer");
+  OGV_REQUIRE(se_mlp_shape_ok(Cm, Cs), "se_mlp_bwd: unsupported shape Cm=%d Cs=%d", Cm, Cs);
+  const size_t smem = se_mlp_smem(Cm, Cs);
+  OGV_DISPATCH_ACT(act, ACT, {
+    static bool attr = false;
+    if (!attr) {
+      cudaFuncSetAttribute(se_mlp_bwd_kernel<ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+      attr = true;
+    }
+    se_mlp_bwd_kernel<ACT><<<ogv_ceil_div(B, SE_RB), SE_THREADS, smem, (cudaStream_t)stream>>>(
+        dgate, gate_pre, reinterpret_cast<const bf16*>(s1_pre), reinterpret_cast<const bf16*>(w2),
+        reinterpret_cast<const bf16*>(w1), reinterpret_cast<bf16*>(dgate_c), reinterpret_cast<bf16*>(ds1_pre), dpool, B,
+        Cm, Cs);
+  });
+  return ogv_check_launch("se_mlp_bwd");
 }

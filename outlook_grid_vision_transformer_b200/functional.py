@@ -477,13 +477,17 @@ class MBConvFn(torch.autograd.Function):
         ps1: PreparedLinear = meta["pse1"]
         ps2: PreparedLinear = meta["pse2"]
         cdt = x.dtype
-        pool_c = pool if cdt == torch.float32 else ops.cast(pool, cdt)
-        s1_pre = _empty((g.B, Cs), x, cdt)
-        s1a = _empty((g.B, Cs), x, cdt)
-        ops.gemm(pool_c, ps1.w, s1a, bias=sb1, pre_out=s1_pre, act=act)
-        gate_pre = _empty((g.B, Cm), x, torch.float32)
-        gate = _empty((g.B, Cm), x, torch.float32)
-        ops.gemm(s1a, ps2.w, gate, bias=sb2, pre_out=gate_pre, act="sigmoid")
+        se_fused = ops.se_mlp_supported(Cm, Cs, cdt) and ps1.wt.is_contiguous() and ps2.wt.is_contiguous()
+        if se_fused:  # both 1x1 convs, the casts and the two activations in one launch
+            pool_c, s1_pre, s1a, gate_pre, gate = ops.se_mlp_fwd(pool, ps1.wt, sb1, ps2.wt, sb2, act)
+        else:
+            pool_c = pool if cdt == torch.float32 else ops.cast(pool, cdt)
+            s1_pre = _empty((g.B, Cs), x, cdt)
+            s1a = _empty((g.B, Cs), x, cdt)
+            ops.gemm(pool_c, ps1.w, s1a, bias=sb1, pre_out=s1_pre, act=act)
+            gate_pre = _empty((g.B, Cm), x, torch.float32)
+            gate = _empty((g.B, Cm), x, torch.float32)
+            ops.gemm(s1a, ps2.w, gate, bias=sb2, pre_out=gate_pre, act="sigmoid")
         d_act = ops.bn_act_gate(d_pre, s2[2], s2[3], gate, g.B, g.P, act)
         # project
         o_pre = _empty((M, C), x)
@@ -550,19 +554,25 @@ class MBConvFn(torch.autograd.Function):
         # squeeze-excite + BN2 backward: one pass over (dd_act, d_pre) yields dgate and the per-image pieces of
         # the BN2 reductions; the tiny SE products then give dpool, and a [B, Cm] kernel finishes dgamma2 / dbeta2
         stats = ops.mbconv_bwd_stats(dd_act, d_pre, s2[2], s2[3], s2[4], s2[5], g.B, g.P, act)
-        dgate_pre = ops.mul_dact(stats[0], gate_pre, "sigmoid")
         ps1: PreparedLinear = meta["pse1"]
         ps2: PreparedLinear = meta["pse2"]
         cdt = x.dtype
-        dgate_c = dgate_pre if cdt == torch.float32 else ops.cast(dgate_pre, cdt)
-        ds1_pre = _empty((g.B, Cs), x, cdt)
-        ops.gemm(dgate_c, ps2.wt, ds1_pre, dact_src=s1_pre, dact=act)
-        ops.wgrad(dgate_c, s1a, dsw2)
-        ops.colsum(dgate_pre, dsb2)
-        dpool = _empty((g.B, Cm), x, torch.float32)
-        ops.gemm(ds1_pre, ps1.wt, dpool)
-        ops.wgrad(ds1_pre, pool, dsw1)
-        ops.colsum(ds1_pre, dsb1)
+        if ops.se_mlp_supported(Cm, Cs, cdt) and ps1.w.is_contiguous() and ps2.w.is_contiguous():
+            # sigma', both dgrads and act' in one launch; the two bias gradients ride with the weight-gradient GEMMs
+            dgate_c, ds1_pre, dpool = ops.se_mlp_bwd(stats[0], gate_pre, s1_pre, ps2.w, ps1.w, act)
+            ops.wgrad(dgate_c, s1a, dsw2, bias_grad=dsb2)
+            ops.wgrad(ds1_pre, pool, dsw1, bias_grad=dsb1)
+        else:
+            dgate_pre = ops.mul_dact(stats[0], gate_pre, "sigmoid")
+            dgate_c = dgate_pre if cdt == torch.float32 else ops.cast(dgate_pre, cdt)
+            ds1_pre = _empty((g.B, Cs), x, cdt)
+            ops.gemm(dgate_c, ps2.wt, ds1_pre, dact_src=s1_pre, dact=act)
+            ops.wgrad(dgate_c, s1a, dsw2)
+            ops.colsum(dgate_pre, dsb2)
+            dpool = _empty((g.B, Cm), x, torch.float32)
+            ops.gemm(ds1_pre, ps1.wt, dpool)
+            ops.wgrad(ds1_pre, pool, dsw1)
+            ops.colsum(ds1_pre, dsb1)
         ops.mbconv_bn2_finalize(stats, gate, dpool, dg2, db2, g.B, g.P)
         dd_pre = ops.dw_bn2_bwd_apply(dd_act, d_pre, gate, dpool, s2[2], s2[3], s2[4], s2[5], g2,
                                       dg2 if training else zM, db2 if training else zM, g.B, g.P, act)

@@ -514,6 +514,46 @@ def se_pool(d_pre, scale2, shift2, B, HW, act: str) -> Tensor:
     return pool
 
 
+def se_mlp_supported(Cm: int, Cs: int, dtype: torch.dtype) -> bool:
+    """True when the one-kernel squeeze-excite MLP serves this shape (bf16 compute mode, small weight matrices).
+    Measured in the replayed step of cfg 2: the FFMA kernel wins at Cm <= 512 (stages 0-1: 23-27 us for what were two
+    tensor-core GEMM launches, two casts and two activations); at Cm = 1024 it takes 66 us and the GEMM route is as fast.
+    OGV_SE_FUSED_MAXCM moves the cut, OGV_SE_FUSED=0 disables the kernel."""
+    if os.environ.get("OGV_SE_FUSED", "1") == "0" or Cm > int(os.environ.get("OGV_SE_FUSED_MAXCM", "512")):
+        return False
+    return bool(_lib.lib().ogv_se_mlp_supported(Cm, Cs, BF16 if dtype == torch.bfloat16 else F32))
+
+
+def se_mlp_fwd(pool: Tensor, w1t: Tensor, b1: Tensor, w2t: Tensor, b2: Tensor, act: str):
+    """pool [B, Cm] fp32; w1t = W1^T [Cm, Cs], w2t = W2^T [Cs, Cm] bf16 (contiguous).
+    -> pool_c, s1_pre, s1a (bf16), gate_pre, gate (fp32)"""
+    B, Cm = pool.shape
+    Cs = w1t.shape[1]
+    dev = pool.device
+    pool_c = torch.empty((B, Cm), device=dev, dtype=torch.bfloat16)
+    s1_pre = torch.empty((B, Cs), device=dev, dtype=torch.bfloat16)
+    s1a = torch.empty((B, Cs), device=dev, dtype=torch.bfloat16)
+    gate_pre = torch.empty((B, Cm), device=dev, dtype=torch.float32)
+    gate = torch.empty((B, Cm), device=dev, dtype=torch.float32)
+    _call("ogv_se_mlp_fwd", _p(pool), _p(w1t), _p(b1), _p(w2t), _p(b2), _p(pool_c), _p(s1_pre), _p(s1a), _p(gate_pre),
+          _p(gate), B, Cm, Cs, ACT[act], _stream())
+    return pool_c, s1_pre, s1a, gate_pre, gate
+
+
+def se_mlp_bwd(dgate: Tensor, gate_pre: Tensor, s1_pre: Tensor, w2: Tensor, w1: Tensor, act: str):
+    """dgate, gate_pre [B, Cm] fp32; s1_pre [B, Cs] bf16; w2 = W2 [Cm, Cs], w1 = W1 [Cs, Cm] bf16 (contiguous).
+    -> dgate_c [B, Cm] bf16, ds1_pre [B, Cs] bf16, dpool [B, Cm] fp32"""
+    B, Cm = dgate.shape
+    Cs = s1_pre.shape[1]
+    dev = dgate.device
+    dgate_c = torch.empty((B, Cm), device=dev, dtype=torch.bfloat16)
+    ds1_pre = torch.empty((B, Cs), device=dev, dtype=torch.bfloat16)
+    dpool = torch.empty((B, Cm), device=dev, dtype=torch.float32)
+    _call("ogv_se_mlp_bwd", _p(dgate), _p(gate_pre), _p(s1_pre), _p(w2), _p(w1), _p(dgate_c), _p(ds1_pre), _p(dpool), B,
+          Cm, Cs, ACT[act], _stream())
+    return dgate_c, ds1_pre, dpool
+
+
 def bn_act_gate(d_pre, scale2, shift2, gate, B, HW, act: str) -> Tensor:
     d_act = torch.empty_like(d_pre)
     _call("ogv_bn_act_gate", _p(d_pre), _p(scale2), _p(shift2), _p(gate), _p(d_act), B, HW, d_pre.shape[1],

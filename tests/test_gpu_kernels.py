@@ -383,3 +383,42 @@ def test_column_reductions_and_streaming_passes_at_scale(dt, C):
         close(dxl, xr.grad, tol(dt) * 2, "layernorm dx")
         close(dgam, wr.grad, scale_t, "layernorm dgamma")
         close(dbet, br.grad, scale_t, "layernorm dbeta")
+
+
+# ------------------------------------------------------------------------ fused squeeze-excite MLP
+@pytest.mark.parametrize("B,Cm,Cs", [(37, 256, 64), (64, 512, 128), (9, 1024, 256), (8, 256, 16), (130, 768, 32)])
+def test_se_mlp_fused_fwd_bwd(B, Cm, Cs):
+    """ogv_se_mlp_fwd / _bwd (both 1x1 convs of SqueezeExcite, mbc_conv.py:17-27, in one kernel per direction) against
+    the same math in fp64 on the bf16-rounded operands; bf16 outputs at 2e-2, fp32 outputs at 2e-3."""
+    from outlook_grid_vision_transformer_b200 import _lib, ops
+    assert _lib.lib().ogv_se_mlp_supported(Cm, Cs, _lib.BF16)
+    g = torch.Generator().manual_seed(B + Cm)
+    rb = lambda t: t.to(torch.bfloat16).double()  # noqa: E731
+    pool = torch.randn(B, Cm, generator=g)
+    w1 = torch.randn(Cs, Cm, generator=g) / Cm ** 0.5
+    w2 = torch.randn(Cm, Cs, generator=g) / Cs ** 0.5
+    b1, b2 = torch.randn(Cs, generator=g) * 0.1, torch.randn(Cm, generator=g) * 0.1
+    w1b, w2b = w1.to(torch.bfloat16), w2.to(torch.bfloat16)
+    pool_c, s1_pre, s1a, gate_pre, gate = ops.se_mlp_fwd(dev(pool), dev(w1b.t().contiguous()), dev(b1),
+                                                          dev(w2b.t().contiguous()), dev(b2), "silu")
+    z1 = rb(pool) @ w1b.double().t() + b1.double()
+    a1 = torch.nn.functional.silu(z1)
+    z2 = rb(a1) @ w2b.double().t() + b2.double()
+    assert torch.equal(pool_c.cpu(), pool.to(torch.bfloat16))
+    close(s1_pre, z1, 2e-2, "s1_pre")
+    close(s1a, a1, 2e-2, "s1a")
+    close(gate_pre, z2, 2e-3, "gate_pre")
+    close(gate, torch.sigmoid(z2), 2e-3, "gate")
+    # backward
+    dgate = torch.randn(B, Cm, generator=g)
+    dgate_c, ds1_pre, dpool = ops.se_mlp_bwd(dev(dgate), gate_pre, s1_pre, dev(w2b), dev(w1b), "silu")
+    zz2 = gate_pre.double().cpu()
+    sg = torch.sigmoid(zz2)
+    dgp = dgate.double() * sg * (1 - sg)
+    close(dgate_c, dgp, 2e-2, "dgate_c")
+    zz1 = s1_pre.double().cpu()
+    s1 = torch.sigmoid(zz1)
+    dsilu = s1 * (1 + zz1 * (1 - s1))
+    ds1 = (rb(dgp) @ w2b.double()) * dsilu
+    close(ds1_pre, ds1, 2e-2, "ds1_pre")
+    close(dpool, rb(ds1) @ w1b.double(), 5e-3, "dpool")

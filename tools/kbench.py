@@ -181,6 +181,10 @@ def main():
         run("se wgrad tc", s, lambda: ops.wgrad(g16, s1_16, dWs), nbytes(g16, s1_16), 2 * B * Cm * Cs)
         run("se wgrad simt", s, lambda: ops.wgrad(g32, s1_32, dWs, engine=ops.ENGINE_SIMT), nbytes(g32, s1_32), 2 * B * Cm * Cs)
         run("se cast", s, lambda: ops.cast(pool32, dt), nbytes(pool32, pool16))
+        if ops.se_mlp_supported(Cm, Cs, dt):
+            w1t16, w2t16 = ws1_16.t().contiguous(), ws2_16.t().contiguous()
+            run("se mlp fused fwd", s, lambda: ops.se_mlp_fwd(pool32, w1t16, bs1, w2t16, bs2, "silu"), nbytes(pool32, g32, gp32), 4 * B * Cm * Cs)
+            run("se mlp fused bwd", s, lambda: ops.se_mlp_bwd(g32, gp32, s1p_16, ws2_16, ws1_16, "silu"), nbytes(pool32, g32, gp32), 4 * B * Cm * Cs)
         # ---- fused MLP (hidden tile on chip): fc1 -> act -> fc2 -> +res in one kernel; backward recomputes it
         for tag, Hd in (("mlp 4C", 4 * C), ("mlp2d 2C", 2 * C)):
             if not ops.mlp_fused_supported(C, Hd, dt):
