@@ -868,7 +868,7 @@ template <> struct DwwShape<8> { static constexpr int NI = 4, NSB = 1, TRS = 8; 
 template <> struct DwwShape<4> { static constexpr int NI = 8, NSB = 1, TRS = 4; };
 
 struct DwwGeom {
-  int B, H, Cm, bands, ntiles, nchunks, nworkers;
+  int B, H, W, Cm, bands, tiles_w, ntiles, nchunks, nworkers;  // W = IMAGE width = tiles_w x the tile width
 };
 
 template <int ACT, int W_>
@@ -923,40 +923,45 @@ dwconv_fwd_walk_kernel(const __grid_constant__ CUtensorMap tm_in, const float* _
     sh2[0] = pk2(sh.x, sh.y); sh2[1] = pk2(sh.z, sh.w);
   }
   float st_s[4] = {0.f, 0.f, 0.f, 0.f}, st_q[4] = {0.f, 0.f, 0.f, 0.f};
-  const bool col_ok[4] = {x0 >= 1, true, true, x0 + 2 < W_};
+  const int Wi = g.W;
   __syncthreads();
 
-  auto tile_coords = [&](int t, int& b0, int& r0) {
-    const int bgrp = t / g.bands;
+  // tile t = ((image group * bands) + band) * tiles_w + column tile (images wider than the tile are cut in columns)
+  auto tile_coords = [&](int t, int& b0, int& r0, int& w0) {
+    const int q = t / g.tiles_w;
+    w0 = (t - q * g.tiles_w) * W_;
+    const int bgrp = q / g.bands;
     b0 = bgrp * NI;
-    r0 = (t - bgrp * g.bands) * TRT;
+    r0 = (q - bgrp * g.bands) * TRT;
   };
   int t = worker;
   if (tid == 0 && t < g.ntiles) {
-    int b0, r0;
-    tile_coords(t, b0, r0);
+    int b0, r0, w0;
+    tile_coords(t, b0, r0, w0);
     ptx::mbar_arrive_expect_tx(&bar[0], (uint32_t)(TILE_ELEMS * sizeof(bf16)));
-    ptx::tma_load_4d(slot0, &tm_in, &bar[0], c0, -1, r0 - 1, b0);
+    ptx::tma_load_4d(slot0, &tm_in, &bar[0], c0, w0 - 1, r0 - 1, b0);
   }
   for (int it = 0; t < g.ntiles; t += g.nworkers, ++it) {
-    int b0, r0;
-    tile_coords(t, b0, r0);
+    int b0, r0, w0;
+    tile_coords(t, b0, r0, w0);
     const int sl = it & 1;
     const int tn = t + g.nworkers;
     // the other slot was last read in iteration it-1, which every thread left through the closing barrier
     if (tid == 0 && tn < g.ntiles) {
-      int nb0, nr0;
-      tile_coords(tn, nb0, nr0);
+      int nb0, nr0, nw0;
+      tile_coords(tn, nb0, nr0, nw0);
       ptx::mbar_arrive_expect_tx(&bar[sl ^ 1], (uint32_t)(TILE_ELEMS * sizeof(bf16)));
-      ptx::tma_load_4d(slot0 + (sl ^ 1) * TILE_ELEMS, &tm_in, &bar[sl ^ 1], c0, -1, nr0 - 1, nb0);
+      ptx::tma_load_4d(slot0 + (sl ^ 1) * TILE_ELEMS, &tm_in, &bar[sl ^ 1], c0, nw0 - 1, nr0 - 1, nb0);
     }
     ptx::mbar_wait(&bar[sl], (it >> 1) & 1);
     const int b = b0 + img;
     if (b < g.B) {
+      // window columns are image columns w0 + x0 - 1 .. w0 + x0 + 2: only the outer two can fall off the IMAGE
+      const bool col_ok[4] = {w0 + x0 >= 1, true, true, w0 + x0 + 2 < Wi};
       const bf16* tcol = slot0 + sl * TILE_ELEMS + ((img * TR2 + rs) * W2 + x0) * DWW_CC + cg * 4;
       const int h0 = r0 + rs;  // image row of the walker's first output; tile row j <-> image row h0 - 1 + j
-      bf16* out = d_pre + (((long long)b * g.H + h0) * W_ + x0) * g.Cm + c;
-      const long long row_stride = (long long)W_ * g.Cm;
+      bf16* out = d_pre + (((long long)b * g.H + h0) * Wi + w0 + x0) * g.Cm + c;
+      const long long row_stride = (long long)Wi * g.Cm;
       f32x2 win[3][4][2];
       auto load_row = [&](int j, f32x2 (&row)[4][2]) {
         const int h = h0 - 1 + j;
@@ -1035,7 +1040,7 @@ dwconv_fwd_walk_kernel(const __grid_constant__ CUtensorMap tm_in, const float* _
 
 template <int ACT, int W_>
 int dww_launch(const void* e_pre, const float* scale1, const float* shift1, const float* w, void* d_pre, float* sum2,
-               float* sumsq2, int B, int H, int Cm, cudaStream_t st) {
+               float* sumsq2, int B, int H, int W, int Cm, cudaStream_t st) {
   using S = DwwShape<W_>;
   constexpr int TRT = S::TRS * S::NSB;
   constexpr int TILE_BYTES = S::NI * (TRT + 2) * (W_ + 2) * DWW_CC * 2;
@@ -1044,9 +1049,10 @@ int dww_launch(const void* e_pre, const float* scale1, const float* shift1, cons
   int occ = 1;
   if (int rc = dw_smem_optin(kern, smem, &occ)) return rc;
   DwwGeom g;
-  g.B = B; g.H = H; g.Cm = Cm;
+  g.B = B; g.H = H; g.W = W; g.Cm = Cm;
   g.bands = (H + TRT - 1) / TRT;
-  const long long nt = (long long)((B + S::NI - 1) / S::NI) * g.bands;
+  g.tiles_w = W / W_;
+  const long long nt = (long long)((B + S::NI - 1) / S::NI) * g.bands * g.tiles_w;
   if (nt > 0x7fffffffLL) { ogv_set_error("dwconv_fwd: too many tiles"); return OGV_ERR_UNSUPPORTED; }
   g.ntiles = (int)nt;
   g.nchunks = Cm / DWW_CC;
@@ -1056,8 +1062,8 @@ int dww_launch(const void* e_pre, const float* scale1, const float* shift1, cons
   g.nworkers = (int)want;
   CUtensorMap tm;
   {
-    unsigned long long dims[4] = {(unsigned long long)Cm, (unsigned long long)W_, (unsigned long long)H, (unsigned long long)B};
-    unsigned long long str[3] = {(unsigned long long)Cm * 2, (unsigned long long)W_ * Cm * 2, (unsigned long long)H * W_ * Cm * 2};
+    unsigned long long dims[4] = {(unsigned long long)Cm, (unsigned long long)W, (unsigned long long)H, (unsigned long long)B};
+    unsigned long long str[3] = {(unsigned long long)Cm * 2, (unsigned long long)W * Cm * 2, (unsigned long long)H * W * Cm * 2};
     unsigned box[4] = {(unsigned)DWW_CC, (unsigned)(W_ + 2), (unsigned)(TRT + 2), (unsigned)S::NI};
     if (int rc = ogv_make_tmap(&tm, e_pre, OGV_BF16, 4, dims, str, box, 0)) return rc;
   }
@@ -1127,24 +1133,27 @@ dwconv_bwd_walk_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_co
   f32x2 a_db = 0ull, a_dg = 0ull;
   __syncthreads();
 
-  auto tile_coords = [&](int t, int& b0, int& r0) {
-    const int bgrp = t / g.bands;
+  const int Wi = g.W;
+  auto tile_coords = [&](int t, int& b0, int& r0, int& w0) {
+    const int q = t / g.tiles_w;
+    w0 = (t - q * g.tiles_w) * W_;
+    const int bgrp = q / g.bands;
     b0 = bgrp * NI;
-    r0 = (t - bgrp * g.bands) * TRT;
+    r0 = (q - bgrp * g.bands) * TRT;
   };
   auto issue = [&](int t, int sl) {
-    int b0, r0;
-    tile_coords(t, b0, r0);
+    int b0, r0, w0;
+    tile_coords(t, b0, r0, w0);
     bf16* dst = slot0 + sl * SLOT;
     ptx::mbar_arrive_expect_tx(&bar[sl], (uint32_t)(SLOT * sizeof(bf16)));
-    ptx::tma_load_4d(dst, &tm_g, &bar[sl], c0, -1, r0 - 1, b0);
-    ptx::tma_load_4d(dst + G_ELEMS, &tm_e, &bar[sl], c0, 0, r0, b0);
+    ptx::tma_load_4d(dst, &tm_g, &bar[sl], c0, w0 - 1, r0 - 1, b0);
+    ptx::tma_load_4d(dst + G_ELEMS, &tm_e, &bar[sl], c0, w0, r0, b0);
   };
   int t = worker;
   if (tid == 0 && t < g.ntiles) issue(t, 0);
   for (int it = 0; t < g.ntiles; t += g.nworkers, ++it) {
-    int b0, r0;
-    tile_coords(t, b0, r0);
+    int b0, r0, w0;
+    tile_coords(t, b0, r0, w0);
     const int sl = it & 1;
     if (tid == 0 && t + g.nworkers < g.ntiles) issue(t + g.nworkers, sl ^ 1);
     ptx::mbar_wait(&bar[sl], (it >> 1) & 1);
@@ -1153,8 +1162,8 @@ dwconv_bwd_walk_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_co
       const bf16* gcol = slot0 + sl * SLOT + ((img * TR2 + rs) * W2 + x0) * DWB_CC + cg * 2;
       const bf16* ecol = slot0 + sl * SLOT + G_ELEMS + ((img * TRT + rs) * W_ + x0) * DWB_CC + cg * 2;
       const int h0 = r0 + rs;
-      bf16* out = du1 + (((long long)b * g.H + h0) * W_ + x0) * g.Cm + c;
-      const long long row_stride = (long long)W_ * g.Cm;
+      bf16* out = du1 + (((long long)b * g.H + h0) * Wi + w0 + x0) * g.Cm + c;
+      const long long row_stride = (long long)Wi * g.Cm;
       f32x2 win[3][4];
       auto load_row = [&](int j, f32x2 (&row)[4]) {
 #pragma unroll
@@ -1229,7 +1238,7 @@ dwconv_bwd_walk_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_co
 template <int ACT, int W_>
 int dwb_walk_launch(const void* dd_pre, const void* e_pre, const float* scale1, const float* shift1, const float* mean1,
                     const float* rstd1, const float* w, void* du1, float* dw, float* dgamma1, float* dbeta1, int B, int H,
-                    int Cm, cudaStream_t st) {
+                    int W, int Cm, cudaStream_t st) {
   using S = DwwShape<W_>;
   constexpr int TRT = S::TRS * S::NSB;
   constexpr int SLOT_BYTES = (S::NI * (TRT + 2) * (W_ + 2) + S::NI * TRT * W_) * DWB_CC * 2;
@@ -1238,9 +1247,10 @@ int dwb_walk_launch(const void* dd_pre, const void* e_pre, const float* scale1, 
   int occ = 1;
   if (int rc = dw_smem_optin(kern, smem, &occ)) return rc;
   DwwGeom g;
-  g.B = B; g.H = H; g.Cm = Cm;
+  g.B = B; g.H = H; g.W = W; g.Cm = Cm;
   g.bands = (H + TRT - 1) / TRT;
-  const long long nt = (long long)((B + S::NI - 1) / S::NI) * g.bands;
+  g.tiles_w = W / W_;
+  const long long nt = (long long)((B + S::NI - 1) / S::NI) * g.bands * g.tiles_w;
   if (nt > 0x7fffffffLL) { ogv_set_error("dwconv_bwd: too many tiles"); return OGV_ERR_UNSUPPORTED; }
   g.ntiles = (int)nt;
   g.nchunks = Cm / DWB_CC;
@@ -1250,8 +1260,8 @@ int dwb_walk_launch(const void* dd_pre, const void* e_pre, const float* scale1, 
   g.nworkers = (int)want;
   CUtensorMap tmg, tme;
   {
-    unsigned long long dims[4] = {(unsigned long long)Cm, (unsigned long long)W_, (unsigned long long)H, (unsigned long long)B};
-    unsigned long long str[3] = {(unsigned long long)Cm * 2, (unsigned long long)W_ * Cm * 2, (unsigned long long)H * W_ * Cm * 2};
+    unsigned long long dims[4] = {(unsigned long long)Cm, (unsigned long long)W, (unsigned long long)H, (unsigned long long)B};
+    unsigned long long str[3] = {(unsigned long long)Cm * 2, (unsigned long long)W * Cm * 2, (unsigned long long)H * W * Cm * 2};
     unsigned boxg[4] = {(unsigned)DWB_CC, (unsigned)(W_ + 2), (unsigned)(TRT + 2), (unsigned)S::NI};
     unsigned boxe[4] = {(unsigned)DWB_CC, (unsigned)W_, (unsigned)TRT, (unsigned)S::NI};
     if (int rc = ogv_make_tmap(&tmg, dd_pre, OGV_BF16, 4, dims, str, boxg, 0)) return rc;
@@ -1280,15 +1290,15 @@ extern "C" int ogv_dwconv_fwd(const void* e_pre, const float* scale1, const floa
     // plain sweep stays the default; OGV_DW_FWD=pf / tile select the other two for A/B runs.
     variant = (e && e[0] == 't') ? 1 : ((e && e[0] == 'p') ? 2 : ((e && e[0] == 's') ? 0 : 3));
   }
-  if (variant == 3 && dtype == OGV_BF16 && (W == 4 || W == 8 || W == 16 || W == 32) && Cm % DWW_CC == 0 &&
+  if (variant == 3 && dtype == OGV_BF16 && (W == 4 || W == 8 || W == 16 || (W >= 32 && W % 32 == 0)) && Cm % DWW_CC == 0 &&
       (reinterpret_cast<uintptr_t>(scale1) & 15) == 0 && (reinterpret_cast<uintptr_t>(shift1) & 15) == 0) {
     cudaStream_t st = (cudaStream_t)stream;
     OGV_DISPATCH_ACT(act, ACT, {
       switch (W) {
-        case 32: return dww_launch<ACT, 32>(e_pre, scale1, shift1, w, d_pre, sum2, sumsq2, B, H, Cm, st);
-        case 16: return dww_launch<ACT, 16>(e_pre, scale1, shift1, w, d_pre, sum2, sumsq2, B, H, Cm, st);
-        case 8: return dww_launch<ACT, 8>(e_pre, scale1, shift1, w, d_pre, sum2, sumsq2, B, H, Cm, st);
-        default: return dww_launch<ACT, 4>(e_pre, scale1, shift1, w, d_pre, sum2, sumsq2, B, H, Cm, st);
+        case 16: return dww_launch<ACT, 16>(e_pre, scale1, shift1, w, d_pre, sum2, sumsq2, B, H, W, Cm, st);
+        case 8: return dww_launch<ACT, 8>(e_pre, scale1, shift1, w, d_pre, sum2, sumsq2, B, H, W, Cm, st);
+        case 4: return dww_launch<ACT, 4>(e_pre, scale1, shift1, w, d_pre, sum2, sumsq2, B, H, W, Cm, st);
+        default: return dww_launch<ACT, 32>(e_pre, scale1, shift1, w, d_pre, sum2, sumsq2, B, H, W, Cm, st);
       }
     });
   }
@@ -1377,14 +1387,14 @@ extern "C" int ogv_dwconv_bwd(const void* dd_pre, const void* e_pre, const float
               "dwconv_bwd: tensors must be 16-byte aligned");
   static int walk = -1;  // OGV_DW_BWD=tile selects the older TMA-tiled strip kernel (A/B measurements)
   if (walk < 0) { const char* e = getenv("OGV_DW_BWD"); walk = (e && e[0] == 't') ? 0 : 1; }
-  if (walk && dtype == OGV_BF16 && (W == 4 || W == 8 || W == 16 || W == 32) && Cm % DWB_CC == 0) {
+  if (walk && dtype == OGV_BF16 && (W == 4 || W == 8 || W == 16 || (W >= 32 && W % 32 == 0)) && Cm % DWB_CC == 0) {
     cudaStream_t st = (cudaStream_t)stream;
     OGV_DISPATCH_ACT(act, ACT, {
       switch (W) {
-        case 32: return dwb_walk_launch<ACT, 32>(dd_pre, e_pre, scale1, shift1, mean1, rstd1, w, du1, dw, dgamma1, dbeta1, B, H, Cm, st);
-        case 16: return dwb_walk_launch<ACT, 16>(dd_pre, e_pre, scale1, shift1, mean1, rstd1, w, du1, dw, dgamma1, dbeta1, B, H, Cm, st);
-        case 8: return dwb_walk_launch<ACT, 8>(dd_pre, e_pre, scale1, shift1, mean1, rstd1, w, du1, dw, dgamma1, dbeta1, B, H, Cm, st);
-        default: return dwb_walk_launch<ACT, 4>(dd_pre, e_pre, scale1, shift1, mean1, rstd1, w, du1, dw, dgamma1, dbeta1, B, H, Cm, st);
+        case 16: return dwb_walk_launch<ACT, 16>(dd_pre, e_pre, scale1, shift1, mean1, rstd1, w, du1, dw, dgamma1, dbeta1, B, H, W, Cm, st);
+        case 8: return dwb_walk_launch<ACT, 8>(dd_pre, e_pre, scale1, shift1, mean1, rstd1, w, du1, dw, dgamma1, dbeta1, B, H, W, Cm, st);
+        case 4: return dwb_walk_launch<ACT, 4>(dd_pre, e_pre, scale1, shift1, mean1, rstd1, w, du1, dw, dgamma1, dbeta1, B, H, W, Cm, st);
+        default: return dwb_walk_launch<ACT, 32>(dd_pre, e_pre, scale1, shift1, mean1, rstd1, w, du1, dw, dgamma1, dbeta1, B, H, W, Cm, st);
       }
     });
   }

@@ -333,9 +333,9 @@ int ol_optin(K kernel, size_t bytes) {
 // ================================================================================================
 constexpr int OLT_CC = 64;
 struct OltGeom {
-  int B, H, W, C, heads, hd, hpc;  // hpc = heads per 64-channel chunk (1 when hd >= 64)
+  int B, H, W, C, heads, hd, hpc;  // W = IMAGE width (a multiple of the tile width); hpc = heads per 64-channel chunk
   long long ld;
-  int TRT, NI, NSB, bands, nchunks;
+  int TRT, NI, NSB, bands, nchunks, tiles_w;
 };
 template <int W_> struct OltShape;
 template <> struct OltShape<32> { static constexpr int NI = 1, NSB = 1, TRS = 8; };
@@ -399,15 +399,18 @@ __global__ void __launch_bounds__(OL_THREADS) outlook_fwd_tile_kernel(const __gr
   __shared__ uint64_t bar;
   const int tid = threadIdx.x;
   const int chunk = blockIdx.x % g.nchunks;
-  const int rest = blockIdx.x / g.nchunks;
+  int rest = blockIdx.x / g.nchunks;
+  const int w0 = (rest % g.tiles_w) * W_;  // images wider than the tile (W = 64, 96, ...) are cut into column tiles
+  rest /= g.tiles_w;
   const int band = rest % g.bands;
   const int b0 = (rest / g.bands) * NI, r0 = band * TRT, c0 = chunk * OLT_CC;
   const int head0 = c0 / g.hd, hpc = g.hpc;
+  const int Wi = g.W;
   if (tid == 0) {
     ptx::mbar_init(&bar, 1);
     ptx::fence_barrier_init();
     ptx::mbar_arrive_expect_tx(&bar, (uint32_t)(TILE_ELEMS * sizeof(bf16)));
-    ptx::tma_load_4d(tile, &tm_v, &bar, c0, -1, r0 - 1, b0);
+    ptx::tma_load_4d(tile, &tm_v, &bar, c0, w0 - 1, r0 - 1, b0);
   }
   // softmax of the tile's centre positions while the box is in flight
   const int nsm = NI * TRT * W_ * hpc;
@@ -417,7 +420,7 @@ __global__ void __launch_bounds__(OL_THREADS) outlook_fwd_tile_kernel(const __gr
     const int b = b0 + img, h = r0 + rr;
     float a[9];
     if (b < g.B && h < g.H) {
-      const bf16* lp = va + (((long long)b * g.H + h) * W_ + w) * g.ld + g.C + (head0 + hl) * 9;
+      const bf16* lp = va + (((long long)b * g.H + h) * Wi + w0 + w) * g.ld + g.C + (head0 + hl) * 9;
       float l[9];
 #pragma unroll
       for (int t = 0; t < 9; ++t) l[t] = ld1(lp + t);
@@ -443,10 +446,10 @@ __global__ void __launch_bounds__(OL_THREADS) outlook_fwd_tile_kernel(const __gr
   const int b = b0 + img;
   const bf16* tcol = tile + ((img * (TRT + 2) + rs) * (W_ + 2) + x0) * OLT_CC + cg * 4;
   const float* wt = A_s + (((img * TRT + rs) * W_ + x0) * hpc + hl) * 12;
-  bf16* out = y + (((long long)b * g.H + r0 + rs) * W_ + x0) * g.C + c0 + cg * 4;
+  bf16* out = y + (((long long)b * g.H + r0 + rs) * Wi + w0 + x0) * g.C + c0 + cg * 4;
   const int rows_left = g.H - (r0 + rs);
   const bool bok = b < g.B;
-  const long long row_stride = (long long)W_ * g.C;
+  const long long row_stride = (long long)Wi * g.C;
   const int wps = hpc * 12;
   auto getw = [&](int j, int p, float (&av)[9]) {
     const float* a = wt + (j * W_ + p) * wps;
@@ -470,20 +473,21 @@ __global__ void __launch_bounds__(OL_THREADS) outlook_fwd_tile_kernel(const __gr
 }
 
 template <typename T>
-int olt_tmap(CUtensorMap* tm, const void* ptr, long long ld, int B, int H, int W, int rows_box, int NI) {
+int olt_tmap(CUtensorMap* tm, const void* ptr, long long ld, int B, int H, int W, int tile_w, int rows_box, int NI) {
   const unsigned long long es = sizeof(T);
   unsigned long long dims[4] = {(unsigned long long)ld, (unsigned long long)W, (unsigned long long)H, (unsigned long long)B};
   unsigned long long str[3] = {(unsigned long long)ld * es, (unsigned long long)W * ld * es, (unsigned long long)H * W * ld * es};
-  unsigned box[4] = {(unsigned)OLT_CC, (unsigned)(W + 2), (unsigned)rows_box, (unsigned)NI};
+  unsigned box[4] = {(unsigned)OLT_CC, (unsigned)(tile_w + 2), (unsigned)rows_box, (unsigned)NI};
   return ogv_make_tmap(tm, ptr, OGV_BF16, 4, dims, str, box, 0);
 }
 
-// the tiled kernels cover bf16, W in {4, 8, 16, 32}, 64-channel chunks with whole (or part of one) heads, 16-byte rows
+// the tiled kernels cover bf16, W in {4, 8, 16} or a multiple of 32 (cut into 32-column tiles), 64-channel chunks with
+// whole (or part of one) heads, 16-byte rows
 inline bool olt_supported(int dtype, int W, int C, int heads, long long ld, const void* a, const void* b) {
   static int off = -1;
   if (off < 0) { const char* e = getenv("OGV_OUTLOOK_TILED"); off = (e && e[0] == '0') ? 1 : 0; }
   if (off || dtype != OGV_BF16) return false;
-  if (!(W == 4 || W == 8 || W == 16 || W == 32)) return false;
+  if (!(W == 4 || W == 8 || W == 16 || (W >= 32 && W % 32 == 0))) return false;
   const int hd = C / heads;
   if (C % OLT_CC || hd % 4 || !(OLT_CC % hd == 0 || hd % OLT_CC == 0)) return false;
   if (ld % 8 || (reinterpret_cast<uintptr_t>(a) & 15) || (reinterpret_cast<uintptr_t>(b) & 15)) return false;
@@ -491,20 +495,21 @@ inline bool olt_supported(int dtype, int W, int C, int heads, long long ld, cons
 }
 
 template <int W_>
-int olt_fwd_launch(const void* va, long long ld, void* y, int B, int H, int C, int heads, cudaStream_t st) {
+int olt_fwd_launch(const void* va, long long ld, void* y, int B, int H, int W, int C, int heads, cudaStream_t st) {
   using S = OltShape<W_>;
   constexpr int TRT = S::TRS * S::NSB;
   OltGeom g;
-  g.B = B; g.H = H; g.W = W_; g.C = C; g.heads = heads; g.hd = C / heads; g.ld = ld;
+  g.B = B; g.H = H; g.W = W; g.C = C; g.heads = heads; g.hd = C / heads; g.ld = ld;
   g.hpc = g.hd >= OLT_CC ? 1 : OLT_CC / g.hd;
   g.TRT = TRT; g.NI = S::NI; g.NSB = S::NSB;
   g.bands = (H + TRT - 1) / TRT;
   g.nchunks = C / OLT_CC;
-  const long long ctas = (long long)((B + S::NI - 1) / S::NI) * g.bands * g.nchunks;
+  g.tiles_w = W / W_;
+  const long long ctas = (long long)((B + S::NI - 1) / S::NI) * g.bands * g.nchunks * g.tiles_w;
   if (ctas > 0x7fffffffLL) { ogv_set_error("outlook_core_fwd: grid too large"); return OGV_ERR_UNSUPPORTED; }
   const size_t smem = (size_t)S::NI * (TRT + 2) * (W_ + 2) * OLT_CC * 2 + (size_t)S::NI * TRT * W_ * g.hpc * 12 * 4;
   CUtensorMap tm;
-  if (int rc = olt_tmap<bf16>(&tm, va, ld, B, H, W_, TRT + 2, S::NI)) return rc;
+  if (int rc = olt_tmap<bf16>(&tm, va, ld, B, H, W, W_, TRT + 2, S::NI)) return rc;
   if (int rc = ol_optin(outlook_fwd_tile_kernel<W_>, smem)) return rc;
   outlook_fwd_tile_kernel<W_><<<(unsigned)ctas, OL_THREADS, smem, st>>>(tm, reinterpret_cast<const bf16*>(va),
                                                                        reinterpret_cast<bf16*>(y), g);
@@ -540,26 +545,29 @@ __global__ void __launch_bounds__(OL_THREADS) outlook_bwd_tile_kernel(const __gr
   __shared__ uint64_t bar;
   const int tid = threadIdx.x;
   const int chunk = blockIdx.x % g.nchunks;
-  const int rest = blockIdx.x / g.nchunks;
+  int rest = blockIdx.x / g.nchunks;
+  const int w0 = (rest % g.tiles_w) * W_;
+  rest /= g.tiles_w;
   const int band = rest % g.bands;
   const int b0 = (rest / g.bands) * NI, r0 = band * TRT, c0 = chunk * OLT_CC;
   const int head0 = c0 / g.hd, hpc = g.hpc;
+  const int Wi = g.W;
   if (tid == 0) {
     ptx::mbar_init(&bar, 1);
     ptx::fence_barrier_init();
     ptx::mbar_arrive_expect_tx(&bar, (uint32_t)(2 * TILE_ELEMS * sizeof(bf16)));
-    ptx::tma_load_4d(gt, &tm_g, &bar, c0, -1, r0 - 1, b0);
-    ptx::tma_load_4d(vt, &tm_v, &bar, c0, -1, r0 - 1, b0);
+    ptx::tma_load_4d(gt, &tm_g, &bar, c0, w0 - 1, r0 - 1, b0);
+    ptx::tma_load_4d(vt, &tm_v, &bar, c0, w0 - 1, r0 - 1, b0);
   }
   // probabilities of every halo position of the tile (zero outside the image)
   const int nsm = NI * TR2 * W2 * hpc;
   for (int i = tid; i < nsm; i += OL_THREADS) {
     const int hl = i % hpc, pos = i / hpc;
     const int wc = pos % W2, hr = (pos / W2) % TR2, img = pos / (W2 * TR2);
-    const int b = b0 + img, h = r0 - 1 + hr, w = wc - 1;
+    const int b = b0 + img, h = r0 - 1 + hr, w = w0 + wc - 1;
     float a[9];
-    if (b < g.B && h >= 0 && h < g.H && w >= 0 && w < W_) {
-      const bf16* lp = va + (((long long)b * g.H + h) * W_ + w) * g.ld + g.C + (head0 + hl) * 9;
+    if (b < g.B && h >= 0 && h < g.H && w >= 0 && w < Wi) {
+      const bf16* lp = va + (((long long)b * g.H + h) * Wi + w) * g.ld + g.C + (head0 + hl) * 9;
       float l[9];
 #pragma unroll
       for (int t = 0; t < 9; ++t) l[t] = ld1(lp + t);
@@ -593,10 +601,10 @@ __global__ void __launch_bounds__(OL_THREADS) outlook_bwd_tile_kernel(const __gr
 #pragma unroll
       for (int s9 = 0; s9 < 9; ++s9) av[s9] = abase[((j + s9 / 3) * W2 + p + s9 % 3) * aps + (8 - s9)];
     };
-    bf16* out = dva + (((long long)b * g.H + r0 + rs) * W_ + x0) * g.ld + c0 + cg * 4;
+    bf16* out = dva + (((long long)b * g.H + r0 + rs) * Wi + w0 + x0) * g.ld + c0 + cg * 4;
     const int rows_left = g.H - (r0 + rs);
     const bool bok = b < g.B;
-    const long long row_stride = (long long)W_ * g.ld;
+    const long long row_stride = (long long)Wi * g.ld;
     olt_walk<W_, TRS>(tcol, getw, [&](int j, const f32x2 (&acc)[2][2]) {
       if (bok && j < rows_left) {
 #pragma unroll
@@ -649,7 +657,7 @@ __global__ void __launch_bounds__(OL_THREADS) outlook_bwd_tile_kernel(const __gr
       dA[t] = lo + hi;
       dot = fmaf(a[t], dA[t], dot);
     }
-    bf16* row = dva + (((long long)b * g.H + h) * W_ + w) * g.ld;
+    bf16* row = dva + (((long long)b * g.H + h) * Wi + w0 + w) * g.ld;
     bf16* out = row + g.C + (head0 + hl) * 9;
 #pragma unroll
     for (int t = 0; t < 9; ++t) st1(out + t, a[t] * (dA[t] - dot));
@@ -658,23 +666,24 @@ __global__ void __launch_bounds__(OL_THREADS) outlook_bwd_tile_kernel(const __gr
 }
 
 template <int W_>
-int olt_bwd_launch(const void* va, long long ld, const void* dy, void* dva, int B, int H, int C, int heads,
+int olt_bwd_launch(const void* va, long long ld, const void* dy, void* dva, int B, int H, int W, int C, int heads,
                    cudaStream_t st) {
   using S = OltShapeB<W_>;
   constexpr int TRT = S::TRS * S::NSB;
   OltGeom g;
-  g.B = B; g.H = H; g.W = W_; g.C = C; g.heads = heads; g.hd = C / heads; g.ld = ld;
+  g.B = B; g.H = H; g.W = W; g.C = C; g.heads = heads; g.hd = C / heads; g.ld = ld;
   g.hpc = g.hd >= OLT_CC ? 1 : OLT_CC / g.hd;
   g.TRT = TRT; g.NI = S::NI; g.NSB = S::NSB;
   g.bands = (H + TRT - 1) / TRT;
   g.nchunks = C / OLT_CC;
-  const long long ctas = (long long)((B + S::NI - 1) / S::NI) * g.bands * g.nchunks;
+  g.tiles_w = W / W_;
+  const long long ctas = (long long)((B + S::NI - 1) / S::NI) * g.bands * g.nchunks * g.tiles_w;
   if (ctas > 0x7fffffffLL) { ogv_set_error("outlook_core_bwd: grid too large"); return OGV_ERR_UNSUPPORTED; }
   const size_t tile = (size_t)S::NI * (TRT + 2) * (W_ + 2) * OLT_CC * 2;
   const size_t smem = 2 * tile + (size_t)S::NI * (TRT + 2) * (W_ + 2) * g.hpc * 12 * 4;
   CUtensorMap tmv, tmg;
-  if (int rc = olt_tmap<bf16>(&tmv, va, ld, B, H, W_, TRT + 2, S::NI)) return rc;
-  if (int rc = olt_tmap<bf16>(&tmg, dy, C, B, H, W_, TRT + 2, S::NI)) return rc;
+  if (int rc = olt_tmap<bf16>(&tmv, va, ld, B, H, W, W_, TRT + 2, S::NI)) return rc;
+  if (int rc = olt_tmap<bf16>(&tmg, dy, C, B, H, W, W_, TRT + 2, S::NI)) return rc;
   if (int rc = ol_optin(outlook_bwd_tile_kernel<W_>, smem)) return rc;
   outlook_bwd_tile_kernel<W_><<<(unsigned)ctas, OL_THREADS, smem, st>>>(tmv, tmg, reinterpret_cast<const bf16*>(va),
                                                                        reinterpret_cast<bf16*>(dva), g);
@@ -699,10 +708,10 @@ extern "C" int ogv_outlook_core_fwd(const void* va, long long ld_va, void* y, in
   cudaStream_t st = (cudaStream_t)stream;
   if (olt_supported(dtype, W, C, heads, ld_va, va, y)) {
     switch (W) {
-      case 32: return olt_fwd_launch<32>(va, ld_va, y, B, H, C, heads, st);
-      case 16: return olt_fwd_launch<16>(va, ld_va, y, B, H, C, heads, st);
-      case 8: return olt_fwd_launch<8>(va, ld_va, y, B, H, C, heads, st);
-      default: return olt_fwd_launch<4>(va, ld_va, y, B, H, C, heads, st);
+      case 16: return olt_fwd_launch<16>(va, ld_va, y, B, H, W, C, heads, st);
+      case 8: return olt_fwd_launch<8>(va, ld_va, y, B, H, W, C, heads, st);
+      case 4: return olt_fwd_launch<4>(va, ld_va, y, B, H, W, C, heads, st);
+      default: return olt_fwd_launch<32>(va, ld_va, y, B, H, W, C, heads, st);
     }
   }
   OlGeom g;
@@ -730,10 +739,10 @@ extern "C" int ogv_outlook_core_bwd(const void* va, long long ld_va, const void*
   if (olt_supported(dtype, W, C, heads, ld_va, va, dva) && C / heads <= OLT_CC && C % 8 == 0 &&
       (reinterpret_cast<uintptr_t>(dy) & 15) == 0) {
     switch (W) {
-      case 32: return olt_bwd_launch<32>(va, ld_va, dy, dva, B, H, C, heads, st);
-      case 16: return olt_bwd_launch<16>(va, ld_va, dy, dva, B, H, C, heads, st);
-      case 8: return olt_bwd_launch<8>(va, ld_va, dy, dva, B, H, C, heads, st);
-      default: return olt_bwd_launch<4>(va, ld_va, dy, dva, B, H, C, heads, st);
+      case 16: return olt_bwd_launch<16>(va, ld_va, dy, dva, B, H, W, C, heads, st);
+      case 8: return olt_bwd_launch<8>(va, ld_va, dy, dva, B, H, W, C, heads, st);
+      case 4: return olt_bwd_launch<4>(va, ld_va, dy, dva, B, H, W, C, heads, st);
+      default: return olt_bwd_launch<32>(va, ld_va, dy, dva, B, H, W, C, heads, st);
     }
   }
   OlGeom g;

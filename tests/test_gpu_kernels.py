@@ -95,7 +95,9 @@ def _outlook_core_ref(va, B, H, W, C, heads):
     # the tiled bf16 kernels (W in {4, 8, 16, 32}, C % 64 == 0): every stage shape, ragged image groups (B not a multiple
     # of the images per tile), heights that are not a multiple of the tile rows, 16- / 32- / 64- / 128-wide heads
     (3, 16, 16, 128, 4), (5, 8, 8, 256, 8), (2, 12, 16, 64, 4), (9, 5, 8, 64, 1), (2, 20, 32, 128, 2), (11, 4, 4, 128, 1),
-    (1, 3, 4, 64, 2), (2, 16, 16, 64, 2)])
+    (1, 3, 4, 64, 2), (2, 16, 16, 64, 2),
+    # images wider than the 32-column tile (64 px stage 0 of cfg 3 / 4): column tiles with a real interior halo
+    (2, 64, 64, 64, 2), (1, 7, 96, 128, 4)])
 def test_outlook_core_fwd_bwd(B, H, W, C, heads, dt):
     from outlook_grid_vision_transformer_b200 import ops
     from outlook_grid_vision_transformer_b200.functional import outlook_npad
@@ -188,7 +190,8 @@ def _dw_ref(e_pre, sc, sh, w, B, H, W):
                                       # the TMA-tile walker forward (bf16, W in {4, 8, 16, 32}, Cm % 64 == 0): stage shapes,
                                       # ragged image groups, heights that are not a multiple of the tile rows, many tiles per CTA
                                       (3, 32, 32, 256), (2, 16, 16, 512), (5, 8, 8, 128), (11, 4, 4, 192), (2, 12, 16, 64),
-                                      (9, 5, 8, 64), (1, 3, 4, 64), (700, 8, 8, 64)])
+                                      (9, 5, 8, 64), (1, 3, 4, 64), (700, 8, 8, 64),
+                                      (2, 64, 64, 128), (1, 10, 96, 64)])
 def test_dwconv_fwd_bwd(B, H, W, Cm, dt):
     from outlook_grid_vision_transformer_b200 import ops
     torch.manual_seed(B + H + Cm)
