@@ -341,7 +341,15 @@ class Workload:
                                     grad_sync=self.sync, use_graph=use_graph, warmup=warm,
                                     grad_clip_norm=float(clip) if clip else None, scheduler=sched, world=world, flat=flat)
             self.step_resident = lambda: self.runner()
-            self.step_host = lambda: float(self.runner(self.x_host, self.y_host))  # H2D of the batch + D2H of the loss
+            # e2e: every step copies ITS batch from pinned host memory (on the copy stream, overlapped with the previous
+            # step: TrainStep.prefetch) and reads a loss back to the host (the previous step's: one-step lag, no stall)
+            def step_host(runner=self.runner, xh=self.x_host, yh=self.y_host):
+                runner.prefetch(xh, yh)
+                runner(staged=True)
+                runner.loss_to_host_async()
+                return runner.previous_loss()
+            self.step_host = step_host
+            self.step_host_sync = lambda: float(self.runner(self.x_host, self.y_host))  # unpipelined variant
             self.eager_body = self.runner._body
         else:
             model, bf16, x_dev, x_host = self.model, self.bf16, self.x_dev, self.x_host
@@ -549,6 +557,10 @@ def measure(w, args, world, dev, steps):
     ms = timed(w.step_resident, steps, world, dev)
     w.step_host()
     ms_e2e = timed(w.step_host, steps, world, dev)
+    if os.environ.get("OGV_BENCH_E2E_AB") == "1" and getattr(w, "step_host_sync", None) is not None:
+        w.step_host_sync()
+        print(f"[e2e A/B] pipelined {ms_e2e:.3f} ms, unpipelined {timed(w.step_host_sync, steps, world, dev):.3f} ms, "
+              f"resident {ms:.3f} ms", file=sys.stderr)
     return ms, ms_e2e
 
 

@@ -183,6 +183,16 @@ int ogv_se_mlp_bwd(const float* dgate, const float* gate_pre, const void* s1_pre
  * ogv_gemm forward and weight gradient. */
 int ogv_im2col3x3(const void* x, void* cols, int B, int H, int W, int Cin, int Kpad, int dtype, void* stream);
 
+/* The Downsample convolution (downsampling.py:41-47: nn.Conv2d(C, 2C, 3, stride 2, padding 1)) and any other 3x3 / pad 1 /
+ * stride 1|2 convolution over a channels_last image with Cin % 8 == 0, as GEMM rows:
+ *   ogv_im2col3x3_vec: cols[(b, oy, ox), (ky*3+kx)*Cin + c] = x[b, oy*s-1+ky, ox*s-1+kx, c], zero outside the image;
+ *                      Ho = (H-1)/s + 1, Wo = (W-1)/s + 1; forward = ogv_gemm(cols, W2), weight gradient = ogv_gemm
+ *                      (dY^T cols) with W2[co, (ky*3+kx)*Cin + c] = weight[co, c, ky, kx];
+ *   ogv_col2im3x3_vec: the input gradient from dcols = dY x W2 (ogv_gemm): dx[b, iy, ix, c] = sum of the patch entries
+ *                      that were copies of that pixel (replaces autograd's convolution_backward input branch). */
+int ogv_im2col3x3_vec(const void* x, void* cols, int B, int H, int W, int Cin, int stride, int dtype, void* stream);
+int ogv_col2im3x3_vec(const void* dcols, void* dx, int B, int H, int W, int Cin, int stride, int dtype, void* stream);
+
 /* conv -> BatchNorm -> act units around the blocks (stem_head.py:23-32, downsampling.py:28-65), the BN + act part:
  * out = act(scale*x + shift); backward with g = dy * act'(scale*x + shift) recomputed in both passes:
  * dbeta += sum g, dgamma += sum g*xhat; dx = gamma*rstd*(g - dbeta/n - xhat*dgamma/n). */

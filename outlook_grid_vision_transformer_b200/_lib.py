@@ -68,6 +68,8 @@ SIGNATURES = {
     "ogv_se_mlp_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "ogv_se_mlp_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "ogv_im2col3x3": [_P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "ogv_im2col3x3_vec": [_P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "ogv_col2im3x3_vec": [_P, _P, _I, _I, _I, _I, _I, _I, _P],
     "ogv_bn_act_apply": [_P, _P, _P, _P, _L, _I, _I, _I, _P],
     "ogv_bn_act_bwd_reduce": [_P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _P],
     "ogv_bn_act_bwd_apply": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _P],

@@ -351,6 +351,83 @@ __global__ void im2col3x3_kernel(const T* __restrict__ x, T* __restrict__ cols, 
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// The Downsample convolution (downsampling.py:41-47: 3x3, stride 2, pad 1, C -> 2C) as patches x tcgen05 GEMM.
+// Patches of a channels_last image whose channel count is a multiple of 8: cols[(b, oy, ox), tap*Cin + c] =
+// x[b, oy*s - 1 + ky, ox*s - 1 + kx, c].  Thread = (output pixel, 8 channels): the nine 16-byte loads are issued before the
+// nine stores (144 bytes in flight per thread), Cin/8 neighbouring threads move one contiguous Cin-wide run on both sides.
+// The input gradient is the reverse gather: dcols = dpre x W2 comes from the GEMM, and every input pixel sums the (at
+// most four at stride 2, nine at stride 1) patch entries that were copies of it, in fp32 and in a fixed order.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ void st_raw8(T* p, const Raw8<T>& r);
+template <> __device__ __forceinline__ void st_raw8<float>(float* p, const Raw8<float>& r) {
+  *reinterpret_cast<float4*>(p) = r.a;
+  *reinterpret_cast<float4*>(p + 4) = r.b;
+}
+template <> __device__ __forceinline__ void st_raw8<bf16>(bf16* p, const Raw8<bf16>& r) {
+  *reinterpret_cast<uint4*>(p) = r.u;
+}
+
+template <typename T, int STRIDE>
+__global__ void __launch_bounds__(256) im2col3x3_vec_kernel(const T* __restrict__ x, T* __restrict__ cols, int H, int W,
+                                                            int Ho, int Wo, int cg, unsigned nitems) {
+  const int Cin = cg * 8;
+  for (unsigned it = blockIdx.x * blockDim.x + threadIdx.x; it < nitems; it += gridDim.x * blockDim.x) {
+    const unsigned c = it % (unsigned)cg, p = it / (unsigned)cg;
+    const unsigned ox = p % (unsigned)Wo, q = p / (unsigned)Wo;
+    const unsigned oy = q % (unsigned)Ho, b = q / (unsigned)Ho;
+    const int iy0 = (int)oy * STRIDE - 1, ix0 = (int)ox * STRIDE - 1;
+    const T* img = x + (size_t)b * H * W * Cin + c * 8;
+    Raw8<T> r[9];
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const int iy = iy0 + tap / 3, ix = ix0 + tap % 3;
+      raw8_zero(r[tap]);
+      if ((unsigned)iy < (unsigned)H && (unsigned)ix < (unsigned)W) ld_raw8(img + ((size_t)iy * W + ix) * Cin, r[tap]);
+    }
+    T* dst = cols + (size_t)p * 9 * Cin + c * 8;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) st_raw8(dst + tap * Cin, r[tap]);
+  }
+}
+
+template <typename T, int STRIDE>
+__global__ void __launch_bounds__(256) col2im3x3_vec_kernel(const T* __restrict__ dcols, T* __restrict__ dx, int H, int W,
+                                                            int Ho, int Wo, int cg, unsigned nitems) {
+  const int Cin = cg * 8;
+  for (unsigned it = blockIdx.x * blockDim.x + threadIdx.x; it < nitems; it += gridDim.x * blockDim.x) {
+    const unsigned c = it % (unsigned)cg, p = it / (unsigned)cg;
+    const unsigned ix = p % (unsigned)W, q = p / (unsigned)W;
+    const unsigned iy = q % (unsigned)H, b = q / (unsigned)H;
+    const T* base = dcols + (size_t)b * Ho * Wo * 9 * Cin + c * 8;
+    Raw8<T> r[9];
+    bool on[9];
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      // the output position whose patch holds this pixel at (ky, kx): o*s - 1 + k = i
+      const int ty = (int)iy + 1 - tap / 3, tx = (int)ix + 1 - tap % 3;
+      const int oy = ty / STRIDE, oxx = tx / STRIDE;
+      on[tap] = ty >= 0 && tx >= 0 && ty % STRIDE == 0 && tx % STRIDE == 0 && oy < Ho && oxx < Wo;
+      if (on[tap]) ld_raw8(base + ((size_t)oy * Wo + oxx) * 9 * Cin + tap * Cin, r[tap]);
+    }
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      if (on[tap]) {
+        float v[8];
+        cvt_raw8(r[tap], v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] += v[i];
+      }
+    }
+    st8(dx + (size_t)p * Cin + c * 8, acc);
+  }
+}
+
 }  // namespace
 
 extern "C" int ogv_im2col3x3(const void* x, void* cols, int B, int H, int W, int Cin, int Kpad, int dtype, void* stream) {
@@ -376,6 +453,50 @@ extern "C" int ogv_im2col3x3(const void* x, void* cols, int B, int H, int W, int
     return ogv_check_launch("im2col3x3");
   });
 #undef OGV_IM2COL_CASE
+}
+
+extern "C" int ogv_im2col3x3_vec(const void* x, void* cols, int B, int H, int W, int Cin, int stride, int dtype,
+                                 void* stream) {
+  OGV_REQUIRE(x && cols && B > 0 && H > 0 && W > 0, "im2col3x3_vec: bad args");
+  OGV_REQUIRE(Cin > 0 && Cin % 8 == 0, "im2col3x3_vec: Cin=%d must be a multiple of 8", Cin);
+  OGV_REQUIRE(stride == 1 || stride == 2, "im2col3x3_vec: stride=%d (1 or 2)", stride);
+  const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
+  const long long nitems = (long long)B * Ho * Wo * (Cin / 8);
+  OGV_REQUIRE(nitems < 0x7fffffffLL, "im2col3x3_vec: too many items");
+  long long blocks = (nitems + 255) / 256;
+  const long long cap = (long long)ogv_num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  OGV_DISPATCH_DTYPE(dtype, T, {
+    if (stride == 1)
+      im2col3x3_vec_kernel<T, 1><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+          reinterpret_cast<const T*>(x), reinterpret_cast<T*>(cols), H, W, Ho, Wo, Cin / 8, (unsigned)nitems);
+    else
+      im2col3x3_vec_kernel<T, 2><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+          reinterpret_cast<const T*>(x), reinterpret_cast<T*>(cols), H, W, Ho, Wo, Cin / 8, (unsigned)nitems);
+    return ogv_check_launch("im2col3x3_vec");
+  });
+}
+
+extern "C" int ogv_col2im3x3_vec(const void* dcols, void* dx, int B, int H, int W, int Cin, int stride, int dtype,
+                                 void* stream) {
+  OGV_REQUIRE(dcols && dx && B > 0 && H > 0 && W > 0, "col2im3x3_vec: bad args");
+  OGV_REQUIRE(Cin > 0 && Cin % 8 == 0, "col2im3x3_vec: Cin=%d must be a multiple of 8", Cin);
+  OGV_REQUIRE(stride == 1 || stride == 2, "col2im3x3_vec: stride=%d (1 or 2)", stride);
+  const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
+  const long long nitems = (long long)B * H * W * (Cin / 8);
+  OGV_REQUIRE(nitems < 0x7fffffffLL, "col2im3x3_vec: too many items");
+  long long blocks = (nitems + 255) / 256;
+  const long long cap = (long long)ogv_num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  OGV_DISPATCH_DTYPE(dtype, T, {
+    if (stride == 1)
+      col2im3x3_vec_kernel<T, 1><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+          reinterpret_cast<const T*>(dcols), reinterpret_cast<T*>(dx), H, W, Ho, Wo, Cin / 8, (unsigned)nitems);
+    else
+      col2im3x3_vec_kernel<T, 2><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+          reinterpret_cast<const T*>(dcols), reinterpret_cast<T*>(dx), H, W, Ho, Wo, Cin / 8, (unsigned)nitems);
+    return ogv_check_launch("col2im3x3_vec");
+  });
 }
 
 extern "C" int ogv_nchw_to_nhwc(const void* src, void* dst, int B, int C, int HW, int dtype, void* stream) {

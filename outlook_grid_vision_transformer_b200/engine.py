@@ -233,6 +233,9 @@ class TrainStep:
         self._hyper_host = torch.zeros(5, dtype=torch.float32).pin_memory() if dev.type == "cuda" else torch.zeros(5)
         self.acc = torch.zeros(5, device=dev, dtype=torch.float32)      # loss*B, top1, top3, top5, B
         self.loss: Optional[torch.Tensor] = None
+        self._stage = None          # (x, y staging buffers, ready event, free event) of prefetch()
+        self._copy_stream = None
+        self._loss_host = None      # two pinned scalars + events of loss_to_host_async()
         self.logits: Optional[torch.Tensor] = None                       # static fp32 [B, K] buffer of the last step
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         # one Bernoulli draw for every DropPath of the model (call order), instead of 4 launches per DropPath
@@ -346,12 +349,24 @@ class TrainStep:
             _modules.FORCE_PREP = False
         self._restore(snap)
 
-    def __call__(self, x: Optional[torch.Tensor] = None, y: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """Run one step; x / y (if given) are copied into the static input buffers first.  Returns the loss (device)."""
-        if x is not None:
-            self.x.copy_(x, non_blocking=True)
-        if y is not None:
-            self.y.copy_(y, non_blocking=True)
+    def __call__(self, x: Optional[torch.Tensor] = None, y: Optional[torch.Tensor] = None, *,
+                 staged: bool = False) -> torch.Tensor:
+        """Run one step; x / y (if given) are copied into the static input buffers first; `staged=True` takes the batch
+        that `prefetch()` put into the staging buffers.  Returns the loss (device)."""
+        if staged:
+            if self._stage is None:
+                raise RuntimeError("TrainStep(staged=True) needs a prefetch() first")
+            sx, sy, ready, free = self._stage
+            main = torch.cuda.current_stream(self.x.device)
+            main.wait_event(ready)
+            self.x.copy_(sx, non_blocking=True)   # device-to-device, a few microseconds
+            self.y.copy_(sy, non_blocking=True)
+            free.record(main)
+        else:
+            if x is not None:
+                self.x.copy_(x, non_blocking=True)
+            if y is not None:
+                self.y.copy_(y, non_blocking=True)
         self._write_hyper()
         if self.graph is not None:
             self.graph.replay()
@@ -360,6 +375,46 @@ class TrainStep:
         self.step_num += 1
         _modules.note_parameters_updated()
         return self.loss
+
+    # ------------------------------------------------------------------------------------------ input / loss pipelining
+    def prefetch(self, x_host: torch.Tensor, y_host: torch.Tensor) -> None:
+        """Start the host-to-device copy of the NEXT batch (pinned host tensors) on a copy stream while the current step
+        runs -- what the reference's DataLoader(pin_memory=True) + `.to(device, non_blocking=True)` loop
+        (one_epoch_train.py:85-93) does.  The next `step(staged=True)` consumes it."""
+        dev = self.x.device
+        if self._stage is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            free = torch.cuda.Event()
+            free.record(torch.cuda.current_stream(dev))
+            self._stage = (torch.empty_like(self.x), torch.empty_like(self.y), torch.cuda.Event(), free)
+        sx, sy, ready, free = self._stage
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(free)  # the previous staged batch has been copied into the static buffers
+            sx.copy_(x_host, non_blocking=True)
+            sy.copy_(y_host, non_blocking=True)
+            ready.record(self._copy_stream)
+
+    def loss_to_host_async(self) -> None:
+        """Queue a device-to-host copy of this step's loss into pinned memory (no host synchronisation)."""
+        if self._loss_host is None:
+            self._loss_host = [torch.empty((), dtype=torch.float32).pin_memory() for _ in range(2)]
+            self._loss_evt = [torch.cuda.Event(), torch.cuda.Event()]
+            self._loss_idx, self._loss_count = 0, 0
+        i = self._loss_idx
+        self._loss_count += 1
+        self._loss_host[i].copy_(self.loss.detach().float().reshape(()), non_blocking=True)
+        self._loss_evt[i].record(torch.cuda.current_stream(self.x.device))
+        self._loss_idx = i ^ 1
+
+    def previous_loss(self) -> Optional[float]:
+        """The loss queued by the `loss_to_host_async()` call BEFORE the latest one (waits for that copy only): a one-step
+        lag keeps the host a full step ahead of the device instead of stalling it every iteration."""
+        if self._loss_host is None or self._loss_count < 2:
+            return None
+        i = self._loss_idx  # the slot the next call will overwrite = the older of the two
+        if not self._loss_evt[i].query():
+            self._loss_evt[i].synchronize()
+        return float(self._loss_host[i])
 
     # ------------------------------------------------------------------------------------------ bookkeeping
     def metrics(self, reset: bool = True) -> Dict[str, float]:

@@ -682,9 +682,12 @@ class OutlookCoreFn(torch.autograd.Function):
 # conv -> BatchNorm -> act units around the blocks: ConvStem (stem_head.py:23-32) and Downsample (downsampling.py:28-65)
 # =================================================================================================
 class ConvBnActFn(torch.autograd.Function):
-    """conv -> BatchNorm -> act.  The stem convolution (3x3, stride 1, a few input channels) is patches (ogv_im2col3x3)
-    x tcgen05 GEMM, forward and weight gradient; the Downsample convolutions (3x3 stride 2, C -> 2C) are the library's
-    (cuDNN implicit GEMM through aten, like cuBLAS for a plain GEMM).  Everything after the convolution -- batch
+    """conv -> BatchNorm -> act.  Both convolutions of the callers are patches x tcgen05 GEMM, forward, weight gradient
+    and input gradient: the stem (3x3, stride 1, a few input channels: ogv_im2col3x3, one K tile, no input gradient) and
+    the Downsample convolutions (downsampling.py:41-47: 3x3 stride 2, C -> 2C: ogv_im2col3x3_vec; the input gradient is
+    dcols = dpre x W2 on the GEMM followed by the ogv_col2im3x3_vec gather); the 1x1 convolution of the "pool" kind is a
+    plain GEMM on the rows.  Other geometries (kernel sizes, paddings, channel counts that are not a multiple of 8) go to
+    the library convolution (OGV_CONV_LIB=1 forces it, for A/B measurements).  Everything after the convolution -- batch
     statistics, running-statistics update, normalise + activation, and the whole BatchNorm + activation backward -- runs
     on this package's streaming kernels over the channels_last rows, saving only the pre-BN conv output (the
     activation derivative is recomputed in both backward passes)."""
@@ -697,17 +700,36 @@ class ConvBnActFn(torch.autograd.Function):
         xc = x.to(dt).contiguous(memory_format=torch.channels_last)
         Co, Cin, kh, kw = w.shape
         B = xc.shape[0]
-        # patches x GEMM when the patch row fits one K tile and nobody needs the input gradient (the network input)
-        as_gemm = (kh == 3 and kw == 3 and stride == [1, 1] and padding == [1, 1] and 9 * Cin <= 64
-                   and not x.requires_grad)
-        ops.PROFILER.tag = ("F2", "fwd", B * xc.shape[2] * xc.shape[3] // (stride[0] * stride[1]), Co)
-        if as_gemm:
-            H, W = xc.shape[2], xc.shape[3]
+        # patches x GEMM: "stem" when the patch row fits one K tile and nobody needs the input gradient (the network
+        # input), "vec" for channel counts that are a multiple of 8 (the Downsample convolutions), "1x1" = plain GEMM
+        Hi, Wi = xc.shape[2], xc.shape[3]
+        k3 = kh == 3 and kw == 3 and padding == [1, 1] and stride[0] == stride[1]
+        own = _os.environ.get("OGV_CONV_LIB", "0") != "1"
+        if k3 and stride == [1, 1] and 9 * Cin <= 64 and not x.requires_grad:
+            route = "stem"
+        elif own and k3 and stride[0] in (1, 2) and Cin % 8 == 0:
+            route = "vec"
+        elif own and kh == 1 and kw == 1 and stride == [1, 1] and padding == [0, 0] and Cin % 8 == 0:
+            route = "1x1"
+        else:
+            route = "lib"
+        ops.PROFILER.tag = ("F2", "fwd", B * Hi * Wi // (stride[0] * stride[1]), Co)
+        if route != "lib":
+            if route == "stem":
+                H, W = Hi, Wi
+                kpad = (9 * Cin + 7) // 8 * 8
+                cols = ops.im2col3x3(xc, kpad)
+                w2 = torch.zeros((Co, kpad), device=w.device, dtype=dt)
+                w2[:, :9 * Cin] = w.detach().permute(0, 2, 3, 1).reshape(Co, 9 * Cin)
+            elif route == "vec":
+                H, W = (Hi - 1) // stride[0] + 1, (Wi - 1) // stride[0] + 1
+                cols = ops.im2col3x3_vec(xc, stride[0])
+                w2 = w.detach().permute(0, 2, 3, 1).reshape(Co, 9 * Cin).to(dt)
+            else:
+                H, W = Hi, Wi
+                cols = xc.permute(0, 2, 3, 1).reshape(B * H * W, Cin)
+                w2 = w.detach().reshape(Co, Cin).to(dt)
             M = B * H * W
-            kpad = (9 * Cin + 7) // 8 * 8
-            cols = ops.im2col3x3(xc, kpad)
-            w2 = torch.zeros((Co, kpad), device=w.device, dtype=dt)
-            w2[:, :9 * Cin] = w.detach().permute(0, 2, 3, 1).reshape(Co, 9 * Cin)
             rows = _empty((M, Co), cols)
             ops.gemm(cols, w2, rows)
             saved = (cols, w2)
@@ -729,7 +751,8 @@ class ConvBnActFn(torch.autograd.Function):
         ops.PROFILER.tag = None
         ctx.meta = meta
         ctx.geom = (B, Co, H, W)
-        ctx.as_gemm = as_gemm
+        ctx.in_hw = (Hi, Wi)
+        ctx.route = route
         ctx.w_shape = (Co, Cin, kh, kw)
         ctx.x_needs_grad = x.requires_grad
         ctx.x_dtype = x.dtype
@@ -756,12 +779,21 @@ class ConvBnActFn(torch.autograd.Function):
             # running statistics: BatchNorm is a fixed affine map, dpre = gamma*rstd * g (no batch-mean terms)
             zero = _zeros(Co, gamma)
             dpre = ops.bn_act_bwd_apply(dyr, rows, scale, shift, mean, rstd, gamma.detach(), zero, zero, meta["act"])
-        if ctx.as_gemm:
+        if ctx.route != "lib":
             _, Cin, kh, kw = ctx.w_shape
             dw2 = _zeros((Co, a.shape[1]), gamma)
             ops._wgrad(dpre, a, dw2)  # on the main stream: autograd accumulates the returned view right away
             dw = dw2[:, :kh * kw * Cin].view(Co, kh, kw, Cin).permute(0, 3, 1, 2)
             dx = None
+            if ctx.x_needs_grad:  # never on the "stem" route
+                Hi, Wi = ctx.in_hw
+                w2t = wc.t().contiguous()  # [K, Co]: dcols = dpre x W2
+                dcols = _empty((M, a.shape[1]), dpre)
+                ops.gemm(dpre, w2t, dcols)
+                dxr = dcols if ctx.route == "1x1" else ops.col2im3x3_vec(dcols, B, Hi, Wi, Cin, meta["stride"][0])
+                dx = dxr.view(B, Hi, Wi, Cin).permute(0, 3, 1, 2)
+                if dx.dtype != ctx.x_dtype:
+                    dx = dx.to(ctx.x_dtype)
         else:
             dpre4 = dpre.view(B, H, W, Co).permute(0, 3, 1, 2)
             dx, dw, _ = torch.ops.aten.convolution_backward(dpre4, a, wc, None, meta["stride"], meta["padding"], [1, 1],

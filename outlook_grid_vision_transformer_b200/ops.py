@@ -452,8 +452,8 @@ def bn_bwd_reduce(dy, x, mean, rstd, dgamma, dbeta) -> None:
                                        x.shape[1], dtype_code(x), _stream())
 
 
-def bn_bwd_apply(dy, x, mean, rstd, gamma, dgamma, dbeta) -> Tensor:
-    dx = torch.empty_like(x)
+def bn_bwd_apply(dy, x, mean, rstd, gamma, dgamma, dbeta, out: Optional[Tensor] = None) -> Tensor:
+    dx = torch.empty_like(x) if out is None else out
     _call("ogv_bn_bwd_apply", _p(dy), _p(x), _p(mean), _p(rstd), _p(gamma), _p(dgamma), _p(dbeta), _p(dx),
                                       x.shape[0], x.shape[1], dtype_code(x), _stream())
     return dx
@@ -468,6 +468,30 @@ def im2col3x3(x: Tensor, kpad: int) -> Tensor:
     cols = torch.empty((B * H * W, kpad), device=x.device, dtype=x.dtype)
     _call("ogv_im2col3x3", _p(x), _p(cols), B, H, W, Cin, kpad, dtype_code(x), _stream())
     return cols
+
+
+def im2col3x3_vec(x: Tensor, stride: int) -> Tensor:
+    """channels_last [B, Cin, H, W] (Cin % 8 == 0) -> 3x3 / pad 1 / stride 1|2 patches as rows [B*Ho*Wo, 9*Cin]."""
+    _require_cuda(x)
+    B, Cin, H, W = x.shape
+    if not x.permute(0, 2, 3, 1).is_contiguous():
+        raise ValueError("im2col3x3_vec needs a channels_last tensor")
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    cols = torch.empty((B * Ho * Wo, 9 * Cin), device=x.device, dtype=x.dtype)
+    _call("ogv_im2col3x3_vec", _p(x), _p(cols), B, H, W, Cin, stride, dtype_code(x), _stream())
+    return cols
+
+
+def col2im3x3_vec(dcols: Tensor, B: int, H: int, W: int, Cin: int, stride: int) -> Tensor:
+    """dcols [B*Ho*Wo, 9*Cin] -> input gradient as rows [B*H*W, Cin] (the transpose of im2col3x3_vec)."""
+    _require_cuda(dcols)
+    _rows(dcols, "dcols")
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    if tuple(dcols.shape) != (B * Ho * Wo, 9 * Cin) or not dcols.is_contiguous():
+        raise ValueError(f"col2im3x3_vec: dcols must be a contiguous [{B * Ho * Wo}, {9 * Cin}] tensor")
+    dx = torch.empty((B * H * W, Cin), device=dcols.device, dtype=dcols.dtype)
+    _call("ogv_col2im3x3_vec", _p(dcols), _p(dx), B, H, W, Cin, stride, dtype_code(dcols), _stream())
+    return dx
 
 
 def bn_act_apply(x: Tensor, scale: Tensor, shift: Tensor, act: str) -> Tensor:
@@ -499,8 +523,9 @@ def dwconv_fwd(e_pre, scale1, shift1, w, ssum2, ssq2, B, H, W, act: str) -> Tens
     return d_pre
 
 
-def dwconv_bwd(dd_pre, e_pre, scale1, shift1, mean1, rstd1, w, dw, dgamma1, dbeta1, B, H, W, act: str) -> Tensor:
-    du1 = torch.empty_like(e_pre)
+def dwconv_bwd(dd_pre, e_pre, scale1, shift1, mean1, rstd1, w, dw, dgamma1, dbeta1, B, H, W, act: str,
+               out: Optional[Tensor] = None) -> Tensor:
+    du1 = torch.empty_like(e_pre) if out is None else out
     _call("ogv_dwconv_bwd", _p(dd_pre), _p(e_pre), _p(scale1), _p(shift1), _p(mean1), _p(rstd1), _p(w),
                                     _p(du1), _p(dw), _p(dgamma1), _p(dbeta1), B, H, W, e_pre.shape[1], ACT[act],
                                     dtype_code(e_pre), _stream())
@@ -554,8 +579,8 @@ def se_mlp_bwd(dgate: Tensor, gate_pre: Tensor, s1_pre: Tensor, w2: Tensor, w1: 
     return dgate_c, ds1_pre, dpool
 
 
-def bn_act_gate(d_pre, scale2, shift2, gate, B, HW, act: str) -> Tensor:
-    d_act = torch.empty_like(d_pre)
+def bn_act_gate(d_pre, scale2, shift2, gate, B, HW, act: str, out: Optional[Tensor] = None) -> Tensor:
+    d_act = torch.empty_like(d_pre) if out is None else out
     _call("ogv_bn_act_gate", _p(d_pre), _p(scale2), _p(shift2), _p(gate), _p(d_act), B, HW, d_pre.shape[1],
                                      ACT[act], dtype_code(d_pre), _stream())
     return d_act
@@ -568,9 +593,9 @@ def se_bwd_reduce(dd_act, d_pre, scale2, shift2, B, HW, act: str) -> Tensor:
     return dgate
 
 
-def mbconv_bwd_stats(dd_act, d_pre, scale2, shift2, mean2, rstd2, B, HW, act: str) -> Tensor:
+def mbconv_bwd_stats(dd_act, d_pre, scale2, shift2, mean2, rstd2, B, HW, act: str, out: Optional[Tensor] = None) -> Tensor:
     """-> stats [5, B, Cm] fp32 (stats[0] = dgate); see include/ogv.h."""
-    stats = torch.empty((5, B, d_pre.shape[1]), device=d_pre.device, dtype=torch.float32)
+    stats = torch.empty((5, B, d_pre.shape[1]), device=d_pre.device, dtype=torch.float32) if out is None else out
     _call("ogv_mbconv_bwd_stats", _p(dd_act), _p(d_pre), _p(scale2), _p(shift2), _p(mean2), _p(rstd2), _p(stats), B,
           HW, d_pre.shape[1], ACT[act], dtype_code(d_pre), _stream())
     return stats
@@ -582,8 +607,8 @@ def mbconv_bn2_finalize(stats, gate, dpool, dgamma2, dbeta2, B, HW) -> None:
 
 
 def dw_bn2_bwd_apply(dd_act, d_pre, gate, dpool, scale2, shift2, mean2, rstd2, gamma2, dgamma2, dbeta2, B, HW,
-                     act: str) -> Tensor:
-    dd_pre = torch.empty_like(d_pre)
+                     act: str, out: Optional[Tensor] = None) -> Tensor:
+    dd_pre = torch.empty_like(d_pre) if out is None else out
     _call("ogv_dw_bn2_bwd_apply", _p(dd_act), _p(d_pre), _p(gate), _p(dpool), _p(scale2), _p(shift2), _p(mean2),
           _p(rstd2), _p(gamma2), _p(dgamma2), _p(dbeta2), _p(dd_pre), B, HW, d_pre.shape[1], ACT[act],
           dtype_code(d_pre), _stream())

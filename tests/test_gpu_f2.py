@@ -166,3 +166,58 @@ def test_stem_as_patches_gemm(mode):
     for (k, b), (_, q) in zip(unit.stem.named_buffers(), ref.named_buffers()):
         if b.is_floating_point():
             assert_close(b, q, 1e-3 if mode == "fp32" else 5e-3, f"buffer[{k}]")
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+@pytest.mark.parametrize("stride", [1, 2])
+@pytest.mark.parametrize("shape", [(2, 8, 5, 7), (3, 16, 4, 4), (2, 64, 16, 16), (1, 24, 9, 6), (5, 128, 8, 8)])
+def test_im2col_col2im_vec_bit_exact(shape, stride, dtype):
+    """ogv_im2col3x3_vec against F.unfold and ogv_col2im3x3_vec against F.fold (its transpose) on integer-valued
+    inputs: bit-exact, odd sizes and both strides (downsampling.py:41-47 is stride 2)."""
+    from outlook_grid_vision_transformer_b200 import ops
+    B, C, H, W = shape
+    g = torch.Generator().manual_seed(11)
+    x = torch.randint(-8, 9, shape, generator=g).to(dtype).to(DEV).contiguous(memory_format=torch.channels_last)
+    cols = ops.im2col3x3_vec(x, stride)
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    want = torch.nn.functional.unfold(x.float(), 3, padding=1, stride=stride)       # [B, C*9, Ho*Wo], row c*9 + tap
+    want = want.view(B, C, 9, Ho * Wo).permute(0, 3, 2, 1).reshape(B * Ho * Wo, 9 * C)  # column tap*C + c
+    assert cols.shape == want.shape
+    assert torch.equal(cols.float(), want)
+    d = torch.randint(-4, 5, (B * Ho * Wo, 9 * C), generator=g).to(dtype).to(DEV)
+    dx = ops.col2im3x3_vec(d, B, H, W, C, stride)
+    dn = d.float().view(B, Ho * Wo, 9, C).permute(0, 3, 2, 1).reshape(B, C * 9, Ho * Wo)
+    want_dx = torch.nn.functional.fold(dn, (H, W), 3, padding=1, stride=stride)      # [B, C, H, W]
+    assert torch.equal(dx.float().view(B, H, W, C).permute(0, 3, 1, 2), want_dx)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_downsample_convolution_runs_on_own_kernels(mode):
+    """Downsample's 3x3 stride-2 convolution takes the patches x GEMM route in all three directions (no library
+    convolution in the step) and agrees with the module chain at the stage shapes of cfg 2 (scaled-down batch)."""
+    from outlook_grid_vision_transformer_b200 import functional as OF
+    from outlook_grid_vision_transformer_b200.model import Downsample
+    rtol = 1e-3 if mode == "fp32" else 2e-2
+    for cin, hw in ((64, 32), (128, 16), (256, 8)):
+        torch.manual_seed(12)
+        unit = Downsample(cin, 2 * cin).to(DEV).train()
+        ref = copy.deepcopy(unit.op)
+        x = torch.randn(4, cin, hw, hw, device=DEV).contiguous(memory_format=torch.channels_last)
+        x1, x2 = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+        seen = []
+        orig_i, orig_c = OF.ops.im2col3x3_vec, OF.ops.col2im3x3_vec
+        OF.ops.im2col3x3_vec = lambda *a: (seen.append("im2col"), orig_i(*a))[1]
+        OF.ops.col2im3x3_vec = lambda *a: (seen.append("col2im"), orig_c(*a))[1]
+        try:
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=mode == "bf16"):
+                y, yr = unit(x1), ref(x2)
+            dy = torch.randn_like(y)
+            y.backward(dy)
+            yr.backward(dy)
+        finally:
+            OF.ops.im2col3x3_vec, OF.ops.col2im3x3_vec = orig_i, orig_c
+        assert seen == ["im2col", "col2im"], seen
+        assert_close(y.float(), yr.float(), rtol, f"output C={cin}")
+        assert_close(x1.grad, x2.grad, rtol, f"dx C={cin}")
+        for (k, p), (_, q) in zip(unit.op.named_parameters(), ref.named_parameters()):
+            assert_close(p.grad, q.grad, rtol, f"grad[{k}] C={cin}", atol=1e-6)
