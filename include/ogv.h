@@ -193,6 +193,18 @@ int ogv_im2col3x3(const void* x, void* cols, int B, int H, int W, int Cin, int K
 int ogv_im2col3x3_vec(const void* x, void* cols, int B, int H, int W, int Cin, int stride, int dtype, void* stream);
 int ogv_col2im3x3_vec(const void* dcols, void* dx, int B, int H, int W, int Cin, int stride, int dtype, void* stream);
 
+/* The same convolution as an IMPLICIT GEMM on the tcgen05 engine (bf16, Cin % 64 == 0, output rows that tile 64 / 128
+ * pixels): the patch matrix is never written -- the GEMM's TMA producer fetches each (tap, 64-channel) slice of a tile of
+ * output pixels as one 5-D box of x viewed as {2*Cin, W/2, 2, H/2, B} (stride 2) or {Cin, W, 1, H, B} (stride 1), the zero
+ * padding being the descriptor's out-of-bounds fill.
+ *   ogv_conv3x3_fwd  : y[(b,oy,ox), co] = sum_k cols[.., k] * w2[co, k]          (downsampling.py:41-47 forward)
+ *   ogv_conv3x3_wgrad: dw2[co, k] += sum_pixels dy[pixel, co] * cols[pixel, k]   (fp32, split over pixels, pre-zeroed)
+ * with w2[co, (ky*3+kx)*Cin + c] = weight[co, c, ky, kx].  ogv_conv3x3_supported() -> 1 when the geometry is served. */
+int ogv_conv3x3_supported(int B, int H, int W, int Cin, int Co, int stride);
+int ogv_conv3x3_fwd(const void* x, const void* w2, void* y, int B, int H, int W, int Cin, int Co, int stride, void* stream);
+int ogv_conv3x3_wgrad(const void* x, const void* dy, float* dw2, int B, int H, int W, int Cin, int Co, int stride,
+                      void* stream);
+
 /* conv -> BatchNorm -> act units around the blocks (stem_head.py:23-32, downsampling.py:28-65), the BN + act part:
  * out = act(scale*x + shift); backward with g = dy * act'(scale*x + shift) recomputed in both passes:
  * dbeta += sum g, dgamma += sum g*xhat; dx = gamma*rstd*(g - dbeta/n - xhat*dgamma/n). */

@@ -52,6 +52,17 @@ __device__ __forceinline__ float epi_scalar(const GemmEpi& e, int m, int n, floa
   return round_to<TO>(v);
 }
 
+// One operand of a tcgen05 GEMM as the never-materialised 3x3 / pad 1 patch matrix of a channels_last bf16 image
+// (ogv_gemm_tc.cu: ConvView).  which = 1: the A operand of a forward product (args.A = x, a_rs = 9*Cin, a_cs = 1,
+// M = B*Ho*Wo, K = 9*Cin); which = 2: the B operand of a weight-gradient product (args.B = x, b_rs = 1, b_cs = 9*Cin,
+// N = 9*Cin, K = B*Ho*Wo).
+struct ogv_conv_view {
+  int which;
+  const void* x;
+  int B, H, W, Cin, stride;
+};
+bool ogv_conv_view_supported(const ogv_conv_view& c);
+int ogv_gemm_tc_conv(const ogv_gemm_args& a, const ogv_conv_view& conv, cudaStream_t stream);
 int ogv_gemm_simt(const ogv_gemm_args& a, cudaStream_t stream);
 int ogv_gemm_tc(const ogv_gemm_args& a, cudaStream_t stream);
 bool ogv_gemm_tc_supported(const ogv_gemm_args& a, const char** why);

@@ -18,6 +18,7 @@
 #include "ogv_gemm.cuh"
 #include "ogv_ptx.cuh"
 #include "ogv_stage.cuh"
+#include "ogv_tma.cuh"
 
 namespace {
 
@@ -40,8 +41,36 @@ constexpr int SMEM_LIMIT = 227 * 1024;
 constexpr int BAR_BYTES = (2 * MAX_STAGES + 4 + 2 * EPI_WARPS) * 8 + 16;
 constexpr int ONES_BYTES = 2048;  // B operand of the row-sum MMA: 16 rows x 64 k of bf16 ones (K-major)
 
+// Patch view: one operand of the GEMM is the (never materialised) im2col matrix of a channels_last bf16 image,
+//   cols[(b, oy, ox), (ky*3 + kx)*Cin + c] = x[b, oy*s - 1 + ky, ox*s - 1 + kx, c]        (3x3, pad 1, stride s = 1 | 2)
+// A 64-channel slice of one tap for a run of output pixels is ONE 5-D TMA box of x viewed as
+//   s = 2: {2*Cin (w-parity, c), W/2, 2 (h-parity), H/2, B}      s = 1: {Cin, W, 1, H, B}
+// -- box {64, Wo, 1, rows, images}: whole output rows, so the tile lands in shared memory in the row order of the
+// output matrix and with the same 128B-swizzled layout as a 2-D box of the materialised matrix; the taps that fall off
+// the image are the descriptor's zero fill (coordinate -1 / past the end).
+struct ConvView {
+  int which;   // 0: none; 1: the K-major A operand (forward: rows = pixels, k = patch columns);
+               // 2: the MN-major B operand (weight gradient: n = patch columns, k = pixels)
+  int Cin, stride, Wo, rpi /* Ho*Wo */, B;
+};
+
+__device__ __forceinline__ void conv_patch_load(void* dst, const CUtensorMap* tm, uint64_t* bar, const ConvView& cv,
+                                                int row0, int col0) {
+  const int tap = col0 / cv.Cin, c0 = col0 - tap * cv.Cin;
+  const int ky = tap / 3, kx = tap - 3 * ky;
+  int b0 = row0 / cv.rpi;
+  const int oy0 = (row0 - b0 * cv.rpi) / cv.Wo;
+  if (tap >= 9) b0 = cv.B;  // columns past the patch matrix (N tail of a weight-gradient tile): all zero fill
+  if (cv.stride == 2)
+    ptx::tma_load_5d(dst, tm, bar, (kx != 1 ? cv.Cin : 0) + c0, kx == 0 ? -1 : 0, ky != 1 ? 1 : 0,
+                     oy0 + (ky == 0 ? -1 : 0), b0);
+  else
+    ptx::tma_load_5d(dst, tm, bar, c0, kx - 1, 0, oy0 + ky - 1, b0);
+}
+
 struct TcParams {
   int M, N, K;
+  ConvView cv;
   int a_mn, b_mn;
   int m_tiles, n_tiles, splits, chunks_per_split, k_chunks;
   int stages;       // smem ring depth
@@ -195,7 +224,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           uint8_t* sa = smem + stage * STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
           const int k0 = kc * TC_BK;
-          if (!p.a_mn) {
+          if (p.cv.which == 1) {
+#pragma unroll
+            for (int i = 0; i < MT; ++i)  // 128 output pixels x 64 channels of one tap
+              conv_patch_load(sa + i * (TC_BM * TC_BK * 2), &tmA, &full_bar[stage], p.cv, m0 + i * TC_BM, k0);
+          } else if (!p.a_mn) {
 #pragma unroll
             for (int i = 0; i < MT; ++i)  // box {64 k, 128 rows} per M sub-tile
               ptx::tma_load_2d(sa + i * (TC_BM * TC_BK * 2), &tmA, &full_bar[stage], k0, m0 + i * TC_BM);
@@ -204,7 +237,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int j = 0; j < TC_BM / 64; ++j)  // box {64 mn, 64 k-rows}
               ptx::tma_load_2d(sa + j * 8192, &tmA, &full_bar[stage], m0 + 64 * j, k0);
           }
-          if (!p.b_mn) {
+          if (p.cv.which == 2) {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)  // 64 pixels (k rows) x 64 patch columns
+              conv_patch_load(sb + j * 8192, &tmB, &full_bar[stage], p.cv, k0, n0 + 64 * j);
+          } else if (!p.b_mn) {
             ptx::tma_load_2d(sb, &tmB, &full_bar[stage], k0, n0);  // box {64 k, BN rows}
           } else {
 #pragma unroll
@@ -574,7 +611,58 @@ bool ogv_gemm_tc_supported(const ogv_gemm_args& a, const char** why) {
   return true;
 }
 
-int ogv_gemm_tc(const ogv_gemm_args& a, cudaStream_t stream) {
+// Box geometry of the patch view for tiles of `rows` output pixels: whole output rows of one image, or whole images.
+static bool conv_box(const ogv_conv_view& c, int rows, unsigned (&box)[5]) {
+  if (c.stride != 1 && c.stride != 2) return false;
+  if (c.Cin % 64 != 0 || c.B < 1 || c.H < 1 || c.W < 1) return false;
+  if (c.stride == 2 && ((c.H | c.W) & 1)) return false;
+  const int Ho = c.H / c.stride, Wo = c.W / c.stride, rpi = Ho * Wo;
+  if (Wo > rows || rows % Wo != 0) return false;
+  int bh, bb;
+  if (rpi >= rows) {
+    if (rpi % rows != 0) return false;
+    bh = rows / Wo; bb = 1;
+  } else {
+    if (rows % rpi != 0) return false;
+    bh = Ho; bb = rows / rpi;
+  }
+  box[0] = 64; box[1] = (unsigned)Wo; box[2] = 1; box[3] = (unsigned)bh; box[4] = (unsigned)bb;
+  return true;
+}
+
+bool ogv_conv_view_supported(const ogv_conv_view& c) {
+  unsigned box[5];
+  return conv_box(c, 128, box) && conv_box(c, 64, box) && (reinterpret_cast<uintptr_t>(c.x) % 16 == 0);
+}
+
+static int make_conv_tmap(CUtensorMap* tm, const ogv_conv_view& c, int rows) {
+  unsigned box[5];
+  if (!conv_box(c, rows, box)) {
+    ogv_set_error("gemm_tc: patch view not expressible (B=%d H=%d W=%d Cin=%d stride=%d, %d-row tiles)", c.B, c.H, c.W,
+                  c.Cin, c.stride, rows);
+    return OGV_ERR_UNSUPPORTED;
+  }
+  const unsigned long long C = (unsigned long long)c.Cin, W = (unsigned long long)c.W, H = (unsigned long long)c.H;
+  unsigned long long dims[5], str[4];
+  if (c.stride == 2) {
+    dims[0] = 2 * C; dims[1] = W / 2; dims[2] = 2; dims[3] = H / 2; dims[4] = (unsigned long long)c.B;
+    str[0] = 2 * C * 2; str[1] = W * C * 2; str[2] = 2 * W * C * 2; str[3] = H * W * C * 2;
+  } else {
+    dims[0] = C; dims[1] = W; dims[2] = 1; dims[3] = H; dims[4] = (unsigned long long)c.B;
+    str[0] = C * 2; str[1] = W * C * 2; str[2] = W * C * 2; str[3] = H * W * C * 2;
+  }
+  return ogv_make_tmap(tm, c.x, OGV_BF16, 5, dims, str, box, 3);
+}
+
+static int gemm_tc_run(const ogv_gemm_args& a, const ogv_conv_view* conv, cudaStream_t stream);
+
+int ogv_gemm_tc(const ogv_gemm_args& a, cudaStream_t stream) { return gemm_tc_run(a, nullptr, stream); }
+
+int ogv_gemm_tc_conv(const ogv_gemm_args& a, const ogv_conv_view& conv, cudaStream_t stream) {
+  return gemm_tc_run(a, &conv, stream);
+}
+
+static int gemm_tc_run(const ogv_gemm_args& a, const ogv_conv_view* conv, cudaStream_t stream) {
   const char* why = "";
   if (!ogv_gemm_tc_supported(a, &why)) {
     ogv_set_error("gemm_tc: unsupported problem: %s", why);
@@ -588,6 +676,15 @@ int ogv_gemm_tc(const ogv_gemm_args& a, cudaStream_t stream) {
   p.M = a.M; p.N = a.N; p.K = a.K;
   p.a_mn = operand_major(a.a_rs, a.a_cs);
   p.b_mn = operand_major(a.b_rs, a.b_cs);
+  p.cv.which = 0;
+  if (conv && conv->which) {
+    if ((conv->which == 1 && p.a_mn != 0) || (conv->which == 2 && p.b_mn != 1) || (conv->which != 1 && conv->which != 2)) {
+      ogv_set_error("gemm_tc: patch view on an operand of the wrong major-ness");
+      return OGV_ERR_ARG;
+    }
+    p.cv.which = conv->which; p.cv.Cin = conv->Cin; p.cv.stride = conv->stride; p.cv.B = conv->B;
+    p.cv.Wo = conv->W / conv->stride; p.cv.rpi = (conv->H / conv->stride) * p.cv.Wo;
+  }
   const int BN = a.N <= 64 ? 64 : (a.N <= 128 ? 128 : 256);
   // two 128-row sub-tiles per work item for narrow bf16 outputs with enough rows to keep every SM busy
   static int mt_mode = -1;  // OGV_GEMM_MT=1 forces single sub-tiles (A/B measurements)
@@ -631,10 +728,12 @@ int ogv_gemm_tc(const ogv_gemm_args& a, cudaStream_t stream) {
 
   CUtensorMap tms[5];
   int rc;
-  if (!p.a_mn) rc = make_tmap(&tms[0], a.A, a.K, a.M, a.a_rs, 64, TC_BM, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (p.cv.which == 1) rc = make_conv_tmap(&tms[0], *conv, TC_BM);
+  else if (!p.a_mn) rc = make_tmap(&tms[0], a.A, a.K, a.M, a.a_rs, 64, TC_BM, CU_TENSOR_MAP_SWIZZLE_128B);
   else rc = make_tmap(&tms[0], a.A, a.M, a.K, a.a_cs, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
-  if (!p.b_mn) rc = make_tmap(&tms[1], a.B, a.K, a.N, a.b_rs, 64, BN, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (p.cv.which == 2) rc = make_conv_tmap(&tms[1], *conv, 64);
+  else if (!p.b_mn) rc = make_tmap(&tms[1], a.B, a.K, a.N, a.b_rs, 64, BN, CU_TENSOR_MAP_SWIZZLE_128B);
   else rc = make_tmap(&tms[1], a.B, a.N, a.K, a.b_cs, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
   tms[2] = tms[0]; tms[3] = tms[0]; tms[4] = tms[0];  // placeholders, never dereferenced when unused
@@ -654,4 +753,56 @@ int ogv_gemm_tc(const ogv_gemm_args& a, cudaStream_t stream) {
       return obf ? launch_tc<128, bf16, 1>(tms, p, stream) : launch_tc<128, float, 1>(tms, p, stream);
     default: return obf ? launch_tc<256, bf16, 1>(tms, p, stream) : launch_tc<256, float, 1>(tms, p, stream);
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 3x3 / pad 1 / stride 1|2 convolution over channels_last bf16 rows as an implicit GEMM (include/ogv.h)
+// ---------------------------------------------------------------------------------------------
+extern "C" int ogv_conv3x3_supported(int B, int H, int W, int Cin, int Co, int stride) {
+  ogv_conv_view c{1, reinterpret_cast<const void*>(uintptr_t(16)), B, H, W, Cin, stride};
+  return (Co > 0 && Co % 8 == 0 && ogv_conv_view_supported(c)) ? 1 : 0;
+}
+
+extern "C" int ogv_conv3x3_fwd(const void* x, const void* w2, void* y, int B, int H, int W, int Cin, int Co, int stride,
+                               void* stream) {
+  OGV_REQUIRE(x && w2 && y, "conv3x3_fwd: null pointer");
+  ogv_conv_view c{1, x, B, H, W, Cin, stride};
+  if (!(Co > 0 && Co % 8 == 0 && ogv_conv_view_supported(c))) {
+    ogv_set_error("conv3x3_fwd: unsupported geometry B=%d H=%d W=%d Cin=%d Co=%d stride=%d", B, H, W, Cin, Co, stride);
+    return OGV_ERR_UNSUPPORTED;
+  }
+  ogv_gemm_args a;
+  memset(&a, 0, sizeof(a));
+  a.A = x; a.a_rs = 9LL * Cin; a.a_cs = 1;
+  a.B = w2; a.b_rs = 9LL * Cin; a.b_cs = 1;
+  a.D = y; a.ldd = Co;
+  a.M = B * (H / stride) * (W / stride); a.N = Co; a.K = 9 * Cin;
+  a.in_dtype = OGV_BF16; a.out_dtype = OGV_BF16;
+  a.rows_per_scale = 1; a.split_k = 1;
+  return ogv_gemm_tc_conv(a, c, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int ogv_conv3x3_wgrad(const void* x, const void* dy, float* dw2, int B, int H, int W, int Cin, int Co,
+                                 int stride, void* stream) {
+  OGV_REQUIRE(x && dy && dw2, "conv3x3_wgrad: null pointer");
+  ogv_conv_view c{2, x, B, H, W, Cin, stride};
+  if (!(Co > 0 && Co % 8 == 0 && ogv_conv_view_supported(c))) {
+    ogv_set_error("conv3x3_wgrad: unsupported geometry B=%d H=%d W=%d Cin=%d Co=%d stride=%d", B, H, W, Cin, Co, stride);
+    return OGV_ERR_UNSUPPORTED;
+  }
+  const int Mo = B * (H / stride) * (W / stride);
+  ogv_gemm_args a;
+  memset(&a, 0, sizeof(a));
+  a.A = dy; a.a_rs = 1; a.a_cs = Co;          // A(m = co, k = pixel) = dy[pixel, co]
+  a.B = x; a.b_rs = 1; a.b_cs = 9LL * Cin;    // B(n = patch column, k = pixel): the patch view
+  a.D = dw2; a.ldd = 9LL * Cin;
+  a.M = Co; a.N = 9 * Cin; a.K = Mo;
+  a.in_dtype = OGV_BF16; a.out_dtype = OGV_F32;
+  a.rows_per_scale = 1; a.accumulate = 1;
+  // one split-K work item per CTA at most (every item ends with a full tile of fp32 reductions)
+  const int tiles = ogv_ceil_div(Co, 128) * ogv_ceil_div(9 * Cin, 256);
+  int split = ogv_num_sms() / tiles;
+  if (split > ogv_ceil_div(Mo, 256)) split = ogv_ceil_div(Mo, 256);
+  a.split_k = split < 1 ? 1 : split;
+  return ogv_gemm_tc_conv(a, c, reinterpret_cast<cudaStream_t>(stream));
 }

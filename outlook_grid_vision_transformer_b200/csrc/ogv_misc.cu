@@ -428,6 +428,56 @@ __global__ void __launch_bounds__(256) col2im3x3_vec_kernel(const T* __restrict_
   }
 }
 
+// stride 2, even H and W: thread = (2 x 2 input quad, 8 channels).  The quad (2j+py, 2i+px) collects exactly nine patch
+// entries -- taps (1,1) (1,2) (2,1) (2,2) of output (j, i), (1,0) (2,0) of (j, i+1), (0,1) (0,2) of (j+1, i) and (0,0)
+// of (j+1, i+1) -- so every thread has nine independent 16-byte loads in flight and no lane diverges on parity.
+template <typename T>
+__global__ void __launch_bounds__(256) col2im3x3_s2_quad_kernel(const T* __restrict__ dcols, T* __restrict__ dx, int Ho,
+                                                                int Wo, int cg, unsigned nitems) {
+  const int Cin = cg * 8;
+  const size_t rowlen = (size_t)9 * Cin;
+  for (unsigned it = blockIdx.x * blockDim.x + threadIdx.x; it < nitems; it += gridDim.x * blockDim.x) {
+    const unsigned c = it % (unsigned)cg, q = it / (unsigned)cg;  // q = (b*Ho + j)*Wo + i: the output pixel (j, i)
+    const unsigned i = q % (unsigned)Wo, bj = q / (unsigned)Wo;
+    const unsigned j = bj % (unsigned)Ho;
+    const bool right = i + 1 < (unsigned)Wo, down = j + 1 < (unsigned)Ho;
+    const T* r00 = dcols + (size_t)q * rowlen + c * 8;
+    const T* r01 = r00 + rowlen;
+    const T* r10 = r00 + (size_t)Wo * rowlen;
+    const T* r11 = r10 + rowlen;
+    Raw8<T> t4, t5, t7, t8, t3, t6, t1, t2, t0;
+    ld_raw8(r00 + 4 * Cin, t4); ld_raw8(r00 + 5 * Cin, t5); ld_raw8(r00 + 7 * Cin, t7); ld_raw8(r00 + 8 * Cin, t8);
+    raw8_zero(t3); raw8_zero(t6); raw8_zero(t1); raw8_zero(t2); raw8_zero(t0);
+    if (right) { ld_raw8(r01 + 3 * Cin, t3); ld_raw8(r01 + 6 * Cin, t6); }
+    if (down) { ld_raw8(r10 + 1 * Cin, t1); ld_raw8(r10 + 2 * Cin, t2); }
+    if (right && down) ld_raw8(r11, t0);
+    float a[8], b[8], o[8];
+    // (2j, 2i)
+    T* d00 = dx + (((size_t)bj * 2) * (2 * Wo) + 2 * i) * Cin + c * 8;
+    cvt_raw8(t4, o);
+    st8(d00, o);
+    // (2j, 2i+1)
+    cvt_raw8(t5, a); cvt_raw8(t3, b);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = a[k] + b[k];
+    st8(d00 + Cin, o);
+    // (2j+1, 2i)
+    T* d10 = d00 + (size_t)2 * Wo * Cin;
+    cvt_raw8(t7, a); cvt_raw8(t1, b);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = a[k] + b[k];
+    st8(d10, o);
+    // (2j+1, 2i+1)
+    cvt_raw8(t8, a); cvt_raw8(t6, b);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = a[k] + b[k];
+    cvt_raw8(t2, a); cvt_raw8(t0, b);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = (o[k] + a[k]) + b[k];
+    st8(d10 + Cin, o);
+  }
+}
+
 }  // namespace
 
 extern "C" int ogv_im2col3x3(const void* x, void* cols, int B, int H, int W, int Cin, int Kpad, int dtype, void* stream) {
@@ -488,6 +538,16 @@ extern "C" int ogv_col2im3x3_vec(const void* dcols, void* dx, int B, int H, int 
   long long blocks = (nitems + 255) / 256;
   const long long cap = (long long)ogv_num_sms() * 8;
   if (blocks > cap) blocks = cap;
+  if (stride == 2 && H % 2 == 0 && W % 2 == 0) {
+    const long long nq = nitems / 4;
+    long long qb = (nq + 255) / 256;
+    if (qb > cap) qb = cap;
+    OGV_DISPATCH_DTYPE(dtype, T, {
+      col2im3x3_s2_quad_kernel<T><<<(unsigned)qb, 256, 0, (cudaStream_t)stream>>>(
+          reinterpret_cast<const T*>(dcols), reinterpret_cast<T*>(dx), Ho, Wo, Cin / 8, (unsigned)nq);
+      return ogv_check_launch("col2im3x3_vec");
+    });
+  }
   OGV_DISPATCH_DTYPE(dtype, T, {
     if (stride == 1)
       col2im3x3_vec_kernel<T, 1><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(

@@ -723,15 +723,22 @@ class ConvBnActFn(torch.autograd.Function):
                 w2[:, :9 * Cin] = w.detach().permute(0, 2, 3, 1).reshape(Co, 9 * Cin)
             elif route == "vec":
                 H, W = (Hi - 1) // stride[0] + 1, (Wi - 1) // stride[0] + 1
-                cols = ops.im2col3x3_vec(xc, stride[0])
                 w2 = w.detach().permute(0, 2, 3, 1).reshape(Co, 9 * Cin).to(dt)
+                if ops.conv3x3_supported(xc, Co, stride[0]):
+                    route = "implicit"  # no patch matrix at all: 5-D TMA boxes of x feed the GEMM
+                    cols = xc
+                else:
+                    cols = ops.im2col3x3_vec(xc, stride[0])
             else:
                 H, W = Hi, Wi
                 cols = xc.permute(0, 2, 3, 1).reshape(B * H * W, Cin)
                 w2 = w.detach().reshape(Co, Cin).to(dt)
             M = B * H * W
-            rows = _empty((M, Co), cols)
-            ops.gemm(cols, w2, rows)
+            if route == "implicit":
+                rows = ops.conv3x3_fwd(xc, w2, stride[0])
+            else:
+                rows = _empty((M, Co), cols)
+                ops.gemm(cols, w2, rows)
             saved = (cols, w2)
         else:
             wc = w.detach().to(dt).contiguous(memory_format=torch.channels_last)
@@ -781,14 +788,18 @@ class ConvBnActFn(torch.autograd.Function):
             dpre = ops.bn_act_bwd_apply(dyr, rows, scale, shift, mean, rstd, gamma.detach(), zero, zero, meta["act"])
         if ctx.route != "lib":
             _, Cin, kh, kw = ctx.w_shape
-            dw2 = _zeros((Co, a.shape[1]), gamma)
-            ops._wgrad(dpre, a, dw2)  # on the main stream: autograd accumulates the returned view right away
+            dw2 = _zeros((Co, wc.shape[1]), gamma)
+            # on the main stream: autograd accumulates the returned view right away
+            if ctx.route == "implicit":
+                ops.conv3x3_wgrad(a, dpre, dw2, meta["stride"][0])
+            else:
+                ops._wgrad(dpre, a, dw2)
             dw = dw2[:, :kh * kw * Cin].view(Co, kh, kw, Cin).permute(0, 3, 1, 2)
             dx = None
             if ctx.x_needs_grad:  # never on the "stem" route
                 Hi, Wi = ctx.in_hw
                 w2t = wc.t().contiguous()  # [K, Co]: dcols = dpre x W2
-                dcols = _empty((M, a.shape[1]), dpre)
+                dcols = _empty((M, wc.shape[1]), dpre)
                 ops.gemm(dpre, w2t, dcols)
                 dxr = dcols if ctx.route == "1x1" else ops.col2im3x3_vec(dcols, B, Hi, Wi, Cin, meta["stride"][0])
                 dx = dxr.view(B, Hi, Wi, Cin).permute(0, 3, 1, 2)

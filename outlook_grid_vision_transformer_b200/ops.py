@@ -494,6 +494,49 @@ def col2im3x3_vec(dcols: Tensor, B: int, H: int, W: int, Cin: int, stride: int) 
     return dx
 
 
+def conv3x3_supported(x: Tensor, Co: int, stride: int) -> bool:
+    """True when the implicit-GEMM convolution (ogv_conv3x3_fwd / _wgrad) serves this channels_last bf16 image."""
+    if x.dtype != torch.bfloat16 or os.environ.get("OGV_CONV_IMPLICIT", "1") == "0":
+        return False
+    B, Cin, H, W = x.shape
+    return bool(_lib.lib().ogv_conv3x3_supported(B, H, W, Cin, Co, stride))
+
+
+def conv3x3_fwd(x: Tensor, w2: Tensor, stride: int) -> Tensor:
+    """channels_last bf16 x [B, Cin, H, W], w2 [Co, 9*Cin] (column (ky*3+kx)*Cin + c) -> rows [B*Ho*Wo, Co]: the 3x3 / pad 1
+    convolution as an implicit GEMM (the patch matrix is never written; 5-D TMA boxes of x feed the tcgen05 pipeline)."""
+    _require_cuda(x, w2)
+    B, Cin, H, W = x.shape
+    Co = w2.shape[0]
+    if not x.permute(0, 2, 3, 1).is_contiguous() or not w2.is_contiguous() or w2.shape[1] != 9 * Cin:
+        raise ValueError("conv3x3_fwd needs a channels_last image and a contiguous [Co, 9*Cin] weight")
+    Mo = B * (H // stride) * (W // stride)
+    y = torch.empty((Mo, Co), device=x.device, dtype=x.dtype)
+    if PROFILER.enabled:
+        PROFILER.cur_flops = 2 * Mo * Co * 9 * Cin
+        PROFILER.cur_label = f"ogv_conv3x3_fwd[{Mo}x{Co}x{9 * Cin} s{stride}]"
+        PROFILER.cur_kernel = f"gemm_tc_kernel<{64 if Co <= 64 else (128 if Co <= 128 else 256)}, __nv_bfloat16>"
+    _call("ogv_conv3x3_fwd", _p(x), _p(w2), _p(y), B, H, W, Cin, Co, stride, _stream())
+    return y
+
+
+def conv3x3_wgrad(x: Tensor, dy: Tensor, dw2: Tensor, stride: int) -> Tensor:
+    """dw2[co, (ky*3+kx)*Cin + c] += sum over output pixels of dy[pixel, co] * patch[pixel, ...]  (dw2 fp32, pre-zeroed)."""
+    _require_cuda(x, dy, dw2)
+    B, Cin, H, W = x.shape
+    Mo, Co = dy.shape
+    _f32(dw2, "dw2")
+    if (not x.permute(0, 2, 3, 1).is_contiguous() or not dy.is_contiguous() or tuple(dw2.shape) != (Co, 9 * Cin)
+            or Mo != B * (H // stride) * (W // stride)):
+        raise ValueError("conv3x3_wgrad: shape / layout mismatch")
+    if PROFILER.enabled:
+        PROFILER.cur_flops = 2 * Mo * Co * 9 * Cin
+        PROFILER.cur_label = f"ogv_conv3x3_wgrad[{Co}x{9 * Cin}x{Mo} s{stride}]"
+        PROFILER.cur_kernel = "gemm_tc_kernel<256, float>"
+    _call("ogv_conv3x3_wgrad", _p(x), _p(dy), _p(dw2), B, H, W, Cin, Co, stride, _stream())
+    return dw2
+
+
 def bn_act_apply(x: Tensor, scale: Tensor, shift: Tensor, act: str) -> Tensor:
     """out = act(scale*x + shift) on rows [M, C]  (the BN + act of stem_head.py:23-32 / downsampling.py:28-65)"""
     _rows(x, "x")

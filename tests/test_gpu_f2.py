@@ -205,9 +205,10 @@ def test_downsample_convolution_runs_on_own_kernels(mode):
         x = torch.randn(4, cin, hw, hw, device=DEV).contiguous(memory_format=torch.channels_last)
         x1, x2 = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
         seen = []
-        orig_i, orig_c = OF.ops.im2col3x3_vec, OF.ops.col2im3x3_vec
-        OF.ops.im2col3x3_vec = lambda *a: (seen.append("im2col"), orig_i(*a))[1]
-        OF.ops.col2im3x3_vec = lambda *a: (seen.append("col2im"), orig_c(*a))[1]
+        names = ("im2col3x3_vec", "col2im3x3_vec", "conv3x3_fwd", "conv3x3_wgrad")
+        orig = {n: getattr(OF.ops, n) for n in names}
+        for n in names:
+            setattr(OF.ops, n, (lambda n: lambda *a: (seen.append(n), orig[n](*a))[1])(n))
         try:
             with torch.autocast("cuda", dtype=torch.bfloat16, enabled=mode == "bf16"):
                 y, yr = unit(x1), ref(x2)
@@ -215,9 +216,40 @@ def test_downsample_convolution_runs_on_own_kernels(mode):
             y.backward(dy)
             yr.backward(dy)
         finally:
-            OF.ops.im2col3x3_vec, OF.ops.col2im3x3_vec = orig_i, orig_c
-        assert seen == ["im2col", "col2im"], seen
+            for n in names:
+                setattr(OF.ops, n, orig[n])
+        # bf16: implicit GEMM (no patch matrix); fp32: materialised patches through the three-plane fp32 GEMM
+        want = ["conv3x3_fwd", "conv3x3_wgrad", "col2im3x3_vec"] if mode == "bf16" else ["im2col3x3_vec", "col2im3x3_vec"]
+        assert seen == want, seen
         assert_close(y.float(), yr.float(), rtol, f"output C={cin}")
         assert_close(x1.grad, x2.grad, rtol, f"dx C={cin}")
         for (k, p), (_, q) in zip(unit.op.named_parameters(), ref.named_parameters()):
             assert_close(p.grad, q.grad, rtol, f"grad[{k}] C={cin}", atol=1e-6)
+
+
+@pytest.mark.parametrize("shape,stride", [((4, 64, 32, 32), 2), ((3, 128, 16, 16), 2), ((4, 256, 8, 8), 2), ((3, 256, 8, 8), 2),
+                                          ((2, 64, 16, 16), 1), ((5, 64, 8, 8), 1), ((2, 64, 64, 64), 2), ((9, 128, 4, 4), 1)])
+def test_implicit_conv_equals_materialised_patches(shape, stride):
+    """ogv_conv3x3_fwd / ogv_conv3x3_wgrad (5-D TMA boxes of x as the GEMM operand) against the same GEMMs on the
+    materialised patch matrix, integer-valued operands: bit-exact (every sum is exact in fp32), including batches that
+    do not fill the last 128-pixel tile and images smaller than a tile."""
+    from outlook_grid_vision_transformer_b200 import ops
+    B, C, H, W = shape
+    Co = 2 * C if C < 256 else 384
+    g = torch.Generator().manual_seed(13)
+    x = torch.randint(-4, 5, shape, generator=g).to(torch.bfloat16).to(DEV).contiguous(memory_format=torch.channels_last)
+    w2 = torch.randint(-2, 3, (Co, 9 * C), generator=g).to(torch.bfloat16).to(DEV)
+    if not ops.conv3x3_supported(x, Co, stride):
+        pytest.skip("geometry not served by the implicit path")
+    cols = ops.im2col3x3_vec(x, stride)
+    Mo = cols.shape[0]
+    want = torch.empty((Mo, Co), device=DEV, dtype=torch.bfloat16)
+    ops.gemm(cols, w2, want)
+    got = ops.conv3x3_fwd(x, w2, stride)
+    assert torch.equal(got, want)
+    assert torch.equal(got.float(), (cols.float() @ w2.float().t()).to(torch.bfloat16).float())
+    dy = torch.randint(-2, 3, (Mo, Co), generator=g).to(torch.bfloat16).to(DEV)
+    dw_want = dy.float().t() @ cols.float()
+    dw = torch.zeros((Co, 9 * C), device=DEV)
+    ops.conv3x3_wgrad(x, dy, dw, stride)
+    assert torch.equal(dw, dw_want)
