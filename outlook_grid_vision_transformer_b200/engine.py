@@ -230,7 +230,12 @@ class TrainStep:
         self.x = example_x.clone()
         self.y = example_y.clone()
         self.hyper = torch.zeros(5, device=dev, dtype=torch.float32)
-        self._hyper_host = torch.zeros(5, dtype=torch.float32).pin_memory() if dev.type == "cuda" else torch.zeros(5)
+        # pinned staging slots for the per-step hyper-parameters: the host may run several replays ahead of the device,
+        # so a slot is rewritten only after the asynchronous copy that read it has executed (event per slot)
+        self._hyper_ring = [torch.zeros(5, dtype=torch.float32).pin_memory() if dev.type == "cuda" else torch.zeros(5)
+                            for _ in range(4)]
+        self._hyper_evt = [None] * 4
+        self._hyper_i = 0
         self.acc = torch.zeros(5, device=dev, dtype=torch.float32)      # loss*B, top1, top3, top5, B
         self.loss: Optional[torch.Tensor] = None
         self._stage = None          # (x, y staging buffers, ready event, free event) of prefetch()
@@ -262,13 +267,21 @@ class TrainStep:
 
     def _write_hyper(self) -> None:
         t = self.step_num + 1
-        h = self._hyper_host
+        i = self._hyper_i
+        self._hyper_i = (i + 1) % len(self._hyper_ring)
+        if self._hyper_evt[i] is not None:
+            self._hyper_evt[i].synchronize()  # the copy issued four steps ago: done long before, except far ahead of the device
+        h = self._hyper_ring[i]
         h[0] = self.current_lr()
         h[1] = 1.0 - self.betas[0] ** t
         h[2] = 1.0 - self.betas[1] ** t
         h[3] = 1.0 / self.world
         h[4] = float(self.grad_clip_norm) if self.grad_clip_norm else 0.0
         self.hyper.copy_(h, non_blocking=True)
+        if self.hyper.is_cuda:
+            if self._hyper_evt[i] is None:
+                self._hyper_evt[i] = torch.cuda.Event()
+            self._hyper_evt[i].record(torch.cuda.current_stream(self.hyper.device))
 
     # ------------------------------------------------------------------------------------------ the step
     def _body(self):

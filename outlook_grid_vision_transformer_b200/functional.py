@@ -824,6 +824,72 @@ def conv_bn_act(x: Tensor, w: Tensor, gamma: Tensor, beta: Tensor, *, running, s
 
 
 
+# =================================================================================================
+# classifier head: BatchNorm2d -> global average pool -> Linear  (Model_A_OutGridNet.py:52-53,65-67)
+# =================================================================================================
+class HeadFn(torch.autograd.Function):
+    """logits = Linear(mean_hw(BatchNorm(x))) on rows [B*HW, C].  Statistics (ogv_colstats / ogv_bn_finalize), the
+    normalise + pool as ONE pass (ogv_se_pool with the identity activation: the normalised map is never written), the
+    classifier and its three gradients on the GEMM engine, BatchNorm backward on the streaming kernels."""
+
+    @staticmethod
+    def forward(ctx, rows, gamma, beta, wc, bc, meta):
+        B, HW, training, dt = meta["B"], meta["HW"], meta["training"], meta["dtype"]
+        rm, rv = meta["running"]
+        rows = rows.contiguous()
+        M, C = rows.shape
+        K = wc.shape[0]
+        ops.PROFILER.tag = ("F2", "fwd", M, C)
+        st = _scratch_zeros(6 * C, rows)
+        ssum, ssq, scale, shift, mean, rstd = (st[i * C:(i + 1) * C] for i in range(6))
+        if training:
+            ops.colstats(rows, ssum, ssq)
+        ops.bn_finalize(ssum, ssq, gamma, beta, rm, rv, scale, shift, mean, rstd, M, meta["eps"], meta["momentum"], training)
+        pool = ops.se_pool(rows, scale, shift, B, HW, "none")          # [B, C] fp32
+        pool_c = pool if dt == torch.float32 else pool.to(dt)
+        w_c = wc.detach() if dt == torch.float32 else wc.detach().to(dt)
+        logits = _empty((B, K), rows, dt)
+        ops.gemm(pool_c, w_c, logits, bias=bc.detach() if bc is not None else None)
+        ops.PROFILER.tag = None
+        ctx.meta = meta
+        ctx.st = st
+        ctx.has_bias = bc is not None
+        ctx.save_for_backward(rows, gamma, pool_c, w_c)
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        rows, gamma, pool_c, w_c = ctx.saved_tensors
+        meta = ctx.meta
+        B, HW, training = meta["B"], meta["HW"], meta["training"]
+        M, C = rows.shape
+        K = w_c.shape[0]
+        st = ctx.st
+        mean, rstd = st[4 * C:5 * C], st[5 * C:6 * C]
+        ops.PROFILER.tag = ("F2", "bwd", M, C)
+        dl = dlogits.to(pool_c.dtype).contiguous()
+        dw = _zeros((K, C), gamma)
+        ops._wgrad(dl, pool_c, dw)
+        db = dlogits.float().sum(0) if ctx.has_bias else None  # [B, classes]: a few hundred KB
+        dpool = _empty((B, C), rows, torch.float32)
+        ops.gemm(dl, w_c.t().contiguous(), dpool)
+        # every position of an image receives dpool / HW
+        dyr = (dpool * (1.0 / HW)).to(rows.dtype).repeat_interleave(HW, dim=0)
+        red = _scratch_zeros(2 * C, rows)
+        dgamma, dbeta = red[:C], red[C:]
+        ops.bn_bwd_reduce(dyr, rows, mean, rstd, dgamma, dbeta)
+        zero = None if training else _zeros(C, gamma)
+        dx = ops.bn_bwd_apply(dyr, rows, mean, rstd, gamma.detach(), dgamma if training else zero, dbeta if training else zero)
+        ops.PROFILER.tag = None
+        return dx, dgamma.clone(), dbeta.clone(), dw, db, None
+
+
+def head(rows: Tensor, gamma: Tensor, beta: Tensor, wc: Tensor, bc: Optional[Tensor], *, B: int, HW: int, running,
+         eps: float, momentum: float, training: bool, dtype: torch.dtype) -> Tensor:
+    meta = dict(B=B, HW=HW, running=running, eps=eps, momentum=momentum, training=training, dtype=dtype)
+    return HeadFn.apply(rows, gamma, beta, wc, bc, meta)
+
+
 class LayerNormRowsFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, b, eps):

@@ -3,10 +3,12 @@ Model B (OutlookerFrontGridNet, src/Model_B_OutGridNet.py:11-100), re-stated so 
 self-contained on a box without the reference checkout.  Constructor signatures, attribute names
 and state_dict keys match the reference, so its checkpoints load with strict=True.
 
-SURVEY section 8 row (f2): in the conv -> BatchNorm -> act units of the stem and the Downsample layers only the k x k
-convolution itself is the library's (cuDNN through aten); batch statistics, normalise + activation and their backward
-run on this package's streaming kernels (functional.ConvBnActFn).  The head (BatchNorm on [B, C, 4, 4], global average
-pool, classifier) stays on PyTorch: 16K rows, latency only.
+SURVEY section 8 row (f2): the conv -> BatchNorm -> act units of the stem and the Downsample layers run on this
+package's kernels (functional.ConvBnActFn): the stem convolution as patches x tcgen05 GEMM, the 3x3 stride-2 Downsample
+convolution as an implicit GEMM (5-D TMA boxes of the image feed the tcgen05 pipeline; input gradient through a
+col2im gather), batch statistics, normalise + activation and their backward on the streaming kernels.  The head
+(BatchNorm on [B, C, 4, 4], global average pool, classifier) is functional.HeadFn: statistics, normalise + pool in one
+pass, the classifier and its gradients on the GEMM engine.
 """
 from __future__ import annotations
 
@@ -126,8 +128,26 @@ class _Backbone(nn.Module):
         return x
 
     def _head(self, x):
-        x = self.head_norm(x)
-        return self.classifier(x.mean(dim=(2, 3)))
+        bn, fc = self.head_norm, self.classifier
+        fused = (x.is_cuda and isinstance(bn, nn.BatchNorm2d) and isinstance(fc, nn.Linear) and bn.affine
+                 and bn.track_running_stats and x.shape[1] % 8 == 0
+                 and not any(m._forward_hooks or m._forward_pre_hooks or m._backward_hooks for m in (bn, fc)))
+        if not fused:
+            x = bn(x)
+            return fc(x.mean(dim=(2, 3)))
+        training = bn.training
+        if training and bn.num_batches_tracked is not None:
+            bn.num_batches_tracked.add_(1)
+        if training and bn.momentum is None:
+            momentum = 1.0 / float(bn.num_batches_tracked)
+        else:
+            momentum = bn.momentum if bn.momentum is not None else 0.0
+        dt = _compute_dtype(x)
+        rows, geom = OF.to_rows(x)
+        rows = rows.to(dt) if rows.dtype != dt else rows
+        return OF.head(rows, bn.weight, bn.bias, fc.weight, fc.bias, B=geom.B, HW=geom.H * geom.W,
+                       running=(bn.running_mean, bn.running_var), eps=bn.eps, momentum=momentum, training=training,
+                       dtype=dt)
 
 
 class MaxOutNet(_Backbone):

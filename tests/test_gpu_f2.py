@@ -253,3 +253,56 @@ def test_implicit_conv_equals_materialised_patches(shape, stride):
     dw = torch.zeros((Co, 9 * C), device=DEV)
     ops.conv3x3_wgrad(x, dy, dw, stride)
     assert torch.equal(dw, dw_want)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("training", [True, False], ids=["train", "eval"])
+@pytest.mark.parametrize("shape,classes", [((6, 384, 4, 4), 100), ((5, 64, 2, 2), 200), ((16, 128, 8, 8), 10)])
+def test_head_matches_torch_modules(shape, classes, training, mode):
+    """BatchNorm2d -> global average pool -> Linear (Model_A_OutGridNet.py:52-53,65-67) on own kernels against the
+    PyTorch modules: logits, input / BatchNorm / classifier gradients, running statistics."""
+    from outlook_grid_vision_transformer_b200.model import _Backbone
+    from outlook_grid_vision_transformer_b200.config import StageCfg
+    from outlook_grid_vision_transformer_b200 import functional as OF
+    torch.manual_seed(14)
+    B, C, H, W = shape
+
+    class Net(_Backbone):
+        def __init__(self):
+            super().__init__()
+            self.head_norm = nn.BatchNorm2d(C)
+            self.classifier = nn.Linear(C, classes)
+
+    net = Net().to(DEV).train(training)
+    with torch.no_grad():
+        net.head_norm.weight.uniform_(0.5, 1.5)
+        net.head_norm.bias.uniform_(-0.5, 0.5)
+        net.head_norm.running_mean.uniform_(-0.2, 0.2)
+        net.head_norm.running_var.uniform_(0.5, 1.5)
+    ref = copy.deepcopy(net)
+    rtol = 1e-3 if mode == "fp32" else 2e-2
+    x = torch.randn(shape, device=DEV).contiguous(memory_format=torch.channels_last)
+    x1, x2 = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    seen = []
+    orig = OF.head
+    OF.head = lambda *a, **k: (seen.append(1), orig(*a, **k))[1]
+    try:
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=mode == "bf16"):
+            y = net._head(x1)
+            yr = ref.classifier(ref.head_norm(x2).mean(dim=(2, 3)))
+    finally:
+        OF.head = orig
+    assert seen, "the head did not take the fused path"
+    assert y.shape == yr.shape == (B, classes) and y.dtype == yr.dtype
+    dy = torch.randn(y.shape, device=DEV).to(y.dtype)
+    y.backward(dy)
+    yr.backward(dy)
+    assert_close(y.float(), yr.float(), rtol, "logits")
+    assert_close(x1.grad, x2.grad, rtol, "dx")
+    for (k, p), (_, q) in zip(net.named_parameters(), ref.named_parameters()):
+        assert_close(p.grad, q.grad, rtol, f"grad[{k}]", atol=1e-6)
+    for (k, b), (_, q) in zip(net.named_buffers(), ref.named_buffers()):
+        if b.is_floating_point():
+            assert_close(b, q, 1e-3 if mode == "fp32" else 5e-3, f"buffer[{k}]")
+        else:
+            assert int(b) == int(q) == (1 if training else 0), k
