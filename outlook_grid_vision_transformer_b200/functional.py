@@ -713,7 +713,7 @@ class ConvBnActFn(torch.autograd.Function):
             route = "1x1"
         else:
             route = "lib"
-        ops.PROFILER.tag = ("F2", "fwd", B * Hi * Wi // (stride[0] * stride[1]), Co)
+        ops.PROFILER.tag = ("F2", "fwd", B * Hi * Wi // (stride[0] * stride[1]), Co, kh * kw * Cin, B * Hi * Wi * Cin)
         if route != "lib":
             if route == "stem":
                 H, W = Hi, Wi
@@ -776,7 +776,8 @@ class ConvBnActFn(torch.autograd.Function):
         st = ctx.st
         scale, shift, mean, rstd = (st[i * Co:(i + 1) * Co] for i in range(2, 6))
         dyr = dy.to(rows.dtype).contiguous(memory_format=torch.channels_last).permute(0, 2, 3, 1).reshape(M, Co)
-        ops.PROFILER.tag = ("F2", "bwd", M, Co)
+        ops.PROFILER.tag = ("F2", "bwd", M, Co, ctx.w_shape[1] * ctx.w_shape[2] * ctx.w_shape[3],
+                            B * ctx.in_hw[0] * ctx.in_hw[1] * ctx.w_shape[1])
         red = _scratch_zeros(2 * Co, rows)
         dgamma, dbeta = red[:Co], red[Co:]
         ops.bn_act_bwd_reduce(dyr, rows, scale, shift, mean, rstd, dgamma, dbeta, meta["act"])
@@ -839,7 +840,7 @@ class HeadFn(torch.autograd.Function):
         rows = rows.contiguous()
         M, C = rows.shape
         K = wc.shape[0]
-        ops.PROFILER.tag = ("F2", "fwd", M, C)
+        ops.PROFILER.tag = ("HEAD", "fwd", M, C)
         st = _scratch_zeros(6 * C, rows)
         ssum, ssq, scale, shift, mean, rstd = (st[i * C:(i + 1) * C] for i in range(6))
         if training:
@@ -866,7 +867,7 @@ class HeadFn(torch.autograd.Function):
         K = w_c.shape[0]
         st = ctx.st
         mean, rstd = st[4 * C:5 * C], st[5 * C:6 * C]
-        ops.PROFILER.tag = ("F2", "bwd", M, C)
+        ops.PROFILER.tag = ("HEAD", "bwd", M, C)
         dl = dlogits.to(pool_c.dtype).contiguous()
         dw = _zeros((K, C), gamma)
         ops._wgrad(dl, pool_c, dw)
