@@ -196,6 +196,37 @@ def main():
             run(f"fused {tag} fwd", s, lambda: ops.mlp_fwd(x, wa, ba, wb, bC, act="gelu", residual=dy), nbytes(x, dy, out_c), 4 * M * Hd * C)
             run(f"fused {tag} bwd", s, lambda: ops.mlp_bwd(x, dy, wa, wbt, wat, ba, act="gelu"),
                 nbytes(x, dy, out_c) + 2 * M * Hd * 2, 6 * M * Hd * C)
+        # ---- Downsample convolution C -> 2C, 3x3 stride 2 (downsampling.py:41-47): implicit GEMM / materialised patches /
+        #      the library's convolution, all three directions
+        if s < 3:
+            Co, Ho = STAGES[s + 1]["C"], H // 2
+            Mo = B * Ho * Ho
+            xi = x.view(B, H, W, C).permute(0, 3, 1, 2)                      # channels_last image
+            w4 = (torch.randn(Co, C, 3, 3, device=dev) * 0.05)
+            w2 = w4.permute(0, 2, 3, 1).reshape(Co, 9 * C).to(dt).contiguous()
+            w2t = w2.t().contiguous()
+            dyo = torch.randn(Mo, Co, device=dev).to(dt)
+            dw2 = torch.zeros(Co, 9 * C, **f32)
+            cfl = 2 * Mo * Co * 9 * C
+            if ops.conv3x3_supported(xi, Co, 2):
+                run("conv implicit fwd", s, lambda: ops.conv3x3_fwd(xi, w2, 2), nbytes(x, dyo), cfl)
+                run("conv implicit wgrad", s, lambda: ops.conv3x3_wgrad(xi, dyo, dw2, 2), nbytes(x, dyo), cfl)
+            cols = ops.im2col3x3_vec(xi, 2)
+            yo = torch.empty(Mo, Co, device=dev, dtype=dt)
+            run("conv im2col", s, lambda: ops.im2col3x3_vec(xi, 2), nbytes(x, cols))
+            run("conv patches fwd gemm", s, lambda: ops.gemm(cols, w2, yo), nbytes(cols, yo), cfl)
+            run("conv patches wgrad", s, lambda: ops._wgrad(dyo, cols, dw2), nbytes(cols, dyo), cfl)
+            dcols = torch.empty_like(cols)
+            run("conv dgrad gemm", s, lambda: ops.gemm(dyo, w2t, dcols), nbytes(dcols, dyo), cfl)
+            run("conv dgrad col2im", s, lambda: ops.col2im3x3_vec(dcols, B, H, W, C, 2), nbytes(dcols, x))
+            wl = w4.to(dt).contiguous(memory_format=torch.channels_last)
+            dyo4 = dyo.view(B, Ho, Ho, Co).permute(0, 3, 1, 2)
+            conv = torch.ops.aten.convolution
+            convb = torch.ops.aten.convolution_backward
+            run("conv library fwd", s, lambda: conv(xi, wl, None, [2, 2], [1, 1], [1, 1], False, [0, 0], 1), nbytes(x, dyo), cfl)
+            run("conv library dgrad", s, lambda: convb(dyo4, xi, wl, None, [2, 2], [1, 1], [1, 1], False, [0, 0], 1, [True, False, False]), nbytes(x, dyo), cfl)
+            run("conv library wgrad", s, lambda: convb(dyo4, xi, wl, None, [2, 2], [1, 1], [1, 1], False, [0, 0], 1, [False, True, False]), nbytes(x, dyo), cfl)
+            del cols, dcols, yo, dyo
         del x, dy, wide, z, h, out_c, q3
         torch.cuda.empty_cache()
     Path(a.out).parent.mkdir(exist_ok=True)
