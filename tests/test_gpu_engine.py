@@ -223,3 +223,52 @@ def test_bulk_weight_refresh_equals_per_layer_casts():
         assert not M._BULK_FRESH
     assert losses[0] == pytest.approx(losses[1], rel=5e-3), f"{losses}"
     assert losses[1][-1] < losses[1][0]
+
+
+def test_prefetched_batches_and_lagged_loss_equal_the_plain_loop():
+    """TrainStep.prefetch / step(staged=True) / loss_to_host_async / previous_loss (the bench's e2e path, the reference's
+    pinned-memory + non_blocking loader loop, one_epoch_train.py:85-93): every step trains on ITS batch and the loss
+    read back with a one-step lag is the loss of the step before -- same numbers as copying each batch synchronously."""
+    from outlook_grid_vision_transformer_b200.engine import TrainStep, WarmupCosineLR
+    batches = [_data(seed=20 + i) for i in range(6)]
+    hosts = [(x.cpu().pin_memory(), y.cpu().pin_memory()) for x, y in batches]
+    mk = lambda: TrainStep(_model(), lambda lg, yy: F.cross_entropy(lg, yy, label_smoothing=0.1), *batches[0], lr=2e-3,
+                           autocast_bf16=False, use_graph=True, warmup=2, grad_clip_norm=1.0, eps=1e-6,
+                           scheduler=WarmupCosineLR(2e-3, 12, 3, 1e-5))  # noqa: E731
+    plain = mk()
+    want = [float(plain(xh, yh)) for xh, yh in hosts]
+    piped = mk()
+    got = []
+    for xh, yh in hosts:
+        piped.prefetch(xh, yh)
+        piped(staged=True)
+        piped.loss_to_host_async()
+        got.append(piped.previous_loss())
+    torch.cuda.synchronize()
+    assert got[0] is None
+    assert got[1:] == pytest.approx(want[:-1], rel=2e-4), f"{got} vs {want}"   # atomics reorder sums between runs
+    for (k, p), (_, q) in zip(piped.model.named_parameters(), plain.model.named_parameters()):
+        if k.endswith("mhsa.qkv.bias"):  # the key bias gradient is pure summation noise (softmax shift invariance)
+            continue
+        torch.testing.assert_close(p.detach(), q.detach(), rtol=2e-3, atol=2e-5, msg=lambda m: f"{k}: {m}")
+
+
+def test_hyper_parameters_survive_a_host_running_ahead():
+    """The host may queue many replays before the device starts the first one: every step must still see ITS learning rate
+    and bias corrections (pinned staging slots in a ring guarded by events), i.e. 10 steps queued without a
+    synchronisation produce the losses of 10 steps synchronised one by one (warm-up schedule: the LR changes 4x over the
+    first steps, so a step that read a later step's slot shows up at once)."""
+    from outlook_grid_vision_transformer_b200.engine import TrainStep, WarmupCosineLR
+    x, y = _data()
+    mk = lambda: TrainStep(_model(), lambda lg, yy: F.cross_entropy(lg, yy), x, y, lr=2e-3, autocast_bf16=False,
+                           use_graph=True, warmup=2, eps=1e-6, grad_clip_norm=0.5,
+                           scheduler=WarmupCosineLR(2e-3, 12, 4, 1e-5))  # noqa: E731
+    a, b = mk(), mk()
+    la, lb = [], []
+    for _ in range(10):
+        la.append(float(a()))          # synchronises every step
+    for _ in range(10):
+        lb.append(b().detach().clone())  # queued: no host synchronisation until the end
+    torch.cuda.synchronize()
+    lb = [float(t) for t in lb]
+    assert lb == pytest.approx(la, rel=5e-4), f"{lb} vs {la}"
