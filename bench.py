@@ -346,7 +346,7 @@ class Workload:
             # the reference's schedule (train_full_model.py:60-66): warm-up + cosine over epochs * steps/epoch
             total = int(tcfg.get("epochs", 100)) * 48
             sched = WarmupCosineLR(lr, total, int(float(tcfg.get("warmup_ratio", 0.05)) * total), float(tcfg.get("min_lr", 0.0)))
-            self.runner = TrainStep(self.model, lambda lg, yy: F.cross_entropy(lg, yy, label_smoothing=ls), self.x_dev, self.y_dev,
+            self.runner = TrainStep(self.model, lambda lg, yy: og.cross_entropy(lg, yy, label_smoothing=ls), self.x_dev, self.y_dev,
                                     lr=lr, weight_decay=float(tcfg.get("weight_decay", 0.05)), autocast_bf16=self.bf16,
                                     grad_sync=self.sync, use_graph=use_graph, warmup=warm,
                                     grad_clip_norm=float(clip) if clip else None, scheduler=sched, world=world, flat=flat)

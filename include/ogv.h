@@ -288,6 +288,16 @@ int ogv_adamw_flat(float* p, const float* g, float* m, float* v, const unsigned*
 int ogv_train_metrics(const float* logits, long long ld, const long long* labels, int B, int K, const float* loss,
                       float* acc, void* stream);
 
+/* The training criterion nn.CrossEntropyLoss(label_smoothing=eps), mean reduction (train_full_model.py:52,
+ * one_epoch_train.py:95-97) as one kernel per direction:
+ *   ogv_xent_fwd: lse[i] = logsumexp(logits[i, :]); *loss += mean_i (1-eps)*(lse_i - x_i[y_i]) + eps*(lse_i - mean_k x_i[k])
+ *                 (loss pre-zeroed by the caller; labels int64 in [0, K), no ignore_index)
+ *   ogv_xent_bwd: dlogits[i, k] = *gout / B * (exp(x_ik - lse_i) - (1-eps)*[k == y_i] - eps/K)   (gout NULL: 1) */
+int ogv_xent_fwd(const void* logits, long long ld, const long long* labels, int B, int K, float smoothing, int dtype,
+                 float* lse, float* loss, void* stream);
+int ogv_xent_bwd(const void* logits, long long ld, const long long* labels, const float* lse, const float* gout, int B,
+                 int K, float smoothing, int dtype, void* dlogits, long long ldd, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Fused MLP (north_star kernel 4):  y = residual + row_scale[m / rows_per_scale] * ( act(x W1^T + b1) W2^T + b2 )
  * in ONE tcgen05 kernel -- MLP2d (outlook_attention.py:43-49) and MLP (Out_Grid_Block.py:24-32) with the residual /

@@ -5,6 +5,7 @@ CPU path and no Triton / torch.compile path.
 """
 from .dropin import find_reference_root, install, uninstall
 from .config import BASELINE_CONFIGS, StageCfg, build_stages, load_yaml
+from .functional import cross_entropy
 from .model import (ConvStem, Downsample, DownsampleConfig, MaxOutNet, OutlookerFrontGridNet, build_model,
                     make_dpr)
 from .modules import (MLP, AttentionConfig, DropPath, GridAttention2D, GridAttention2DConfig, GridOnlyBlock,

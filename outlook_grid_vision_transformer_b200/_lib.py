@@ -88,6 +88,8 @@ SIGNATURES = {
     "ogv_grid_attn_bwd": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "ogv_grid_attn_probs": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "ogv_adamw": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _F, _F, _F, _P],
+    "ogv_xent_fwd": [_P, _L, _P, _I, _I, _F, _I, _P, _P, _P],
+    "ogv_xent_bwd": [_P, _L, _P, _P, _P, _I, _I, _F, _I, _P, _L, _P],
     "ogv_sumsq": [_P, _L, _P, _P],
     "ogv_adamw_flat": [_P, _P, _P, _P, _P, _L, _P, _P, _P, _F, _F, _F, _F, _P, _P],
     "ogv_train_metrics": [_P, _L, _P, _I, _I, _P, _P, _P],

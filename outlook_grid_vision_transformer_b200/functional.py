@@ -891,6 +891,36 @@ def head(rows: Tensor, gamma: Tensor, beta: Tensor, wc: Tensor, bc: Optional[Ten
     return HeadFn.apply(rows, gamma, beta, wc, bc, meta)
 
 
+# =================================================================================================
+# training criterion: nn.CrossEntropyLoss(label_smoothing=eps), mean reduction (train_full_model.py:52)
+# =================================================================================================
+class CrossEntropyFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, labels, smoothing):
+        logits = logits if logits.stride(-1) == 1 else logits.contiguous()
+        loss = _zeros(1, logits)
+        lse = ops.xent_fwd(logits, labels, smoothing, loss)
+        ctx.smoothing = smoothing
+        ctx.save_for_backward(logits, labels, lse)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, gout):
+        logits, labels, lse = ctx.saved_tensors
+        g = gout.detach().float().reshape(1).contiguous()
+        return ops.xent_bwd(logits, labels, lse, g, ctx.smoothing), None, None
+
+
+def cross_entropy(logits: Tensor, target: Tensor, label_smoothing: float = 0.0) -> Tensor:
+    """`F.cross_entropy(logits, target, label_smoothing=...)` with mean reduction on [B, K] logits and int64 class
+    indices, as one kernel per direction (ogv_xent_fwd / ogv_xent_bwd).  Anything else the PyTorch function accepts
+    (class weights, ignore_index, probabilities as targets, other reductions, CPU tensors) goes to PyTorch."""
+    if (logits.is_cuda and logits.dim() == 2 and target.dim() == 1 and target.dtype == torch.int64
+            and logits.dtype in (torch.float32, torch.bfloat16)):
+        return CrossEntropyFn.apply(logits, target.contiguous(), float(label_smoothing))
+    return torch.nn.functional.cross_entropy(logits, target, label_smoothing=label_smoothing)
+
+
 class LayerNormRowsFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, b, eps):

@@ -775,6 +775,31 @@ def adamw_flat(p: Tensor, g: Tensor, m: Tensor, v: Tensor, decay_bits: Tensor, h
           float(beta1), float(beta2), float(eps), float(weight_decay), _p(skipped), _stream())
 
 
+def xent_fwd(logits: Tensor, labels: Tensor, smoothing: float, loss: Tensor) -> Tensor:
+    """loss[0] += mean cross entropy with label smoothing of logits [B, K] (fp32 / bf16) vs int64 labels; -> lse [B] fp32."""
+    _require_cuda(logits, labels, loss)
+    _rows(logits, "logits")
+    _f32(loss, "loss")
+    if labels.dtype != torch.int64 or labels.dim() != 1 or labels.shape[0] != logits.shape[0] or not labels.is_contiguous():
+        raise ValueError("xent_fwd: labels must be a contiguous int64 vector with one entry per row")
+    B, K = logits.shape
+    lse = torch.empty(B, device=logits.device, dtype=torch.float32)
+    _call("ogv_xent_fwd", _p(logits), logits.stride(0), _p(labels), B, K, float(smoothing), dtype_code(logits), _p(lse),
+          _p(loss), _stream())
+    return lse
+
+
+def xent_bwd(logits: Tensor, labels: Tensor, lse: Tensor, gout: Optional[Tensor], smoothing: float) -> Tensor:
+    """-> dlogits [B, K] (dtype of logits) = gout / B * (softmax - (1-eps)*onehot - eps/K)."""
+    _require_cuda(logits, labels, lse, gout)
+    _f32(gout, "gout")
+    B, K = logits.shape
+    dl = torch.empty((B, K), device=logits.device, dtype=logits.dtype)
+    _call("ogv_xent_bwd", _p(logits), logits.stride(0), _p(labels), _p(lse), _p(gout), B, K, float(smoothing),
+          dtype_code(logits), _p(dl), dl.stride(0), _stream())
+    return dl
+
+
 def train_metrics(logits: Tensor, labels: Tensor, loss: Optional[Tensor], acc: Tensor) -> None:
     """acc[5] += {loss*B, top-1, top-3, top-5 hits, B} (fp32 logits [B, K], int64 labels)."""
     _require_cuda(logits, labels, loss, acc)

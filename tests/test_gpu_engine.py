@@ -272,3 +272,28 @@ def test_hyper_parameters_survive_a_host_running_ahead():
     torch.cuda.synchronize()
     lb = [float(t) for t in lb]
     assert lb == pytest.approx(la, rel=5e-4), f"{lb} vs {la}"
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+@pytest.mark.parametrize("smoothing", [0.0, 0.1])
+@pytest.mark.parametrize("B,K", [(1024, 100), (7, 200), (33, 10), (4, 1000)])
+def test_cross_entropy_kernel_matches_torch(B, K, smoothing, dtype):
+    """og.cross_entropy (ogv_xent_fwd / ogv_xent_bwd) against F.cross_entropy: the criterion of the reference's loop
+    (nn.CrossEntropyLoss(label_smoothing), train_full_model.py:52), loss and gradient, with an upstream gradient."""
+    import outlook_grid_vision_transformer_b200 as og
+    g = torch.Generator().manual_seed(B + K)
+    x = (torch.randn(B, K, generator=g) * 3).to(DEV).to(dtype)
+    y = torch.randint(0, K, (B,), generator=g).to(DEV)
+    x1, x2 = x.clone().requires_grad_(True), x.float().clone().requires_grad_(True)
+    l1 = og.cross_entropy(x1, y, label_smoothing=smoothing)
+    l2 = F.cross_entropy(x2, y, label_smoothing=smoothing)
+    (l1 * 1.7).backward()
+    (l2 * 1.7).backward()
+    assert l1.shape == l2.shape == ()
+    rtol = 1e-5 if dtype == torch.float32 else 1e-4     # the loss itself is fp32 either way (bf16: same rounded inputs)
+    assert float(l1) == pytest.approx(float(l2), rel=rtol)
+    tol = dict(rtol=1e-4, atol=1e-8) if dtype == torch.float32 else dict(rtol=1e-2, atol=1e-6)   # bf16: the stored gradient
+    torch.testing.assert_close(x1.grad.float(), x2.grad, **tol)
+    # other signatures fall through to PyTorch
+    w = og.cross_entropy(x.float().cpu(), y.cpu(), label_smoothing=smoothing)
+    assert float(w) == pytest.approx(float(l2), rel=1e-4)
