@@ -706,7 +706,12 @@ static int gemm_tc_run(const ogv_gemm_args& a, const ogv_conv_view* conv, cudaSt
   const bool staged = obf && !a.accumulate && tma_ok(a.D, a.ldd) && (!a.pre_out || tma_ok(a.pre_out, a.ld_pre)) &&
                       (!a.residual || tma_ok(a.residual, a.ld_res)) && (!a.dact_src || tma_ok(a.dact_src, a.ld_dact)) &&
                       !(a.residual && a.dact_src);
-  const int MT = (mt_mode >= 2 && BN <= (mt_mode >= 3 ? 128 : 64) && staged && p.a_mn == 0 && !a.row_sum && a.M >= 2 * 256 * ogv_num_sms()) ? 2 : 1;
+  // the implicit convolution is bound by the L2 -> shared-memory fill (a weight tile per 128-pixel tile): two pixel
+  // sub-tiles per weight tile also at BN = 128 (OGV_CONV_MT=1 keeps single sub-tiles, for A/B measurements)
+  static int conv_mt = -1;
+  if (conv_mt < 0) { const char* e = getenv("OGV_CONV_MT"); conv_mt = e ? atoi(e) : 2; }
+  const int mt_bn_max = (mt_mode >= 3 || (p.cv.which == 1 && conv_mt >= 2)) ? 128 : 64;
+  const int MT = (mt_mode >= 2 && BN <= mt_bn_max && staged && p.a_mn == 0 && !a.row_sum && a.M >= 2 * 256 * ogv_num_sms()) ? 2 : 1;
   p.m_tiles = ogv_ceil_div(a.M, TC_BM * MT);
   p.slots = staged ? (a.pre_out ? 4 : 2) : 0;
   p.col_stats = (a.col_sum != nullptr) ? 1 : 0;
