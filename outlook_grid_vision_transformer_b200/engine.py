@@ -144,9 +144,11 @@ class FlatState:
         self.n_decay = sum(p.numel() for n, p in zip(self.names, self.params) if not no_decay(n))
         # module marks: branches accumulate parameter gradients in place; MBConv BatchNorm counters share one arena
         nbt = []
+        from . import model as _model  # the callers around the blocks: conv -> BN -> act units and the head
+
         for m in model.modules():
             if isinstance(m, (_modules.MLP2d, _modules.MLP, _modules.OutlookAttention2d, _modules.MBConv,
-                              _modules.MultiHeadSelfAttention)):
+                              _modules.MultiHeadSelfAttention, _model.ConvStem, _model.Downsample, _model._Backbone)):
                 m.__dict__["_ogv_direct"] = True
             if isinstance(m, _modules.OutlookAttention2d) and fused.get(m.v.weight) is m:
                 C, nl = m.v.weight.shape[0], m.attn.weight.shape[0]

@@ -764,6 +764,7 @@ class ConvBnActFn(torch.autograd.Function):
         ctx.x_needs_grad = x.requires_grad
         ctx.x_dtype = x.dtype
         ctx.st = st  # a view of the per-step scratch arena (shared version counter): kept as an attribute
+        ctx.params = (w, gamma, beta)
         ctx.save_for_backward(saved[0], saved[1], rows, gamma)
         return out.view(B, H, W, Co).permute(0, 3, 1, 2)
 
@@ -778,8 +779,15 @@ class ConvBnActFn(torch.autograd.Function):
         dyr = dy.to(rows.dtype).contiguous(memory_format=torch.channels_last).permute(0, 2, 3, 1).reshape(M, Co)
         ops.PROFILER.tag = ("F2", "bwd", M, Co, ctx.w_shape[1] * ctx.w_shape[2] * ctx.w_shape[3],
                             B * ctx.in_hw[0] * ctx.in_hw[1] * ctx.w_shape[1])
-        red = _scratch_zeros(2 * Co, rows)
-        dgamma, dbeta = red[:Co], red[Co:]
+        # engine "direct" mode: the BatchNorm reductions and the weight gradient accumulate straight into the parameters'
+        # views of the flat gradient arena (zeroed once per step), nothing is handed back to autograd
+        direct = _is_direct(meta, ctx.params)
+        pw, pg, pb = ctx.params
+        if direct:
+            dgamma, dbeta = pg.grad, pb.grad
+        else:
+            red = _scratch_zeros(2 * Co, rows)
+            dgamma, dbeta = red[:Co], red[Co:]
         ops.bn_act_bwd_reduce(dyr, rows, scale, shift, mean, rstd, dgamma, dbeta, meta["act"])
         if meta["training"]:
             dpre = ops.bn_act_bwd_apply(dyr, rows, scale, shift, mean, rstd, gamma.detach(), dgamma, dbeta, meta["act"])
@@ -789,7 +797,16 @@ class ConvBnActFn(torch.autograd.Function):
             dpre = ops.bn_act_bwd_apply(dyr, rows, scale, shift, mean, rstd, gamma.detach(), zero, zero, meta["act"])
         if ctx.route != "lib":
             _, Cin, kh, kw = ctx.w_shape
-            dw2 = _zeros((Co, wc.shape[1]), gamma)
+            # the weight gradient in the GEMM's [Co, (ky, kx, c)] layout: that IS the storage order of a channels_last
+            # weight, so in direct mode the GEMM accumulates into the arena view itself
+            dw2 = None
+            if direct and wc.shape[1] == kh * kw * Cin:
+                wg = pw.grad.permute(0, 2, 3, 1)
+                if wg.is_contiguous():
+                    dw2 = wg.reshape(Co, kh * kw * Cin)
+            dw_in_place = dw2 is not None
+            if dw2 is None:
+                dw2 = _zeros((Co, wc.shape[1]), gamma)
             # on the main stream: autograd accumulates the returned view right away
             if ctx.route == "implicit":
                 ops.conv3x3_wgrad(a, dpre, dw2, meta["stride"][0])
@@ -814,13 +831,18 @@ class ConvBnActFn(torch.autograd.Function):
             if dx is not None and dx.dtype != ctx.x_dtype:
                 dx = dx.to(ctx.x_dtype)
         ops.PROFILER.tag = None
+        if direct:
+            if not (ctx.route != "lib" and dw_in_place):
+                pw.grad.add_(dw.to(pw.grad.dtype))
+            _notify(ctx.params)
+            return dx, None, None, None, None
         return dx, dw, dgamma.clone(), dbeta.clone(), None
 
 
 def conv_bn_act(x: Tensor, w: Tensor, gamma: Tensor, beta: Tensor, *, running, stride: int, padding: int, act: str,
-                eps: float, momentum: float, training: bool, dtype: torch.dtype) -> Tensor:
+                eps: float, momentum: float, training: bool, dtype: torch.dtype, direct: bool = False) -> Tensor:
     meta = dict(running=running, stride=[stride, stride], padding=[padding, padding], act=act, eps=eps,
-                momentum=momentum, training=training, dtype=dtype)
+                momentum=momentum, training=training, dtype=dtype, direct=direct)
     return ConvBnActFn.apply(x, w, gamma, beta, meta)
 
 
@@ -855,6 +877,7 @@ class HeadFn(torch.autograd.Function):
         ctx.meta = meta
         ctx.st = st
         ctx.has_bias = bc is not None
+        ctx.params = (gamma, beta, wc, bc)
         ctx.save_for_backward(rows, gamma, pool_c, w_c)
         return logits
 
@@ -869,25 +892,35 @@ class HeadFn(torch.autograd.Function):
         mean, rstd = st[4 * C:5 * C], st[5 * C:6 * C]
         ops.PROFILER.tag = ("HEAD", "bwd", M, C)
         dl = dlogits.to(pool_c.dtype).contiguous()
-        dw = _zeros((K, C), gamma)
+        pg, pb, pwc, pbc = ctx.params
+        direct = _is_direct(meta, ctx.params) and pwc.grad.is_contiguous()
+        dw = pwc.grad if direct else _zeros((K, C), gamma)
         ops._wgrad(dl, pool_c, dw)
         db = dlogits.float().sum(0) if ctx.has_bias else None  # [B, classes]: a few hundred KB
         dpool = _empty((B, C), rows, torch.float32)
         ops.gemm(dl, w_c.t().contiguous(), dpool)
         # every position of an image receives dpool / HW
         dyr = (dpool * (1.0 / HW)).to(rows.dtype).repeat_interleave(HW, dim=0)
-        red = _scratch_zeros(2 * C, rows)
-        dgamma, dbeta = red[:C], red[C:]
+        if direct:
+            dgamma, dbeta = pg.grad, pb.grad
+        else:
+            red = _scratch_zeros(2 * C, rows)
+            dgamma, dbeta = red[:C], red[C:]
         ops.bn_bwd_reduce(dyr, rows, mean, rstd, dgamma, dbeta)
         zero = None if training else _zeros(C, gamma)
         dx = ops.bn_bwd_apply(dyr, rows, mean, rstd, gamma.detach(), dgamma if training else zero, dbeta if training else zero)
         ops.PROFILER.tag = None
+        if direct:
+            if db is not None:
+                pbc.grad.add_(db)
+            _notify(ctx.params)
+            return dx, None, None, None, None, None
         return dx, dgamma.clone(), dbeta.clone(), dw, db, None
 
 
 def head(rows: Tensor, gamma: Tensor, beta: Tensor, wc: Tensor, bc: Optional[Tensor], *, B: int, HW: int, running,
-         eps: float, momentum: float, training: bool, dtype: torch.dtype) -> Tensor:
-    meta = dict(B=B, HW=HW, running=running, eps=eps, momentum=momentum, training=training, dtype=dtype)
+         eps: float, momentum: float, training: bool, dtype: torch.dtype, direct: bool = False) -> Tensor:
+    meta = dict(B=B, HW=HW, running=running, eps=eps, momentum=momentum, training=training, dtype=dtype, direct=direct)
     return HeadFn.apply(rows, gamma, beta, wc, bc, meta)
 
 

@@ -20,12 +20,12 @@ import torch.nn as nn
 
 from . import functional as OF
 from .config import StageCfg, build_stages
-from .modules import GridOnlyBlock, OutGridBlock, OutlookerBlock2d, _act_name, _compute_dtype, make_activation
+from .modules import GridOnlyBlock, OutGridBlock, OutlookerBlock2d, _act_name, _compute_dtype, _direct, make_activation
 
 DownsampleType = Literal["conv", "pool"]
 
 
-def _conv_bn_act(seq: nn.Sequential, x: torch.Tensor) -> torch.Tensor:
+def _conv_bn_act(seq: nn.Sequential, x: torch.Tensor, owner: nn.Module = None) -> torch.Tensor:
     """Run a (Conv2d, BatchNorm2d, act) Sequential: fused BatchNorm + activation kernels on CUDA; the plain module chain
     when a hook sits on one of the three (it must see the tensors the reference would hand it), when the layout is not
     the fused one (no BatchNorm, conv bias, channel count not a multiple of 8), or off the GPU (construction-time shape
@@ -49,7 +49,8 @@ def _conv_bn_act(seq: nn.Sequential, x: torch.Tensor) -> torch.Tensor:
         momentum = bn.momentum if bn.momentum is not None else 0.0
     return OF.conv_bn_act(x, conv.weight, bn.weight, bn.bias, running=(bn.running_mean, bn.running_var),
                           stride=conv.stride[0], padding=conv.padding[0], act=_act_name(act), eps=bn.eps,
-                          momentum=momentum, training=training, dtype=_compute_dtype(x))
+                          momentum=momentum, training=training, dtype=_compute_dtype(x),
+                          direct=owner is not None and _direct(owner))
 
 
 def make_dpr(total_blocks: int, dpr_max: float) -> List[float]:
@@ -69,7 +70,7 @@ class ConvStem(nn.Module):
                                   make_activation(act))
 
     def forward(self, x):
-        return _conv_bn_act(self.stem, x)
+        return _conv_bn_act(self.stem, x, self)
 
 
 @dataclass(frozen=True)
@@ -100,7 +101,7 @@ class Downsample(nn.Module):
             raise ValueError("cfg.kind must be 'conv' or 'pool'")
 
     def forward(self, x):
-        return _conv_bn_act(self.op, x)
+        return _conv_bn_act(self.op, x, self)
 
 
 def _with_drop_path(scfg: StageCfg, p: float) -> StageCfg:
@@ -147,7 +148,7 @@ class _Backbone(nn.Module):
         rows = rows.to(dt) if rows.dtype != dt else rows
         return OF.head(rows, bn.weight, bn.bias, fc.weight, fc.bias, B=geom.B, HW=geom.H * geom.W,
                        running=(bn.running_mean, bn.running_var), eps=bn.eps, momentum=momentum, training=training,
-                       dtype=dt)
+                       dtype=dt, direct=_direct(self))
 
 
 class MaxOutNet(_Backbone):
