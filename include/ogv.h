@@ -198,10 +198,13 @@ int ogv_col2im3x3_vec(const void* dcols, void* dx, int B, int H, int W, int Cin,
  * output pixels as one 5-D box of x viewed as {2*Cin, W/2, 2, H/2, B} (stride 2) or {Cin, W, 1, H, B} (stride 1), the zero
  * padding being the descriptor's out-of-bounds fill.
  *   ogv_conv3x3_fwd  : y[(b,oy,ox), co] = sum_k cols[.., k] * w2[co, k]          (downsampling.py:41-47 forward)
+ *                      col_sum / col_sumsq (fp32 [Co], nullable): += per-channel sum / sum of squares of the stored
+ *                      outputs -- the BatchNorm batch statistics of the unit, from the GEMM's epilogue
  *   ogv_conv3x3_wgrad: dw2[co, k] += sum_pixels dy[pixel, co] * cols[pixel, k]   (fp32, split over pixels, pre-zeroed)
  * with w2[co, (ky*3+kx)*Cin + c] = weight[co, c, ky, kx].  ogv_conv3x3_supported() -> 1 when the geometry is served. */
 int ogv_conv3x3_supported(int B, int H, int W, int Cin, int Co, int stride);
-int ogv_conv3x3_fwd(const void* x, const void* w2, void* y, int B, int H, int W, int Cin, int Co, int stride, void* stream);
+int ogv_conv3x3_fwd(const void* x, const void* w2, void* y, float* col_sum, float* col_sumsq, int B, int H, int W, int Cin,
+                    int Co, int stride, void* stream);
 int ogv_conv3x3_wgrad(const void* x, const void* dy, float* dw2, int B, int H, int W, int Cin, int Co, int stride,
                       void* stream);
 

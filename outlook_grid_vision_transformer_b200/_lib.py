@@ -71,7 +71,7 @@ SIGNATURES = {
     "ogv_im2col3x3_vec": [_P, _P, _I, _I, _I, _I, _I, _I, _P],
     "ogv_col2im3x3_vec": [_P, _P, _I, _I, _I, _I, _I, _I, _P],
     "ogv_conv3x3_supported": [_I, _I, _I, _I, _I, _I],
-    "ogv_conv3x3_fwd": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "ogv_conv3x3_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "ogv_conv3x3_wgrad": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "ogv_bn_act_apply": [_P, _P, _P, _P, _L, _I, _I, _I, _P],
     "ogv_bn_act_bwd_reduce": [_P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _P],

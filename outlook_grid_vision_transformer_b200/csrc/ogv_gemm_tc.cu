@@ -768,8 +768,8 @@ extern "C" int ogv_conv3x3_supported(int B, int H, int W, int Cin, int Co, int s
   return (Co > 0 && Co % 8 == 0 && ogv_conv_view_supported(c)) ? 1 : 0;
 }
 
-extern "C" int ogv_conv3x3_fwd(const void* x, const void* w2, void* y, int B, int H, int W, int Cin, int Co, int stride,
-                               void* stream) {
+extern "C" int ogv_conv3x3_fwd(const void* x, const void* w2, void* y, float* col_sum, float* col_sumsq, int B, int H,
+                               int W, int Cin, int Co, int stride, void* stream) {
   OGV_REQUIRE(x && w2 && y, "conv3x3_fwd: null pointer");
   ogv_conv_view c{1, x, B, H, W, Cin, stride};
   if (!(Co > 0 && Co % 8 == 0 && ogv_conv_view_supported(c))) {
@@ -784,6 +784,7 @@ extern "C" int ogv_conv3x3_fwd(const void* x, const void* w2, void* y, int B, in
   a.M = B * (H / stride) * (W / stride); a.N = Co; a.K = 9 * Cin;
   a.in_dtype = OGV_BF16; a.out_dtype = OGV_BF16;
   a.rows_per_scale = 1; a.split_k = 1;
+  a.col_sum = col_sum; a.col_sumsq = col_sumsq;
   return ogv_gemm_tc_conv(a, c, reinterpret_cast<cudaStream_t>(stream));
 }
 

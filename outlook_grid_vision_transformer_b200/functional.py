@@ -437,6 +437,10 @@ def grid_branch(x, ln_w, ln_b, wqkv, bqkv, wp, bp, scale, *, pq, pp, geom: Geom,
 # =================================================================================================
 # MBConv (expand 1x1 + BN + act -> depthwise 3x3 + BN + act -> SE -> project 1x1 + BN, + residual)
 # =================================================================================================
+_CONV_STATS_FUSED = _os.environ.get("OGV_CONV_STATS_FUSED", "1") == "1"
+_BN3_FUSED = _os.environ.get("OGV_BN3_STATS_FUSED", "1") == "1"  # 0: separate colstats pass (A/B: +0.12..0.18 ms per step)
+
+
 class MBConvFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, we, g1, b1, wdw, g2, b2, sw1, sb1, sw2, sb2, wp, g3, b3, meta):
@@ -461,7 +465,8 @@ class MBConvFn(torch.autograd.Function):
         e_pre = _empty((M, Cm), x)
         # BN1 batch statistics: a separate streaming pass.  Fusing them into this GEMM's epilogue was measured
         # SLOWER (358 us vs 192 + 107 us at stage 0): the epilogue warps of a C -> 4C GEMM are its critical path.
-        # (The narrow project GEMM below does take its statistics from the epilogue.)
+        # (The narrow project GEMM below and the convolutions of the conv -> BN -> act units do take their statistics
+        # from the epilogue: 12 launches fewer per step, 0 .. 0.15 ms depending on the box.)
         ops.gemm(x, pe.w, e_pre)
         if training:
             ops.colstats(e_pre, s1[0], s1[1])
@@ -491,9 +496,14 @@ class MBConvFn(torch.autograd.Function):
         d_act = ops.bn_act_gate(d_pre, s2[2], s2[3], gate, g.B, g.P, act)
         # project
         o_pre = _empty((M, C), x)
-        ops.gemm(d_act, ppj.w, o_pre)
-        if training:
-            ops.colstats(o_pre, s3[0], s3[1])
+        if training and _BN3_FUSED and x.dtype == torch.bfloat16:
+            # BN3 batch statistics from the narrow project GEMM's epilogue (its A operand, 4x wider than its output, is what
+            # bounds it: the epilogue warps have the slack the C -> 4C expand GEMM's do not)
+            ops.gemm(d_act, ppj.w, o_pre, col_sum=s3[0], col_sumsq=s3[1])
+        else:
+            ops.gemm(d_act, ppj.w, o_pre)
+            if training:
+                ops.colstats(o_pre, s3[0], s3[1])
         ops.bn_finalize(s3[0], s3[1], g3, b3, rm3, rv3, s3[2], s3[3], s3[4], s3[5], M, eps, mom, training)
         y = ops.bn_apply(o_pre, s3[2], s3[3], x if meta["use_res"] else None)
         ctx.meta = meta
@@ -734,11 +744,18 @@ class ConvBnActFn(torch.autograd.Function):
                 cols = xc.permute(0, 2, 3, 1).reshape(B * H * W, Cin)
                 w2 = w.detach().reshape(Co, Cin).to(dt)
             M = B * H * W
+            # batch statistics from the GEMM's epilogue (bf16 staged epilogue; the separate pass otherwise)
+            fused_stats = training and _CONV_STATS_FUSED and dt == torch.bfloat16 and Co % 8 == 0
+            st = _scratch_zeros(6 * Co, xc)
             if route == "implicit":
-                rows = ops.conv3x3_fwd(xc, w2, stride[0])
+                rows = ops.conv3x3_fwd(xc, w2, stride[0], col_sum=st[:Co] if fused_stats else None,
+                                       col_sumsq=st[Co:2 * Co] if fused_stats else None)
             else:
                 rows = _empty((M, Co), cols)
-                ops.gemm(cols, w2, rows)
+                if fused_stats:
+                    ops.gemm(cols, w2, rows, col_sum=st[:Co], col_sumsq=st[Co:2 * Co])
+                else:
+                    ops.gemm(cols, w2, rows)
             saved = (cols, w2)
         else:
             wc = w.detach().to(dt).contiguous(memory_format=torch.channels_last)
@@ -748,9 +765,10 @@ class ConvBnActFn(torch.autograd.Function):
             M = B * H * W
             rows = y_pre.permute(0, 2, 3, 1).reshape(M, Co)
             saved = (xc, wc)
-        st = _scratch_zeros(6 * Co, rows)
+            fused_stats = False
+            st = _scratch_zeros(6 * Co, rows)
         ssum, ssq, scale, shift, mean, rstd = (st[i * Co:(i + 1) * Co] for i in range(6))
-        if training:
+        if training and not fused_stats:
             ops.colstats(rows, ssum, ssq)
         ops.bn_finalize(ssum, ssq, gamma, beta, rm, rv, scale, shift, mean, rstd, M, meta["eps"], meta["momentum"],
                         training)

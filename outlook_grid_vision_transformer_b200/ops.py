@@ -502,7 +502,8 @@ def conv3x3_supported(x: Tensor, Co: int, stride: int) -> bool:
     return bool(_lib.lib().ogv_conv3x3_supported(B, H, W, Cin, Co, stride))
 
 
-def conv3x3_fwd(x: Tensor, w2: Tensor, stride: int) -> Tensor:
+def conv3x3_fwd(x: Tensor, w2: Tensor, stride: int, col_sum: Optional[Tensor] = None,
+                col_sumsq: Optional[Tensor] = None) -> Tensor:
     """channels_last bf16 x [B, Cin, H, W], w2 [Co, 9*Cin] (column (ky*3+kx)*Cin + c) -> rows [B*Ho*Wo, Co]: the 3x3 / pad 1
     convolution as an implicit GEMM (the patch matrix is never written; 5-D TMA boxes of x feed the tcgen05 pipeline)."""
     _require_cuda(x, w2)
@@ -516,7 +517,9 @@ def conv3x3_fwd(x: Tensor, w2: Tensor, stride: int) -> Tensor:
         PROFILER.cur_flops = 2 * Mo * Co * 9 * Cin
         PROFILER.cur_label = f"ogv_conv3x3_fwd[{Mo}x{Co}x{9 * Cin} s{stride}]"
         PROFILER.cur_kernel = f"gemm_tc_kernel<{64 if Co <= 64 else (128 if Co <= 128 else 256)}, __nv_bfloat16>"
-    _call("ogv_conv3x3_fwd", _p(x), _p(w2), _p(y), B, H, W, Cin, Co, stride, _stream())
+    _f32(col_sum, "col_sum")
+    _f32(col_sumsq, "col_sumsq")
+    _call("ogv_conv3x3_fwd", _p(x), _p(w2), _p(y), _p(col_sum), _p(col_sumsq), B, H, W, Cin, Co, stride, _stream())
     return y
 
 

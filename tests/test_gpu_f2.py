@@ -208,7 +208,7 @@ def test_downsample_convolution_runs_on_own_kernels(mode):
         names = ("im2col3x3_vec", "col2im3x3_vec", "conv3x3_fwd", "conv3x3_wgrad")
         orig = {n: getattr(OF.ops, n) for n in names}
         for n in names:
-            setattr(OF.ops, n, (lambda n: lambda *a: (seen.append(n), orig[n](*a))[1])(n))
+            setattr(OF.ops, n, (lambda n: lambda *a, **k: (seen.append(n), orig[n](*a, **k))[1])(n))
         try:
             with torch.autocast("cuda", dtype=torch.bfloat16, enabled=mode == "bf16"):
                 y, yr = unit(x1), ref(x2)
