@@ -109,6 +109,8 @@ def main():
         run("rowscale[M,C]", s, lambda: ops.rowscale(dy, scale_b, P), nbytes(dy, dy))
         run("bn_apply[M,C]", s, lambda: ops.bn_apply(x, ones_c, zeros_c, dy), nbytes(x, x, x))
         run("bn_bwd_reduce[M,C]", s, lambda: ops.bn_bwd_reduce(dy, x, zeros_c, ones_c, dg, db), nbytes(x, x))
+        run("colstats[M,C]", s, lambda: ops.colstats(x, dg, db), nbytes(x))
+        run("bn_act_bwd_reduce[M,C]", s, lambda: ops.bn_act_bwd_reduce(dy, x, ones_c, zeros_c, zeros_c, ones_c, dg, db, "silu"), nbytes(x, x))
         run("bn_bwd_apply[M,C]", s, lambda: ops.bn_bwd_apply(dy, x, zeros_c, ones_c, ones_c, dg, db), nbytes(x, x, x))
         run("bn_bwd_apply[M,4C]", s, lambda: ops.bn_bwd_apply(wide, wide2, mu, rs, gm, acc2[0], acc2[1]), nbytes(wide, wide, wide))
         # ---- MBConv interior
