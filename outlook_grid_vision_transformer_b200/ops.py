@@ -452,8 +452,8 @@ def bn_bwd_reduce(dy, x, mean, rstd, dgamma, dbeta) -> None:
                                        x.shape[1], dtype_code(x), _stream())
 
 
-def bn_bwd_apply(dy, x, mean, rstd, gamma, dgamma, dbeta, out: Optional[Tensor] = None) -> Tensor:
-    dx = torch.empty_like(x) if out is None else out
+def bn_bwd_apply(dy, x, mean, rstd, gamma, dgamma, dbeta) -> Tensor:
+    dx = torch.empty_like(x)
     _call("ogv_bn_bwd_apply", _p(dy), _p(x), _p(mean), _p(rstd), _p(gamma), _p(dgamma), _p(dbeta), _p(dx),
                                       x.shape[0], x.shape[1], dtype_code(x), _stream())
     return dx
@@ -569,9 +569,8 @@ def dwconv_fwd(e_pre, scale1, shift1, w, ssum2, ssq2, B, H, W, act: str) -> Tens
     return d_pre
 
 
-def dwconv_bwd(dd_pre, e_pre, scale1, shift1, mean1, rstd1, w, dw, dgamma1, dbeta1, B, H, W, act: str,
-               out: Optional[Tensor] = None) -> Tensor:
-    du1 = torch.empty_like(e_pre) if out is None else out
+def dwconv_bwd(dd_pre, e_pre, scale1, shift1, mean1, rstd1, w, dw, dgamma1, dbeta1, B, H, W, act: str) -> Tensor:
+    du1 = torch.empty_like(e_pre)
     _call("ogv_dwconv_bwd", _p(dd_pre), _p(e_pre), _p(scale1), _p(shift1), _p(mean1), _p(rstd1), _p(w),
                                     _p(du1), _p(dw), _p(dgamma1), _p(dbeta1), B, H, W, e_pre.shape[1], ACT[act],
                                     dtype_code(e_pre), _stream())
@@ -625,8 +624,8 @@ def se_mlp_bwd(dgate: Tensor, gate_pre: Tensor, s1_pre: Tensor, w2: Tensor, w1: 
     return dgate_c, ds1_pre, dpool
 
 
-def bn_act_gate(d_pre, scale2, shift2, gate, B, HW, act: str, out: Optional[Tensor] = None) -> Tensor:
-    d_act = torch.empty_like(d_pre) if out is None else out
+def bn_act_gate(d_pre, scale2, shift2, gate, B, HW, act: str) -> Tensor:
+    d_act = torch.empty_like(d_pre)
     _call("ogv_bn_act_gate", _p(d_pre), _p(scale2), _p(shift2), _p(gate), _p(d_act), B, HW, d_pre.shape[1],
                                      ACT[act], dtype_code(d_pre), _stream())
     return d_act
@@ -639,9 +638,9 @@ def se_bwd_reduce(dd_act, d_pre, scale2, shift2, B, HW, act: str) -> Tensor:
     return dgate
 
 
-def mbconv_bwd_stats(dd_act, d_pre, scale2, shift2, mean2, rstd2, B, HW, act: str, out: Optional[Tensor] = None) -> Tensor:
+def mbconv_bwd_stats(dd_act, d_pre, scale2, shift2, mean2, rstd2, B, HW, act: str) -> Tensor:
     """-> stats [5, B, Cm] fp32 (stats[0] = dgate); see include/ogv.h."""
-    stats = torch.empty((5, B, d_pre.shape[1]), device=d_pre.device, dtype=torch.float32) if out is None else out
+    stats = torch.empty((5, B, d_pre.shape[1]), device=d_pre.device, dtype=torch.float32)
     _call("ogv_mbconv_bwd_stats", _p(dd_act), _p(d_pre), _p(scale2), _p(shift2), _p(mean2), _p(rstd2), _p(stats), B,
           HW, d_pre.shape[1], ACT[act], dtype_code(d_pre), _stream())
     return stats
@@ -653,8 +652,8 @@ def mbconv_bn2_finalize(stats, gate, dpool, dgamma2, dbeta2, B, HW) -> None:
 
 
 def dw_bn2_bwd_apply(dd_act, d_pre, gate, dpool, scale2, shift2, mean2, rstd2, gamma2, dgamma2, dbeta2, B, HW,
-                     act: str, out: Optional[Tensor] = None) -> Tensor:
-    dd_pre = torch.empty_like(d_pre) if out is None else out
+                     act: str) -> Tensor:
+    dd_pre = torch.empty_like(d_pre)
     _call("ogv_dw_bn2_bwd_apply", _p(dd_act), _p(d_pre), _p(gate), _p(dpool), _p(scale2), _p(shift2), _p(mean2),
           _p(rstd2), _p(gamma2), _p(dgamma2), _p(dbeta2), _p(dd_pre), B, HW, d_pre.shape[1], ACT[act],
           dtype_code(d_pre), _stream())
