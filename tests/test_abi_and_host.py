@@ -207,3 +207,38 @@ def test_bulk_refreshed_weight_copies_are_handed_out_only_while_fresh():
     finally:
         M._BULK_FRESH = False
     assert prep.get(True, [w2], torch.float16, build) == 6
+
+
+def test_implicit_convolution_geometry_gate():
+    """ogv_conv3x3_supported is host logic (no GPU): the implicit-GEMM convolution serves exactly the geometries whose
+    128- and 64-pixel tiles are whole output rows / whole images of a channels_last image with Cin % 64 == 0 --
+    every Downsample unit of the BASELINE configs -- and sends everything else to the materialised-patch route."""
+    from outlook_grid_vision_transformer_b200 import _lib
+    ok = _lib.lib().ogv_conv3x3_supported
+    # (B, H, W, Cin, Co, stride): the Downsample units of cfg 2 (32 px) and cfg 3 / 4 (64 px), batch 1024 / 256 / 1
+    for geom in [(1024, 32, 32, 64, 128, 2), (1024, 16, 16, 128, 256, 2), (1024, 8, 8, 256, 384, 2),
+                 (256, 64, 64, 64, 128, 2), (256, 32, 32, 128, 256, 2), (1, 16, 16, 256, 512, 2), (3, 8, 8, 64, 64, 1)]:
+        assert ok(*geom) == 1, geom
+    for geom, why in [((8, 32, 32, 48, 96, 2), "Cin % 64 (the 7M net: materialised patches)"),
+                      ((8, 31, 32, 64, 128, 2), "odd height at stride 2"),
+                      ((8, 48, 48, 64, 128, 2), "24 output columns do not tile 128 pixels"),
+                      ((8, 32, 32, 64, 100, 2), "Co % 8"),
+                      ((8, 32, 32, 64, 128, 3), "stride"),
+                      ((8, 12, 12, 64, 128, 2), "36-pixel images do not tile 128 pixels")]:
+        assert ok(*geom) == 0, (geom, why)
+
+
+def test_cross_entropy_falls_through_to_torch_off_the_gpu_path():
+    """og.cross_entropy is the ogv_xent kernels for [B, K] CUDA logits with int64 class indices; every other signature
+    F.cross_entropy accepts goes to PyTorch unchanged (here: CPU tensors, probabilities as targets)."""
+    import torch.nn.functional as F
+    import outlook_grid_vision_transformer_b200 as og
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(6, 10, generator=g, requires_grad=True)
+    y = torch.randint(0, 10, (6,), generator=g)
+    a = og.cross_entropy(x, y, label_smoothing=0.1)
+    b = F.cross_entropy(x, y, label_smoothing=0.1)
+    assert torch.equal(a, b)
+    a.backward()
+    p = torch.softmax(torch.randn(6, 10, generator=g), dim=1)
+    assert torch.equal(og.cross_entropy(x, p), F.cross_entropy(x, p))
