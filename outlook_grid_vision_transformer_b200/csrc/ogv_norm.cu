@@ -281,7 +281,7 @@ __global__ void bn_apply_kernel(const T* __restrict__ x, const float* __restrict
 }
 
 template <typename T>
-__global__ void __launch_bounds__(COLREDUCE_THREADS) bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+__global__ void __launch_bounds__(COLREDUCE_THREADS, 2) bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x,
                                      const float* __restrict__ mean, const float* __restrict__ rstd,
                                      float* __restrict__ dgamma, float* __restrict__ dbeta, long long M, int nv) {
   float acc[2][8];
@@ -396,7 +396,7 @@ bn_act_apply_kernel(const T* __restrict__ x, const float* __restrict__ scale, co
 }
 
 template <typename T, int ACT>
-__global__ void __launch_bounds__(COLREDUCE_THREADS)
+__global__ void __launch_bounds__(COLREDUCE_THREADS, 2)
 bn_act_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ scale,
                          const float* __restrict__ shift, const float* __restrict__ mean,
                          const float* __restrict__ rstd, float* __restrict__ dgamma, float* __restrict__ dbeta,
