@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(COLREDUCE_THREADS) colsum_kernel(const T* __re
 // y = x * scale[row / rows_per_scale] and out[n] += sum_m y[m,n] in one pass (DropPath backward feeding
 // the bias gradient of the branch's last linear layer).
 template <typename T>
-__global__ void __launch_bounds__(COLREDUCE_THREADS) rowscale_colsum_kernel(const T* __restrict__ x,
+__global__ void __launch_bounds__(COLREDUCE_THREADS, 3) rowscale_colsum_kernel(const T* __restrict__ x,
                                                                             const float* __restrict__ scale,
                                                                             T* __restrict__ y, float* __restrict__ out,
                                                                             long long M, int nv, unsigned rows_per_scale) {

@@ -107,6 +107,8 @@ def main():
         run("colstats[M,4C]", s, lambda: ops.colstats(wide, acc2[0], acc2[1]), nbytes(wide))
         scale_b = torch.rand(B, **f32)
         run("rowscale[M,C]", s, lambda: ops.rowscale(dy, scale_b, P), nbytes(dy, dy))
+        run("rowscale_colsum[M,C]", s, lambda: ops.rowscale_colsum(dy, scale_b, P, dg), nbytes(dy, dy))
+        run("rowscale_colsum[M,C] no store", s, lambda: ops.rowscale_colsum(dy, scale_b, P, dg, store=False), nbytes(dy))
         run("bn_apply[M,C]", s, lambda: ops.bn_apply(x, ones_c, zeros_c, dy), nbytes(x, x, x))
         run("bn_bwd_reduce[M,C]", s, lambda: ops.bn_bwd_reduce(dy, x, zeros_c, ones_c, dg, db), nbytes(x, x))
         run("colstats[M,C]", s, lambda: ops.colstats(x, dg, db), nbytes(x))
