@@ -567,9 +567,16 @@ def measure(w, args, world, dev, steps):
     # Both numbers are taken from the same starting state: tools/e2e_probe.py shows that on a power-capped box the step
     # drifts from ~30.6 to ~31.3 ms during the first seconds of sustained load WHICHEVER variant runs (resident replays
     # measured second are as slow as end-to-end steps measured second; the host->device copy itself is hidden behind
-    # the previous step), so the second measurement starts after a short idle like the first one did.
+    # the previous step), so BOTH timed regions start the same way: a short idle, two untimed steps, K timed steps.
+    import torch
+
+    idle = float(os.environ.get("OGV_BENCH_IDLE_S", "2.0"))
+    torch.cuda.synchronize()
+    time.sleep(idle)
+    w.step_resident()
+    w.step_resident()
     ms = timed(w.step_resident, steps, world, dev)
-    time.sleep(float(os.environ.get("OGV_BENCH_IDLE_S", "2.0")))
+    time.sleep(idle)
     w.step_host()
     w.step_host()
     ms_e2e = timed(w.step_host, steps, world, dev)
